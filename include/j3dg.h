@@ -1,0 +1,187 @@
+/*
+ * j3dg.h — C ABI of the B200-native renderer for j3d's data-parallel hot path.
+ *
+ * This is the drop-in boundary: every entry point below replaces one call site of
+ * the reference's std::thread/TBB renderer (j3d has no FFI/plugin layer of its own;
+ * the seams are C++ call sites, cited per function as reference file:line relative
+ * to the j3d source tree).  Plain pointers and sizes only; no C++/torch types.
+ * All functions return 0 (J3DG_OK) on success or a negative J3DG_E* code; the text
+ * of the last error is available through j3dg_last_error().  Nothing throws across
+ * the boundary.  A context is single-caller (externally synchronised, exactly like
+ * j3d's `canvas`, which view guards with one mutex — j3d/view.cpp:1262).
+ *
+ * Buffers named *_out / *_inout may be HOST or DEVICE pointers; the library detects
+ * which (cudaPointerGetAttributes) and copies over PCIe only for host pointers.
+ * Calls are synchronous on return for host buffers; for device buffers work is
+ * enqueued on the context stream (j3dg_ctx_set_stream) and NOT synchronised.
+ */
+#ifndef J3DG_H
+#define J3DG_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define J3DG_OK 0
+#define J3DG_EINVAL (-1)   /* bad argument */
+#define J3DG_ECUDA (-2)    /* CUDA runtime error (see j3dg_last_error) */
+#define J3DG_ENOMEM (-3)   /* device allocation failed */
+#define J3DG_ENODEV (-4)   /* no CUDA device / wrong architecture: there is NO CPU fallback */
+
+/* canvas::canvas_settings (j3d/canvas.h:16-25), one bit per bool, same order. */
+#define J3DG_ONE_BIT      (1u << 0)
+#define J3DG_SHADOW       (1u << 1)
+#define J3DG_EDGES        (1u << 2)
+#define J3DG_WIREFRAME    (1u << 3)
+#define J3DG_SHADING      (1u << 4)
+#define J3DG_TEXTURED     (1u << 5)
+#define J3DG_VERTEXCOLORS (1u << 6)
+/* settings.cpp:7-13 defaults: edges, shading, textured, vertexcolors */
+#define J3DG_DEFAULT_FLAGS (J3DG_EDGES | J3DG_SHADING | J3DG_TEXTURED | J3DG_VERTEXCOLORS)
+
+/* The 32-byte per-pixel record, byte-compatible with `struct pixel` (j3d/pixel.h:11-27).
+ * NB the reference's naming: object_id is the TRIANGLE index within its mesh (or the
+ * POINT index after a splat); db_id identifies the object; u,v are the camera-space
+ * normal x,y; depth is the ray parameter t (== camera-space z distance). */
+typedef struct j3dg_pixel {
+  uint8_t mark, r, g, b; /* mark bit0 = shadowed, bit1 = r,g,b valid */
+  float u, v;
+  float depth;
+  uint32_t object_id;
+  float barycentric_u, barycentric_v;
+  uint32_t db_id;
+} j3dg_pixel;
+
+/* Everything update_canvas / canvas_to_image / render_pointclouds_on_image read from
+ * `canvas` and `scene` per frame (j3d/canvas.cpp:677-705, 287-300, 973-983).
+ * Matrices are column-major float[16] exactly as jtk::float4x4 stores them. */
+typedef struct j3dg_view {
+  uint32_t width, height;     /* canvas size (im.width(), im.height()) */
+  float near_plane;           /* camera::nearClippingPlane (0.1 by default) */
+  float diagonal;             /* scene::diagonal (largest bbox extent, scene.cpp:86-88) */
+  float projection[16];       /* canvas::projection_matrix */
+  float projection_inv[16];   /* canvas::projection_matrix_inv */
+  float cs[16];               /* scene::coordinate_system (camera -> world) */
+  float cs_inv[16];           /* scene::coordinate_system_inv */
+  float pivot[3];             /* scene::pivot (only the shadow light uses it) */
+  uint32_t flags;             /* J3DG_* settings bits */
+} j3dg_view;
+
+typedef struct j3dg_ctx j3dg_ctx;
+typedef struct j3dg_mesh j3dg_mesh;
+typedef struct j3dg_cloud j3dg_cloud;
+
+/* Sizes / timings of one built mesh (what j3d shows as "bvh construction (s)",
+ * j3d/view.cpp:230-232, 894-898, plus the device layout numbers DESIGN.md quotes). */
+typedef struct j3dg_mesh_info {
+  uint32_t nr_of_vertices, nr_of_triangles;
+  uint32_t nr_of_nodes;        /* 8-wide nodes */
+  uint32_t nr_of_leaf_triangles; /* triangle records (== nr_of_triangles) */
+  uint32_t node_bytes, triangle_bytes; /* sizeof one node / one triangle record */
+  float build_ms;              /* device time of the last BVH build (CUDA events) */
+  float upload_ms;             /* host->device copy time of the last create */
+  float bbox_min[3], bbox_max[3];
+  float sah_cost;              /* SAH cost of the wide BVH (diagnostic) */
+} j3dg_mesh_info;
+
+/* Per-stage device times of the last frame calls, CUDA events on the ctx stream. */
+typedef struct j3dg_timings {
+  float cast_ms, shade_ms, splat_ms, copy_ms;
+  uint64_t rays;               /* primary + shadow rays traced by the last cast */
+  uint32_t kernel_launches;    /* kernels launched by the library since the last reset */
+} j3dg_timings;
+
+/* ---- context ------------------------------------------------------------- */
+/* One context per process per GPU (one process per GPU; multi-GPU plumbing is
+ * torch.distributed/NCCL above this ABI).  Fails with J3DG_ENODEV if `device` is
+ * not a CUDA device of compute capability 10.x.  */
+int j3dg_ctx_create(int device, j3dg_ctx** out);
+void j3dg_ctx_destroy(j3dg_ctx* ctx);
+const char* j3dg_last_error(const j3dg_ctx* ctx); /* ctx may be NULL: global string */
+/* Run all library work on this cudaStream_t (0 = the context's own stream). */
+int j3dg_ctx_set_stream(j3dg_ctx* ctx, void* cuda_stream);
+int j3dg_ctx_synchronize(j3dg_ctx* ctx);
+int j3dg_ctx_timings(j3dg_ctx* ctx, j3dg_timings* out, int reset);
+/* Per-stage CUDA-event timing on/off (default on; off removes the event records). */
+int j3dg_ctx_set_profiling(j3dg_ctx* ctx, int enabled);
+
+/* ---- BVH build: replaces `new qbvh(triangles, vertices)` + compute_triangle_normals
+ *      + compute_bb in add_object (j3d/scene.cpp:8-25; jtk/qbvh.h:1679-1686). -------
+ * vertices: nv x 3 float (jtk::vec3<float>), triangles: nt x 3 uint32.
+ * vertex_colors: nullable, nv x 3 float in [0,1] (mesh::vertex_colors).
+ * uv: nullable, nt x 6 float (mesh::uv_coordinates), texture: nullable tex_h rows of
+ * tex_stride uint32 0xAABBGGRR (jtk::image<uint32_t>).
+ * cs: nullable (identity) column-major object->world matrix (mesh::cs).
+ * The vertex/triangle arrays may be host or device pointers; they are copied. */
+int j3dg_mesh_create(j3dg_ctx* ctx, const float* vertices, uint32_t nv,
+                     const uint32_t* triangles, uint32_t nt,
+                     const float* vertex_colors, const float* uv,
+                     const uint32_t* texture, uint32_t tex_w, uint32_t tex_h, uint32_t tex_stride,
+                     const float* cs, uint32_t db_id, j3dg_mesh** out);
+void j3dg_mesh_destroy(j3dg_mesh* mesh);                 /* scene.cpp:40-48 remove_object */
+int j3dg_mesh_rebuild(j3dg_mesh* mesh);                  /* rebuild the BVH from resident data */
+int j3dg_mesh_info_get(const j3dg_mesh* mesh, j3dg_mesh_info* out);
+int j3dg_mesh_set_cs(j3dg_mesh* mesh, const float* cs);  /* mesh::cs / scene_object::cs */
+/* Device arrays of the built BVH (for NCCL broadcast above the ABI): kind 0 = wide
+ * nodes, 1 = triangle records.  Returns device pointer + byte size. */
+int j3dg_mesh_bvh_buffer(j3dg_mesh* mesh, int kind, void** dev_ptr, size_t* bytes);
+/* Create a mesh whose BVH will be received rather than built: allocates node /
+ * triangle arrays of the given sizes (then fill them via j3dg_mesh_bvh_buffer). */
+int j3dg_mesh_create_empty(j3dg_ctx* ctx, uint32_t nv, uint32_t nt, uint32_t nr_of_nodes,
+                           const float* cs, uint32_t db_id, j3dg_mesh** out);
+
+/* Generic closest-hit query with qbvh::find_closest_triangle semantics
+ * (jtk/qbvh.h:1701-1852): rays are n x 8 floats {ox,oy,oz, dx,dy,dz, t_near, t_far},
+ * t may be negative, closest = smallest |t|, strict t_near < t < t_far.
+ * hits are n x 4 floats {u, v, distance, found(0/1)}, ids n x uint32 triangle index. */
+int j3dg_mesh_find_closest(j3dg_mesh* mesh, const float* rays, uint32_t n, float* hits, uint32_t* triangle_ids);
+
+/* ---- ray cast: replaces canvas::update_canvas (j3d/canvas.cpp:677-874), i.e.
+ *      qbvh_two_level_with_transformations::find_closest_triangle per pixel
+ *      (jtk/qbvh.h:3303-3387) + hit->pixel + shadow ray.  Inclusive rect, clamped
+ *      like the reference.  pixels_out: host or device, stride in pixels. -------- */
+int j3dg_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nr_of_meshes, const j3dg_view* view,
+              int x0, int y0, int x1, int y1, j3dg_pixel* pixels_out, uint32_t stride);
+
+/* ---- shading: replaces canvas::canvas_to_image (j3d/canvas.cpp:582-670) incl. the
+ *      background copy of canvas::render_scene (canvas.cpp:893-898).
+ *      matcap: mh rows of mstride uint32; background nullable (then rgba_inout keeps
+ *      its content on miss pixels, like the reference's `im`). ------------------- */
+int j3dg_shade(j3dg_ctx* ctx, const j3dg_pixel* pixels, uint32_t pixel_stride, const j3dg_view* view,
+               const uint32_t* matcap, uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity_clr,
+               const uint32_t* background, uint32_t* rgba_inout, uint32_t rgba_stride);
+
+/* ---- point clouds: replaces canvas::render_pointclouds_on_image
+ *      (j3d/canvas.cpp:952-1030) = jtk::bind/_draw/present (jtk/render.h:254-865). -- */
+int j3dg_cloud_create(j3dg_ctx* ctx, const float* positions, const float* normals, const uint32_t* colors,
+                      uint32_t n, const float* cs, uint32_t db_id, j3dg_cloud** out);
+void j3dg_cloud_destroy(j3dg_cloud* cloud);
+/* pixels_in: the buffer the z-buffer is seeded from (view::_pixels); pixels_inout: the
+ * buffer the splat patches (canvas::_canvas); they may alias.  rgba_inout: canvas::im. */
+int j3dg_splat(j3dg_ctx* ctx, j3dg_cloud* const* clouds, uint32_t nr_of_clouds, const j3dg_view* view,
+               const j3dg_pixel* pixels_in, j3dg_pixel* pixels_inout, uint32_t pixel_stride,
+               uint32_t* rgba_inout, uint32_t rgba_stride);
+
+/* ---- whole frame: view::render_scene (j3d/view.cpp:421-430) in one call:
+ *      cast -> (snapshot) -> shade -> splat, everything resident on the device; only
+ *      the requested outputs cross PCIe.  pixels_out / rgba_out nullable. ---------- */
+int j3dg_render_frame(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nr_of_meshes,
+                      j3dg_cloud* const* clouds, uint32_t nr_of_clouds, const j3dg_view* view,
+                      const uint32_t* matcap, uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity_clr,
+                      uint32_t bg_top, uint32_t bg_bottom,
+                      j3dg_pixel* pixels_out, uint32_t* rgba_out);
+/* Upload a matcap once and reuse it (frames then pass matcap == NULL). */
+int j3dg_ctx_set_matcap(j3dg_ctx* ctx, const uint32_t* matcap, uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity_clr);
+
+/* Traversal statistics of the device BVH for the given view (a counting pass, not the
+ * timed kernel): mean wide-node visits and triangle tests per primary ray.  SURVEY §8d. */
+int j3dg_cast_stats(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nr_of_meshes, const j3dg_view* view,
+                    double* nodes_per_ray, double* tris_per_ray);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* J3DG_H */

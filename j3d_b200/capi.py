@@ -1,0 +1,394 @@
+"""ctypes binding of the C ABI (include/j3dg.h) plus the host-math helpers of
+libj3dg_host.so and the procedural input generators of libj3d_synth.so.
+
+This is the Python face of the *product*: it loads libj3dg.so (hand-written sm_100a CUDA)
+and fails loudly if that library is missing or no B200-class GPU is present.  Nothing in
+here touches oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+
+ONE_BIT, SHADOW, EDGES, WIREFRAME, SHADING, TEXTURED, VERTEXCOLORS = (1 << i for i in range(7))
+DEFAULT_FLAGS = EDGES | SHADING | TEXTURED | VERTEXCOLORS
+
+PIXEL_DTYPE = np.dtype(
+    [("mark", "u1"), ("r", "u1"), ("g", "u1"), ("b", "u1"), ("u", "<f4"), ("v", "<f4"), ("depth", "<f4"),
+     ("object_id", "<u4"), ("barycentric_u", "<f4"), ("barycentric_v", "<f4"), ("db_id", "<u4")]
+)
+assert PIXEL_DTYPE.itemsize == 32
+
+
+class View(C.Structure):
+    _fields_ = [
+        ("width", C.c_uint32), ("height", C.c_uint32), ("near_plane", C.c_float), ("diagonal", C.c_float),
+        ("projection", C.c_float * 16), ("projection_inv", C.c_float * 16), ("cs", C.c_float * 16),
+        ("cs_inv", C.c_float * 16), ("pivot", C.c_float * 3), ("flags", C.c_uint32),
+    ]
+
+    def copy(self) -> "View":
+        v = View()
+        C.memmove(C.byref(v), C.byref(self), C.sizeof(View))
+        return v
+
+
+class MeshInfo(C.Structure):
+    _fields_ = [
+        ("nr_of_vertices", C.c_uint32), ("nr_of_triangles", C.c_uint32), ("nr_of_nodes", C.c_uint32),
+        ("nr_of_leaf_triangles", C.c_uint32), ("node_bytes", C.c_uint32), ("triangle_bytes", C.c_uint32),
+        ("build_ms", C.c_float), ("upload_ms", C.c_float), ("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3),
+        ("sah_cost", C.c_float),
+    ]
+
+
+class Timings(C.Structure):
+    _fields_ = [("cast_ms", C.c_float), ("shade_ms", C.c_float), ("splat_ms", C.c_float), ("copy_ms", C.c_float),
+                ("rays", C.c_uint64), ("kernel_launches", C.c_uint32)]
+
+
+_vp = C.c_void_p
+_u32 = C.c_uint32
+_fp = C.POINTER(C.c_float)
+
+
+def _ptr(a):
+    """numpy array / int device pointer / None -> c_void_p"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return _vp(a)
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+        return _vp(a.ctypes.data)
+    if hasattr(a, "data_ptr"):  # torch tensor (device or pinned host)
+        return _vp(a.data_ptr())
+    raise TypeError(type(a))
+
+
+_lib = None
+_host = None
+_synth = None
+
+
+def lib() -> C.CDLL:
+    """The CUDA product library.  No fallback: raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        path = PKG / "libj3dg.so"
+        if not path.exists():
+            raise RuntimeError(f"{path} is missing: run `python -m j3d_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(str(path), mode=C.RTLD_GLOBAL)
+        L.j3dg_last_error.restype = C.c_char_p
+        L.j3dg_last_error.argtypes = [_vp]
+        L.j3dg_ctx_create.argtypes = [C.c_int, C.POINTER(_vp)]
+        L.j3dg_ctx_destroy.argtypes = [_vp]
+        L.j3dg_ctx_destroy.restype = None
+        L.j3dg_ctx_set_stream.argtypes = [_vp, _vp]
+        L.j3dg_ctx_synchronize.argtypes = [_vp]
+        L.j3dg_ctx_timings.argtypes = [_vp, C.POINTER(Timings), C.c_int]
+        L.j3dg_ctx_set_profiling.argtypes = [_vp, C.c_int]
+        L.j3dg_mesh_create.argtypes = [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _u32, C.POINTER(_vp)]
+        L.j3dg_mesh_destroy.argtypes = [_vp]
+        L.j3dg_mesh_destroy.restype = None
+        L.j3dg_mesh_rebuild.argtypes = [_vp]
+        L.j3dg_mesh_info_get.argtypes = [_vp, C.POINTER(MeshInfo)]
+        L.j3dg_mesh_set_cs.argtypes = [_vp, _vp]
+        L.j3dg_mesh_bvh_buffer.argtypes = [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_size_t)]
+        L.j3dg_mesh_create_empty.argtypes = [_vp, _u32, _u32, _u32, _vp, _u32, C.POINTER(_vp)]
+        L.j3dg_mesh_find_closest.argtypes = [_vp, _vp, _u32, _vp, _vp]
+        L.j3dg_cast.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(View), C.c_int, C.c_int, C.c_int, C.c_int, _vp, _u32]
+        L.j3dg_shade.argtypes = [_vp, _vp, _u32, C.POINTER(View), _vp, _u32, _u32, _u32, _u32, _vp, _vp, _u32]
+        L.j3dg_cloud_create.argtypes = [_vp, _vp, _vp, _vp, _u32, _vp, _u32, C.POINTER(_vp)]
+        L.j3dg_cloud_destroy.argtypes = [_vp]
+        L.j3dg_cloud_destroy.restype = None
+        L.j3dg_splat.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(View), _vp, _vp, _u32, _vp, _u32]
+        L.j3dg_render_frame.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(_vp), _u32, C.POINTER(View),
+                                        _vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp]
+        L.j3dg_ctx_set_matcap.argtypes = [_vp, _vp, _u32, _u32, _u32, _u32]
+        L.j3dg_cast_stats.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(View), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+def host() -> C.CDLL:
+    global _host
+    if _host is None:
+        path = PKG / "libj3dg_host.so"
+        if not path.exists():
+            raise RuntimeError(f"{path} is missing: run `python -m j3d_b200.build`")
+        H = C.CDLL(str(path))
+        H.j3dgh_make_projection.argtypes = [_u32, _u32, _fp, _fp, _fp]
+        H.j3dgh_invert_orthonormal.argtypes = [_fp, _fp]
+        H.j3dgh_matrix_multiply.argtypes = [_fp, _fp, _fp]
+        H.j3dgh_unzoom.argtypes = [_fp, _fp, _fp, _fp, _fp, _fp]
+        H.j3dgh_orbit.argtypes = [_fp, _fp, C.c_float, _fp, _fp]
+        H.j3dgh_make_matcap.argtypes = [C.c_int, _vp, C.POINTER(_u32)]
+        H.j3dgh_fill_background.argtypes = [_u32, _u32, _u32, _u32, _u32, _vp]
+        H.j3dgh_compute_bb.argtypes = [_vp, _u32, _fp, _fp]
+        H.j3dgh_transform_bbox.argtypes = [_fp, _fp, _fp, _fp, _fp]
+        _host = H
+    return _host
+
+
+def synth() -> C.CDLL:
+    global _synth
+    if _synth is None:
+        path = PKG / "libj3d_synth.so"
+        if not path.exists():
+            raise RuntimeError(f"{path} is missing: run `python -m j3d_b200.build`")
+        S = C.CDLL(str(path))
+        S.synth_icosphere_counts.argtypes = [_u32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        S.synth_icosphere.argtypes = [_u32, C.c_float, _u32, _vp, _vp]
+        S.synth_shuffle_triangles.argtypes = [_vp, C.c_uint64, C.c_uint64]
+        S.synth_cloud_range.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, _vp, _vp, _vp]
+        S.synth_vertex_colors.argtypes = [_vp, C.c_uint64, _u32, _vp]
+        _synth = S
+    return _synth
+
+
+# ---------------------------------------------------------------------------------------
+# procedural inputs
+# ---------------------------------------------------------------------------------------
+def icosphere(f: int, noise: float = 0.05, seed: int = 1234, shuffle_seed: int | None = None):
+    """Noised geodesic icosphere: (vertices [V,3] f32, triangles [T,3] u32), T = 20 f^2."""
+    S = synth()
+    nv, nt = C.c_uint64(), C.c_uint64()
+    S.synth_icosphere_counts(f, C.byref(nv), C.byref(nt))
+    verts = np.empty((nv.value, 3), np.float32)
+    tris = np.empty((nt.value, 3), np.uint32)
+    S.synth_icosphere(f, noise, seed, _ptr(verts), _ptr(tris))
+    if shuffle_seed is not None:
+        S.synth_shuffle_triangles(_ptr(tris), nt.value, shuffle_seed)
+    return verts, tris
+
+
+def cloud(n: int, seed: int = 42, noise: float = 0.05, first: int = 0):
+    S = synth()
+    pos = np.empty((n, 3), np.float32)
+    nrm = np.empty((n, 3), np.float32)
+    clr = np.empty((n,), np.uint32)
+    S.synth_cloud_range(first, n, seed, noise, _ptr(pos), _ptr(nrm), _ptr(clr))
+    return pos, nrm, clr
+
+
+def vertex_colors(verts: np.ndarray, seed: int = 7) -> np.ndarray:
+    out = np.empty_like(verts)
+    synth().synth_vertex_colors(_ptr(verts), verts.shape[0], seed, _ptr(out))
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# host math (camera / pose / matcap), one implementation shared with the C++ canvas mirror
+# ---------------------------------------------------------------------------------------
+def _f16():
+    return (C.c_float * 16)()
+
+
+def make_view(width: int, height: int, bb_min, bb_max, flags: int = DEFAULT_FLAGS) -> View:
+    """Default camera (camera.cpp:5-16) + unzoom pose (scene.cpp:91-111) for one bbox."""
+    H = host()
+    v = View()
+    v.width, v.height, v.flags = width, height, flags
+    near = C.c_float()
+    H.j3dgh_make_projection(width, height, C.byref(near), v.projection, v.projection_inv)
+    v.near_plane = near.value
+    mn = (C.c_float * 3)(*[float(x) for x in bb_min])
+    mx = (C.c_float * 3)(*[float(x) for x in bb_max])
+    diag = C.c_float()
+    H.j3dgh_unzoom(mn, mx, C.byref(diag), v.pivot, v.cs, v.cs_inv)
+    v.diagonal = diag.value
+    return v
+
+
+def orbit_view(v0: View, angle_deg: float) -> View:
+    v = v0.copy()
+    host().j3dgh_orbit(v0.cs_inv, v0.pivot, float(angle_deg), v.cs, v.cs_inv)
+    return v
+
+
+def make_matcap(kind: int = 0):
+    out = np.empty((512, 512), np.uint32)
+    cav = C.c_uint32()
+    host().j3dgh_make_matcap(kind, _ptr(out), C.byref(cav))
+    return out, cav.value
+
+
+def fill_background(w: int, h: int, top: int = 0xFF000000, bottom: int = 0xFF404040) -> np.ndarray:
+    out = np.empty((h, w), np.uint32)
+    host().j3dgh_fill_background(w, h, w, top, bottom, _ptr(out))
+    return out
+
+
+def compute_bb(verts: np.ndarray):
+    mn, mx = (C.c_float * 3)(), (C.c_float * 3)()
+    host().j3dgh_compute_bb(_ptr(verts), verts.shape[0], mn, mx)
+    return np.array(mn[:], np.float32), np.array(mx[:], np.float32)
+
+
+# ---------------------------------------------------------------------------------------
+# object wrappers over the C ABI
+# ---------------------------------------------------------------------------------------
+class J3dgError(RuntimeError):
+    pass
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self._L = lib()
+        self._h = _vp()
+        rc = self._L.j3dg_ctx_create(device, C.byref(self._h))
+        if rc != 0:
+            raise J3dgError(f"j3dg_ctx_create({device}) = {rc}: {self._L.j3dg_last_error(None).decode()}")
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise J3dgError(f"{what} = {rc}: {self._L.j3dg_last_error(self._h).decode()}")
+
+    def close(self):
+        if self._h:
+            self._L.j3dg_ctx_destroy(self._h)
+            self._h = _vp()
+
+    def set_stream(self, stream_ptr: int):
+        self._check(self._L.j3dg_ctx_set_stream(self._h, _vp(stream_ptr)), "j3dg_ctx_set_stream")
+
+    def synchronize(self):
+        self._check(self._L.j3dg_ctx_synchronize(self._h), "j3dg_ctx_synchronize")
+
+    def set_profiling(self, on: bool):
+        self._check(self._L.j3dg_ctx_set_profiling(self._h, int(on)), "j3dg_ctx_set_profiling")
+
+    def timings(self, reset: bool = False) -> Timings:
+        t = Timings()
+        self._check(self._L.j3dg_ctx_timings(self._h, C.byref(t), int(reset)), "j3dg_ctx_timings")
+        return t
+
+    def set_matcap(self, matcap: np.ndarray, cavity: int):
+        h, w = matcap.shape
+        self._check(self._L.j3dg_ctx_set_matcap(self._h, _ptr(matcap), w, h, w, cavity), "j3dg_ctx_set_matcap")
+
+    # -- meshes ---------------------------------------------------------------------
+    def mesh_create(self, verts, tris, vcolors=None, uv=None, texture=None, cs=None, db_id: int = 0x20000000,
+                    nv: int | None = None, nt: int | None = None) -> "Mesh":
+        nv = verts.shape[0] if nv is None else nv
+        nt = tris.shape[0] if nt is None else nt
+        tw = th = 0
+        if texture is not None:
+            th, tw = texture.shape
+        h = _vp()
+        csb = None if cs is None else np.ascontiguousarray(cs, np.float32)
+        self._check(self._L.j3dg_mesh_create(self._h, _ptr(verts), nv, _ptr(tris), nt, _ptr(vcolors), _ptr(uv),
+                                             _ptr(texture), tw, th, tw, _ptr(csb), db_id, C.byref(h)), "j3dg_mesh_create")
+        return Mesh(self, h)
+
+    def mesh_create_empty(self, nv: int, nt: int, nr_nodes: int, cs=None, db_id: int = 0x20000000) -> "Mesh":
+        h = _vp()
+        csb = None if cs is None else np.ascontiguousarray(cs, np.float32)
+        self._check(self._L.j3dg_mesh_create_empty(self._h, nv, nt, nr_nodes, _ptr(csb), db_id, C.byref(h)), "j3dg_mesh_create_empty")
+        return Mesh(self, h)
+
+    def cloud_create(self, pos, nrm=None, clr=None, cs=None, db_id: int = 0x40000000, n: int | None = None) -> "Cloud":
+        n = pos.shape[0] if n is None else n
+        h = _vp()
+        csb = None if cs is None else np.ascontiguousarray(cs, np.float32)
+        self._check(self._L.j3dg_cloud_create(self._h, _ptr(pos), _ptr(nrm), _ptr(clr), n, _ptr(csb), db_id, C.byref(h)), "j3dg_cloud_create")
+        return Cloud(self, h)
+
+    # -- frame stages -----------------------------------------------------------------
+    @staticmethod
+    def _handles(objs):
+        arr = (_vp * max(1, len(objs)))(*[o._h for o in objs])
+        return arr
+
+    def cast(self, meshes, view: View, out=None, rect=None, stride: int | None = None):
+        """canvas::update_canvas.  out: numpy PIXEL_DTYPE [H,W] (host) or device pointer/tensor."""
+        w, h = view.width, view.height
+        if out is None:
+            out = np.zeros((h, w), PIXEL_DTYPE)
+            out["object_id"] = 0xFFFFFFFF
+        x0, y0, x1, y1 = rect if rect is not None else (0, 0, w - 1, h - 1)
+        self._check(self._L.j3dg_cast(self._h, self._handles(meshes), len(meshes), C.byref(view), x0, y0, x1, y1,
+                                      _ptr(out), stride or w), "j3dg_cast")
+        return out
+
+    def shade(self, pixels, view: View, matcap: np.ndarray, cavity: int, background=None, out=None,
+              pixel_stride: int | None = None, rgba_stride: int | None = None):
+        w, h = view.width, view.height
+        if out is None:
+            out = np.zeros((h, w), np.uint32)
+        mh, mw = matcap.shape
+        self._check(self._L.j3dg_shade(self._h, _ptr(pixels), pixel_stride or w, C.byref(view), _ptr(matcap), mw, mh, mw, cavity,
+                                       _ptr(background), _ptr(out), rgba_stride or w), "j3dg_shade")
+        return out
+
+    def splat(self, clouds, view: View, pixels_in, pixels_inout, rgba_inout, pixel_stride: int | None = None,
+              rgba_stride: int | None = None):
+        w = view.width
+        self._check(self._L.j3dg_splat(self._h, self._handles(clouds), len(clouds), C.byref(view), _ptr(pixels_in),
+                                       _ptr(pixels_inout), pixel_stride or w, _ptr(rgba_inout), rgba_stride or w), "j3dg_splat")
+
+    def render_frame(self, meshes, clouds, view: View, matcap=None, cavity: int = 0, bg_top=0xFF000000, bg_bottom=0xFF404040,
+                     pixels_out=None, rgba_out=None):
+        """view::render_scene in one call; matcap None = the one set by set_matcap."""
+        mw = mh = 0
+        if matcap is not None:
+            mh, mw = matcap.shape
+        self._check(self._L.j3dg_render_frame(self._h, self._handles(meshes), len(meshes), self._handles(clouds), len(clouds),
+                                              C.byref(view), _ptr(matcap), mw, mh, mw, cavity, bg_top, bg_bottom,
+                                              _ptr(pixels_out), _ptr(rgba_out)), "j3dg_render_frame")
+
+    def cast_stats(self, meshes, view: View):
+        a, b = C.c_double(), C.c_double()
+        self._check(self._L.j3dg_cast_stats(self._h, self._handles(meshes), len(meshes), C.byref(view), C.byref(a), C.byref(b)),
+                    "j3dg_cast_stats")
+        return a.value, b.value
+
+
+class Mesh:
+    def __init__(self, ctx: Context, h):
+        self.ctx, self._h = ctx, h
+
+    def destroy(self):
+        if self._h:
+            self.ctx._L.j3dg_mesh_destroy(self._h)
+            self._h = _vp()
+
+    def info(self) -> MeshInfo:
+        i = MeshInfo()
+        self.ctx._check(self.ctx._L.j3dg_mesh_info_get(self._h, C.byref(i)), "j3dg_mesh_info_get")
+        return i
+
+    def rebuild(self):
+        self.ctx._check(self.ctx._L.j3dg_mesh_rebuild(self._h), "j3dg_mesh_rebuild")
+
+    def set_cs(self, cs):
+        csb = np.ascontiguousarray(cs, np.float32)
+        self.ctx._check(self.ctx._L.j3dg_mesh_set_cs(self._h, _ptr(csb)), "j3dg_mesh_set_cs")
+
+    def bvh_buffer(self, kind: int):
+        p, n = _vp(), C.c_size_t()
+        self.ctx._check(self.ctx._L.j3dg_mesh_bvh_buffer(self._h, kind, C.byref(p), C.byref(n)), "j3dg_mesh_bvh_buffer")
+        return p.value, n.value
+
+    def find_closest(self, rays: np.ndarray):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        hits = np.zeros((n, 4), np.float32)
+        ids = np.zeros((n,), np.uint32)
+        self.ctx._check(self.ctx._L.j3dg_mesh_find_closest(self._h, _ptr(rays), n, _ptr(hits), _ptr(ids)), "j3dg_mesh_find_closest")
+        return hits, ids
+
+
+class Cloud:
+    def __init__(self, ctx: Context, h):
+        self.ctx, self._h = ctx, h
+
+    def destroy(self):
+        if self._h:
+            self.ctx._L.j3dg_cloud_destroy(self._h)
+            self._h = _vp()

@@ -1,0 +1,291 @@
+// j3dg_host.h — host-side (C++) mirror of the j3d interfaces that sit directly above the
+// GPU hot path: camera, scene (add_object / prepare_scene / unzoom), matcap and canvas.
+// Same names, argument meaning and call order as the reference so that view::render_scene
+// (j3d/view.cpp:421-430) can drive `j3dg::canvas` unchanged; all per-pixel / per-triangle /
+// per-point work happens behind the C ABI in include/j3dg.h (libj3dg.so, sm_100a CUDA).
+// There is no CPU rendering path here: every render entry point fails loudly (throws
+// std::runtime_error carrying j3dg_last_error) when the CUDA library reports an error.
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+#include <list>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "j3dg.h"
+
+extern "C" {
+// Pure host math exported by libj3dg_host.so (also used from Python through ctypes).
+void j3dgh_make_projection(uint32_t w, uint32_t h, float* near_plane, float* projection, float* projection_inv);
+void j3dgh_invert_orthonormal(const float* m, float* out);
+void j3dgh_matrix_multiply(const float* a, const float* b, float* out);
+void j3dgh_matrix_vector_multiply(const float* m, const float* v, float* out);
+void j3dgh_transform_bbox(const float* cs, const float* bb_min, const float* bb_max, float* out_min, float* out_max);
+void j3dgh_unzoom(const float* bb_min, const float* bb_max, float* diagonal, float* pivot, float* cs, float* cs_inv);
+void j3dgh_orbit(const float* cs_inv0, const float* pivot, float angle_deg, float* cs, float* cs_inv);
+void j3dgh_make_matcap(int type, uint32_t* out_512x512, uint32_t* cavity_clr);
+void j3dgh_fill_background(uint32_t w, uint32_t h, uint32_t stride, uint32_t clr_top, uint32_t clr_bottom, uint32_t* out);
+void j3dgh_compute_bb(const float* vertices, uint32_t nv, float* bb_min, float* bb_max);
+}
+
+namespace j3dg {
+
+using pixel = j3dg_pixel;  // j3d/pixel.h:11-27, byte-identical
+
+struct float4x4 {  // column-major like jtk::float4x4
+  float f[16];
+  float& operator[](int i) { return f[i]; }
+  const float& operator[](int i) const { return f[i]; }
+  static float4x4 identity() {
+    float4x4 m;
+    std::memset(m.f, 0, sizeof(m.f));
+    m.f[0] = m.f[5] = m.f[10] = m.f[15] = 1.f;
+    return m;
+  }
+};
+
+// j3d/mesh.h:25-36 (the members the renderer reads)
+struct mesh {
+  std::vector<float> vertices;          // 3 per vertex
+  std::vector<uint32_t> triangles;      // 3 per triangle
+  std::vector<float> vertex_colors;     // optional, 3 per vertex in [0,1]
+  std::vector<float> uv_coordinates;    // optional, 6 per triangle
+  std::vector<uint32_t> texture;        // optional, texture_w * texture_h, 0xAABBGGRR
+  uint32_t texture_w = 0, texture_h = 0;
+  float4x4 cs = float4x4::identity();
+  double acceleration_structure_construction_time_in_s = 0.0;
+};
+
+// j3d/pc.h:23-31
+struct pc {
+  std::vector<float> vertices;
+  std::vector<float> normals;
+  std::vector<uint32_t> vertex_colors;
+  float4x4 cs = float4x4::identity();
+};
+
+// j3d/scene.h:10-52.  scene_object owns the device mesh (where the reference owns the qbvh).
+struct scene_object {
+  uint32_t db_id = 0;
+  const mesh* p_mesh = nullptr;
+  float min_bb[3], max_bb[3];
+  float4x4 cs;
+  j3dg_mesh* bvh = nullptr;  // GPU BVH + resident geometry (replaces std::unique_ptr<jtk::qbvh>)
+};
+struct scene_pointcloud {
+  uint32_t db_id = 0;
+  const pc* p_pc = nullptr;
+  float min_bb[3], max_bb[3];
+  float4x4 cs;
+  j3dg_cloud* cloud = nullptr;
+};
+struct scene {
+  float4x4 coordinate_system = float4x4::identity(), coordinate_system_inv = float4x4::identity();
+  float pivot[3] = {0, 0, 0};
+  float min_bb[3] = {0, 0, 0}, max_bb[3] = {0, 0, 0};
+  float diagonal = 0.f;
+  std::list<scene_object> objects;
+  std::list<scene_pointcloud> pointclouds;
+};
+
+// j3d/matcap.h
+struct matcap {
+  std::vector<uint32_t> im;  // 512 x 512
+  uint32_t w = 0, h = 0;
+  uint32_t cavity_clr = 0;
+};
+inline void make_matcap(matcap& m, int type) {  // 0 red wax (default), 1 gray, 2 brown, 3 sketch
+  m.w = m.h = 512;
+  m.im.resize(512 * 512);
+  j3dgh_make_matcap(type, m.im.data(), &m.cavity_clr);
+}
+inline void make_matcap_red_wax(matcap& m) { make_matcap(m, 0); }
+
+class context {  // one per process / GPU
+ public:
+  explicit context(int device = 0) {
+    if (j3dg_ctx_create(device, &_ctx) != J3DG_OK)
+      throw std::runtime_error(std::string("j3dg_ctx_create: ") + j3dg_last_error(nullptr));
+  }
+  ~context() { j3dg_ctx_destroy(_ctx); }
+  context(const context&) = delete;
+  context& operator=(const context&) = delete;
+  j3dg_ctx* get() const { return _ctx; }
+  void check(int rc, const char* what) const {
+    if (rc != J3DG_OK) throw std::runtime_error(std::string(what) + ": " + j3dg_last_error(_ctx));
+  }
+
+ private:
+  j3dg_ctx* _ctx = nullptr;
+};
+
+// add_object (j3d/scene.cpp:8-36): uploads the mesh, builds normals + bbox + BVH on the GPU.
+inline void add_object(context& ctx, uint32_t db_id, scene& s, mesh& m) {
+  scene_object obj;
+  obj.db_id = db_id;
+  obj.p_mesh = &m;
+  obj.cs = m.cs;
+  const uint32_t nv = (uint32_t)(m.vertices.size() / 3), nt = (uint32_t)(m.triangles.size() / 3);
+  ctx.check(j3dg_mesh_create(ctx.get(), m.vertices.data(), nv, m.triangles.data(), nt,
+                             m.vertex_colors.empty() ? nullptr : m.vertex_colors.data(),
+                             m.uv_coordinates.empty() ? nullptr : m.uv_coordinates.data(),
+                             m.texture.empty() ? nullptr : m.texture.data(), m.texture_w, m.texture_h, m.texture_w,
+                             m.cs.f, db_id, &obj.bvh),
+            "j3dg_mesh_create");
+  j3dg_mesh_info info;
+  j3dg_mesh_info_get(obj.bvh, &info);
+  std::memcpy(obj.min_bb, info.bbox_min, 12);
+  std::memcpy(obj.max_bb, info.bbox_max, 12);
+  m.acceleration_structure_construction_time_in_s = (info.build_ms + info.upload_ms) * 1e-3;
+  s.objects.emplace_back(obj);
+}
+inline void add_object(context& ctx, uint32_t db_id, scene& s, pc& p) {
+  scene_pointcloud obj;
+  obj.db_id = db_id;
+  obj.p_pc = &p;
+  obj.cs = p.cs;
+  const uint32_t n = (uint32_t)(p.vertices.size() / 3);
+  ctx.check(j3dg_cloud_create(ctx.get(), p.vertices.data(), p.normals.empty() ? nullptr : p.normals.data(),
+                              p.vertex_colors.empty() ? nullptr : p.vertex_colors.data(), n, p.cs.f, db_id, &obj.cloud),
+            "j3dg_cloud_create");
+  j3dgh_compute_bb(p.vertices.data(), n, obj.min_bb, obj.max_bb);
+  s.pointclouds.emplace_back(obj);
+}
+// remove_object (j3d/scene.cpp:40-48)
+inline void remove_object(uint32_t id, scene& s) {
+  for (auto it = s.objects.begin(); it != s.objects.end(); ++it)
+    if (it->db_id == id) { j3dg_mesh_destroy(it->bvh); s.objects.erase(it); break; }
+  for (auto it = s.pointclouds.begin(); it != s.pointclouds.end(); ++it)
+    if (it->db_id == id) { j3dg_cloud_destroy(it->cloud); s.pointclouds.erase(it); break; }
+}
+// prepare_scene (j3d/scene.cpp:50-89)
+inline void prepare_scene(scene& s) {
+  bool first = true;
+  auto merge = [&](const float4x4& cs, const float* mn, const float* mx) {
+    float a[3], b[3];
+    j3dgh_transform_bbox(cs.f, mn, mx, a, b);
+    for (int j = 0; j < 3; ++j) {
+      if (first || a[j] < s.min_bb[j]) s.min_bb[j] = a[j];
+      if (first || b[j] > s.max_bb[j]) s.max_bb[j] = b[j];
+    }
+    first = false;
+  };
+  for (const auto& o : s.objects) merge(o.cs, o.min_bb, o.max_bb);
+  for (const auto& o : s.pointclouds) merge(o.cs, o.min_bb, o.max_bb);
+  if (first)
+    for (int j = 0; j < 3; ++j) s.min_bb[j] = s.max_bb[j] = 0.f;
+  s.diagonal = s.max_bb[0] - s.min_bb[0];
+  if (s.max_bb[1] - s.min_bb[1] > s.diagonal) s.diagonal = s.max_bb[1] - s.min_bb[1];
+  if (s.max_bb[2] - s.min_bb[2] > s.diagonal) s.diagonal = s.max_bb[2] - s.min_bb[2];
+}
+// unzoom (j3d/scene.cpp:91-111)
+inline void unzoom(scene& s) {
+  float d;
+  j3dgh_unzoom(s.min_bb, s.max_bb, &d, s.pivot, s.coordinate_system.f, s.coordinate_system_inv.f);
+}
+
+// canvas (j3d/canvas.h:11-102): same public surface for the render path.
+class canvas {
+ public:
+  struct canvas_settings {  // j3d/canvas.h:16-25
+    bool one_bit = false, shadow = false, edges = true, wireframe = false, shading = true, textured = true, vertexcolors = true;
+  };
+
+  canvas(context& ctx, uint32_t w, uint32_t h) : _ctx(ctx) { resize(w, h); }
+
+  void resize(uint32_t w, uint32_t h) {  // canvas.cpp:117-134
+    _w = w;
+    _h = h;
+    _stride = (w + 3u) & ~3u;  // jtk::image<uint32_t> row padding (image.h:181-185)
+    im.assign((size_t)_stride * h, 0);
+    background.assign((size_t)_stride * h, 0);
+    _canvas.assign((size_t)w * h, pixel{});
+    for (auto& p : _canvas) { p.db_id = 0; p.object_id = (uint32_t)-1; }
+    j3dgh_make_projection(w, h, &_near, projection_matrix.f, projection_matrix_inv.f);
+  }
+  void set_background_color(uint32_t clr_top = 0xff000000, uint32_t clr_bottom = 0xff404040) {  // canvas.cpp:136-139
+    _bg_top = clr_top;
+    _bg_bottom = clr_bottom;
+    j3dgh_fill_background(_w, _h, _stride, clr_top, clr_bottom, background.data());
+  }
+  uint32_t width() const { return _w; }
+  uint32_t height() const { return _h; }
+  void update_settings(const canvas_settings& s) { _settings = s; }
+  const float4x4& get_projection_matrix() const { return projection_matrix; }
+  const float4x4& get_inverse_projection_matrix() const { return projection_matrix_inv; }
+  const std::vector<pixel>& get_pixels() const { return _canvas; }
+  const std::vector<uint32_t>& get_image() const { return im; }
+  uint32_t image_stride() const { return _stride; }
+
+  // canvas::update_canvas (canvas.cpp:677-874): inclusive rect, clamped by the library
+  void update_canvas(std::vector<pixel>& out, int x0, int y0, int x1, int y1, const scene& s) {
+    if (out.size() != (size_t)_w * _h) out.assign((size_t)_w * _h, pixel{});
+    std::vector<j3dg_mesh*> meshes;
+    for (const auto& o : s.objects)
+      if (o.bvh) { j3dg_mesh_set_cs(o.bvh, o.cs.f); meshes.push_back(o.bvh); }
+    j3dg_view v = make_view(s);
+    _ctx.check(j3dg_cast(_ctx.get(), meshes.data(), (uint32_t)meshes.size(), &v, x0, y0, x1, y1, out.data(), _w), "j3dg_cast");
+  }
+  void update_canvas(int x0, int y0, int x1, int y1, const scene& s) { update_canvas(_canvas, x0, y0, x1, y1, s); }
+
+  // canvas::render_scene (canvas.cpp:876-898)
+  void render_scene(std::vector<pixel>& out, const scene* s) {
+    if (s)
+      update_canvas(out, 0, 0, (int)_w - 1, (int)_h - 1, *s);
+    else {
+      out.assign((size_t)_w * _h, pixel{});
+      for (auto& p : out) { p.db_id = 0; p.object_id = (uint32_t)-1; }
+    }
+  }
+  void render_scene(const scene* s) {
+    im = background;
+    render_scene(_canvas, s);
+  }
+  // canvas::canvas_to_image (canvas.cpp:582-670)
+  void canvas_to_image(const std::vector<pixel>& cnv, const matcap& mc, const scene& s) {
+    j3dg_view v = make_view(s);
+    _ctx.check(j3dg_shade(_ctx.get(), cnv.data(), _w, &v, mc.im.data(), mc.w, mc.h, mc.w, mc.cavity_clr, nullptr, im.data(), _stride),
+               "j3dg_shade");
+  }
+  // canvas::render_pointclouds_on_image (canvas.cpp:952-1030)
+  void render_pointclouds_on_image(const scene* s, const std::vector<pixel>& pix) {
+    if (!s || s->pointclouds.empty()) return;
+    std::vector<j3dg_cloud*> clouds;
+    for (const auto& o : s->pointclouds) clouds.push_back(o.cloud);
+    j3dg_view v = make_view(*s);
+    _ctx.check(j3dg_splat(_ctx.get(), clouds.data(), (uint32_t)clouds.size(), &v, pix.data(), _canvas.data(), _w, im.data(), _stride),
+               "j3dg_splat");
+  }
+
+  j3dg_view make_view(const scene& s) const {
+    j3dg_view v;
+    v.width = _w;
+    v.height = _h;
+    v.near_plane = _near;
+    v.diagonal = s.diagonal;
+    std::memcpy(v.projection, projection_matrix.f, 64);
+    std::memcpy(v.projection_inv, projection_matrix_inv.f, 64);
+    std::memcpy(v.cs, s.coordinate_system.f, 64);
+    std::memcpy(v.cs_inv, s.coordinate_system_inv.f, 64);
+    std::memcpy(v.pivot, s.pivot, 12);
+    v.flags = (_settings.one_bit ? J3DG_ONE_BIT : 0) | (_settings.shadow ? J3DG_SHADOW : 0) | (_settings.edges ? J3DG_EDGES : 0) |
+              (_settings.wireframe ? J3DG_WIREFRAME : 0) | (_settings.shading ? J3DG_SHADING : 0) |
+              (_settings.textured ? J3DG_TEXTURED : 0) | (_settings.vertexcolors ? J3DG_VERTEXCOLORS : 0);
+    return v;
+  }
+
+ private:
+  context& _ctx;
+  uint32_t _w = 0, _h = 0, _stride = 0;
+  float _near = 0.1f;
+  uint32_t _bg_top = 0xff000000, _bg_bottom = 0xff404040;
+  std::vector<uint32_t> im, background;
+  std::vector<pixel> _canvas;
+  float4x4 projection_matrix, projection_matrix_inv;
+  canvas_settings _settings;
+};
+
+}  // namespace j3dg

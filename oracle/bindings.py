@@ -1,0 +1,249 @@
+"""ctypes bindings of the two CPU checkers.  TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module.  The product package (j3d_b200) never does.
+
+  Oracle   oracle/libj3d_oracle.so   plain-C restatement of the reference algorithm
+  Ref      oracle/_ref/libj3d_ref.so the unmodified reference compiled from /root/reference
+                                      (prebuilt here; travels to the GPU box as a .so)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE.parent))
+from j3d_b200.capi import PIXEL_DTYPE, View  # noqa: E402  (struct layouts only)
+
+_vp, _u32, _fp = C.c_void_p, C.c_uint32, C.POINTER(C.c_float)
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return _vp(a.ctypes.data)
+
+
+def ref_available() -> bool:
+    return (HERE / "_ref" / "libj3d_ref.so").exists()
+
+
+class Oracle:
+    """Plain-C restatement (j3d_oracle.c)."""
+
+    def __init__(self):
+        path = HERE / "libj3d_oracle.so"
+        if not path.exists():
+            raise RuntimeError(f"{path} missing: run `make -C oracle oracle`")
+        L = C.CDLL(str(path))
+        L.orc_make_projection.argtypes = [_u32, _u32, _fp, _fp, _fp]
+        L.orc_unzoom.argtypes = [_fp, _fp, _fp, _fp, _fp, _fp]
+        L.orc_make_matcap.argtypes = [C.c_int, _vp, C.POINTER(_u32)]
+        L.orc_fill_background.argtypes = [_u32, _u32, _u32, _u32, _vp]
+        L.orc_mesh_create.restype = _vp
+        L.orc_mesh_create.argtypes = [_vp, _u32, _vp, _u32, _vp, _vp, _vp, _u32, _u32, _vp, _u32]
+        L.orc_mesh_destroy.argtypes = [_vp]
+        L.orc_mesh_normals.restype = _vp
+        L.orc_mesh_normals.argtypes = [_vp]
+        L.orc_mesh_bbox.argtypes = [_vp, _fp, _fp]
+        L.orc_find_closest.argtypes = [_vp, _vp, _u32, _vp, _vp]
+        L.orc_cast.argtypes = [C.POINTER(_vp), _u32, C.POINTER(View), C.c_int, C.c_int, C.c_int, C.c_int, _vp, _u32]
+        L.orc_shade.argtypes = [_vp, _u32, C.POINTER(View), _vp, _u32, _u32, _u32, _vp, _u32]
+        L.orc_splat.argtypes = [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_u32), C.POINTER(_vp),
+                                C.POINTER(_u32), _u32, C.POINTER(View), _vp, _vp, _u32, _vp, _u32]
+        self.L = L
+
+    def make_view(self, w, h, bb_min, bb_max, flags) -> View:
+        v = View()
+        v.width, v.height, v.flags = w, h, flags
+        near = C.c_float()
+        self.L.orc_make_projection(w, h, C.byref(near), v.projection, v.projection_inv)
+        v.near_plane = near.value
+        mn = (C.c_float * 3)(*[float(x) for x in bb_min])
+        mx = (C.c_float * 3)(*[float(x) for x in bb_max])
+        d = C.c_float()
+        self.L.orc_unzoom(mn, mx, C.byref(d), v.pivot, v.cs, v.cs_inv)
+        v.diagonal = d.value
+        return v
+
+    def make_matcap(self, kind=0):
+        out = np.empty((512, 512), np.uint32)
+        cav = _u32()
+        self.L.orc_make_matcap(kind, _p(out), C.byref(cav))
+        return out, cav.value
+
+    def fill_background(self, w, h, top=0xFF000000, bottom=0xFF404040):
+        out = np.empty((h, w), np.uint32)
+        self.L.orc_fill_background(w, h, top, bottom, _p(out))
+        return out
+
+    def mesh(self, verts, tris, vcolors=None, uv=None, texture=None, cs=None, db_id=0x20000000):
+        tw = th = 0
+        if texture is not None:
+            th, tw = texture.shape
+        csb = None if cs is None else np.ascontiguousarray(cs, np.float32)
+        h = self.L.orc_mesh_create(_p(verts), verts.shape[0], _p(tris), tris.shape[0], _p(vcolors), _p(uv), _p(texture), tw, th, _p(csb), db_id)
+        return OracleMesh(self, h, tris.shape[0])
+
+    def cast(self, meshes, view: View, rect=None, out=None):
+        w, h = view.width, view.height
+        if out is None:
+            out = np.zeros((h, w), PIXEL_DTYPE)
+            out["object_id"] = 0xFFFFFFFF
+        x0, y0, x1, y1 = rect if rect is not None else (0, 0, w - 1, h - 1)
+        arr = (_vp * max(1, len(meshes)))(*[m.h for m in meshes])
+        self.L.orc_cast(arr, len(meshes), C.byref(view), x0, y0, x1, y1, _p(out), w)
+        return out
+
+    def shade(self, pixels, view: View, matcap, cavity, rgba):
+        """rgba: [H,W] u32 pre-filled with the background; modified in place."""
+        mh, mw = matcap.shape
+        self.L.orc_shade(_p(pixels), view.width, C.byref(view), _p(matcap), mw, mh, cavity, _p(rgba), view.width)
+        return rgba
+
+    def splat(self, clouds, view: View, pixels_in, pixels_inout, rgba):
+        """clouds: list of (pos, nrm|None, clr|None, cs|None, db_id)."""
+        n = len(clouds)
+        pos = (_vp * n)(*[_p(c[0]) for c in clouds])
+        nrm = (_vp * n)(*[_p(c[1]) for c in clouds])
+        clr = (_vp * n)(*[_p(c[2]) for c in clouds])
+        cnt = (_u32 * n)(*[c[0].shape[0] for c in clouds])
+        keep = [None if c[3] is None else np.ascontiguousarray(c[3], np.float32) for c in clouds]
+        css = (_vp * n)(*[_p(k) for k in keep])
+        ids = (_u32 * n)(*[c[4] for c in clouds])
+        self.L.orc_splat(pos, nrm, clr, cnt, css, ids, n, C.byref(view), _p(pixels_in), _p(pixels_inout), view.width, _p(rgba), view.width)
+
+
+class OracleMesh:
+    def __init__(self, orc: Oracle, h, nt):
+        self.orc, self.h, self.nt = orc, h, nt
+
+    def normals(self):
+        p = self.orc.L.orc_mesh_normals(self.h)
+        return np.ctypeslib.as_array(C.cast(p, _fp), shape=(self.nt, 3)).copy()
+
+    def bbox(self):
+        mn, mx = (C.c_float * 3)(), (C.c_float * 3)()
+        self.orc.L.orc_mesh_bbox(self.h, mn, mx)
+        return np.array(mn[:], np.float32), np.array(mx[:], np.float32)
+
+    def find_closest(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        hits = np.zeros((n, 4), np.float32)
+        ids = np.zeros((n,), np.uint32)
+        self.orc.L.orc_find_closest(self.h, _p(rays), n, _p(hits), _p(ids))
+        return hits, ids
+
+    def destroy(self):
+        if self.h:
+            self.orc.L.orc_mesh_destroy(self.h)
+            self.h = None
+
+
+class Ref:
+    """The unmodified reference renderer (oracle/_ref/libj3d_ref.so)."""
+
+    def __init__(self, w, h):
+        path = HERE / "_ref" / "libj3d_ref.so"
+        if not path.exists():
+            raise RuntimeError(f"{path} missing: run `make -C oracle ref` where /root/reference exists")
+        L = C.CDLL(str(path))
+        L.ref_create.restype = _vp
+        L.ref_create.argtypes = [_u32, _u32]
+        L.ref_destroy.argtypes = [_vp]
+        L.ref_add_mesh.restype = _u32
+        L.ref_add_mesh.argtypes = [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _vp, _u32, _u32, _vp]
+        L.ref_add_cloud.restype = _u32
+        L.ref_add_cloud.argtypes = [_vp, _vp, _vp, _vp, _u32, _vp]
+        L.ref_unzoom.argtypes = [_vp]
+        L.ref_get_view.argtypes = [_vp, C.POINTER(View)]
+        L.ref_set_view.argtypes = [_vp, C.POINTER(View)]
+        L.ref_set_matcap.argtypes = [_vp, C.c_int]
+        L.ref_get_matcap.argtypes = [_vp, _vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]
+        L.ref_render.argtypes = [_vp, _u32]
+        L.ref_get_pixels.argtypes = [_vp, C.c_int, _vp]
+        L.ref_get_image.argtypes = [_vp, _vp]
+        L.ref_get_times.argtypes = [_vp, C.POINTER(C.c_double)]
+        L.ref_time_qbvh.restype = C.c_double
+        L.ref_time_qbvh.argtypes = [_vp, _u32, _vp, _u32, C.POINTER(_u32)]
+        L.ref_find_closest.argtypes = [_vp, _u32, _vp, _u32, _u32, _vp, _u32, _vp, _vp]
+        L.ref_hardware_concurrency.restype = C.c_int
+        self.L, self.w, self.h = L, w, h
+        self.s = L.ref_create(w, h)
+
+    def close(self):
+        if self.s:
+            self.L.ref_destroy(self.s)
+            self.s = None
+
+    def cores(self):
+        return self.L.ref_hardware_concurrency()
+
+    def add_mesh(self, verts, tris, vcolors=None, uv=None, texture=None, cs=None):
+        tw = th = 0
+        if texture is not None:
+            th, tw = texture.shape
+        csb = None if cs is None else np.ascontiguousarray(cs, np.float32)
+        return self.L.ref_add_mesh(self.s, _p(verts), verts.shape[0], _p(tris), tris.shape[0], _p(vcolors), _p(uv), _p(texture), tw, th, _p(csb))
+
+    def add_cloud(self, pos, nrm=None, clr=None, cs=None):
+        csb = None if cs is None else np.ascontiguousarray(cs, np.float32)
+        return self.L.ref_add_cloud(self.s, _p(pos), _p(nrm), _p(clr), pos.shape[0], _p(csb))
+
+    def unzoom(self):
+        self.L.ref_unzoom(self.s)
+
+    def view(self) -> View:
+        v = View()
+        self.L.ref_get_view(self.s, C.byref(v))
+        return v
+
+    def set_view(self, v: View):
+        self.L.ref_set_view(self.s, C.byref(v))
+
+    def set_matcap(self, kind):
+        self.L.ref_set_matcap(self.s, kind)
+
+    def matcap(self):
+        w, h, cav = _u32(), _u32(), _u32()
+        self.L.ref_get_matcap(self.s, None, C.byref(w), C.byref(h), C.byref(cav))
+        out = np.empty((h.value, w.value), np.uint32)
+        self.L.ref_get_matcap(self.s, _p(out), C.byref(w), C.byref(h), C.byref(cav))
+        return out, cav.value
+
+    def render(self, stages=7):
+        self.L.ref_render(self.s, stages)
+
+    def pixels(self, which=0):
+        out = np.zeros((self.h, self.w), PIXEL_DTYPE)
+        self.L.ref_get_pixels(self.s, which, _p(out))
+        return out
+
+    def image(self):
+        out = np.zeros((self.h, self.w), np.uint32)
+        self.L.ref_get_image(self.s, _p(out))
+        return out
+
+    def times(self):
+        t = (C.c_double * 5)()
+        self.L.ref_get_times(self.s, t)
+        return dict(build=t[0], cast=t[1], shade=t[2], splat=t[3], copy=t[4])
+
+    def time_qbvh(self, verts, tris):
+        n = _u32()
+        t = self.L.ref_time_qbvh(_p(verts), verts.shape[0], _p(tris), tris.shape[0], C.byref(n))
+        return t, n.value
+
+    def find_closest(self, verts, tris, rays, leaf_size=32):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        hits = np.zeros((n, 4), np.float32)
+        ids = np.zeros((n,), np.uint32)
+        self.L.ref_find_closest(_p(verts), verts.shape[0], _p(tris), tris.shape[0], leaf_size, _p(rays), n, _p(hits), _p(ids))
+        return hits, ids
