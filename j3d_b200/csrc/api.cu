@@ -1,0 +1,567 @@
+// api.cu — the C ABI (include/j3dg.h): contexts, mesh / cloud handles, host<->device staging
+// and the per-frame orchestration of view::render_scene (j3d/view.cpp:421-430).
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace {
+std::mutex g_err_mutex;
+std::string g_last_error = "";
+}
+
+void j3dg_set_error(j3dg_ctx* ctx, const std::string& msg) {
+  if (ctx) ctx->error = msg;
+  std::lock_guard<std::mutex> lock(g_err_mutex);
+  g_last_error = msg;
+}
+
+int j3dg_cuda_fail(j3dg_ctx* ctx, cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+  j3dg_set_error(ctx, buf);
+  cudaGetLastError();
+  return e == cudaErrorMemoryAllocation ? J3DG_ENOMEM : J3DG_ECUDA;
+}
+
+bool j3dg_is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int j3dg_reserve(j3dg_ctx* ctx, void** ptr, size_t* cap, size_t bytes) {
+  if (*cap >= bytes && *ptr) return J3DG_OK;
+  if (*ptr) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+  }
+  const size_t want = std::max<size_t>(bytes, 256);
+  cudaError_t e = cudaMalloc(ptr, want);
+  if (e != cudaSuccess) {
+    *ptr = nullptr;
+    char buf[256];
+    snprintf(buf, sizeof(buf), "out of device memory reserving %zu bytes: %s", want, cudaGetErrorString(e));
+    j3dg_set_error(ctx, buf);
+    cudaGetLastError();
+    return J3DG_ENOMEM;
+  }
+  *cap = want;
+  return J3DG_OK;
+}
+
+void j3dg_invert_orthonormal_host(const float* m, float* out) {  // jtk invert_orthonormal, qbvh.h:4460-4467
+  float r[16];
+  const float c0[4] = {m[0], m[4], m[8], 0.f}, c1[4] = {m[1], m[5], m[9], 0.f}, c2[4] = {m[2], m[6], m[10], 0.f};
+  for (int k = 0; k < 4; ++k) {
+    r[k] = c0[k]; r[4 + k] = c1[k]; r[8 + k] = c2[k];
+    volatile float a = c0[k] * m[12], b = c1[k] * m[13], c = c2[k] * m[14];
+    volatile float s = a + b;
+    s = s + c;
+    r[12 + k] = -s;
+  }
+  r[15] = 1.f;
+  memcpy(out, r, sizeof(r));
+}
+
+namespace {
+
+const float kIdentity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+
+template <class T>
+int upload(j3dg_ctx* ctx, T** dst, const T* src, size_t count) {
+  *dst = nullptr;
+  if (!src || !count) return J3DG_OK;
+  cudaError_t e = cudaMalloc((void**)dst, count * sizeof(T));
+  if (e != cudaSuccess) {
+    *dst = nullptr;
+    j3dg_set_error(ctx, std::string("out of device memory: ") + cudaGetErrorString(e));
+    cudaGetLastError();
+    return J3DG_ENOMEM;
+  }
+  CU_CHECK(ctx, cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyDefault, ctx->stream));
+  return J3DG_OK;
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+  return ms;
+}
+
+int check_overflow(j3dg_ctx* ctx) {
+  unsigned long long st[4];
+  CU_CHECK(ctx, cudaMemcpyAsync(st, ctx->d_stats, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if ((uint32_t)st[2]) {
+    j3dg_set_error(ctx, "traversal stack overflow (BVH deeper than the kernel's stack)");
+    return J3DG_ECUDA;
+  }
+  return J3DG_OK;
+}
+
+}  // namespace
+
+// ---- context ---------------------------------------------------------------------------------
+J3DG_API int j3dg_ctx_create(int device, j3dg_ctx** out) {
+  if (!out) return J3DG_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    j3dg_set_error(nullptr, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    return J3DG_ENODEV;
+  }
+  if (device < 0 || device >= count) { j3dg_set_error(nullptr, "invalid device ordinal"); return J3DG_EINVAL; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); j3dg_set_error(nullptr, "cudaGetDeviceProperties failed"); return J3DG_ENODEV; }
+  if (prop.major != 10) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "device %d (%s) is sm_%d%d; libj3dg is built for sm_100a only and has no fallback", device, prop.name, prop.major, prop.minor);
+    j3dg_set_error(nullptr, buf);
+    return J3DG_ENODEV;
+  }
+  j3dg_ctx* ctx = new j3dg_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    j3dg_set_error(nullptr, "cannot create a CUDA stream");
+    cudaGetLastError();
+    delete ctx;
+    return J3DG_ECUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  if (cudaMalloc((void**)&ctx->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+    j3dg_set_error(nullptr, "cannot allocate device memory");
+    delete ctx;
+    return J3DG_ENOMEM;
+  }
+  cudaMemset(ctx->d_stats, 0, 4 * sizeof(unsigned long long));
+  *out = ctx;
+  return J3DG_OK;
+}
+
+J3DG_API void j3dg_ctx_destroy(j3dg_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_pixels); cudaFree(ctx->d_pixels_in); cudaFree(ctx->d_rgba); cudaFree(ctx->d_bg); cudaFree(ctx->d_packed);
+  cudaFree(ctx->d_matcap); cudaFree(ctx->d_meshes); cudaFree(ctx->d_stats); cudaFree(ctx->d_misc);
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+J3DG_API const char* j3dg_last_error(const j3dg_ctx* ctx) {
+  if (ctx) return ctx->error.c_str();
+  std::lock_guard<std::mutex> lock(g_err_mutex);
+  static thread_local std::string copy;
+  copy = g_last_error;
+  return copy.c_str();
+}
+
+J3DG_API int j3dg_ctx_set_stream(j3dg_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return J3DG_EINVAL;
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return J3DG_OK;
+}
+
+J3DG_API int j3dg_ctx_synchronize(j3dg_ctx* ctx) {
+  if (!ctx) return J3DG_EINVAL;
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return J3DG_OK;
+}
+
+J3DG_API int j3dg_ctx_set_profiling(j3dg_ctx* ctx, int enabled) {
+  if (!ctx) return J3DG_EINVAL;
+  ctx->profiling = enabled != 0;
+  return J3DG_OK;
+}
+
+J3DG_API int j3dg_ctx_timings(j3dg_ctx* ctx, j3dg_timings* out, int reset) {
+  if (!ctx || !out) return J3DG_EINVAL;
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->profiling) {
+    ctx->timings.cast_ms = elapsed(ctx->ev[0], ctx->ev[1]);
+    ctx->timings.shade_ms = elapsed(ctx->ev[2], ctx->ev[3]);
+    ctx->timings.splat_ms = elapsed(ctx->ev[4], ctx->ev[5]);
+  }
+  unsigned long long st[4];
+  CU_CHECK(ctx, cudaMemcpy(st, ctx->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
+  *out = ctx->timings;
+  out->rays += st[3];  // one shadow ray per hit pixel when shadows were on
+  out->kernel_launches = ctx->launches;
+  if (reset) { ctx->launches = 0; }
+  return J3DG_OK;
+}
+
+// ---- meshes ------------------------------------------------------------------------------------
+J3DG_API int j3dg_mesh_create(j3dg_ctx* ctx, const float* vertices, uint32_t nv, const uint32_t* triangles, uint32_t nt,
+                              const float* vertex_colors, const float* uv, const uint32_t* texture, uint32_t tex_w, uint32_t tex_h,
+                              uint32_t tex_stride, const float* cs, uint32_t db_id, j3dg_mesh** out) {
+  if (!ctx || !out || (nv && !vertices) || (nt && !triangles)) { j3dg_set_error(ctx, "j3dg_mesh_create: bad argument"); return J3DG_EINVAL; }
+  if (nt >= (1u << 29)) { j3dg_set_error(ctx, "j3dg_mesh_create: more than 2^29 triangles"); return J3DG_EINVAL; }
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  j3dg_mesh* m = new j3dg_mesh();
+  m->ctx = ctx; m->nv = nv; m->nt = nt; m->db_id = db_id;
+  memcpy(m->cs, cs ? cs : kIdentity, sizeof(m->cs));
+  j3dg_invert_orthonormal_host(m->cs, m->cs_inv);
+  int rc;
+  cudaEventRecord(ctx->ev[6], ctx->stream);
+  if ((rc = upload(ctx, &m->d_vertices, vertices, (size_t)nv * 3)) != J3DG_OK) { j3dg_mesh_destroy(m); return rc; }
+  if ((rc = upload(ctx, &m->d_indices, triangles, (size_t)nt * 3)) != J3DG_OK) { j3dg_mesh_destroy(m); return rc; }
+  if ((rc = upload(ctx, &m->d_vcolors, vertex_colors, (size_t)nv * 3)) != J3DG_OK) { j3dg_mesh_destroy(m); return rc; }
+  if (uv && texture && tex_w && tex_h) {
+    if ((rc = upload(ctx, &m->d_uv, uv, (size_t)nt * 6)) != J3DG_OK) { j3dg_mesh_destroy(m); return rc; }
+    if (cudaMalloc((void**)&m->d_texture, (size_t)tex_w * tex_h * 4) != cudaSuccess) { cudaGetLastError(); j3dg_mesh_destroy(m); j3dg_set_error(ctx, "out of device memory (texture)"); return J3DG_ENOMEM; }
+    if (cudaMemcpy2DAsync(m->d_texture, (size_t)tex_w * 4, texture, (size_t)(tex_stride ? tex_stride : tex_w) * 4, (size_t)tex_w * 4, tex_h, cudaMemcpyDefault, ctx->stream) != cudaSuccess) {
+      cudaGetLastError(); j3dg_mesh_destroy(m); j3dg_set_error(ctx, "texture upload failed"); return J3DG_ECUDA;
+    }
+    m->tex_w = tex_w; m->tex_h = tex_h;
+  }
+  cudaEventRecord(ctx->ev[7], ctx->stream);
+  cudaEventSynchronize(ctx->ev[7]);
+  m->info.upload_ms = elapsed(ctx->ev[6], ctx->ev[7]);
+  rc = j3dg_build_bvh(m);
+  if (rc != J3DG_OK) { j3dg_mesh_destroy(m); return rc; }
+  *out = m;
+  return J3DG_OK;
+}
+
+J3DG_API int j3dg_mesh_create_empty(j3dg_ctx* ctx, uint32_t nv, uint32_t nt, uint32_t nr_of_nodes, const float* cs, uint32_t db_id, j3dg_mesh** out) {
+  if (!ctx || !out) return J3DG_EINVAL;
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  j3dg_mesh* m = new j3dg_mesh();
+  m->ctx = ctx; m->nv = nv; m->nt = nt; m->db_id = db_id;
+  memcpy(m->cs, cs ? cs : kIdentity, sizeof(m->cs));
+  j3dg_invert_orthonormal_host(m->cs, m->cs_inv);
+  if ((nr_of_nodes && cudaMalloc((void**)&m->d_nodes, (size_t)nr_of_nodes * sizeof(WideNode)) != cudaSuccess) ||
+      (nt && cudaMalloc((void**)&m->d_tris, (size_t)nt * sizeof(TriRec)) != cudaSuccess)) {
+    cudaGetLastError();
+    j3dg_mesh_destroy(m);
+    j3dg_set_error(ctx, "out of device memory (received BVH)");
+    return J3DG_ENOMEM;
+  }
+  m->node_cap = m->nr_nodes = nr_of_nodes;
+  m->info.nr_of_vertices = nv; m->info.nr_of_triangles = nt; m->info.nr_of_nodes = nr_of_nodes; m->info.nr_of_leaf_triangles = nt;
+  m->info.node_bytes = sizeof(WideNode); m->info.triangle_bytes = sizeof(TriRec);
+  *out = m;
+  return J3DG_OK;
+}
+
+J3DG_API void j3dg_mesh_destroy(j3dg_mesh* m) {
+  if (!m) return;
+  if (m->ctx) { cudaSetDevice(m->ctx->device); cudaStreamSynchronize(m->ctx->stream); }
+  cudaFree(m->d_vertices); cudaFree(m->d_indices); cudaFree(m->d_vcolors); cudaFree(m->d_uv); cudaFree(m->d_texture);
+  cudaFree(m->d_nodes); cudaFree(m->d_tris);
+  delete m;
+}
+
+J3DG_API int j3dg_mesh_rebuild(j3dg_mesh* m) {
+  if (!m || !m->d_vertices) return J3DG_EINVAL;
+  return j3dg_build_bvh(m);
+}
+
+J3DG_API int j3dg_mesh_info_get(const j3dg_mesh* m, j3dg_mesh_info* out) {
+  if (!m || !out) return J3DG_EINVAL;
+  *out = m->info;
+  return J3DG_OK;
+}
+
+J3DG_API int j3dg_mesh_set_cs(j3dg_mesh* m, const float* cs) {
+  if (!m) return J3DG_EINVAL;
+  memcpy(m->cs, cs ? cs : kIdentity, sizeof(m->cs));
+  j3dg_invert_orthonormal_host(m->cs, m->cs_inv);
+  return J3DG_OK;
+}
+
+J3DG_API int j3dg_mesh_bvh_buffer(j3dg_mesh* m, int kind, void** dev_ptr, size_t* bytes) {
+  if (!m || !dev_ptr || !bytes) return J3DG_EINVAL;
+  if (kind == 0) { *dev_ptr = m->d_nodes; *bytes = (size_t)m->nr_nodes * sizeof(WideNode); }
+  else if (kind == 1) { *dev_ptr = m->d_tris; *bytes = (size_t)m->nt * sizeof(TriRec); }
+  else return J3DG_EINVAL;
+  return J3DG_OK;
+}
+
+J3DG_API int j3dg_mesh_find_closest(j3dg_mesh* m, const float* rays, uint32_t n, float* hits, uint32_t* triangle_ids) {
+  if (!m || (n && (!rays || !hits || !triangle_ids))) return J3DG_EINVAL;
+  j3dg_ctx* ctx = m->ctx;
+  if (!n) return J3DG_OK;
+  float *d_rays = nullptr, *d_hits = nullptr;
+  uint32_t* d_ids = nullptr;
+  CU_CHECK(ctx, cudaMalloc((void**)&d_rays, (size_t)n * 32));
+  CU_CHECK(ctx, cudaMalloc((void**)&d_hits, (size_t)n * 16));
+  CU_CHECK(ctx, cudaMalloc((void**)&d_ids, (size_t)n * 4));
+  CU_CHECK(ctx, cudaMemcpyAsync(d_rays, rays, (size_t)n * 32, cudaMemcpyDefault, ctx->stream));
+  int rc = j3dg_launch_find_closest(m, d_rays, n, d_hits, d_ids);
+  if (rc == J3DG_OK) {
+    CU_CHECK(ctx, cudaMemcpyAsync(hits, d_hits, (size_t)n * 16, cudaMemcpyDefault, ctx->stream));
+    CU_CHECK(ctx, cudaMemcpyAsync(triangle_ids, d_ids, (size_t)n * 4, cudaMemcpyDefault, ctx->stream));
+    rc = check_overflow(ctx);
+  }
+  cudaFree(d_rays); cudaFree(d_hits); cudaFree(d_ids);
+  return rc;
+}
+
+// ---- clouds ------------------------------------------------------------------------------------
+J3DG_API int j3dg_cloud_create(j3dg_ctx* ctx, const float* positions, const float* normals, const uint32_t* colors, uint32_t n,
+                               const float* cs, uint32_t db_id, j3dg_cloud** out) {
+  if (!ctx || !out || (n && !positions)) { j3dg_set_error(ctx, "j3dg_cloud_create: bad argument"); return J3DG_EINVAL; }
+  if (n >= 0xFFFFFFFEu) { j3dg_set_error(ctx, "j3dg_cloud_create: too many points"); return J3DG_EINVAL; }
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  j3dg_cloud* c = new j3dg_cloud();
+  c->ctx = ctx; c->n = n; c->db_id = db_id;
+  memcpy(c->cs, cs ? cs : kIdentity, sizeof(c->cs));
+  int rc;
+  if ((rc = upload(ctx, &c->d_pos, positions, (size_t)n * 3)) != J3DG_OK || (rc = upload(ctx, &c->d_nrm, normals, (size_t)n * 3)) != J3DG_OK ||
+      (rc = upload(ctx, &c->d_clr, colors, (size_t)n)) != J3DG_OK) {
+    j3dg_cloud_destroy(c);
+    return rc;
+  }
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = c;
+  return J3DG_OK;
+}
+
+J3DG_API void j3dg_cloud_destroy(j3dg_cloud* c) {
+  if (!c) return;
+  if (c->ctx) { cudaSetDevice(c->ctx->device); cudaStreamSynchronize(c->ctx->stream); }
+  cudaFree(c->d_pos); cudaFree(c->d_nrm); cudaFree(c->d_clr);
+  delete c;
+}
+
+// ---- frame stages ------------------------------------------------------------------------------
+namespace {
+
+int stage_matcap(j3dg_ctx* ctx, const uint32_t* matcap, uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity,
+                 const uint32_t** d_out, uint32_t* ow, uint32_t* oh, uint32_t* ostride, uint32_t* ocav) {
+  if (!matcap) {
+    if (!ctx->d_matcap || !ctx->mw) { j3dg_set_error(ctx, "no matcap: pass one or call j3dg_ctx_set_matcap first"); return J3DG_EINVAL; }
+    *d_out = ctx->d_matcap; *ow = ctx->mw; *oh = ctx->mh; *ostride = ctx->mstride; *ocav = ctx->cavity;
+    return J3DG_OK;
+  }
+  if (!mw || !mh) { j3dg_set_error(ctx, "empty matcap"); return J3DG_EINVAL; }
+  if (!mstride) mstride = mw;
+  if (j3dg_is_device_ptr(matcap)) { *d_out = matcap; *ow = mw; *oh = mh; *ostride = mstride; *ocav = cavity; return J3DG_OK; }
+  void* p = ctx->d_matcap;
+  int rc = j3dg_reserve(ctx, &p, &ctx->matcap_cap, (size_t)mw * mh * 4);
+  ctx->d_matcap = (uint32_t*)p;
+  if (rc != J3DG_OK) return rc;
+  CU_CHECK(ctx, cudaMemcpy2DAsync(ctx->d_matcap, (size_t)mw * 4, matcap, (size_t)mstride * 4, (size_t)mw * 4, mh, cudaMemcpyDefault, ctx->stream));
+  ctx->mw = mw; ctx->mh = mh; ctx->mstride = mw; ctx->cavity = cavity;
+  *d_out = ctx->d_matcap; *ow = mw; *oh = mh; *ostride = mw; *ocav = cavity;
+  return J3DG_OK;
+}
+
+int ensure_background(j3dg_ctx* ctx, uint32_t w, uint32_t h, uint32_t top, uint32_t bottom) {
+  if (ctx->d_bg && ctx->bg_w == w && ctx->bg_h == h && ctx->bg_top == top && ctx->bg_bottom == bottom) return J3DG_OK;
+  void* p = ctx->d_bg;
+  int rc = j3dg_reserve(ctx, &p, &ctx->bg_cap, (size_t)w * h * 4);
+  ctx->d_bg = (uint32_t*)p;
+  if (rc != J3DG_OK) return rc;
+  rc = j3dg_launch_background(ctx, w, h, top, bottom, ctx->d_bg, w);
+  if (rc != J3DG_OK) return rc;
+  ctx->bg_w = w; ctx->bg_h = h; ctx->bg_top = top; ctx->bg_bottom = bottom;
+  return J3DG_OK;
+}
+
+}  // namespace
+
+J3DG_API int j3dg_ctx_set_matcap(j3dg_ctx* ctx, const uint32_t* matcap, uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity) {
+  if (!ctx || !matcap || !mw || !mh) return J3DG_EINVAL;
+  if (!mstride) mstride = mw;
+  void* p = ctx->d_matcap;
+  int rc = j3dg_reserve(ctx, &p, &ctx->matcap_cap, (size_t)mw * mh * 4);
+  ctx->d_matcap = (uint32_t*)p;
+  if (rc != J3DG_OK) return rc;
+  CU_CHECK(ctx, cudaMemcpy2DAsync(ctx->d_matcap, (size_t)mw * 4, matcap, (size_t)mstride * 4, (size_t)mw * 4, mh, cudaMemcpyDefault, ctx->stream));
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->mw = mw; ctx->mh = mh; ctx->mstride = mw; ctx->cavity = cavity;
+  return J3DG_OK;
+}
+
+J3DG_API int j3dg_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const j3dg_view* view, int x0, int y0, int x1, int y1,
+                       j3dg_pixel* pixels_out, uint32_t stride) {
+  if (!ctx || !view || !pixels_out || (nm && !meshes)) { j3dg_set_error(ctx, "j3dg_cast: bad argument"); return J3DG_EINVAL; }
+  cudaSetDevice(ctx->device);
+  const uint32_t w = view->width, h = view->height;
+  if (!w || !h) return J3DG_OK;
+  if (!stride) stride = w;
+  if (j3dg_is_device_ptr(pixels_out)) return j3dg_launch_cast(ctx, meshes, nm, view, x0, y0, x1, y1, pixels_out, stride, false);
+  // host destination: render into the context's device canvas, copy the updated rectangle back
+  int rc = j3dg_reserve(ctx, &ctx->d_pixels, &ctx->pixels_cap, (size_t)w * h * sizeof(j3dg_pixel));
+  if (rc != J3DG_OK) return rc;
+  rc = j3dg_launch_cast(ctx, meshes, nm, view, x0, y0, x1, y1, (j3dg_pixel*)ctx->d_pixels, w, false);
+  if (rc != J3DG_OK) return rc;
+  int cx0 = std::min(std::max(x0, 0), (int)w - 1), cy0 = std::min(std::max(y0, 0), (int)h - 1);
+  int cx1 = std::min(std::max(x1, 0), (int)w - 1), cy1 = std::min(std::max(y1, 0), (int)h - 1);
+  if (cx1 >= cx0 && cy1 >= cy0) {
+    CU_CHECK(ctx, cudaMemcpy2DAsync(pixels_out + (size_t)cy0 * stride + cx0, (size_t)stride * sizeof(j3dg_pixel),
+                                    (j3dg_pixel*)ctx->d_pixels + (size_t)cy0 * w + cx0, (size_t)w * sizeof(j3dg_pixel),
+                                    (size_t)(cx1 - cx0 + 1) * sizeof(j3dg_pixel), (size_t)(cy1 - cy0 + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return check_overflow(ctx);
+}
+
+J3DG_API int j3dg_shade(j3dg_ctx* ctx, const j3dg_pixel* pixels, uint32_t pixel_stride, const j3dg_view* view, const uint32_t* matcap,
+                        uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity_clr, const uint32_t* background,
+                        uint32_t* rgba_inout, uint32_t rgba_stride) {
+  if (!ctx || !view || !pixels || !rgba_inout) { j3dg_set_error(ctx, "j3dg_shade: bad argument"); return J3DG_EINVAL; }
+  cudaSetDevice(ctx->device);
+  const uint32_t w = view->width, h = view->height;
+  if (!w || !h) return J3DG_OK;
+  if (!pixel_stride) pixel_stride = w;
+  if (!rgba_stride) rgba_stride = w;
+  const uint32_t* d_mc; uint32_t dmw, dmh, dms, dcav;
+  int rc = stage_matcap(ctx, matcap, mw, mh, mstride, cavity_clr, &d_mc, &dmw, &dmh, &dms, &dcav);
+  if (rc != J3DG_OK) return rc;
+  const bool px_dev = j3dg_is_device_ptr(pixels), out_dev = j3dg_is_device_ptr(rgba_inout);
+  const j3dg_pixel* d_px = pixels;
+  uint32_t d_pstride = pixel_stride;
+  if (!px_dev) {
+    rc = j3dg_reserve(ctx, &ctx->d_pixels_in, &ctx->pixels_in_cap, (size_t)w * h * sizeof(j3dg_pixel));
+    if (rc != J3DG_OK) return rc;
+    CU_CHECK(ctx, cudaMemcpy2DAsync(ctx->d_pixels_in, (size_t)w * sizeof(j3dg_pixel), pixels, (size_t)pixel_stride * sizeof(j3dg_pixel),
+                                    (size_t)w * sizeof(j3dg_pixel), h, cudaMemcpyHostToDevice, ctx->stream));
+    d_px = (const j3dg_pixel*)ctx->d_pixels_in;
+    d_pstride = w;
+  }
+  uint32_t* d_out = rgba_inout;
+  uint32_t d_rstride = rgba_stride;
+  if (!out_dev) {
+    void* p = ctx->d_rgba;
+    rc = j3dg_reserve(ctx, &p, &ctx->rgba_cap, (size_t)w * h * 4);
+    ctx->d_rgba = (uint32_t*)p;
+    if (rc != J3DG_OK) return rc;
+    d_out = ctx->d_rgba;
+    d_rstride = w;
+    if (!background)  // miss pixels keep the caller's content (canvas::im after the background copy)
+      CU_CHECK(ctx, cudaMemcpy2DAsync(d_out, (size_t)w * 4, rgba_inout, (size_t)rgba_stride * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  const uint32_t* d_bg = nullptr;
+  uint32_t bg_stride = w;
+  if (background) {
+    if (j3dg_is_device_ptr(background)) d_bg = background;
+    else {
+      void* p = ctx->d_bg;
+      rc = j3dg_reserve(ctx, &p, &ctx->bg_cap, (size_t)w * h * 4);
+      ctx->d_bg = (uint32_t*)p;
+      if (rc != J3DG_OK) return rc;
+      ctx->bg_w = 0;  // content is the caller's, not a generated gradient
+      CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_bg, background, (size_t)w * h * 4, cudaMemcpyHostToDevice, ctx->stream));
+      d_bg = ctx->d_bg;
+    }
+  }
+  rc = j3dg_launch_shade(ctx, d_px, d_pstride, view, d_mc, dmw, dmh, dms, dcav, d_bg, bg_stride, d_out, d_rstride);
+  if (rc != J3DG_OK) return rc;
+  if (!out_dev) {
+    CU_CHECK(ctx, cudaMemcpy2DAsync(rgba_inout, (size_t)rgba_stride * 4, d_out, (size_t)w * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return J3DG_OK;
+}
+
+J3DG_API int j3dg_splat(j3dg_ctx* ctx, j3dg_cloud* const* clouds, uint32_t nc, const j3dg_view* view, const j3dg_pixel* pixels_in,
+                        j3dg_pixel* pixels_inout, uint32_t pixel_stride, uint32_t* rgba_inout, uint32_t rgba_stride) {
+  if (!ctx || !view || !pixels_in || !pixels_inout || !rgba_inout || (nc && !clouds)) { j3dg_set_error(ctx, "j3dg_splat: bad argument"); return J3DG_EINVAL; }
+  cudaSetDevice(ctx->device);
+  const uint32_t w = view->width, h = view->height;
+  if (!w || !h || !nc) return J3DG_OK;
+  if (!pixel_stride) pixel_stride = w;
+  if (!rgba_stride) rgba_stride = w;
+  const bool in_dev = j3dg_is_device_ptr(pixels_in), io_dev = j3dg_is_device_ptr(pixels_inout), rgba_dev = j3dg_is_device_ptr(rgba_inout);
+  if (in_dev && io_dev && rgba_dev)
+    return j3dg_launch_splat(ctx, clouds, nc, view, pixels_in, pixels_inout, pixel_stride, rgba_inout, rgba_stride);
+  if (in_dev || io_dev || rgba_dev) { j3dg_set_error(ctx, "j3dg_splat: buffers must be all host or all device"); return J3DG_EINVAL; }
+  int rc = j3dg_reserve(ctx, &ctx->d_pixels_in, &ctx->pixels_in_cap, (size_t)w * h * sizeof(j3dg_pixel));
+  if (rc != J3DG_OK) return rc;
+  rc = j3dg_reserve(ctx, &ctx->d_pixels, &ctx->pixels_cap, (size_t)w * h * sizeof(j3dg_pixel));
+  if (rc != J3DG_OK) return rc;
+  void* p = ctx->d_rgba;
+  rc = j3dg_reserve(ctx, &p, &ctx->rgba_cap, (size_t)w * h * 4);
+  ctx->d_rgba = (uint32_t*)p;
+  if (rc != J3DG_OK) return rc;
+  const size_t prow = (size_t)w * sizeof(j3dg_pixel);
+  CU_CHECK(ctx, cudaMemcpy2DAsync(ctx->d_pixels_in, prow, pixels_in, (size_t)pixel_stride * sizeof(j3dg_pixel), prow, h, cudaMemcpyHostToDevice, ctx->stream));
+  CU_CHECK(ctx, cudaMemcpy2DAsync(ctx->d_pixels, prow, pixels_inout, (size_t)pixel_stride * sizeof(j3dg_pixel), prow, h, cudaMemcpyHostToDevice, ctx->stream));
+  CU_CHECK(ctx, cudaMemcpy2DAsync(ctx->d_rgba, (size_t)w * 4, rgba_inout, (size_t)rgba_stride * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice, ctx->stream));
+  rc = j3dg_launch_splat(ctx, clouds, nc, view, (const j3dg_pixel*)ctx->d_pixels_in, (j3dg_pixel*)ctx->d_pixels, w, ctx->d_rgba, w);
+  if (rc != J3DG_OK) return rc;
+  CU_CHECK(ctx, cudaMemcpy2DAsync(pixels_inout, (size_t)pixel_stride * sizeof(j3dg_pixel), ctx->d_pixels, prow, prow, h, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_CHECK(ctx, cudaMemcpy2DAsync(rgba_inout, (size_t)rgba_stride * 4, ctx->d_rgba, (size_t)w * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return J3DG_OK;
+}
+
+J3DG_API int j3dg_render_frame(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, j3dg_cloud* const* clouds, uint32_t nc,
+                               const j3dg_view* view, const uint32_t* matcap, uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity_clr,
+                               uint32_t bg_top, uint32_t bg_bottom, j3dg_pixel* pixels_out, uint32_t* rgba_out) {
+  if (!ctx || !view || (nm && !meshes) || (nc && !clouds)) { j3dg_set_error(ctx, "j3dg_render_frame: bad argument"); return J3DG_EINVAL; }
+  cudaSetDevice(ctx->device);
+  const uint32_t w = view->width, h = view->height;
+  if (!w || !h) return J3DG_OK;
+  const uint32_t* d_mc; uint32_t dmw, dmh, dms, dcav;
+  int rc = stage_matcap(ctx, matcap, mw, mh, mstride, cavity_clr, &d_mc, &dmw, &dmh, &dms, &dcav);
+  if (rc != J3DG_OK) return rc;
+  if ((rc = ensure_background(ctx, w, h, bg_top, bg_bottom)) != J3DG_OK) return rc;
+  const bool px_dev = j3dg_is_device_ptr(pixels_out), rgba_dev = j3dg_is_device_ptr(rgba_out);
+  j3dg_pixel* d_px = pixels_out;
+  if (!px_dev) {
+    if ((rc = j3dg_reserve(ctx, &ctx->d_pixels, &ctx->pixels_cap, (size_t)w * h * sizeof(j3dg_pixel))) != J3DG_OK) return rc;
+    d_px = (j3dg_pixel*)ctx->d_pixels;
+  }
+  uint32_t* d_rgba = rgba_out;
+  if (!rgba_dev) {
+    void* p = ctx->d_rgba;
+    rc = j3dg_reserve(ctx, &p, &ctx->rgba_cap, (size_t)w * h * 4);
+    ctx->d_rgba = (uint32_t*)p;
+    if (rc != J3DG_OK) return rc;
+    d_rgba = ctx->d_rgba;
+  }
+  // view::render_scene: cast -> shade (on the pre-splat records) -> splat
+  if ((rc = j3dg_launch_cast(ctx, meshes, nm, view, 0, 0, (int)w - 1, (int)h - 1, d_px, w, false)) != J3DG_OK) return rc;
+  if ((rc = j3dg_launch_shade(ctx, d_px, w, view, d_mc, dmw, dmh, dms, dcav, ctx->d_bg, w, d_rgba, w)) != J3DG_OK) return rc;
+  if (nc && (rc = j3dg_launch_splat(ctx, clouds, nc, view, d_px, d_px, w, d_rgba, w)) != J3DG_OK) return rc;
+  bool copied = false;
+  if (pixels_out && !px_dev) { CU_CHECK(ctx, cudaMemcpyAsync(pixels_out, d_px, (size_t)w * h * sizeof(j3dg_pixel), cudaMemcpyDeviceToHost, ctx->stream)); copied = true; }
+  if (rgba_out && !rgba_dev) { CU_CHECK(ctx, cudaMemcpyAsync(rgba_out, d_rgba, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->stream)); copied = true; }
+  if (copied) return check_overflow(ctx);
+  return J3DG_OK;
+}
+
+J3DG_API int j3dg_cast_stats(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const j3dg_view* view, double* nodes_per_ray, double* tris_per_ray) {
+  if (!ctx || !view || (nm && !meshes)) return J3DG_EINVAL;
+  cudaSetDevice(ctx->device);
+  const uint32_t w = view->width, h = view->height;
+  if (!w || !h) return J3DG_EINVAL;
+  int rc = j3dg_reserve(ctx, &ctx->d_pixels, &ctx->pixels_cap, (size_t)w * h * sizeof(j3dg_pixel));
+  if (rc != J3DG_OK) return rc;
+  j3dg_view v = *view;
+  v.flags &= ~J3DG_SHADOW;  // primary rays only
+  const bool prof = ctx->profiling;
+  ctx->profiling = false;
+  rc = j3dg_launch_cast(ctx, meshes, nm, &v, 0, 0, (int)w - 1, (int)h - 1, (j3dg_pixel*)ctx->d_pixels, w, true);
+  ctx->profiling = prof;
+  if (rc != J3DG_OK) return rc;
+  unsigned long long st[4];
+  CU_CHECK(ctx, cudaMemcpyAsync(st, ctx->d_stats, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  const double rays = (double)w * h;
+  if (nodes_per_ray) *nodes_per_ray = (double)st[0] / rays;
+  if (tris_per_ray) *tris_per_ray = (double)st[1] / rays;
+  return J3DG_OK;
+}

@@ -1,0 +1,485 @@
+// build.cu — GPU BVH build.  Replaces `new qbvh(triangles, vertices)` + compute_triangle_normals
+// + compute_bb of add_object (j3d/scene.cpp:8-25; jtk/qbvh.h:1679-1686, 2133-2459, 5299-5339).
+//
+// Not a port of the reference's top-down binned-SAH QBVH: the closest hit does not depend on
+// the tree, so the tree is built the way a GPU builds one:
+//   1. vertex bbox (== compute_bb)                               bbox_kernel
+//   2. 48-bit Morton code of each triangle's box centre           morton_kernel
+//   3. LSD radix sort of (code, triangle)                         sort.cuh
+//   4. binary radix tree over the sorted codes (Karras 2012)      radix_tree_kernel
+//   5. leaf boxes + pre-gathered 48-byte triangle records,
+//      bottom-up box fit                                          refit_kernel
+//   6. top-down collapse into 8-wide quantised 96-byte nodes,
+//      opening the largest-area child first (SAH-greedy)          collapse_kernel (one launch per level)
+// Every subtree of the radix tree owns a contiguous range of the sorted triangle records, so a
+// leaf reference is just (first, count).
+#include "common.cuh"
+#include "sort.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+constexpr int MORTON_BITS_PER_AXIS = 16;
+constexpr int MORTON_BITS = 3 * MORTON_BITS_PER_AXIS;
+
+// ---- 1. bbox ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __host__ __forceinline__ float ordered_to_float(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  float f;
+#ifdef __CUDA_ARCH__
+  f = __uint_as_float(b);
+#else
+  memcpy(&f, &b, 4);
+#endif
+  return f;
+}
+
+__global__ void bbox_init_kernel(uint32_t* bb) {
+  if (threadIdx.x < 3) bb[threadIdx.x] = 0xFFFFFFFFu;
+  else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ v, uint32_t nv, uint32_t* __restrict__ bb) {
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float c = v[3 * i + j];
+      mn[j] = fminf(mn[j], c);
+      mx[j] = fmaxf(mx[j], c);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    for (int o = 16; o; o >>= 1) {
+      mn[j] = fminf(mn[j], __shfl_xor_sync(0xffffffffu, mn[j], o));
+      mx[j] = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], o));
+    }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      atomicMin(&bb[j], float_to_ordered(mn[j]));
+      atomicMax(&bb[3 + j], float_to_ordered(mx[j]));
+    }
+  }
+}
+
+// ---- 2. Morton codes ------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t spread16(uint32_t x) {  // 16 bits -> every third bit
+  uint64_t v = x & 0xffffu;
+  v = (v | (v << 32)) & 0x00ff00000000ffffull;  // not used for 16 bits but keeps the pattern general
+  v = (v | (v << 16)) & 0x00ff0000ff0000ffull;
+  v = (v | (v << 8)) & 0xf00f00f00f00f00full;
+  v = (v | (v << 4)) & 0x30c30c30c30c30c3ull;
+  v = (v | (v << 2)) & 0x9249249249249249ull;
+  return v;
+}
+
+__global__ void __launch_bounds__(256) morton_kernel(const float* __restrict__ verts, const uint32_t* __restrict__ idx, uint32_t nt,
+                                                      const uint32_t* __restrict__ bb, uint64_t* __restrict__ keys) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nt) return;
+  float mn[3], inv[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    mn[j] = ordered_to_float(bb[j]);
+    float ext = ordered_to_float(bb[3 + j]) - mn[j];
+    inv[j] = ext > 0.f ? 65535.99f / ext : 0.f;
+  }
+  const uint32_t i0 = idx[3 * (size_t)t], i1 = idx[3 * (size_t)t + 1], i2 = idx[3 * (size_t)t + 2];
+  uint32_t q[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float a = verts[3 * (size_t)i0 + j], b = verts[3 * (size_t)i1 + j], c = verts[3 * (size_t)i2 + j];
+    const float lo = fminf(a, fminf(b, c)), hi = fmaxf(a, fmaxf(b, c));
+    const float ctr = 0.5f * (lo + hi);
+    float f = (ctr - mn[j]) * inv[j];
+    f = fminf(fmaxf(f, 0.f), 65535.f);
+    q[j] = (uint32_t)f;
+  }
+  keys[t] = (spread16(q[0]) << 2) | (spread16(q[1]) << 1) | spread16(q[2]);
+}
+
+// ---- 4. binary radix tree (Karras 2012) ----------------------------------------------------
+// Node numbering: inner nodes 0..n-2 (root 0), leaf k = n-1+k.
+struct BinTree {
+  int2* children;    // [n-1]
+  uint2* range;      // [n-1] first,last sorted leaf
+  uint32_t* parent;  // [2n-1]
+  uint32_t* flags;   // [n-1]
+  float4* bmin;      // [2n-1]
+  float4* bmax;      // [2n-1]
+};
+
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  const uint64_t a = keys[i], b = keys[j];
+  if (a != b) return __clzll((long long)(a ^ b));
+  return 64 + __clz(i ^ j);
+}
+
+__global__ void __launch_bounds__(256) radix_tree_kernel(const uint64_t* __restrict__ keys, int n, BinTree t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int s = lmax >> 1; s >= 1; s >>= 1)
+    if (delta(keys, n, i, i + (l + s) * d) > dmin) l += s;
+  const int j = i + l * d;
+  const int dnode = delta(keys, n, i, j);
+  int s = 0;
+  int div = 2;
+  int tstep = (l + div - 1) / div;
+  while (true) {
+    if (delta(keys, n, i, i + (s + tstep) * d) > dnode) s += tstep;
+    if (tstep == 1) break;
+    div <<= 1;
+    tstep = (l + div - 1) / div;
+  }
+  const int gamma = i + s * d + min(d, 0);
+  const int lo = min(i, j), hi = max(i, j);
+  const int left = (lo == gamma) ? (n - 1 + gamma) : gamma;
+  const int right = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+  t.children[i] = make_int2(left, right);
+  t.range[i] = make_uint2((uint32_t)lo, (uint32_t)hi);
+  t.parent[left] = (uint32_t)i;
+  t.parent[right] = (uint32_t)i;
+  t.flags[i] = 0;
+  if (i == 0) t.parent[0] = 0xFFFFFFFFu;
+}
+
+// ---- 5. leaf records + bottom-up fit -------------------------------------------------------
+__global__ void __launch_bounds__(256) refit_kernel(const float* __restrict__ verts, const uint32_t* __restrict__ idx,
+                                                     const uint32_t* __restrict__ sorted_tri, int n, BinTree t, TriRec* __restrict__ recs) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t tri = sorted_tri[k];
+  const uint32_t i0 = idx[3 * (size_t)tri], i1 = idx[3 * (size_t)tri + 1], i2 = idx[3 * (size_t)tri + 2];
+  const float3 a = make_float3(verts[3 * (size_t)i0], verts[3 * (size_t)i0 + 1], verts[3 * (size_t)i0 + 2]);
+  const float3 b = make_float3(verts[3 * (size_t)i1], verts[3 * (size_t)i1 + 1], verts[3 * (size_t)i1 + 2]);
+  const float3 c = make_float3(verts[3 * (size_t)i2], verts[3 * (size_t)i2 + 1], verts[3 * (size_t)i2 + 2]);
+  TriRec r;
+  r.v0 = make_float4(a.x, a.y, a.z, __uint_as_float(tri));
+  r.v1 = make_float4(b.x, b.y, b.z, 0.f);
+  r.v2 = make_float4(c.x, c.y, c.z, 0.f);
+  recs[k] = r;
+  float4 mn = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.f);
+  float4 mx = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.f);
+  uint32_t cur = (uint32_t)(n - 1 + k);
+  t.bmin[cur] = mn;
+  t.bmax[cur] = mx;
+  if (n == 1) return;
+  __threadfence();
+  uint32_t p = t.parent[cur];
+  while (p != 0xFFFFFFFFu) {
+    if (atomicAdd(&t.flags[p], 1u) == 0u) return;  // first arrival: the sibling subtree finishes this node
+    const int2 ch = t.children[p];
+    const uint32_t other = ((uint32_t)ch.x == cur) ? (uint32_t)ch.y : (uint32_t)ch.x;
+    const float4 omn = __ldcg(&t.bmin[other]);
+    const float4 omx = __ldcg(&t.bmax[other]);
+    mn = make_float4(fminf(mn.x, omn.x), fminf(mn.y, omn.y), fminf(mn.z, omn.z), 0.f);
+    mx = make_float4(fmaxf(mx.x, omx.x), fmaxf(mx.y, omx.y), fmaxf(mx.z, omx.z), 0.f);
+    t.bmin[p] = mn;
+    t.bmax[p] = mx;
+    __threadfence();
+    cur = p;
+    p = t.parent[p];
+  }
+}
+
+// ---- 6. collapse to 8-wide quantised nodes ---------------------------------------------------
+struct WorkItem { uint32_t bin; uint32_t wide; };
+
+__device__ __forceinline__ float half_area(float4 mn, float4 mx) {
+  const float dx = mx.x - mn.x, dy = mx.y - mn.y, dz = mx.z - mn.z;
+  return dx * dy + dy * dz + dz * dx;
+}
+
+__device__ __forceinline__ uint32_t pick_exponent(float extent) {
+  // smallest biased exponent e with extent <= 255 * 2^(e-127) (plus one for rounding slack)
+  float s = extent / 255.f;
+  uint32_t bits = __float_as_uint(s);
+  uint32_t e = (bits >> 23) & 0xffu;
+  if (bits & 0x7fffffu) e += 1;
+  if (e < 1) e = 1;
+  if (e > 254) e = 254;
+  return e;
+}
+
+__global__ void __launch_bounds__(128) collapse_kernel(BinTree t, int n, const WorkItem* __restrict__ in, const uint32_t* __restrict__ in_count,
+                                                        WorkItem* __restrict__ out, uint32_t* __restrict__ out_count,
+                                                        WideNode* __restrict__ nodes, uint32_t* __restrict__ node_count, uint32_t node_cap,
+                                                        uint32_t* __restrict__ overflow) {
+  const uint32_t count = *in_count;
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
+    const WorkItem item = in[w];
+    // candidate children: binary node ids (inner < n-1, leaf >= n-1)
+    uint32_t cand[8];
+    float area[8];  // < 0 for entries that cannot be opened (single triangles)
+    int nc = 2;
+    {
+      const int2 ch = t.children[item.bin];
+      cand[0] = (uint32_t)ch.x;
+      cand[1] = (uint32_t)ch.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) area[i] = (cand[i] >= (uint32_t)(n - 1)) ? -1.f : half_area(t.bmin[cand[i]], t.bmax[cand[i]]);
+    while (nc < 8) {
+      int best = -1;
+      float ba = -1.f;
+      for (int i = 0; i < nc; ++i)
+        if (area[i] > ba) { ba = area[i]; best = i; }
+      if (best < 0) break;
+      const int2 ch = t.children[cand[best]];
+      cand[best] = (uint32_t)ch.x;
+      cand[nc] = (uint32_t)ch.y;
+      area[best] = ((uint32_t)ch.x >= (uint32_t)(n - 1)) ? -1.f : fmaxf(half_area(t.bmin[(uint32_t)ch.x], t.bmax[(uint32_t)ch.x]), 0.f);
+      area[nc] = ((uint32_t)ch.y >= (uint32_t)(n - 1)) ? -1.f : fmaxf(half_area(t.bmin[(uint32_t)ch.y], t.bmax[(uint32_t)ch.y]), 0.f);
+      ++nc;
+    }
+    // node box = box of the binary node
+    const float4 nmn = t.bmin[item.bin], nmx = t.bmax[item.bin];
+    WideNode node;
+    node.ox = nmn.x; node.oy = nmn.y; node.oz = nmn.z;
+    uint32_t e[3] = {pick_exponent(nmx.x - nmn.x), pick_exponent(nmx.y - nmn.y), pick_exponent(nmx.z - nmn.z)};
+    const float org[3] = {nmn.x, nmn.y, nmn.z};
+    float4 cmn[8], cmx[8];
+    for (int i = 0; i < nc; ++i) { cmn[i] = t.bmin[cand[i]]; cmx[i] = t.bmax[cand[i]]; }
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+      for (;;) {
+        const float scale = __uint_as_float(e[ax] << 23);
+        const float inv = 1.f / scale;
+        bool ok = true;
+        for (int i = 0; i < nc; ++i) {
+          const float lo = ax == 0 ? cmn[i].x : ax == 1 ? cmn[i].y : cmn[i].z;
+          const float hi = ax == 0 ? cmx[i].x : ax == 1 ? cmx[i].y : cmx[i].z;
+          int ql = (int)floorf((lo - org[ax]) * inv);
+          int qh = (int)ceilf((hi - org[ax]) * inv);
+          ql = max(0, min(ql, 255));
+          qh = max(0, qh);
+          // conservative against the rounding of the decode fl(q*scale + origin)
+          while (ql > 0 && __fmaf_rn((float)ql, scale, org[ax]) > lo) --ql;
+          while (qh <= 255 && __fmaf_rn((float)qh, scale, org[ax]) < hi) ++qh;
+          if (qh > 255) { ok = false; break; }
+          node.qlo[ax][i] = (uint8_t)ql;
+          node.qhi[ax][i] = (uint8_t)qh;
+        }
+        if (ok) break;
+        e[ax] += 1;
+      }
+      for (int i = nc; i < 8; ++i) { node.qlo[ax][i] = 255; node.qhi[ax][i] = 0; }
+    }
+    node.ex = (uint8_t)e[0]; node.ey = (uint8_t)e[1]; node.ez = (uint8_t)e[2];
+    node.nchild = (uint8_t)nc;
+    for (int i = 0; i < 8; ++i) node.child[i] = J3DG_EMPTY_CHILD;
+    for (int i = 0; i < nc; ++i) {
+      const uint32_t c = cand[i];
+      if (c >= (uint32_t)(n - 1)) {
+        node.child[i] = J3DG_LEAF_BIT | (c - (uint32_t)(n - 1));  // count-1 = 0
+      } else {
+        const uint2 r = t.range[c];
+        const uint32_t cnt = r.y - r.x + 1;
+        if (cnt <= J3DG_MAX_LEAF) {
+          node.child[i] = J3DG_LEAF_BIT | ((cnt - 1) << 29) | r.x;
+        } else {
+          const uint32_t wi = atomicAdd(node_count, 1u);
+          if (wi >= node_cap) { *overflow = 1u; node.child[i] = J3DG_EMPTY_CHILD; node.qlo[0][i] = 255; node.qhi[0][i] = 0; continue; }
+          node.child[i] = wi;
+          const uint32_t oi = atomicAdd(out_count, 1u);
+          out[oi] = WorkItem{c, wi};
+        }
+      }
+    }
+    nodes[item.wide] = node;
+  }
+}
+
+// n == 1: a root with a single leaf child
+__global__ void single_triangle_root_kernel(BinTree t, WideNode* nodes) {
+  const float4 mn = t.bmin[0], mx = t.bmax[0];
+  WideNode node;
+  node.ox = mn.x; node.oy = mn.y; node.oz = mn.z;
+  const float ext[3] = {mx.x - mn.x, mx.y - mn.y, mx.z - mn.z};
+  uint32_t e[3];
+  for (int ax = 0; ax < 3; ++ax) {
+    e[ax] = pick_exponent(ext[ax]) + 1;
+    for (int i = 0; i < 8; ++i) { node.qlo[ax][i] = 255; node.qhi[ax][i] = 0; }
+    node.qlo[ax][0] = 0;
+    node.qhi[ax][0] = 255;
+  }
+  node.ex = (uint8_t)e[0]; node.ey = (uint8_t)e[1]; node.ez = (uint8_t)e[2];
+  node.nchild = 1;
+  for (int i = 0; i < 8; ++i) node.child[i] = J3DG_EMPTY_CHILD;
+  node.child[0] = J3DG_LEAF_BIT | 0u;
+  nodes[0] = node;
+}
+
+__global__ void init_queue_kernel(WorkItem* q, uint32_t* counts, uint32_t* node_count, uint32_t* overflow) {
+  q[0] = WorkItem{0u, 0u};
+  counts[0] = 1u;
+  counts[1] = 0u;
+  *node_count = 1u;
+  *overflow = 0u;
+}
+__global__ void reset_count_kernel(uint32_t* c) { *c = 0u; }
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  template <class T> T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = (T*)(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+}  // namespace
+
+// Builds m->d_nodes / m->d_tris from m->d_vertices / m->d_indices (device resident).
+int j3dg_build_bvh(j3dg_mesh* m) {
+  j3dg_ctx* ctx = m->ctx;
+  const uint32_t n = m->nt;
+  cudaStream_t st = ctx->stream;
+  m->info.nr_of_vertices = m->nv;
+  m->info.nr_of_triangles = n;
+  m->info.nr_of_leaf_triangles = n;
+  m->info.node_bytes = sizeof(WideNode);
+  m->info.triangle_bytes = sizeof(TriRec);
+  m->info.sah_cost = 0.f;
+
+  // ---- scratch arena ----
+  const size_t nn = n ? n : 1;
+  size_t need = 4096;
+  need += 256 + 8 * sizeof(uint32_t);                               // bbox + counters
+  need += 2 * (256 + nn * sizeof(uint64_t)) + 2 * (256 + nn * sizeof(uint32_t));  // keys/vals ping-pong
+  need += 256 + rsort::scratch_bytes(n);
+  need += 256 + nn * sizeof(int2) + 256 + nn * sizeof(uint2) + 256 + 2 * nn * sizeof(uint32_t) + 256 + nn * sizeof(uint32_t);
+  need += 2 * (256 + 2 * nn * sizeof(float4));
+  need += 2 * (256 + nn * sizeof(WorkItem));
+  if (j3dg_reserve(ctx, &ctx->d_misc, &ctx->misc_cap, need) != J3DG_OK) return J3DG_ENOMEM;
+  Arena ar;
+  ar.base = (char*)ctx->d_misc;
+  ar.cap = ctx->misc_cap;
+  uint32_t* d_bb = ar.take<uint32_t>(8);
+  uint32_t* d_counts = ar.take<uint32_t>(8);  // [0],[1] queue sizes, [2] node count, [3] overflow
+  uint64_t* keys_a = ar.take<uint64_t>(nn);
+  uint64_t* keys_b = ar.take<uint64_t>(nn);
+  uint32_t* vals_a = ar.take<uint32_t>(nn);
+  uint32_t* vals_b = ar.take<uint32_t>(nn);
+  uint32_t* sort_scratch = ar.take<uint32_t>(rsort::scratch_bytes(n) / 4);
+  BinTree bt;
+  bt.children = ar.take<int2>(nn);
+  bt.range = ar.take<uint2>(nn);
+  bt.parent = ar.take<uint32_t>(2 * nn);
+  bt.flags = ar.take<uint32_t>(nn);
+  bt.bmin = ar.take<float4>(2 * nn);
+  bt.bmax = ar.take<float4>(2 * nn);
+  WorkItem* q0 = ar.take<WorkItem>(nn);
+  WorkItem* q1 = ar.take<WorkItem>(nn);
+
+  // ---- output arrays ----
+  if (!m->d_tris && n) {
+    if (cudaMalloc((void**)&m->d_tris, (size_t)n * sizeof(TriRec)) != cudaSuccess) {
+      j3dg_set_error(ctx, "out of device memory (triangle records)");
+      return J3DG_ENOMEM;
+    }
+  }
+  uint32_t cap = std::max<uint32_t>(16u, n / 3 + 1024u);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (m->node_cap < cap) {
+      if (m->d_nodes) cudaFree(m->d_nodes);
+      m->d_nodes = nullptr;
+      if (cudaMalloc((void**)&m->d_nodes, (size_t)cap * sizeof(WideNode)) != cudaSuccess) {
+        j3dg_set_error(ctx, "out of device memory (BVH nodes)");
+        return J3DG_ENOMEM;
+      }
+      m->node_cap = cap;
+    }
+    CU_CHECK(ctx, cudaEventRecord(ctx->ev[6], st));
+    // 1. bbox
+    bbox_init_kernel<<<1, 32, 0, st>>>(d_bb);
+    KERNEL_CHECK(ctx);
+    if (m->nv) {
+      const int blocks = (int)std::min<size_t>(((size_t)m->nv + 255) / 256, (size_t)ctx->sm_count * 8);
+      bbox_kernel<<<blocks, 256, 0, st>>>(m->d_vertices, m->nv, d_bb);
+      KERNEL_CHECK(ctx);
+    }
+    uint32_t h_counts[8] = {0, 0, 1, 0, 0, 0, 0, 0};
+    if (n) {
+      const uint32_t tb = (n + 255) / 256;
+      morton_kernel<<<tb, 256, 0, st>>>(m->d_vertices, m->d_indices, n, d_bb, keys_a);
+      KERNEL_CHECK(ctx);
+      bool in_b = false;
+      int rc = rsort::sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, n, MORTON_BITS, sort_scratch, &in_b);
+      if (rc != J3DG_OK) return rc;
+      const uint64_t* keys = in_b ? keys_b : keys_a;
+      const uint32_t* vals = in_b ? vals_b : vals_a;
+      if (n > 1) {
+        radix_tree_kernel<<<(n - 1 + 255) / 256, 256, 0, st>>>(keys, (int)n, bt);
+        KERNEL_CHECK(ctx);
+      }
+      refit_kernel<<<tb, 256, 0, st>>>(m->d_vertices, m->d_indices, vals, (int)n, bt, m->d_tris);
+      KERNEL_CHECK(ctx);
+      if (n == 1) {
+        single_triangle_root_kernel<<<1, 1, 0, st>>>(bt, m->d_nodes);
+        KERNEL_CHECK(ctx);
+      } else {
+        init_queue_kernel<<<1, 1, 0, st>>>(q0, d_counts, d_counts + 2, d_counts + 3);
+        KERNEL_CHECK(ctx);
+        // Level-synchronous collapse without host round trips: a fixed-size grid strides over
+        // the device-side queue; the loop runs until the host sees an empty level (checked every
+        // 8 levels to keep syncs rare).
+        const int grid = ctx->sm_count * 8;
+        int level = 0;
+        for (;;) {
+          for (int k = 0; k < 8; ++k, ++level) {
+            WorkItem* qi = (level & 1) ? q1 : q0;
+            WorkItem* qo = (level & 1) ? q0 : q1;
+            uint32_t* ci = d_counts + (level & 1);
+            uint32_t* co = d_counts + ((level + 1) & 1);
+            collapse_kernel<<<grid, 128, 0, st>>>(bt, (int)n, qi, ci, qo, co, m->d_nodes, d_counts + 2, m->node_cap, d_counts + 3);
+            KERNEL_CHECK(ctx);
+            reset_count_kernel<<<1, 1, 0, st>>>(ci);
+            KERNEL_CHECK(ctx);
+          }
+          CU_CHECK(ctx, cudaMemcpyAsync(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
+          CU_CHECK(ctx, cudaStreamSynchronize(st));
+          if (h_counts[level & 1] == 0 || h_counts[3]) break;
+          if (level > 4096) { j3dg_set_error(ctx, "BVH collapse did not terminate"); return J3DG_ECUDA; }
+        }
+      }
+    }
+    CU_CHECK(ctx, cudaEventRecord(ctx->ev[7], st));
+    CU_CHECK(ctx, cudaEventSynchronize(ctx->ev[7]));
+    if (h_counts[3]) {  // node array too small for a degenerate tree: retry with the hard bound
+      cap = std::max<uint32_t>(16u, n);
+      continue;
+    }
+    float ms = 0.f;
+    CU_CHECK(ctx, cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]));
+    m->info.build_ms = ms;
+    m->nr_nodes = n ? h_counts[2] : 0;
+    m->info.nr_of_nodes = m->nr_nodes;
+    uint32_t h_bb[6];
+    CU_CHECK(ctx, cudaMemcpy(h_bb, d_bb, sizeof(h_bb), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < 3; ++j) {
+      m->info.bbox_min[j] = m->nv ? ordered_to_float(h_bb[j]) : 0.f;
+      m->info.bbox_max[j] = m->nv ? ordered_to_float(h_bb[3 + j]) : 0.f;
+    }
+    return J3DG_OK;
+  }
+  j3dg_set_error(ctx, "BVH node allocation overflow");
+  return J3DG_ECUDA;
+}

@@ -1,0 +1,177 @@
+// common.cuh — shared device/host definitions of the sm_100a renderer (libj3dg.so).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+#include <string>
+#include <vector>
+
+#include "j3dg.h"
+
+#define J3DG_API extern "C" __attribute__((visibility("default")))
+
+// ---------------------------------------------------------------------------------------
+// Device data layout (DESIGN.md "Data layout in HBM")
+// ---------------------------------------------------------------------------------------
+
+// 8-wide BVH node, 96 bytes = exactly three 32-byte sectors, 32-byte aligned.
+// Child boxes are quantised to 8 bits per plane relative to (origin, 2^exp) — decoded box
+// fl(origin + q * 2^e) is guaranteed by the builder to contain the child's true box.
+// child[i]: bit31 = 0 -> index of an inner node; bit31 = 1 -> leaf:
+//           bits 29..30 = triangle count - 1 (1..4), bits 0..28 = first triangle record.
+// Empty slots have an inverted box (qlo = 255, qhi = 0) and child = J3DG_EMPTY_CHILD.
+struct __align__(32) WideNode {
+  float ox, oy, oz;      // quantisation origin = node box minimum
+  uint8_t ex, ey, ez;    // biased float exponents: scale_axis = uint_as_float(e << 23)
+  uint8_t nchild;        // number of used slots (diagnostic)
+  uint8_t qlo[3][8];     // [axis][slot]
+  uint8_t qhi[3][8];
+  uint32_t child[8];
+};
+static_assert(sizeof(WideNode) == 96, "WideNode must be 96 bytes");
+
+#define J3DG_LEAF_BIT 0x80000000u
+#define J3DG_EMPTY_CHILD 0xFFFFFFFFu
+#define J3DG_MAX_LEAF 4
+#define J3DG_LEAF_FIRST_MASK 0x1FFFFFFFu
+
+// Pre-gathered triangle record, 48 bytes, in Morton-sorted order so that every BVH subtree
+// owns a contiguous range.  Raw vertex positions (the Woop test needs v - origin exactly as
+// the reference computes it); .w lanes carry the original triangle index.
+struct __align__(16) TriRec {
+  float4 v0;  // xyz, w = __uint_as_float(original triangle index)
+  float4 v1;  // xyz, w unused (0)
+  float4 v2;  // xyz, w unused (0)
+};
+static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
+
+// What a traversal kernel needs of one mesh.
+struct MeshDev {
+  const WideNode* nodes;
+  const TriRec* tris;
+  const uint32_t* indices;     // nt x 3 original indices (vertex colours / uv lookups)
+  const float* vertices;       // nv x 3 (unused by traversal; kept for consumers)
+  const float* vertex_colors;  // nullable
+  const float* uv;             // nullable, nt x 6
+  const uint32_t* texture;     // nullable
+  uint32_t tex_w, tex_h, tex_stride;
+  uint32_t nt;
+  uint32_t db_id;
+  float cs[16];                // object -> world
+  float cs_inv[16];            // invert_orthonormal(cs), canvas.cpp:734
+  float root_min[3], root_max[3];
+};
+
+struct ViewDev {
+  uint32_t width, height;
+  float near_plane, diagonal;
+  float pinv[16];
+  float cs[16];
+  float cs_inv[16];
+  float origin[4];  // cs * (0,0,0,1)
+  float light[4];   // cs * (pivot + 3*diagonal, 1)
+  uint32_t flags;
+};
+
+// ---------------------------------------------------------------------------------------
+// Exactly-rounded arithmetic: the reference is built for plain SSE (no FMA), so every
+// parity-critical product/sum must round separately.  These intrinsics are never contracted.
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+static __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+static __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+static __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+static __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+static __device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+
+// jtk matrix_vector_multiply (qbvh.h:4564-4568): c0*v0 + c1*v1 + c2*v2 + c3*v3, left to right
+static __device__ __forceinline__ float4 mat_vec(const float* __restrict__ m, float4 v) {
+  float4 r;
+  r.x = fadd(fadd(fadd(fmul(m[0], v.x), fmul(m[4], v.y)), fmul(m[8], v.z)), fmul(m[12], v.w));
+  r.y = fadd(fadd(fadd(fmul(m[1], v.x), fmul(m[5], v.y)), fmul(m[9], v.z)), fmul(m[13], v.w));
+  r.z = fadd(fadd(fadd(fmul(m[2], v.x), fmul(m[6], v.y)), fmul(m[10], v.z)), fmul(m[14], v.w));
+  r.w = fadd(fadd(fadd(fmul(m[3], v.x), fmul(m[7], v.y)), fmul(m[11], v.z)), fmul(m[15], v.w));
+  return r;
+}
+#endif
+
+// ---------------------------------------------------------------------------------------
+// Host-side plumbing
+// ---------------------------------------------------------------------------------------
+struct j3dg_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  bool profiling = true;
+  cudaEvent_t ev[8] = {};
+  j3dg_timings timings = {};
+  uint32_t launches = 0;
+  int sm_count = 148;
+  // frame scratch (grown on demand)
+  void* d_pixels = nullptr; size_t pixels_cap = 0;
+  void* d_pixels_in = nullptr; size_t pixels_in_cap = 0;
+  uint32_t* d_rgba = nullptr; size_t rgba_cap = 0;
+  uint32_t* d_bg = nullptr; size_t bg_cap = 0; uint32_t bg_w = 0, bg_h = 0, bg_top = 0, bg_bottom = 0;
+  unsigned long long* d_packed = nullptr; size_t packed_cap = 0;
+  uint32_t* d_matcap = nullptr; size_t matcap_cap = 0; uint32_t mw = 0, mh = 0, mstride = 0, cavity = 0;
+  MeshDev* d_meshes = nullptr; size_t meshes_cap = 0;
+  unsigned long long* d_stats = nullptr;
+  void* d_misc = nullptr; size_t misc_cap = 0;
+};
+
+void j3dg_set_error(j3dg_ctx* ctx, const std::string& msg);
+int j3dg_cuda_fail(j3dg_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
+bool j3dg_is_device_ptr(const void* p);
+int j3dg_reserve(j3dg_ctx* ctx, void** ptr, size_t* cap, size_t bytes);
+
+#define CU_CHECK(ctx, call)                                                         \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) return j3dg_cuda_fail((ctx), e__, #call, __FILE__, __LINE__); \
+  } while (0)
+#define KERNEL_CHECK(ctx)                                                           \
+  do {                                                                              \
+    (ctx)->launches++;                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) return j3dg_cuda_fail((ctx), e__, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+struct j3dg_mesh {
+  j3dg_ctx* ctx = nullptr;
+  uint32_t nv = 0, nt = 0, db_id = 0;
+  float* d_vertices = nullptr;
+  uint32_t* d_indices = nullptr;
+  float* d_vcolors = nullptr;
+  float* d_uv = nullptr;
+  uint32_t* d_texture = nullptr;
+  uint32_t tex_w = 0, tex_h = 0;
+  WideNode* d_nodes = nullptr; uint32_t node_cap = 0; uint32_t nr_nodes = 0;
+  TriRec* d_tris = nullptr;
+  float cs[16];
+  float cs_inv[16];
+  j3dg_mesh_info info = {};
+};
+
+struct j3dg_cloud {
+  j3dg_ctx* ctx = nullptr;
+  uint32_t n = 0, db_id = 0;
+  float* d_pos = nullptr;
+  float* d_nrm = nullptr;
+  uint32_t* d_clr = nullptr;
+  float cs[16];
+};
+
+// stage entry points implemented in the other translation units (device pointers only)
+int j3dg_build_bvh(j3dg_mesh* m);
+int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const j3dg_view* view,
+                     int x0, int y0, int x1, int y1, j3dg_pixel* d_pixels, uint32_t stride, bool stats);
+int j3dg_launch_shade(j3dg_ctx* ctx, const j3dg_pixel* d_pixels, uint32_t pstride, const j3dg_view* view,
+                      const uint32_t* d_matcap, uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity,
+                      const uint32_t* d_bg, uint32_t bg_stride, uint32_t* d_rgba, uint32_t rstride);
+int j3dg_launch_splat(j3dg_ctx* ctx, j3dg_cloud* const* clouds, uint32_t nc, const j3dg_view* view,
+                      const j3dg_pixel* d_px_in, j3dg_pixel* d_px_inout, uint32_t pstride, uint32_t* d_rgba, uint32_t rstride);
+int j3dg_launch_background(j3dg_ctx* ctx, uint32_t w, uint32_t h, uint32_t top, uint32_t bottom, uint32_t* d_out, uint32_t stride);
+int j3dg_launch_find_closest(j3dg_mesh* m, const float* d_rays, uint32_t n, float* d_hits, uint32_t* d_ids);
+void j3dg_invert_orthonormal_host(const float* m, float* out);

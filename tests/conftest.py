@@ -1,0 +1,56 @@
+import os
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def native():
+    """Build (if needed) every native artefact that can be built on this machine."""
+    from j3d_b200 import build
+    build.build_synth()
+    build.build_host()
+    build.build_oracle()
+    if not (ROOT / "j3d_b200" / "libj3dg.so").exists():
+        build.build_cuda()
+    return True
+
+
+@pytest.fixture(scope="session")
+def oracle(native):
+    from oracle.bindings import Oracle
+    return Oracle()
+
+
+@pytest.fixture(scope="session")
+def ctx(native):
+    import j3d_b200 as j
+    c = j.Context(0)  # raises loudly without a B200: there is no fallback path
+    yield c
+    c.close()

@@ -1,0 +1,290 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes over
+include/j3dg.h), against the CPU oracle (oracle/j3d_oracle.c) on the same seeded inputs, and
+against the unmodified reference (oracle/_ref) when its prebuilt library travelled along.
+Run with `pytest -m gpu` on a B200.
+"""
+import numpy as np
+import pytest
+
+import j3d_b200 as j
+from parity import compare_pixels, compare_rgba, MISS
+
+pytestmark = pytest.mark.gpu
+
+FMAX = float(np.finfo(np.float32).max)
+
+
+def cube():
+    v = np.array([[-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1], [-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1]], np.float32)
+    t = np.array([[0, 1, 2], [0, 2, 3], [7, 6, 5], [7, 5, 4], [1, 0, 4], [1, 4, 5], [2, 1, 5], [2, 5, 6], [3, 2, 6], [3, 6, 7], [0, 3, 7], [0, 7, 4]], np.uint32)
+    return v, t
+
+
+def test_cube_known_answer(ctx):
+    """jtk.tests/qbvh_tests.cpp:708-749 (find_closest_with_ray) through j3dg_mesh_find_closest."""
+    v, t = cube()
+    m = ctx.mesh_create(v, t)
+    rays = np.array([[0.8, -0.5, 0.8, 1, 0, 0, 0, FMAX], [0.8, -0.5, 0.8, 1, 0, 0, -FMAX, 0], [0.8, -0.5, 0.8, 1, 0, 0, -FMAX, FMAX]], np.float32)
+    hits, ids = m.find_closest(rays)
+    assert abs(hits[0, 2] - 0.2) <= 1e-6 and ids[0] == 6
+    assert abs(hits[1, 2] + 1.8) <= 1e-6 and ids[1] == 10
+    assert abs(hits[2, 2] - 0.2) <= 1e-6 and ids[2] == 6
+    assert (hits[:, 3] == 1).all()
+    m.destroy()
+
+
+def test_find_closest_random_rays(ctx, oracle):
+    verts, tris = j.icosphere(9)
+    rng = np.random.default_rng(5)
+    n = 4000
+    org = rng.normal(size=(n, 3)).astype(np.float32) * 2.0
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    rays = np.concatenate([org, d, np.full((n, 1), -FMAX, np.float32), np.full((n, 1), FMAX, np.float32)], axis=1).astype(np.float32)
+    rays[: n // 2, 6] = 0.0
+    m = ctx.mesh_create(verts, tris)
+    hits, ids = m.find_closest(rays)
+    om = oracle.mesh(verts, tris)
+    ohits, oids = om.find_closest(rays)
+    assert (hits[:, 3] == ohits[:, 3]).mean() > 0.999
+    both = (hits[:, 3] == 1) & (ohits[:, 3] == 1)
+    assert (ids[both] == oids[both]).mean() > 0.999
+    same = both & (ids == oids)
+    assert np.abs(hits[same, 2] - ohits[same, 2]).max() <= 1e-5 * np.abs(ohits[same, 2]).max()
+    m.destroy(); om.destroy()
+
+
+def _scene(f, w, h, flags, angle, with_colors=False):
+    verts, tris = j.icosphere(f)
+    vc = j.vertex_colors(verts) if with_colors else None
+    mn, mx = j.compute_bb(verts)
+    v = j.make_view(w, h, mn, mx, flags)
+    if angle:
+        v = j.orbit_view(v, angle)
+    return verts, tris, vc, v
+
+
+@pytest.mark.parametrize("f,w,h,flags,angle,colors", [
+    (12, 480, 270, j.DEFAULT_FLAGS, 0.0, False),
+    (40, 640, 360, j.DEFAULT_FLAGS | j.SHADOW, 33.0, True),
+    (25, 333, 201, j.DEFAULT_FLAGS, -71.0, True),            # ragged canvas size (not a multiple of the tile)
+    (3, 64, 48, j.DEFAULT_FLAGS | j.SHADOW, 10.0, False),     # 180 triangles
+])
+def test_cast_matches_oracle(ctx, oracle, f, w, h, flags, angle, colors):
+    verts, tris, vc, v = _scene(f, w, h, flags, angle, colors)
+    m = ctx.mesh_create(verts, tris, vcolors=vc)
+    got = ctx.cast([m], v)
+    om = oracle.mesh(verts, tris, vcolors=vc)
+    want = oracle.cast([om], v)
+    st = compare_pixels(got, want, tag=f"f={f}")
+    assert st["hits"] > 0
+    m.destroy(); om.destroy()
+
+
+def test_cast_two_objects_textured(ctx, oracle):
+    w, h = 640, 360
+    verts, tris = j.icosphere(30)
+    vc = j.vertex_colors(verts)
+    v2, t2 = j.icosphere(10)
+    cs = np.eye(4, dtype=np.float32)
+    a = 0.7
+    cs[0, 0], cs[0, 1], cs[1, 0], cs[1, 1] = np.cos(a), np.sin(a), -np.sin(a), np.cos(a)
+    cs[3, :3] = [1.5, 0.3, -0.5]
+    uv = np.random.default_rng(1).random((t2.shape[0], 6), dtype=np.float32)
+    tex = (np.random.default_rng(2).integers(0, 2 ** 32, (64, 48), dtype=np.uint64)).astype(np.uint32) | np.uint32(0xFF000000)
+    mn = np.minimum(verts.min(0), v2.min(0) + cs[3, :3] - 0.2)
+    mx = np.maximum(verts.max(0), v2.max(0) + cs[3, :3] + 0.2)
+    v = j.orbit_view(j.make_view(w, h, mn, mx, j.DEFAULT_FLAGS | j.SHADOW), -20.0)
+    m1 = ctx.mesh_create(verts, tris, vcolors=vc, db_id=0x20000000)
+    m2 = ctx.mesh_create(v2, t2, uv=uv, texture=tex, cs=cs.reshape(-1), db_id=0x20000001)
+    got = ctx.cast([m1, m2], v)
+    o1 = oracle.mesh(verts, tris, vcolors=vc, db_id=0x20000000)
+    o2 = oracle.mesh(v2, t2, uv=uv, texture=tex, cs=cs.reshape(-1), db_id=0x20000001)
+    want = oracle.cast([o1, o2], v)
+    compare_pixels(got, want, tag="two objects")
+    assert (got["db_id"] == 0x20000001).sum() > 1000
+    for x in (m1, m2):
+        x.destroy()
+
+
+def test_cast_rect_and_empty_scene(ctx, oracle):
+    verts, tris, vc, v = _scene(10, 200, 120, j.DEFAULT_FLAGS, 5.0)
+    m = ctx.mesh_create(verts, tris)
+    full = ctx.cast([m], v)
+    part = np.zeros_like(full)
+    part["object_id"] = 0x12345678  # must stay untouched outside the rectangle
+    ctx.cast([m], v, out=part, rect=(50, 30, 149, 89))
+    assert (part[30:90, 50:150].tobytes() == full[30:90, 50:150].tobytes())
+    outside = np.ones(part.shape, bool)
+    outside[30:90, 50:150] = False
+    assert (part["object_id"][outside] == 0x12345678).all()
+    # clamping of an out-of-range rectangle (canvas.cpp:682-698)
+    clamped = ctx.cast([m], v, rect=(-5, -5, 10_000, 10_000))
+    assert clamped.tobytes() == full.tobytes()
+    # no objects: every pixel is the miss record (canvas.cpp:744-760)
+    empty = ctx.cast([], v)
+    assert (empty["object_id"] == MISS).all() and (empty["db_id"] == 0).all() and (empty["depth"] == np.float32(FMAX)).all()
+    m.destroy()
+
+
+@pytest.mark.parametrize("flags", [
+    j.DEFAULT_FLAGS, j.DEFAULT_FLAGS & ~j.EDGES, j.DEFAULT_FLAGS | j.WIREFRAME, j.DEFAULT_FLAGS | j.ONE_BIT,
+    j.DEFAULT_FLAGS | j.SHADOW, j.SHADOW | j.EDGES | j.VERTEXCOLORS, j.SHADOW | j.VERTEXCOLORS,
+])
+def test_shade_matches_oracle(ctx, oracle, flags):
+    """Shading in isolation: both sides shade the SAME (oracle-made) pixel buffer."""
+    w, h = 512, 300
+    verts, tris, vc, v = _scene(30, w, h, flags, 33.0, True)
+    om = oracle.mesh(verts, tris, vcolors=vc)
+    px = oracle.cast([om], v)
+    mc, cav = j.make_matcap(0)
+    bg = j.fill_background(w, h)
+    want = oracle.shade(px, v, mc, cav, bg.copy())
+    got = ctx.shade(px, v, mc, cav, background=bg)
+    st = compare_rgba(got, want, tag=hex(flags))
+    assert st["gt1"] <= 0.0005 * w * h
+    # background == None keeps the caller's content on miss pixels
+    mine = np.full((h, w), 0xFF123456, np.uint32)
+    got2 = ctx.shade(px, v, mc, cav, background=None, out=mine)
+    miss = px["object_id"] == MISS
+    assert (got2[miss] == 0xFF123456).all() and (got2[~miss] == got[~miss]).all()
+    om.destroy()
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_shade_all_matcaps(ctx, oracle, kind):
+    w, h = 320, 200
+    verts, tris, vc, v = _scene(20, w, h, j.DEFAULT_FLAGS, 12.0)
+    om = oracle.mesh(verts, tris)
+    px = oracle.cast([om], v)
+    mc, cav = j.make_matcap(kind)
+    bg = j.fill_background(w, h)
+    want = oracle.shade(px, v, mc, cav, bg.copy())
+    got = ctx.shade(px, v, mc, cav, background=bg)
+    compare_rgba(got, want, tag=f"matcap {kind}")
+    om.destroy()
+
+
+@pytest.mark.parametrize("n,flags", [(200003, j.DEFAULT_FLAGS), (50001, j.DEFAULT_FLAGS | j.ONE_BIT), (100002, j.DEFAULT_FLAGS & ~j.SHADING), (7, j.DEFAULT_FLAGS), (4, j.DEFAULT_FLAGS)])
+def test_splat_matches_oracle(ctx, oracle, n, flags):
+    w, h = 320, 180
+    verts, tris = j.icosphere(8)
+    verts = (verts * 0.6).astype(np.float32)
+    pos, nrm, clr = j.cloud(n)
+    mn, mx = j.compute_bb(np.concatenate([verts, pos]))
+    v = j.orbit_view(j.make_view(w, h, mn, mx, flags), 15.0)
+    om = oracle.mesh(verts, tris)
+    px = oracle.cast([om], v)
+    mc, cav = j.make_matcap(0)
+    rgba0 = oracle.shade(px, v, mc, cav, j.fill_background(w, h))
+    want_px, want_rgba = px.copy(), rgba0.copy()
+    oracle.splat([(pos, nrm, clr, None, 0x40000000)], v, px, want_px, want_rgba)
+    cl = ctx.cloud_create(pos, nrm, clr)
+    got_px, got_rgba = px.copy(), rgba0.copy()
+    ctx.splat([cl], v, px, got_px, got_rgba)
+    is_pt = want_px["db_id"] == 0x40000000
+    assert is_pt.sum() > 0
+    idm = (got_px["object_id"] != want_px["object_id"]) | (got_px["db_id"] != want_px["db_id"])
+    # the reference's 4-wide z-test lets a later lane of the same SIMD packet overwrite an earlier one
+    # (render.h:783-807); the atomicMax splat resolves those by depth -> allow <= 0.01 % of pixels
+    assert idm.sum() <= max(1, 1e-4 * w * h), f"{idm.sum()} pixels differ"
+    ok = ~idm
+    assert (got_px["depth"][ok] == want_px["depth"][ok]).all()
+    assert (got_rgba[ok] == want_rgba[ok]).all()
+    cl.destroy(); om.destroy()
+
+
+def test_splat_two_clouds_and_transform(ctx, oracle):
+    w, h = 256, 160
+    p1, n1, c1 = j.cloud(30001, seed=1)
+    p2, n2, c2 = j.cloud(20002, seed=2)
+    cs = np.eye(4, dtype=np.float32)
+    cs[3, :3] = [0.4, -0.2, 0.3]
+    mn, mx = j.compute_bb(np.concatenate([p1, p2 + cs[3, :3]]))
+    v = j.orbit_view(j.make_view(w, h, mn, mx, j.DEFAULT_FLAGS), 40.0)
+    px = np.zeros((h, w), j.PIXEL_DTYPE)
+    px["object_id"] = MISS
+    px["depth"] = np.float32(FMAX)
+    rgba0 = j.fill_background(w, h)
+    want_px, want_rgba = px.copy(), rgba0.copy()
+    oracle.splat([(p1, n1, c1, None, 0x40000000), (p2, n2, c2, cs.reshape(-1), 0x40000001)], v, px, want_px, want_rgba)
+    a = ctx.cloud_create(p1, n1, c1, db_id=0x40000000)
+    b = ctx.cloud_create(p2, n2, c2, cs=cs.reshape(-1), db_id=0x40000001)
+    got_px, got_rgba = px.copy(), rgba0.copy()
+    ctx.splat([a, b], v, px, got_px, got_rgba)
+    idm = (got_px["object_id"] != want_px["object_id"]) | (got_px["db_id"] != want_px["db_id"])
+    assert idm.sum() <= max(1, 1e-4 * w * h)
+    assert (got_rgba[~idm] == want_rgba[~idm]).all()
+    assert ((got_px["db_id"] == 0x40000001).sum() > 100) and ((got_px["db_id"] == 0x40000000).sum() > 100)
+    a.destroy(); b.destroy()
+
+
+def test_render_frame_equals_stages(ctx, oracle):
+    """j3dg_render_frame == cast -> shade -> splat composed by hand (view::render_scene order)."""
+    w, h = 400, 240
+    verts, tris, vc, v = _scene(20, w, h, j.DEFAULT_FLAGS | j.SHADOW, 25.0, True)
+    pos, nrm, clr = j.cloud(60001)
+    pos = (pos * 1.3).astype(np.float32)
+    m = ctx.mesh_create(verts, tris, vcolors=vc)
+    cl = ctx.cloud_create(pos, nrm, clr)
+    mc, cav = j.make_matcap(0)
+    px = ctx.cast([m], v)
+    rgba = ctx.shade(px, v, mc, cav, background=j.fill_background(w, h))
+    px2 = px.copy()
+    ctx.splat([cl], v, px, px2, rgba)
+    fpx = np.zeros((h, w), j.PIXEL_DTYPE)
+    frgba = np.zeros((h, w), np.uint32)
+    ctx.render_frame([m], [cl], v, mc, cav, pixels_out=fpx, rgba_out=frgba)
+    assert fpx.tobytes() == px2.tobytes()
+    assert (frgba == rgba).all()
+    # and the whole frame against the oracle
+    om = oracle.mesh(verts, tris, vcolors=vc)
+    opx = oracle.cast([om], v)
+    orgba = oracle.shade(opx, v, mc, cav, j.fill_background(w, h))
+    opx2 = opx.copy()
+    oracle.splat([(pos, nrm, clr, None, 0x40000000)], v, opx, opx2, orgba)
+    compare_rgba(frgba, orgba, tag="frame")
+    m.destroy(); cl.destroy(); om.destroy()
+
+
+def test_degenerate_inputs(ctx, oracle):
+    """Edge cases: single triangle, duplicated triangles, zero-area triangles, unreferenced vertices."""
+    w, h = 160, 120
+    v3 = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [5, 5, 5]], np.float32)
+    for tris in (np.array([[0, 1, 2]], np.uint32),
+                 np.array([[0, 1, 2]] * 9, np.uint32),
+                 np.array([[0, 1, 2], [0, 0, 1], [1, 1, 1], [2, 1, 0]], np.uint32)):
+        view = j.make_view(w, h, [0, 0, 0], [1, 1, 0.5])
+        m = ctx.mesh_create(v3, tris)
+        got = ctx.cast([m], view)
+        om = oracle.mesh(v3, tris)
+        want = oracle.cast([om], view)
+        assert ((got["object_id"] != MISS) == (want["object_id"] != MISS)).all()
+        hit = want["object_id"] != MISS
+        assert hit.sum() > 0
+        assert np.abs(got["depth"][hit] - want["depth"][hit]).max() <= 1e-5 * want["depth"][hit].max()
+        m.destroy(); om.destroy()
+
+
+def test_reference_library_agrees(ctx):
+    """CUDA path vs the unmodified reference (prebuilt oracle/_ref), when it travelled along."""
+    from oracle.bindings import Ref, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref/libj3d_ref.so not present on this box")
+    w, h = 640, 360
+    verts, tris = j.icosphere(59)  # config A mesh (69 620 triangles)
+    ref = Ref(w, h)
+    ref.add_mesh(verts, tris)
+    ref.unzoom()
+    v = ref.view()
+    v.flags = j.DEFAULT_FLAGS | j.SHADOW
+    ref.set_view(v)
+    ref.render(7)
+    want_px, want_rgba = ref.pixels(0), ref.image()
+    m = ctx.mesh_create(verts, tris)
+    mc, cav = j.make_matcap(0)
+    got_px = np.zeros((h, w), j.PIXEL_DTYPE)
+    got_rgba = np.zeros((h, w), np.uint32)
+    ctx.render_frame([m], [], v, mc, cav, pixels_out=got_px, rgba_out=got_rgba)
+    compare_pixels(got_px, want_px, tag="vs reference")
+    compare_rgba(got_rgba, want_rgba, tag="vs reference")
+    ref.close(); m.destroy()
