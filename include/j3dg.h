@@ -87,11 +87,13 @@ typedef struct j3dg_mesh_info {
   float sah_cost;              /* SAH cost of the wide BVH (diagnostic) */
 } j3dg_mesh_info;
 
-/* Per-stage device times of the last frame calls, CUDA events on the ctx stream. */
+/* Per-stage device times, CUDA events on the ctx stream, SUMMED over every stage launch since
+ * the last reset (j3dg_ctx_timings(..., reset=1)); *_count = launches summed. */
 typedef struct j3dg_timings {
   float cast_ms, shade_ms, splat_ms, copy_ms;
-  uint64_t rays;               /* primary + shadow rays traced by the last cast */
+  uint32_t cast_count, shade_count, splat_count;
   uint32_t kernel_launches;    /* kernels launched by the library since the last reset */
+  uint64_t rays;               /* primary + shadow rays traced since the last reset */
 } j3dg_timings;
 
 /* ---- context ------------------------------------------------------------- */

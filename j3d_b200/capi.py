@@ -48,7 +48,8 @@ class MeshInfo(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [("cast_ms", C.c_float), ("shade_ms", C.c_float), ("splat_ms", C.c_float), ("copy_ms", C.c_float),
-                ("rays", C.c_uint64), ("kernel_launches", C.c_uint32)]
+                ("cast_count", C.c_uint32), ("shade_count", C.c_uint32), ("splat_count", C.c_uint32),
+                ("kernel_launches", C.c_uint32), ("rays", C.c_uint64)]
 
 
 _vp = C.c_void_p

@@ -158,6 +158,7 @@ J3DG_API void j3dg_ctx_destroy(j3dg_ctx* ctx) {
   cudaFree(ctx->d_pixels); cudaFree(ctx->d_pixels_in); cudaFree(ctx->d_rgba); cudaFree(ctx->d_bg); cudaFree(ctx->d_packed);
   cudaFree(ctx->d_matcap); cudaFree(ctx->d_meshes); cudaFree(ctx->d_stats); cudaFree(ctx->d_misc);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& r : ctx->ring) { for (auto e : r.a) cudaEventDestroy(e); for (auto e : r.b) cudaEventDestroy(e); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -192,17 +193,55 @@ J3DG_API int j3dg_ctx_set_profiling(j3dg_ctx* ctx, int enabled) {
 J3DG_API int j3dg_ctx_timings(j3dg_ctx* ctx, j3dg_timings* out, int reset) {
   if (!ctx || !out) return J3DG_EINVAL;
   CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  if (ctx->profiling) {
-    ctx->timings.cast_ms = elapsed(ctx->ev[0], ctx->ev[1]);
-    ctx->timings.shade_ms = elapsed(ctx->ev[2], ctx->ev[3]);
-    ctx->timings.splat_ms = elapsed(ctx->ev[4], ctx->ev[5]);
-  }
+  float sums[3] = {0.f, 0.f, 0.f};
+  for (int s = 0; s < 3; ++s)
+    for (uint32_t i = 0; i < ctx->ring[s].used; ++i) sums[s] += elapsed(ctx->ring[s].a[i], ctx->ring[s].b[i]);
   unsigned long long st[4];
   CU_CHECK(ctx, cudaMemcpy(st, ctx->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
-  *out = ctx->timings;
-  out->rays += st[3];  // one shadow ray per hit pixel when shadows were on
+  memset(out, 0, sizeof(*out));
+  out->cast_ms = sums[0]; out->shade_ms = sums[1]; out->splat_ms = sums[2];
+  out->cast_count = ctx->ring[0].used; out->shade_count = ctx->ring[1].used; out->splat_count = ctx->ring[2].used;
+  out->rays = ctx->rays_primary + st[3];  // one shadow ray per hit pixel when shadows were on
   out->kernel_launches = ctx->launches;
-  if (reset) { ctx->launches = 0; }
+  if (reset) {
+    ctx->launches = 0;
+    ctx->rays_primary = 0;
+    for (auto& r : ctx->ring) r.used = 0;
+    CU_CHECK(ctx, cudaMemset(ctx->d_stats + 3, 0, sizeof(unsigned long long)));
+  }
+  return J3DG_OK;
+}
+
+// Event pairs are taken from a ring that grows on demand; when a stage was launched more
+// often than the ring holds since the last reset, the oldest slot is reused (the sum then
+// covers the most recent launches only).
+static int ring_slot(j3dg_ctx* ctx, int stage, bool begin) {
+  auto& r = ctx->ring[stage];
+  const uint32_t cap = 8192;
+  uint32_t i = begin ? r.used : r.used - 1;
+  if (begin && r.used >= cap) { r.used = cap - 1; i = r.used; }
+  if (i >= r.a.size()) {
+    cudaEvent_t ea, eb;
+    if (cudaEventCreate(&ea) != cudaSuccess || cudaEventCreate(&eb) != cudaSuccess) return -1;
+    r.a.push_back(ea); r.b.push_back(eb);
+  }
+  return (int)i;
+}
+
+int j3dg_stage_begin(j3dg_ctx* ctx, int stage) {
+  if (!ctx->profiling) return J3DG_OK;
+  const int i = ring_slot(ctx, stage, true);
+  if (i < 0) { j3dg_set_error(ctx, "cudaEventCreate failed"); return J3DG_ECUDA; }
+  CU_CHECK(ctx, cudaEventRecord(ctx->ring[stage].a[i], ctx->stream));
+  ctx->ring[stage].used++;
+  return J3DG_OK;
+}
+
+int j3dg_stage_end(j3dg_ctx* ctx, int stage) {
+  if (!ctx->profiling) return J3DG_OK;
+  const int i = ring_slot(ctx, stage, false);
+  if (i < 0) return J3DG_OK;
+  CU_CHECK(ctx, cudaEventRecord(ctx->ring[stage].b[i], ctx->stream));
   return J3DG_OK;
 }
 

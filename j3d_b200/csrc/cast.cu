@@ -424,23 +424,23 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
     if (rc != J3DG_OK) return rc;
   }
   if (used) CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_meshes, host.data(), sizeof(MeshDev) * used, cudaMemcpyHostToDevice, ctx->stream));
-  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats, 0, 3 * sizeof(unsigned long long), ctx->stream));  // [3] accumulates until reset
   ViewDev vd;
   j3dg_make_view_dev(view, vd);
   const int rw = x1 - x0 + 1, rh = y1 - y0 + 1;
   dim3 grid((rw + TILE_W * BLOCK_TILES_X - 1) / (TILE_W * BLOCK_TILES_X), (rh + TILE_H * BLOCK_TILES_Y - 1) / (TILE_H * BLOCK_TILES_Y));
-  if (ctx->profiling) CU_CHECK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  { int rc = j3dg_stage_begin(ctx, 0); if (rc != J3DG_OK) return rc; }
   if (stats)
     cast_kernel<true><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(ctx->d_meshes, used, vd, x0, y0, x1, y1, d_pixels, stride, ctx->d_stats);
   else
     cast_kernel<false><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(ctx->d_meshes, used, vd, x0, y0, x1, y1, d_pixels, stride, ctx->d_stats);
   KERNEL_CHECK(ctx);
-  if (ctx->profiling) CU_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-  if (ctx->profiling && (view->flags & J3DG_SHADOW)) {
+  { int rc = j3dg_stage_end(ctx, 0); if (rc != J3DG_OK) return rc; }
+  if (ctx->profiling && (view->flags & J3DG_SHADOW)) {  // one shadow ray per hit pixel: count them
     count_hits_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_pixels, stride, x0, y0, rw, rh, ctx->d_stats + 3);
     KERNEL_CHECK(ctx);
   }
-  ctx->timings.rays = (uint64_t)rw * rh;  // shadow rays are added when the timings are read
+  ctx->rays_primary += (uint64_t)rw * rh;  // shadow rays (d_stats[3]) are added when the timings are read
   return J3DG_OK;
 }
 
@@ -449,7 +449,7 @@ int j3dg_launch_find_closest(j3dg_mesh* m, const float* d_rays, uint32_t n, floa
   if (!n) return J3DG_OK;
   MeshDev d;
   fill_mesh_dev(m, d);
-  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats, 0, 3 * sizeof(unsigned long long), ctx->stream));
   find_closest_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d, d_rays, n, d_hits, d_ids, (uint32_t*)(ctx->d_stats + 2));
   KERNEL_CHECK(ctx);
   return J3DG_OK;

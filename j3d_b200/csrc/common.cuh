@@ -105,7 +105,13 @@ struct j3dg_ctx {
   cudaStream_t stream = nullptr;
   std::string error;
   bool profiling = true;
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[8] = {};          // [6],[7]: build / upload timing
+  struct EventRing {               // begin/end event pairs of one stage, summed when timings are read
+    std::vector<cudaEvent_t> a, b;
+    uint32_t used = 0;
+  } ring[3];                       // 0 cast, 1 shade, 2 splat
+  uint64_t rays_primary = 0;
+  uint32_t shadow_casts = 0;
   j3dg_timings timings = {};
   uint32_t launches = 0;
   int sm_count = 148;
@@ -122,6 +128,8 @@ struct j3dg_ctx {
 };
 
 void j3dg_set_error(j3dg_ctx* ctx, const std::string& msg);
+int j3dg_stage_begin(j3dg_ctx* ctx, int stage);  // records the begin event of the next pair (no-op if !profiling)
+int j3dg_stage_end(j3dg_ctx* ctx, int stage);
 int j3dg_cuda_fail(j3dg_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
 bool j3dg_is_device_ptr(const void* p);
 int j3dg_reserve(j3dg_ctx* ctx, void** ptr, size_t* cap, size_t bytes);

@@ -217,11 +217,10 @@ int j3dg_launch_shade(j3dg_ctx* ctx, const j3dg_pixel* d_pixels, uint32_t pstrid
   memcpy(s.pinv, view->projection_inv, 64);
   s.matcap = d_matcap; s.mw = mw; s.mh = mh; s.mstride = mstride; s.cavity = cavity;
   dim3 grid((s.w + 31) / 32, (s.h + 7) / 8);
-  if (ctx->profiling) CU_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+  { int rc = j3dg_stage_begin(ctx, 1); if (rc != J3DG_OK) return rc; }
   shade_kernel<<<grid, 256, 0, ctx->stream>>>(d_pixels, pstride, s, d_bg, bg_stride, d_rgba, rstride);
   KERNEL_CHECK(ctx);
-  if (ctx->profiling) CU_CHECK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-  return J3DG_OK;
+  return j3dg_stage_end(ctx, 1);
 }
 
 int j3dg_launch_background(j3dg_ctx* ctx, uint32_t w, uint32_t h, uint32_t top, uint32_t bottom, uint32_t* d_out, uint32_t stride) {

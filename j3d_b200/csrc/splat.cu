@@ -156,7 +156,7 @@ int j3dg_launch_splat(j3dg_ctx* ctx, j3dg_cloud* const* clouds, uint32_t nc, con
     if (rc != J3DG_OK) return rc;
   }
   dim3 pgrid((w + 31) / 32, (h + 7) / 8);
-  if (ctx->profiling) CU_CHECK(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+  { int rc = j3dg_stage_begin(ctx, 2); if (rc != J3DG_OK) return rc; }
   seed_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_px_in, pstride, w, h, ctx->d_packed);
   KERNEL_CHECK(ctx);
   for (uint32_t c = 0; c < nc; ++c) {
@@ -181,6 +181,5 @@ int j3dg_launch_splat(j3dg_ctx* ctx, j3dg_cloud* const* clouds, uint32_t nc, con
     resolve_kernel<<<pgrid, 256, 0, ctx->stream>>>(s, cl->d_nrm, cl->d_clr, ctx->d_packed, d_px_inout, pstride, d_rgba, rstride);
     KERNEL_CHECK(ctx);
   }
-  if (ctx->profiling) CU_CHECK(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
-  return J3DG_OK;
+  return j3dg_stage_end(ctx, 2);
 }

@@ -1,0 +1,104 @@
+"""Multi-GPU plumbing above the C ABI: one process per GPU, torch.distributed (NCCL over NVLink on
+the GPU box, gloo in the CPU tests).  The path shards only where it does so naturally
+(SURVEY §8e): the mesh is replicated, the BVH is built once and broadcast, orbit frames or
+screen tiles are partitioned, rank 0 gathers the results.  There is no collective inside the
+ray cast itself.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+# ---- partitioning (pure functions; tested on CPU with gloo, world_size 2) -------------------
+def frames_for_rank(n_frames: int, rank: int, world: int) -> list[int]:
+    """Orbit sweep: frame k goes to rank k mod world (round robin keeps neighbouring poses apart,
+    so every rank sees the same mix of cheap and expensive views)."""
+    return list(range(rank, n_frames, world))
+
+
+def tiles(width: int, height: int, tile: int = 64) -> list[tuple[int, int, int, int]]:
+    """Inclusive (x0, y0, x1, y1) rectangles covering the canvas, row-major."""
+    out = []
+    for y in range(0, height, tile):
+        for x in range(0, width, tile):
+            out.append((x, y, min(x + tile, width) - 1, min(y + tile, height) - 1))
+    return out
+
+
+def _morton2(x: int, y: int) -> int:
+    r = 0
+    for b in range(16):
+        r |= ((x >> b) & 1) << (2 * b) | ((y >> b) & 1) << (2 * b + 1)
+    return r
+
+
+def tiles_for_rank(width: int, height: int, rank: int, world: int, tile: int = 64):
+    """Screen tiles interleaved over ranks in Morton order (silhouette-heavy regions are spread)."""
+    ts = sorted(tiles(width, height, tile), key=lambda t: _morton2(t[0] // tile, t[1] // tile))
+    return ts[rank::world]
+
+
+def row_bands(height: int, world: int) -> list[tuple[int, int]]:
+    """Contiguous inclusive row bands [y0, y1], as equal as possible."""
+    base, rem = divmod(height, world)
+    out, y = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((y, y + n - 1))
+        y += n
+    return out
+
+
+# ---- collectives -----------------------------------------------------------------------------
+class _DevBuf:
+    """Zero-copy view of a raw device allocation for torch (CUDA array interface)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def device_bytes(ptr: int, nbytes: int, device) -> torch.Tensor:
+    return torch.as_tensor(_DevBuf(ptr, nbytes), device=device)
+
+
+def broadcast_bvh(mesh, src: int = 0, device=None, chunk: int = 1 << 30):
+    """Broadcast the built BVH (wide nodes + triangle records) in place from `src`."""
+    for kind in (0, 1):
+        ptr, nbytes = mesh.bvh_buffer(kind)
+        if not nbytes:
+            continue
+        t = device_bytes(ptr, nbytes, device)
+        for off in range(0, nbytes, chunk):
+            dist.broadcast(t[off: off + chunk], src)
+
+
+def gather_rows(local: torch.Tensor, bands: list[tuple[int, int]], dst: int = 0) -> torch.Tensor | None:
+    """Gather contiguous row bands of an image (rank r owns rows bands[r]) on `dst`."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if rank == dst:
+        parts = [torch.empty((b[1] - b[0] + 1,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for b in bands]
+        parts[dst] = local
+        reqs = [dist.irecv(parts[r], src=r) for r in range(world) if r != dst]
+        for q in reqs:
+            q.wait()
+        return torch.cat(parts, dim=0)
+    dist.send(local.contiguous(), dst=dst)
+    return None
+
+
+def gather_frames(frame: torch.Tensor, dst: int = 0) -> list[torch.Tensor] | None:
+    """One frame per rank -> list of frames on `dst` (orbit sweep step)."""
+    world = dist.get_world_size()
+    out = [torch.empty_like(frame) for _ in range(world)] if dist.get_rank() == dst else None
+    dist.gather(frame, out, dst=dst)
+    return out
+
+
+def allreduce_max_u64(t: torch.Tensor) -> torch.Tensor:
+    """Per-pixel max of the packed (depth, id) splat words for a point-range-sharded cloud.
+    NCCL has no uint64 max; the words are < 2^63 (positive float bits in the top half), so the
+    signed int64 max is identical."""
+    dist.all_reduce(t.view(torch.int64), op=dist.ReduceOp.MAX)
+    return t
