@@ -1,0 +1,70 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes exercising the partition + gather helpers
+the multi-GPU bench uses (frames round-robin, row bands, tiles, gather to rank 0, packed-word max)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from j3d_b200 import dist as jd
+
+
+def test_partitions_cover_exactly_once():
+    for world in (1, 2, 3, 8):
+        frames = sorted(sum((jd.frames_for_rank(360, r, world) for r in range(world)), []))
+        assert frames == list(range(360))
+        bands = jd.row_bands(1080, world)
+        assert bands[0][0] == 0 and bands[-1][1] == 1079 and all(bands[i][1] + 1 == bands[i + 1][0] for i in range(world - 1))
+        cover = np.zeros((270, 480), np.int32)
+        for r in range(world):
+            for (x0, y0, x1, y1) in jd.tiles_for_rank(480, 270, r, world, tile=64):
+                cover[y0:y1 + 1, x0:x1 + 1] += 1
+        assert (cover == 1).all()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        h, w = 37, 16
+        bands = jd.row_bands(h, world)
+        full = torch.arange(h * w, dtype=torch.int32).reshape(h, w)
+        y0, y1 = bands[rank]
+        got = jd.gather_rows(full[y0:y1 + 1].clone(), bands, dst=0)
+        frames = jd.gather_frames(torch.full((4, 4), rank, dtype=torch.int32), dst=0)
+        packed = torch.tensor([(10 + rank) << 32 | 5, (20 - rank) << 32 | rank], dtype=torch.int64)
+        jd.allreduce_max_u64(packed)
+        if rank == 0:
+            assert torch.equal(got, full)
+            assert [int(f[0, 0]) for f in frames] == list(range(world))
+        assert packed.tolist() == [(10 + world - 1) << 32 | 5, 20 << 32 | 0]
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gather_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(100)
+        assert p.exitcode == 0
+    assert sorted(out.keys()) == [0, 1]

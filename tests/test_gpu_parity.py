@@ -288,3 +288,173 @@ def test_reference_library_agrees(ctx):
     compare_pixels(got_px, want_px, tag="vs reference")
     compare_rgba(got_rgba, want_rgba, tag="vs reference")
     ref.close(); m.destroy()
+
+
+# ---- golden fixtures (produced by the unmodified reference; tests/golden/make_golden.py) --------
+from golden_util import CASES, load  # noqa: E402
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_matches_golden(ctx, name):
+    g = load(name)
+    v = g["view"]
+    m = ctx.mesh_create(g["verts"], g["tris"], vcolors=g["vc"])
+    clouds = []
+    if g["cloud"] is not None:
+        clouds = [ctx.cloud_create(*g["cloud"])]
+    mc, cav = j.make_matcap(0)
+    px = ctx.cast([m], v)
+    compare_pixels(px, g["pixels"], tag=name)
+    rgba = ctx.shade(px, v, mc, cav, background=j.fill_background(v.width, v.height))
+    if clouds:
+        after = px.copy()
+        ctx.splat(clouds, v, px, after, rgba)
+        want = g["pixels_after_splat"]
+        ok = (after["object_id"] == want["object_id"]) & (after["db_id"] == want["db_id"])
+        assert (~ok).sum() <= max(1, 1e-4 * ok.size)
+        assert np.allclose(after["depth"][ok], want["depth"][ok], rtol=1e-5)
+    compare_rgba(rgba, g["rgba"], tag=name)
+    m.destroy()
+    for c in clouds:
+        c.destroy()
+
+
+# ---- BASELINE.json full size (config B: 28 037 120 triangles, 1080p): size-independent properties ----
+def _numpy_closest(verts, tris, org, d, t_near):
+    """Brute-force restatement of the Woop test over ALL triangles for one ray (float32, unfused)."""
+    f = np.float32
+    org = org.astype(f); d = d.astype(f)
+    a = np.abs(d)
+    kz = 2
+    if a[0] > a[1]:
+        if a[0] > a[2]:
+            kz = 0
+    elif a[1] > a[2]:
+        kz = 1
+    kx = (kz + 1) % 3
+    ky = (kx + 1) % 3
+    if d[kz] < 0:
+        kx, ky = ky, kx
+    Sz = f(1.0) / d[kz]
+    Sx = d[kx] * Sz
+    Sy = d[ky] * Sz
+    best_t, best_id = np.inf, -1
+    CH = 4_000_000
+    for s in range(0, tris.shape[0], CH):
+        t = tris[s:s + CH]
+        A = verts[t[:, 0]] - org
+        B = verts[t[:, 1]] - org
+        Cc = verts[t[:, 2]] - org
+        Ax = A[:, kx] - Sx * A[:, kz]; Ay = A[:, ky] - Sy * A[:, kz]
+        Bx = B[:, kx] - Sx * B[:, kz]; By = B[:, ky] - Sy * B[:, kz]
+        Cx = Cc[:, kx] - Sx * Cc[:, kz]; Cy = Cc[:, ky] - Sy * Cc[:, kz]
+        U = Cx * By - Cy * Bx; V = Ax * Cy - Ay * Cx; Wd = Bx * Ay - By * Ax
+        inside = ((U <= 0) & (V <= 0) & (Wd <= 0)) | ((U >= 0) & (V >= 0) & (Wd >= 0))
+        det = (U + V) + Wd
+        ok = inside & (det != 0)
+        idx = np.nonzero(ok)[0]
+        if idx.size == 0:
+            continue
+        T = (U[idx] * (Sz * A[idx, kz]) + V[idx] * (Sz * B[idx, kz])) + Wd[idx] * (Sz * Cc[idx, kz])
+        tt = T * (f(1.0) / det[idx])
+        good = tt > t_near
+        if good.any():
+            k = np.argmin(np.where(good, tt, np.inf))
+            if tt[k] < best_t:
+                best_t, best_id = float(tt[k]), int(s + idx[k])
+    return best_t, best_id
+
+
+@pytest.fixture(scope="module")
+def config_b(ctx):
+    verts, tris = j.icosphere(1184)
+    m = ctx.mesh_create(verts, tris)
+    mn, mx = j.compute_bb(verts)
+    v = j.make_view(1920, 1080, mn, mx)
+    yield verts, tris, m, v
+    m.destroy()
+
+
+@pytest.mark.timeout(600)
+def test_full_size_build_and_cast_properties(ctx, config_b):
+    verts, tris, m, v = config_b
+    info = m.info()
+    assert info.nr_of_triangles == 28037120 and info.nr_of_nodes > 0
+    assert info.build_ms < 100.0, f"BVH build took {info.build_ms} ms (target: sub-100 ms)"
+    assert np.allclose(list(info.bbox_min), verts.min(0)) and np.allclose(list(info.bbox_max), verts.max(0))
+    px = ctx.cast([m], v)
+    hit = px["object_id"] != MISS
+    assert 600_000 < hit.sum() < 900_000
+    # barycentrics inside the triangle, ids in range, depth positive, normals unit-bounded
+    assert (px["object_id"][hit] < tris.shape[0]).all()
+    bu, bv = px["barycentric_u"][hit], px["barycentric_v"][hit]
+    assert (bu >= -1e-5).all() and (bv >= -1e-5).all() and (bu + bv <= 1 + 1e-5).all()
+    assert (px["depth"][hit] > v.diagonal / 100).all()
+    assert (px["u"][hit] ** 2 + px["v"][hit] ** 2 <= 1 + 1e-5).all()
+    # the hit point reconstructed from the barycentrics lies on the ray at parameter depth
+    ys, xs = np.nonzero(hit)
+    sel = np.random.default_rng(0).choice(len(ys), 2000, replace=False)
+    ys, xs = ys[sel], xs[sel]
+    t = tris[px["object_id"][ys, xs]]
+    k = 1 - px["barycentric_u"][ys, xs] - px["barycentric_v"][ys, xs]
+    p = verts[t[:, 0]] * k[:, None] + verts[t[:, 1]] * px["barycentric_u"][ys, xs][:, None] + verts[t[:, 2]] * px["barycentric_v"][ys, xs][:, None]
+    pinv = np.array(list(v.projection_inv), np.float64).reshape(4, 4).T
+    cs = np.array(list(v.cs), np.float64).reshape(4, 4).T
+    sp = np.stack([2 * ((xs + 0.5) / 1920) - 1, 2 * ((ys + 0.5) / 1080) - 1, np.full(len(xs), v.near_plane), np.ones(len(xs))], 1)
+    d = (pinv @ sp.T).T
+    d[:, 3] = 0
+    d = (cs @ d.T).T[:, :3]
+    o = cs[:3, 3]
+    q = o + d * px["depth"][ys, xs][:, None].astype(np.float64)
+    assert np.abs(q - p).max() < 2e-5
+    # idempotence: a second cast and a cast after a rebuild give the identical buffer
+    px2 = ctx.cast([m], v)
+    assert px2.tobytes() == px.tobytes()
+    m.rebuild()
+    px3 = ctx.cast([m], v)
+    same = px3["object_id"] == px["object_id"]
+    assert same.mean() > 0.9999 and (px3["depth"][same] == px["depth"][same]).all()
+
+
+@pytest.mark.timeout(900)
+def test_full_size_samples_against_brute_force(ctx, config_b):
+    """A handful of pixels of the 28 M-triangle frame against an exhaustive float32 Woop test."""
+    verts, tris, m, v = config_b
+    px = ctx.cast([m], v)
+    pinv = np.array(list(v.projection_inv), np.float32).reshape(4, 4).T
+    cs = np.array(list(v.cs), np.float32).reshape(4, 4).T
+    f = np.float32
+    for (x, y) in [(960, 540), (700, 400), (1200, 800), (961, 131), (5, 5), (624, 540)]:
+        sp = np.array([f(2) * ((f(x) + f(0.5)) / f(1920)) - f(1), f(2) * ((f(y) + f(0.5)) / f(1080)) - f(1), f(v.near_plane), f(1)], f)
+        d = ((pinv[:, 0] * sp[0] + pinv[:, 1] * sp[1]) + pinv[:, 2] * sp[2]) + pinv[:, 3] * sp[3]
+        d[3] = 0
+        d = ((cs[:, 0] * d[0] + cs[:, 1] * d[1]) + cs[:, 2] * d[2]) + cs[:, 3] * d[3]
+        t, tid = _numpy_closest(verts, tris, cs[:3, 3].copy(), d[:3], f(v.diagonal) / f(100))
+        got = px[y, x]
+        if tid < 0:
+            assert got["object_id"] == MISS
+        else:
+            assert abs(got["depth"] - t) <= 1e-5 * t
+            assert got["object_id"] == tid or abs(got["depth"] - t) <= 1e-6 * t
+
+
+@pytest.mark.timeout(900)
+def test_full_size_triangle_order_invariance(ctx, config_b):
+    """The closest hit does not depend on the triangle order the builder sees: a shuffled copy of the
+    mesh renders the same depth buffer, and its ids map back through the permutation."""
+    verts, tris, m, v = config_b
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(tris.shape[0])
+    sh = np.ascontiguousarray(tris[perm])
+    m2 = ctx.mesh_create(verts, sh)
+    assert m2.info().build_ms < 150.0
+    a = ctx.cast([m], v)
+    b = ctx.cast([m2], v)
+    hit = a["object_id"] != MISS
+    assert ((b["object_id"] != MISS) == hit).mean() > 0.99999
+    both = hit & (b["object_id"] != MISS)
+    mapped = perm[b["object_id"][both]]
+    same = mapped == a["object_id"][both]
+    assert same.mean() > 0.9999
+    assert np.abs(a["depth"][both] - b["depth"][both]).max() <= 1e-5 * a["depth"][both].max()
+    m2.destroy()
