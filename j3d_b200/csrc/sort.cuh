@@ -15,7 +15,7 @@ constexpr int RADIX = 256;
 constexpr int WARPS = THREADS / 32;
 constexpr size_t SCATTER_SMEM = (size_t)TILE * 8 + (size_t)TILE * 4 + (size_t)WARPS * RADIX * 4 + RADIX * 4 * 2;
 
-__global__ void __launch_bounds__(THREADS) histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int shift,
+static __global__ void __launch_bounds__(THREADS) histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int shift,
                                                              uint32_t* __restrict__ table, uint32_t ntiles) {
   __shared__ uint32_t hist[RADIX];
   hist[threadIdx.x] = 0;
@@ -63,7 +63,7 @@ static __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint
   return r;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_chunk_sums(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ sums) {
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_chunk_sums(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ sums) {
   __shared__ uint32_t total;
   size_t base = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_ITEMS;
   uint32_t s = 0;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_chunk_sums(const uint32_t* 
   if (threadIdx.x == 0) sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_serial(uint32_t* __restrict__ sums, uint32_t nchunks) {
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_sums_serial(uint32_t* __restrict__ sums, uint32_t nchunks) {
   // single block: scan the chunk totals in strips of SCAN_THREADS
   __shared__ uint32_t total;
   uint32_t carry = 0;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_sums_serial(uint32_t* __res
   }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_apply(uint32_t* __restrict__ data, size_t n, const uint32_t* __restrict__ sums) {
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_apply(uint32_t* __restrict__ data, size_t n, const uint32_t* __restrict__ sums) {
   __shared__ uint32_t total;
   size_t base = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_ITEMS;
   uint32_t v[SCAN_ITEMS];
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply(uint32_t* __restrict_
 }
 
 // ---- stable scatter ------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+static __global__ void __launch_bounds__(THREADS) scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                            uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                            uint32_t n, int shift, const uint32_t* __restrict__ table, uint32_t ntiles,
                                                            int iota_vals) {
