@@ -183,6 +183,11 @@ int j3dg_ctx_set_matcap(j3dg_ctx* ctx, const uint32_t* matcap, uint32_t mw, uint
 int j3dg_cast_stats(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nr_of_meshes, const j3dg_view* view,
                     double* nodes_per_ray, double* tris_per_ray);
 
+/* Diagnostic companion of j3dg_cast_stats: per-pixel node visits / triangle tests of the
+ * counting pass, width*height uint32 each (host pointers, row-major, stride = width). */
+int j3dg_cast_cost_image(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nr_of_meshes, const j3dg_view* view,
+                         uint32_t* nodes_out, uint32_t* tris_out);
+
 #ifdef __cplusplus
 }
 #endif

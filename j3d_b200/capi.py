@@ -8,6 +8,7 @@ here touches oracle/.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
@@ -80,7 +81,8 @@ def lib() -> C.CDLL:
     """The CUDA product library.  No fallback: raises if it has not been built."""
     global _lib
     if _lib is None:
-        path = PKG / "libj3dg.so"
+        # J3DG_LIB: developer knob to load another BUILD of the same CUDA library (kernel tuning variants)
+        path = Path(os.environ["J3DG_LIB"]) if os.environ.get("J3DG_LIB") else PKG / "libj3dg.so"
         if not path.exists():
             raise RuntimeError(f"{path} is missing: run `python -m j3d_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
         L = C.CDLL(str(path), mode=C.RTLD_GLOBAL)
@@ -112,6 +114,7 @@ def lib() -> C.CDLL:
                                         _vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp]
         L.j3dg_ctx_set_matcap.argtypes = [_vp, _vp, _u32, _u32, _u32, _u32]
         L.j3dg_cast_stats.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(View), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.j3dg_cast_cost_image.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(View), _vp, _vp]
         _lib = L
     return _lib
 
@@ -348,6 +351,14 @@ class Context:
         self._check(self._L.j3dg_cast_stats(self._h, self._handles(meshes), len(meshes), C.byref(view), C.byref(a), C.byref(b)),
                     "j3dg_cast_stats")
         return a.value, b.value
+
+    def cast_cost_image(self, meshes, view: View):
+        """Per-pixel (node visits, triangle tests) of the counting pass — diagnostic."""
+        n = np.zeros((view.height, view.width), np.uint32)
+        t = np.zeros((view.height, view.width), np.uint32)
+        self._check(self._L.j3dg_cast_cost_image(self._h, self._handles(meshes), len(meshes), C.byref(view), _ptr(n), _ptr(t)),
+                    "j3dg_cast_cost_image")
+        return n, t
 
 
 class Mesh:

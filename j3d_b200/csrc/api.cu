@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -141,12 +142,12 @@ J3DG_API int j3dg_ctx_create(int device, j3dg_ctx** out) {
   }
   ctx->stream = ctx->own_stream;
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
-  if (cudaMalloc((void**)&ctx->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+  if (cudaMalloc((void**)&ctx->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess) {
     j3dg_set_error(nullptr, "cannot allocate device memory");
     delete ctx;
     return J3DG_ENOMEM;
   }
-  cudaMemset(ctx->d_stats, 0, 4 * sizeof(unsigned long long));
+  cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long));
   *out = ctx;
   return J3DG_OK;
 }
@@ -196,18 +197,18 @@ J3DG_API int j3dg_ctx_timings(j3dg_ctx* ctx, j3dg_timings* out, int reset) {
   float sums[3] = {0.f, 0.f, 0.f};
   for (int s = 0; s < 3; ++s)
     for (uint32_t i = 0; i < ctx->ring[s].used; ++i) sums[s] += elapsed(ctx->ring[s].a[i], ctx->ring[s].b[i]);
-  unsigned long long st[4];
+  unsigned long long st[8];
   CU_CHECK(ctx, cudaMemcpy(st, ctx->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
   memset(out, 0, sizeof(*out));
   out->cast_ms = sums[0]; out->shade_ms = sums[1]; out->splat_ms = sums[2];
   out->cast_count = ctx->ring[0].used; out->shade_count = ctx->ring[1].used; out->splat_count = ctx->ring[2].used;
-  out->rays = ctx->rays_primary + st[3];  // one shadow ray per hit pixel when shadows were on
+  out->rays = ctx->rays_primary + st[4];  // one shadow ray per hit pixel when shadows were on
   out->kernel_launches = ctx->launches;
   if (reset) {
     ctx->launches = 0;
     ctx->rays_primary = 0;
     for (auto& r : ctx->ring) r.used = 0;
-    CU_CHECK(ctx, cudaMemset(ctx->d_stats + 3, 0, sizeof(unsigned long long)));
+    CU_CHECK(ctx, cudaMemset(ctx->d_stats + 4, 0, sizeof(unsigned long long)));
   }
   return J3DG_OK;
 }
@@ -602,5 +603,28 @@ J3DG_API int j3dg_cast_stats(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t n
   const double rays = (double)w * h;
   if (nodes_per_ray) *nodes_per_ray = (double)st[0] / rays;
   if (tris_per_ray) *tris_per_ray = (double)st[1] / rays;
+  return J3DG_OK;
+}
+
+// Diagnostic: the counting pass's per-pixel costs (node visits, triangle tests), w*h uint32 each, host pointers.
+J3DG_API int j3dg_cast_cost_image(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const j3dg_view* view,
+                                  uint32_t* nodes_out, uint32_t* tris_out) {
+  if (!ctx || !view || !nodes_out || !tris_out) return J3DG_EINVAL;
+  double a, b;
+  int rc = j3dg_cast_stats(ctx, meshes, nm, view, &a, &b);
+  if (rc != J3DG_OK) return rc;
+  const size_t n = (size_t)view->width * view->height;
+  std::vector<j3dg_pixel> tmp(n);
+  CU_CHECK(ctx, cudaMemcpy(tmp.data(), ctx->d_pixels, n * sizeof(j3dg_pixel), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) {
+    memcpy(&nodes_out[i], &tmp[i].u, 4);
+    memcpy(&tris_out[i], &tmp[i].v, 4);
+  }
+  if (const char* dbg = getenv("J3DG_DEBUG_TILE_TIMES")) {  // developer diagnostic: raw per-pixel tile start/end (ns, low 32 bits)
+    if (FILE* f = fopen(dbg, "wb")) {
+      for (size_t i = 0; i < n; ++i) { fwrite(&tmp[i].barycentric_u, 4, 1, f); fwrite(&tmp[i].barycentric_v, 4, 1, f); }
+      fclose(f);
+    }
+  }
   return J3DG_OK;
 }

@@ -9,12 +9,19 @@
 // influence which triangle is the closest hit.
 #include "common.cuh"
 
+#include <algorithm>
+#include <type_traits>
+
 namespace {
 
-constexpr int STACK_SIZE = 96;
-constexpr int TILE_W = 8, TILE_H = 4;       // one warp = 8x4 pixels
-constexpr int BLOCK_TILES_X = 4, BLOCK_TILES_Y = 2;
-constexpr int BLOCK_THREADS = 32 * BLOCK_TILES_X * BLOCK_TILES_Y;
+constexpr int STACK_SIZE = 96;               // total traversal stack entries per ray
+constexpr int SM_STACK = 12;                 // of which the first SM_STACK live in shared memory (rest: local memory, rarely touched)
+constexpr int TILE_W = 8, TILE_H = 4;        // one warp = 8x4 pixels
+constexpr int SUPER_W = 4, SUPER_H = 8;      // tiles are handed out super-tile by super-tile (32x32 pixels), row-major inside
+constexpr int BLOCK_THREADS = 128;           // 4 warps; every warp fetches its own tiles (persistent threads)
+#ifndef J3DG_CAST_MIN_BLOCKS
+#define J3DG_CAST_MIN_BLOCKS 6
+#endif
 
 struct RayPre {  // intersect_woop_precompute, qbvh.h:4793-4823
   int kx, ky, kz;
@@ -85,29 +92,64 @@ __device__ __forceinline__ float safe_rcp(float d) {
   return 1.f / d;
 }
 
-__device__ __forceinline__ float ubyte(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
+// Byte i of w as a float without the quarter-rate I2F (XU pipe): PRMT builds the bit pattern of
+// 2^23 + q, the subtraction is exact.  Both instructions run on the full-rate ALU / FMA pipes.
+template <int I>
+__device__ __forceinline__ float ubyte(uint32_t w) {
+  return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)I)), 8388608.f);
+}
+
+// Per-thread traversal stack: the first SM_STACK entries in shared memory (column tid of a
+// [SM_STACK][BLOCK_THREADS] array: conflict-free), deeper entries in local memory.
+struct Stack {
+  uint2* sm;                          // &s_stack[threadIdx.x]
+  uint2 deep[STACK_SIZE - SM_STACK];
+  int sp;
+  __device__ __forceinline__ void push(uint32_t ref, float t, uint32_t* overflow_flag) {
+    const uint2 e = make_uint2(ref, __float_as_uint(t));
+    if (sp < SM_STACK) sm[sp * BLOCK_THREADS] = e;
+    else if (sp < STACK_SIZE) deep[sp - SM_STACK] = e;
+    else { *overflow_flag = 1u; return; }
+    ++sp;
+  }
+  __device__ __forceinline__ uint2 pop() {
+    --sp;
+    return sp < SM_STACK ? sm[sp * BLOCK_THREADS] : deep[sp - SM_STACK];
+  }
+};
 
 // Traverses one mesh.  GENERAL = qbvh semantics for arbitrary (also negative) t ranges:
 // closest = smallest |t|, bounds shrink on the side of the hit (qbvh.h:1812-1823).
 // ANY_HIT returns at the first accepted triangle (shadow rays only need `found`).
+// Control flow is "while-while": all lanes of a warp first descend inner nodes until each holds
+// a leaf (or is done), then all test their leaves — the two phases reconverge separately, so a
+// lane testing triangles never serialises against a lane decoding a node.
 template <bool ANY_HIT, bool GENERAL, bool STATS>
 __device__ __forceinline__ void traverse_mesh(const MeshDev& m, uint32_t mesh_index, float ox, float oy, float oz,
                                               float dx, float dy, float dz, float& t_near, float& t_far, Best& best,
-                                              uint32_t& stat_nodes, uint32_t& stat_tris, uint32_t* overflow_flag) {
+                                              uint32_t& stat_nodes, uint32_t& stat_tris, uint32_t* overflow_flag, Stack& stk) {
   if (m.nt == 0) return;
   const RayPre pre = woop_precompute(dx, dy, dz);
   const float idx = safe_rcp(dx), idy = safe_rcp(dy), idz = safe_rcp(dz);
   const bool negx = idx < 0.f, negy = idy < 0.f, negz = idz < 0.f;
 
-  uint2 stack[STACK_SIZE];
-  int sp = 0;
-  uint32_t cur = 0;  // root node
+  stk.sp = 0;
+  uint32_t cur = 0;  // root node; J3DG_EMPTY_CHILD (which has the leaf bit set) = nothing left
   const WideNode* __restrict__ nodes = m.nodes;
   const TriRec* __restrict__ tris = m.tris;
 
+  auto pop = [&]() -> uint32_t {
+    while (stk.sp > 0) {
+      const uint2 e = stk.pop();
+      // entry points of popped boxes that now lie beyond the shrunk interval are skipped
+      if (GENERAL || __uint_as_float(e.y) <= t_far) return e.x;
+    }
+    return J3DG_EMPTY_CHILD;
+  };
+
   for (;;) {
-    if (!(cur & J3DG_LEAF_BIT)) {
-      // ---- inner node: 8 quantised child boxes ----
+    // ---- phase 1: inner nodes, 8 quantised child boxes each ----
+    while (!(cur & J3DG_LEAF_BIT)) {
       const uint4* np = reinterpret_cast<const uint4*>(nodes + cur);
       const uint4 h0 = __ldg(np + 0);  // ox oy oz | ex ey ez n
       const uint4 q0 = __ldg(np + 1);  // qlo x[0..7] | qlo y[0..7]
@@ -116,9 +158,9 @@ __device__ __forceinline__ void traverse_mesh(const MeshDev& m, uint32_t mesh_in
       const uint4 c0 = __ldg(np + 4);
       const uint4 c1 = __ldg(np + 5);
       if (STATS) ++stat_nodes;
-      const float sx = __uint_as_float((h0.w & 0xffu) << 23) * idx;
-      const float sy = __uint_as_float(((h0.w >> 8) & 0xffu) << 23) * idy;
-      const float sz = __uint_as_float(((h0.w >> 16) & 0xffu) << 23) * idz;
+      const float sx = __uint_as_float(__byte_perm(h0.w, 0u, 0x4440u) << 23) * idx;
+      const float sy = __uint_as_float(__byte_perm(h0.w, 0u, 0x4441u) << 23) * idy;
+      const float sz = __uint_as_float(__byte_perm(h0.w, 0u, 0x4442u) << 23) * idz;
       const float bx = (__uint_as_float(h0.x) - ox) * idx;
       const float by = (__uint_as_float(h0.y) - oy) * idy;
       const float bz = (__uint_as_float(h0.z) - oz) * idz;
@@ -129,40 +171,44 @@ __device__ __forceinline__ void traverse_mesh(const MeshDev& m, uint32_t mesh_in
       const uint32_t fy0 = negy ? q0.z : q2.x, fy1 = negy ? q0.w : q2.y;
       const uint32_t nz0 = negz ? q2.z : q1.x, nz1 = negz ? q2.w : q1.y;
       const uint32_t fz0 = negz ? q1.x : q2.z, fz1 = negz ? q1.y : q2.w;
-      const uint32_t child[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
       uint32_t near_ref = J3DG_EMPTY_CHILD;
       float near_t = FLT_MAX;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int b = i & 3;
-        const float tlx = fmaf(ubyte(i < 4 ? nx0 : nx1, b), sx, bx);
-        const float thx = fmaf(ubyte(i < 4 ? fx0 : fx1, b), sx, bx);
-        const float tly = fmaf(ubyte(i < 4 ? ny0 : ny1, b), sy, by);
-        const float thy = fmaf(ubyte(i < 4 ? fy0 : fy1, b), sy, by);
-        const float tlz = fmaf(ubyte(i < 4 ? nz0 : nz1, b), sz, bz);
-        const float thz = fmaf(ubyte(i < 4 ? fz0 : fz1, b), sz, bz);
+      auto test_child = [&](auto IC, uint32_t wnx, uint32_t wfx, uint32_t wny, uint32_t wfy, uint32_t wnz, uint32_t wfz, uint32_t ref) {
+        constexpr int B = decltype(IC)::value;
+        const float tlx = fmaf(ubyte<B>(wnx), sx, bx);
+        const float thx = fmaf(ubyte<B>(wfx), sx, bx);
+        const float tly = fmaf(ubyte<B>(wny), sy, by);
+        const float thy = fmaf(ubyte<B>(wfy), sy, by);
+        const float tlz = fmaf(ubyte<B>(wnz), sz, bz);
+        const float thz = fmaf(ubyte<B>(wfz), sz, bz);
         float tmin = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, t_near));
         float tmax = fminf(fminf(thx, thy), fminf(thz, t_far));
         // conservative padding against rounding of the slab arithmetic
         tmin = fmaf(-fabsf(tmin), 2e-6f, tmin);
         tmax = fmaf(fabsf(tmax), 2e-6f, tmax);
-        if (tmin <= tmax) {
-          uint32_t ref = child[i];
+        if (tmin <= tmax) {  // empty slots have inverted boxes and never pass
           float tt = tmin;
           if (tt < near_t) {  // keep the nearest in registers, push the other one
             const uint32_t r2 = near_ref; const float t2 = near_t;
             near_ref = ref; near_t = tt;
             ref = r2; tt = t2;
           }
-          if (ref != J3DG_EMPTY_CHILD) {
-            if (sp < STACK_SIZE) stack[sp++] = make_uint2(ref, __float_as_uint(tt));
-            else *overflow_flag = 1u;
-          }
+          if (ref != J3DG_EMPTY_CHILD) stk.push(ref, tt, overflow_flag);
         }
-      }
-      if (near_ref != J3DG_EMPTY_CHILD) { cur = near_ref; continue; }
-    } else {
-      // ---- leaf: 1..4 consecutive triangle records ----
+      };
+      test_child(std::integral_constant<int, 0>{}, nx0, fx0, ny0, fy0, nz0, fz0, c0.x);
+      test_child(std::integral_constant<int, 1>{}, nx0, fx0, ny0, fy0, nz0, fz0, c0.y);
+      test_child(std::integral_constant<int, 2>{}, nx0, fx0, ny0, fy0, nz0, fz0, c0.z);
+      test_child(std::integral_constant<int, 3>{}, nx0, fx0, ny0, fy0, nz0, fz0, c0.w);
+      test_child(std::integral_constant<int, 0>{}, nx1, fx1, ny1, fy1, nz1, fz1, c1.x);
+      test_child(std::integral_constant<int, 1>{}, nx1, fx1, ny1, fy1, nz1, fz1, c1.y);
+      test_child(std::integral_constant<int, 2>{}, nx1, fx1, ny1, fy1, nz1, fz1, c1.z);
+      test_child(std::integral_constant<int, 3>{}, nx1, fx1, ny1, fy1, nz1, fz1, c1.w);
+      cur = (near_ref != J3DG_EMPTY_CHILD) ? near_ref : pop();
+    }
+    if (cur == J3DG_EMPTY_CHILD) return;
+    // ---- phase 2: leaves, 1..4 consecutive triangle records each ----
+    do {
       const uint32_t first = cur & J3DG_LEAF_FIRST_MASK;
       const uint32_t cnt = ((cur >> 29) & 3u) + 1u;
       for (uint32_t k = 0; k < cnt; ++k) {
@@ -179,20 +225,15 @@ __device__ __forceinline__ void traverse_mesh(const MeshDev& m, uint32_t mesh_in
           }
         }
       }
-    }
-    // ---- pop ----
-    for (;;) {
-      if (sp == 0) return;
-      const uint2 e = stack[--sp];
-      // entry points of popped boxes that now lie beyond the shrunk interval are skipped
-      if (GENERAL || __uint_as_float(e.y) <= t_far) { cur = e.x; break; }
-    }
+      cur = pop();
+    } while (cur != J3DG_EMPTY_CHILD && (cur & J3DG_LEAF_BIT));
+    if (cur == J3DG_EMPTY_CHILD) return;
   }
 }
 
 template <bool ANY_HIT, bool STATS>
 __device__ __forceinline__ void trace_scene(const MeshDev* __restrict__ meshes, uint32_t nm, float4 org, float4 dir,
-                                            float t_near, float t_far, Best& best, uint32_t& sn, uint32_t& st, uint32_t* ovf) {
+                                            float t_near, float t_far, Best& best, uint32_t& sn, uint32_t& st, uint32_t* ovf, Stack& stk) {
   best.found = false;
   best.t = FLT_MAX;
   for (uint32_t o = 0; o < nm; ++o) {
@@ -200,7 +241,7 @@ __device__ __forceinline__ void trace_scene(const MeshDev* __restrict__ meshes, 
     // qbvh.h:3358-3359: the ray is taken into object space by the inverted object matrix
     const float4 d2 = mat_vec(m.cs_inv, dir);
     const float4 o2 = mat_vec(m.cs_inv, org);
-    traverse_mesh<ANY_HIT, false, STATS>(m, o, o2.x, o2.y, o2.z, d2.x, d2.y, d2.z, t_near, t_far, best, sn, st, ovf);
+    traverse_mesh<ANY_HIT, false, STATS>(m, o, o2.x, o2.y, o2.z, d2.x, d2.y, d2.z, t_near, t_far, best, sn, st, ovf, stk);
     if (ANY_HIT && best.found) return;
   }
 }
@@ -211,17 +252,38 @@ __device__ __forceinline__ float4 transform_point(const float* __restrict__ m, f
   return r;
 }
 
+// stats layout (u64 each): [0] node visits, [1] triangle tests, [2] stack-overflow flag, [3] tile counter of the
+// running launch, [4] hit pixels of shadowed frames (accumulates until the timings are reset).
+//
+// Persistent threads: the grid is sized to fill the machine once (SMs x resident blocks); every WARP pulls the
+// next 8x4-pixel tile from a global counter, so a warp whose rays finish early (background, silhouette) never
+// waits for the slowest warp of its block, and there is no tail of half-empty blocks.  Tiles are numbered
+// super-tile by super-tile (32x32 pixels) so that warps running at the same time work on neighbouring pixels and
+// share the upper BVH levels in L1/L2.
 template <bool STATS>
-__global__ void __launch_bounds__(BLOCK_THREADS) cast_kernel(const MeshDev* __restrict__ meshes, uint32_t nm, ViewDev vw,
+__global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) cast_kernel(const MeshDev* __restrict__ meshes, uint32_t nm, ViewDev vw,
                                                               int x0, int y0, int x1, int y1, j3dg_pixel* __restrict__ out,
                                                               uint32_t stride, unsigned long long* __restrict__ stats) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tx = warp % BLOCK_TILES_X, ty = warp / BLOCK_TILES_X;
-  const int x = x0 + (blockIdx.x * BLOCK_TILES_X + tx) * TILE_W + (lane & (TILE_W - 1));
-  const int y = y0 + (blockIdx.y * BLOCK_TILES_Y + ty) * TILE_H + (lane / TILE_W);
+  __shared__ uint2 s_stack[SM_STACK * BLOCK_THREADS];
+  Stack stk;
+  stk.sm = s_stack + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tiles_x = (uint32_t)(x1 - x0 + TILE_W) / TILE_W, tiles_y = (uint32_t)(y1 - y0 + TILE_H) / TILE_H;
+  const uint32_t supers_x = (tiles_x + SUPER_W - 1) / SUPER_W, supers_y = (tiles_y + SUPER_H - 1) / SUPER_H;
+  const uint32_t total = supers_x * supers_y * (SUPER_W * SUPER_H);
   uint32_t sn = 0, st = 0;
-  const bool active = x <= x1 && y <= y1;
-  if (active) {
+  for (;;) {
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(reinterpret_cast<unsigned int*>(stats + 3), 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= total) break;
+    const uint32_t sup = tile / (SUPER_W * SUPER_H), in = tile % (SUPER_W * SUPER_H);
+    const uint32_t tx = (sup % supers_x) * SUPER_W + (in % SUPER_W), ty = (sup / supers_x) * SUPER_H + (in / SUPER_W);
+    const int x = x0 + (int)tx * TILE_W + (lane & (TILE_W - 1));
+    const int y = y0 + (int)ty * TILE_H + (lane / TILE_W);
+    if (x > x1 || y > y1) continue;  // warp-uniform for whole tiles outside; lanes outside just skip
+    unsigned long long tile_t0 = 0;
+    if (STATS) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tile_t0));
     // canvas.cpp:773-776
     const float w = (float)vw.width, h = (float)vw.height;
     float4 sp;
@@ -234,7 +296,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) cast_kernel(const MeshDev* __re
     dir = mat_vec(vw.cs, dir);
     const float4 org = make_float4(vw.origin[0], vw.origin[1], vw.origin[2], vw.origin[3]);
     Best best;
-    trace_scene<false, STATS>(meshes, nm, org, dir, fdiv(vw.diagonal, 100.f), FLT_MAX, best, sn, st, (uint32_t*)(stats + 2));
+    uint32_t pn = 0, pt = 0;  // this pixel's node visits / triangle tests (STATS only)
+    trace_scene<false, STATS>(meshes, nm, org, dir, fdiv(vw.diagonal, 100.f), FLT_MAX, best, pn, pt, (uint32_t*)(stats + 2), stk);
+    sn += pn; st += pt;
 
     uint4 lo, hi;  // the 32-byte pixel record as two 16-byte stores
     if (best.found) {
@@ -295,7 +359,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) cast_kernel(const MeshDev* __re
         ld.z = fsub(vw.light[2], pos.z); ld.w = fsub(vw.light[3], pos.w);
         Best sh;
         uint32_t dn = 0, dt = 0;
-        trace_scene<true, false>(meshes, nm, pos, ld, 1e-3f, FLT_MAX, sh, dn, dt, (uint32_t*)(stats + 2));
+        trace_scene<true, false>(meshes, nm, pos, ld, 1e-3f, FLT_MAX, sh, dn, dt, (uint32_t*)(stats + 2), stk);
         if (sh.found) mark |= 1u;
       }
       lo.x = mark | (r << 8) | (g << 16) | (b << 24);
@@ -309,6 +373,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS) cast_kernel(const MeshDev* __re
     } else {  // canvas.cpp:859-866
       lo = make_uint4(0u, 0u, 0u, __float_as_uint(FLT_MAX));
       hi = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+    }
+    if (STATS) {  // the counting pass returns per-pixel costs in the u / v slots, tile start / end time (ns) in the barycentric slots
+      __syncwarp();
+      unsigned long long tile_t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tile_t1));
+      lo.y = pn; lo.z = pt; hi.y = (uint32_t)tile_t0; hi.z = (uint32_t)tile_t1;
     }
     uint4* dst = reinterpret_cast<uint4*>(out + (size_t)y * stride + x);
     dst[0] = lo;
@@ -339,8 +409,11 @@ __global__ void __launch_bounds__(256) count_hits_kernel(const j3dg_pixel* __res
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(counter, (unsigned long long)c);
 }
 
-__global__ void __launch_bounds__(128) find_closest_kernel(MeshDev m, const float* __restrict__ rays, uint32_t n,
+__global__ void __launch_bounds__(BLOCK_THREADS) find_closest_kernel(MeshDev m, const float* __restrict__ rays, uint32_t n,
                                                             float* __restrict__ hits, uint32_t* __restrict__ ids, uint32_t* overflow) {
+  __shared__ uint2 s_stack[SM_STACK * BLOCK_THREADS];
+  Stack stk;
+  stk.sm = s_stack + threadIdx.x;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* r = rays + 8 * (size_t)i;
@@ -349,7 +422,7 @@ __global__ void __launch_bounds__(128) find_closest_kernel(MeshDev m, const floa
   best.found = false;
   best.t = FLT_MAX;
   uint32_t sn = 0, st = 0;
-  traverse_mesh<false, true, false>(m, 0, r[0], r[1], r[2], r[3], r[4], r[5], t_near, t_far, best, sn, st, overflow);
+  traverse_mesh<false, true, false>(m, 0, r[0], r[1], r[2], r[3], r[4], r[5], t_near, t_far, best, sn, st, overflow, stk);
   float* h = hits + 4 * (size_t)i;
   h[0] = best.found ? best.u : 0.f;
   h[1] = best.found ? best.v : 0.f;
@@ -424,11 +497,23 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
     if (rc != J3DG_OK) return rc;
   }
   if (used) CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_meshes, host.data(), sizeof(MeshDev) * used, cudaMemcpyHostToDevice, ctx->stream));
-  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats, 0, 3 * sizeof(unsigned long long), ctx->stream));  // [3] accumulates until reset
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));  // [4] accumulates until reset
   ViewDev vd;
   j3dg_make_view_dev(view, vd);
   const int rw = x1 - x0 + 1, rh = y1 - y0 + 1;
-  dim3 grid((rw + TILE_W * BLOCK_TILES_X - 1) / (TILE_W * BLOCK_TILES_X), (rh + TILE_H * BLOCK_TILES_Y - 1) / (TILE_H * BLOCK_TILES_Y));
+  // persistent grid: fill every SM once, never more blocks than there are tiles
+  static int blocks_per_sm[2] = {0, 0};
+  if (!blocks_per_sm[stats ? 1 : 0]) {
+    int nb = 0;
+    cudaError_t e = stats ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cast_kernel<true>, BLOCK_THREADS, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cast_kernel<false>, BLOCK_THREADS, 0);
+    if (e != cudaSuccess) return j3dg_cuda_fail(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor", __FILE__, __LINE__);
+    blocks_per_sm[stats ? 1 : 0] = std::max(nb, 1);
+  }
+  const long long ntiles = (long long)((rw + TILE_W - 1) / TILE_W) * ((rh + TILE_H - 1) / TILE_H);
+  const int warps_per_block = BLOCK_THREADS / 32;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * blocks_per_sm[stats ? 1 : 0],
+                                                                   (ntiles + warps_per_block - 1) / warps_per_block));
   { int rc = j3dg_stage_begin(ctx, 0); if (rc != J3DG_OK) return rc; }
   if (stats)
     cast_kernel<true><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(ctx->d_meshes, used, vd, x0, y0, x1, y1, d_pixels, stride, ctx->d_stats);
@@ -437,10 +522,10 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   KERNEL_CHECK(ctx);
   { int rc = j3dg_stage_end(ctx, 0); if (rc != J3DG_OK) return rc; }
   if (ctx->profiling && (view->flags & J3DG_SHADOW)) {  // one shadow ray per hit pixel: count them
-    count_hits_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_pixels, stride, x0, y0, rw, rh, ctx->d_stats + 3);
+    count_hits_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_pixels, stride, x0, y0, rw, rh, ctx->d_stats + 4);
     KERNEL_CHECK(ctx);
   }
-  ctx->rays_primary += (uint64_t)rw * rh;  // shadow rays (d_stats[3]) are added when the timings are read
+  ctx->rays_primary += (uint64_t)rw * rh;  // shadow rays (d_stats[4]) are added when the timings are read
   return J3DG_OK;
 }
 
@@ -449,8 +534,8 @@ int j3dg_launch_find_closest(j3dg_mesh* m, const float* d_rays, uint32_t n, floa
   if (!n) return J3DG_OK;
   MeshDev d;
   fill_mesh_dev(m, d);
-  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats, 0, 3 * sizeof(unsigned long long), ctx->stream));
-  find_closest_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d, d_rays, n, d_hits, d_ids, (uint32_t*)(ctx->d_stats + 2));
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  find_closest_kernel<<<(n + BLOCK_THREADS - 1) / BLOCK_THREADS, BLOCK_THREADS, 0, ctx->stream>>>(d, d_rays, n, d_hits, d_ids, (uint32_t*)(ctx->d_stats + 2));
   KERNEL_CHECK(ctx);
   return J3DG_OK;
 }
