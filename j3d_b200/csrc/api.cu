@@ -157,7 +157,7 @@ J3DG_API void j3dg_ctx_destroy(j3dg_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->d_pixels); cudaFree(ctx->d_pixels_in); cudaFree(ctx->d_rgba); cudaFree(ctx->d_bg); cudaFree(ctx->d_packed);
-  cudaFree(ctx->d_matcap); cudaFree(ctx->d_meshes); cudaFree(ctx->d_stats); cudaFree(ctx->d_misc);
+  cudaFree(ctx->d_matcap); cudaFree(ctx->d_meshes); cudaFree(ctx->d_stats); cudaFree(ctx->d_misc); cudaFree(ctx->d_shadow);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   for (auto& r : ctx->ring) { for (auto e : r.a) cudaEventDestroy(e); for (auto e : r.b) cudaEventDestroy(e); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -289,12 +289,13 @@ J3DG_API int j3dg_mesh_create_empty(j3dg_ctx* ctx, uint32_t nv, uint32_t nt, uin
   memcpy(m->cs, cs ? cs : kIdentity, sizeof(m->cs));
   j3dg_invert_orthonormal_host(m->cs, m->cs_inv);
   if ((nr_of_nodes && cudaMalloc((void**)&m->d_nodes, (size_t)nr_of_nodes * sizeof(WideNode)) != cudaSuccess) ||
-      (nt && cudaMalloc((void**)&m->d_tris, (size_t)nt * sizeof(TriRec)) != cudaSuccess)) {
+      (nt && cudaMalloc((void**)&m->d_tris, ((size_t)nt + J3DG_TRI_PAD) * sizeof(TriRec)) != cudaSuccess)) {
     cudaGetLastError();
     j3dg_mesh_destroy(m);
     j3dg_set_error(ctx, "out of device memory (received BVH)");
     return J3DG_ENOMEM;
   }
+  if (nt) CU_CHECK(ctx, cudaMemsetAsync(m->d_tris + nt, 0, J3DG_TRI_PAD * sizeof(TriRec), ctx->stream));
   m->node_cap = m->nr_nodes = nr_of_nodes;
   m->info.nr_of_vertices = nv; m->info.nr_of_triangles = nt; m->info.nr_of_nodes = nr_of_nodes; m->info.nr_of_leaf_triangles = nt;
   m->info.node_bytes = sizeof(WideNode); m->info.triangle_bytes = sizeof(TriRec);
@@ -619,12 +620,6 @@ J3DG_API int j3dg_cast_cost_image(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint3
   for (size_t i = 0; i < n; ++i) {
     memcpy(&nodes_out[i], &tmp[i].u, 4);
     memcpy(&tris_out[i], &tmp[i].v, 4);
-  }
-  if (const char* dbg = getenv("J3DG_DEBUG_TILE_TIMES")) {  // developer diagnostic: raw per-pixel tile start/end (ns, low 32 bits)
-    if (FILE* f = fopen(dbg, "wb")) {
-      for (size_t i = 0; i < n; ++i) { fwrite(&tmp[i].barycentric_u, 4, 1, f); fwrite(&tmp[i].barycentric_v, 4, 1, f); }
-      fclose(f);
-    }
   }
   return J3DG_OK;
 }

@@ -216,24 +216,42 @@ __device__ __forceinline__ uint32_t pick_exponent(float extent) {
   return e;
 }
 
+// A candidate child is opened further only while it owns more than J3DG_LEAF_KEEP triangles: the
+// traversal kernel tests all (<= 8) triangles of a leaf in ONE lane-parallel round, so very small
+// leaves only add node levels.
+#ifndef J3DG_LEAF_KEEP
+#define J3DG_LEAF_KEEP 4
+#endif
+
+__device__ __forceinline__ void mark_leaf_end(TriRec* __restrict__ recs, uint32_t last) {
+  reinterpret_cast<uint32_t*>(&recs[last].v1)[3] = 1u;
+}
+
 __global__ void __launch_bounds__(128) collapse_kernel(BinTree t, int n, const WorkItem* __restrict__ in, const uint32_t* __restrict__ in_count,
                                                         WorkItem* __restrict__ out, uint32_t* __restrict__ out_count,
                                                         WideNode* __restrict__ nodes, uint32_t* __restrict__ node_count, uint32_t node_cap,
-                                                        uint32_t* __restrict__ overflow) {
+                                                        uint32_t* __restrict__ overflow, TriRec* __restrict__ recs) {
   const uint32_t count = *in_count;
+  const uint32_t first_leaf = (uint32_t)(n - 1);
   for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
     const WorkItem item = in[w];
     // candidate children: binary node ids (inner < n-1, leaf >= n-1)
     uint32_t cand[8];
-    float area[8];  // < 0 for entries that cannot be opened (single triangles)
+    float area[8];  // < 0 for entries that are not opened (few triangles)
     int nc = 2;
+    auto open_area = [&](uint32_t c) -> float {
+      if (c >= first_leaf) return -1.f;
+      const uint2 r = t.range[c];
+      if (r.y - r.x + 1 <= (uint32_t)J3DG_LEAF_KEEP) return -1.f;
+      return fmaxf(half_area(t.bmin[c], t.bmax[c]), 0.f);
+    };
     {
       const int2 ch = t.children[item.bin];
       cand[0] = (uint32_t)ch.x;
       cand[1] = (uint32_t)ch.y;
+      area[0] = open_area(cand[0]);
+      area[1] = open_area(cand[1]);
     }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) area[i] = (cand[i] >= (uint32_t)(n - 1)) ? -1.f : half_area(t.bmin[cand[i]], t.bmax[cand[i]]);
     while (nc < 8) {
       int best = -1;
       float ba = -1.f;
@@ -243,14 +261,15 @@ __global__ void __launch_bounds__(128) collapse_kernel(BinTree t, int n, const W
       const int2 ch = t.children[cand[best]];
       cand[best] = (uint32_t)ch.x;
       cand[nc] = (uint32_t)ch.y;
-      area[best] = ((uint32_t)ch.x >= (uint32_t)(n - 1)) ? -1.f : fmaxf(half_area(t.bmin[(uint32_t)ch.x], t.bmax[(uint32_t)ch.x]), 0.f);
-      area[nc] = ((uint32_t)ch.y >= (uint32_t)(n - 1)) ? -1.f : fmaxf(half_area(t.bmin[(uint32_t)ch.y], t.bmax[(uint32_t)ch.y]), 0.f);
+      area[best] = open_area((uint32_t)ch.x);
+      area[nc] = open_area((uint32_t)ch.y);
       ++nc;
     }
     // node box = box of the binary node
     const float4 nmn = t.bmin[item.bin], nmx = t.bmax[item.bin];
     WideNode node;
     node.ox = nmn.x; node.oy = nmn.y; node.oz = nmn.z;
+    node.pad0 = 0u;
     uint32_t e[3] = {pick_exponent(nmx.x - nmn.x), pick_exponent(nmx.y - nmn.y), pick_exponent(nmx.z - nmn.z)};
     const float org[3] = {nmn.x, nmn.y, nmn.z};
     float4 cmn[8], cmx[8];
@@ -272,29 +291,32 @@ __global__ void __launch_bounds__(128) collapse_kernel(BinTree t, int n, const W
           while (ql > 0 && __fmaf_rn((float)ql, scale, org[ax]) > lo) --ql;
           while (qh <= 255 && __fmaf_rn((float)qh, scale, org[ax]) < hi) ++qh;
           if (qh > 255) { ok = false; break; }
-          node.qlo[ax][i] = (uint8_t)ql;
-          node.qhi[ax][i] = (uint8_t)qh;
+          node.box[i][ax] = (uint8_t)ql;
+          node.box[i][3 + ax] = (uint8_t)qh;
         }
         if (ok) break;
         e[ax] += 1;
       }
-      for (int i = nc; i < 8; ++i) { node.qlo[ax][i] = 255; node.qhi[ax][i] = 0; }
+      for (int i = nc; i < 8; ++i) { node.box[i][ax] = 255; node.box[i][3 + ax] = 0; }
     }
-    node.ex = (uint8_t)e[0]; node.ey = (uint8_t)e[1]; node.ez = (uint8_t)e[2];
-    node.nchild = (uint8_t)nc;
+    for (int i = 0; i < 8; ++i) { node.box[i][6] = 0x00; node.box[i][7] = 0x4B; }
+    node.sx = __uint_as_float(e[0] << 23); node.sy = __uint_as_float(e[1] << 23); node.sz = __uint_as_float(e[2] << 23);
+    node.nchild = (uint32_t)nc;
     for (int i = 0; i < 8; ++i) node.child[i] = J3DG_EMPTY_CHILD;
     for (int i = 0; i < nc; ++i) {
       const uint32_t c = cand[i];
-      if (c >= (uint32_t)(n - 1)) {
-        node.child[i] = J3DG_LEAF_BIT | (c - (uint32_t)(n - 1));  // count-1 = 0
+      if (c >= first_leaf) {
+        node.child[i] = J3DG_LEAF_BIT | (c - first_leaf);
+        mark_leaf_end(recs, c - first_leaf);
       } else {
         const uint2 r = t.range[c];
         const uint32_t cnt = r.y - r.x + 1;
         if (cnt <= J3DG_MAX_LEAF) {
-          node.child[i] = J3DG_LEAF_BIT | ((cnt - 1) << 29) | r.x;
+          node.child[i] = J3DG_LEAF_BIT | r.x;
+          mark_leaf_end(recs, r.y);
         } else {
           const uint32_t wi = atomicAdd(node_count, 1u);
-          if (wi >= node_cap) { *overflow = 1u; node.child[i] = J3DG_EMPTY_CHILD; node.qlo[0][i] = 255; node.qhi[0][i] = 0; continue; }
+          if (wi >= node_cap) { *overflow = 1u; node.child[i] = J3DG_EMPTY_CHILD; node.box[i][0] = 255; node.box[i][3] = 0; continue; }
           node.child[i] = wi;
           const uint32_t oi = atomicAdd(out_count, 1u);
           out[oi] = WorkItem{c, wi};
@@ -306,22 +328,25 @@ __global__ void __launch_bounds__(128) collapse_kernel(BinTree t, int n, const W
 }
 
 // n == 1: a root with a single leaf child
-__global__ void single_triangle_root_kernel(BinTree t, WideNode* nodes) {
+__global__ void single_triangle_root_kernel(BinTree t, WideNode* nodes, TriRec* recs) {
   const float4 mn = t.bmin[0], mx = t.bmax[0];
   WideNode node;
   node.ox = mn.x; node.oy = mn.y; node.oz = mn.z;
+  node.pad0 = 0u;
   const float ext[3] = {mx.x - mn.x, mx.y - mn.y, mx.z - mn.z};
   uint32_t e[3];
   for (int ax = 0; ax < 3; ++ax) {
-    e[ax] = pick_exponent(ext[ax]) + 1;
-    for (int i = 0; i < 8; ++i) { node.qlo[ax][i] = 255; node.qhi[ax][i] = 0; }
-    node.qlo[ax][0] = 0;
-    node.qhi[ax][0] = 255;
+    e[ax] = min(254u, pick_exponent(ext[ax]) + 1);
+    for (int i = 0; i < 8; ++i) { node.box[i][ax] = 255; node.box[i][3 + ax] = 0; }
+    node.box[0][ax] = 0;
+    node.box[0][3 + ax] = 255;
   }
-  node.ex = (uint8_t)e[0]; node.ey = (uint8_t)e[1]; node.ez = (uint8_t)e[2];
+  for (int i = 0; i < 8; ++i) { node.box[i][6] = 0x00; node.box[i][7] = 0x4B; }
+  node.sx = __uint_as_float(e[0] << 23); node.sy = __uint_as_float(e[1] << 23); node.sz = __uint_as_float(e[2] << 23);
   node.nchild = 1;
   for (int i = 0; i < 8; ++i) node.child[i] = J3DG_EMPTY_CHILD;
   node.child[0] = J3DG_LEAF_BIT | 0u;
+  mark_leaf_end(recs, 0);
   nodes[0] = node;
 }
 
@@ -391,10 +416,11 @@ int j3dg_build_bvh(j3dg_mesh* m) {
 
   // ---- output arrays ----
   if (!m->d_tris && n) {
-    if (cudaMalloc((void**)&m->d_tris, (size_t)n * sizeof(TriRec)) != cudaSuccess) {
+    if (cudaMalloc((void**)&m->d_tris, ((size_t)n + J3DG_TRI_PAD) * sizeof(TriRec)) != cudaSuccess) {
       j3dg_set_error(ctx, "out of device memory (triangle records)");
       return J3DG_ENOMEM;
     }
+    CU_CHECK(ctx, cudaMemsetAsync(m->d_tris + n, 0, J3DG_TRI_PAD * sizeof(TriRec), st));
   }
   uint32_t cap = std::max<uint32_t>(16u, n / 3 + 1024u);
   for (int attempt = 0; attempt < 2; ++attempt) {
@@ -433,7 +459,7 @@ int j3dg_build_bvh(j3dg_mesh* m) {
       refit_kernel<<<tb, 256, 0, st>>>(m->d_vertices, m->d_indices, vals, (int)n, bt, m->d_tris);
       KERNEL_CHECK(ctx);
       if (n == 1) {
-        single_triangle_root_kernel<<<1, 1, 0, st>>>(bt, m->d_nodes);
+        single_triangle_root_kernel<<<1, 1, 0, st>>>(bt, m->d_nodes, m->d_tris);
         KERNEL_CHECK(ctx);
       } else {
         init_queue_kernel<<<1, 1, 0, st>>>(q0, d_counts, d_counts + 2, d_counts + 3);
@@ -449,7 +475,7 @@ int j3dg_build_bvh(j3dg_mesh* m) {
             WorkItem* qo = (level & 1) ? q0 : q1;
             uint32_t* ci = d_counts + (level & 1);
             uint32_t* co = d_counts + ((level + 1) & 1);
-            collapse_kernel<<<grid, 128, 0, st>>>(bt, (int)n, qi, ci, qo, co, m->d_nodes, d_counts + 2, m->node_cap, d_counts + 3);
+            collapse_kernel<<<grid, 128, 0, st>>>(bt, (int)n, qi, ci, qo, co, m->d_nodes, d_counts + 2, m->node_cap, d_counts + 3, m->d_tris);
             KERNEL_CHECK(ctx);
             reset_count_kernel<<<1, 1, 0, st>>>(ci);
             KERNEL_CHECK(ctx);

@@ -3,6 +3,20 @@
 // (jtk/qbvh.h:3303-3387) -> qbvh::find_closest_triangle (1701-1852) with the Woop test
 // (4793-4869), hit -> pixel record (788-834) and the shadow ray (836-857).
 //
+// Mapping onto the GPU ("one ray per 8 lanes"): the BVH is 8 wide and a leaf holds at most 8
+// triangles, so a ray is traversed by a GROUP of 8 lanes — lane c tests child c of the current
+// node (or triangle c of the current leaf), the group votes (ballot), picks the nearest child
+// with three shuffle-min steps and pushes the other hit children onto ONE stack per ray in
+// shared memory.  A warp carries four rays.  Compared with one ray per lane this keeps every
+// lane of a node / leaf test busy on the same cache line, makes one traversal step ~8x shorter
+// (the kernel used to be bound by the serial latency of its slowest 32-ray tiles) and moves the
+// whole stack into shared memory.  Warps are persistent: each pulls 8x4-pixel tiles from a global
+// counter and its four groups pull rays from the tile one by one, so a group whose ray ends
+// early (background, silhouette) immediately starts the next ray.
+//
+// Pipeline of one j3dg_cast: trace<PRIMARY> (raw hit: t, u, v, record slot) -> resolve_kernel
+// (hit -> pixel record; appends shadow rays) -> trace<SHADOW> over the appended list (any hit).
+//
 // Parity rules: the ray, the Woop edge functions, t/u/v, the triangle normal and
 // its two transforms are evaluated with separately rounded mul/add/sub (no FMA), in the
 // reference's operation order.  Only the box tests use FMA — they are conservative and do not
@@ -10,80 +24,38 @@
 #include "common.cuh"
 
 #include <algorithm>
-#include <type_traits>
 
 namespace {
 
-constexpr int STACK_SIZE = 96;               // total traversal stack entries per ray
-constexpr int SM_STACK = 12;                 // of which the first SM_STACK live in shared memory (rest: local memory, rarely touched)
-constexpr int TILE_W = 8, TILE_H = 4;        // one warp = 8x4 pixels
-constexpr int SUPER_W = 4, SUPER_H = 8;      // tiles are handed out super-tile by super-tile (32x32 pixels), row-major inside
-constexpr int BLOCK_THREADS = 128;           // 4 warps; every warp fetches its own tiles (persistent threads)
+constexpr int GROUP = 8;                                  // lanes per ray = children per node = max triangles per leaf
+constexpr int BLOCK_THREADS = 128;
+constexpr int GROUPS_PER_BLOCK = BLOCK_THREADS / GROUP;   // 16 rays in flight per block
+constexpr int STACK_SIZE = 96;                            // entries per ray; 96 * 8 B * 16 = 12 KB shared memory per block
+constexpr int TILE_W = 8, TILE_H = 4;                     // a warp's ray pool = one 8x4 pixel tile
+constexpr int SUPER_W = 4, SUPER_H = 8;                   // tiles are numbered super-tile by super-tile (32x32 pixels)
 #ifndef J3DG_CAST_MIN_BLOCKS
-#define J3DG_CAST_MIN_BLOCKS 6
+#define J3DG_CAST_MIN_BLOCKS 8
 #endif
 
-struct RayPre {  // intersect_woop_precompute, qbvh.h:4793-4823
-  int kx, ky, kz;
-  float Sx, Sy, Sz;
+enum Mode { PRIMARY = 0, SHADOW = 1, RAYLIST = 2 };
+
+struct TraceParams {
+  const MeshDev* meshes;
+  uint32_t nm;
+  ViewDev vw;
+  int x0, y0, x1, y1;
+  j3dg_pixel* out;               // PRIMARY: raw hits are written here; SHADOW: mark bit 0 is set here
+  uint32_t stride;
+  unsigned long long* stats;     // [0] node rounds [1] triangle tests [2] overflow flag [3] pool counter [4] shadow rays (accumulating) [5] shadow list length
+  const float4* shadow_pos;      // SHADOW: ray origins (xyzw as the reference computes them)
+  const uint32_t* shadow_pix;    // SHADOW: pixel offset (y * stride + x) of each ray
+  const float* rays;             // RAYLIST: n x 8 floats
+  float* hits;                   // RAYLIST: n x 4 floats
+  uint32_t* ids;                 // RAYLIST: n triangle ids
+  uint32_t nrays;
 };
 
 __device__ __forceinline__ float pick(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
-
-__device__ __forceinline__ RayPre woop_precompute(float dx, float dy, float dz) {
-  RayPre o;
-  const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
-  o.kz = 2;
-  if (ax > ay) { if (ax > az) o.kz = 0; }
-  else { if (ay > az) o.kz = 1; }
-  o.kx = o.kz == 2 ? 0 : o.kz + 1;
-  o.ky = o.kx == 2 ? 0 : o.kx + 1;
-  const float dkz = pick(dx, dy, dz, o.kz);
-  if (dkz < 0.f) { const int t = o.kx; o.kx = o.ky; o.ky = t; }
-  o.Sz = fdiv(1.f, dkz);
-  o.Sx = fmul(pick(dx, dy, dz, o.kx), o.Sz);
-  o.Sy = fmul(pick(dx, dy, dz, o.ky), o.Sz);
-  return o;
-}
-
-struct Best {
-  float t, u, v;
-  uint32_t slot;   // index of the triangle record
-  uint32_t mesh;
-  bool found;
-};
-
-// One triangle, one lane of intersect_woop (qbvh.h:4825-4869).  Returns true when the triangle
-// is hit inside (t_near, t_far); the reference's reciprocal(det) (rcpps + 1 NR step, ~2e-7) is
-// replaced by the correctly rounded 1/det.
-__device__ __forceinline__ bool woop_test(const float4 v0, const float4 v1, const float4 v2, const RayPre& p,
-                                          float ox, float oy, float oz, float t_near, float t_far, float& t, float& u, float& v) {
-  const float Ax_ = fsub(v0.x, ox), Ay_ = fsub(v0.y, oy), Az_ = fsub(v0.z, oz);
-  const float Bx_ = fsub(v1.x, ox), By_ = fsub(v1.y, oy), Bz_ = fsub(v1.z, oz);
-  const float Cx_ = fsub(v2.x, ox), Cy_ = fsub(v2.y, oy), Cz_ = fsub(v2.z, oz);
-  const float Akz = pick(Ax_, Ay_, Az_, p.kz), Bkz = pick(Bx_, By_, Bz_, p.kz), Ckz = pick(Cx_, Cy_, Cz_, p.kz);
-  const float Ax = fsub(pick(Ax_, Ay_, Az_, p.kx), fmul(p.Sx, Akz));
-  const float Ay = fsub(pick(Ax_, Ay_, Az_, p.ky), fmul(p.Sy, Akz));
-  const float Bx = fsub(pick(Bx_, By_, Bz_, p.kx), fmul(p.Sx, Bkz));
-  const float By = fsub(pick(Bx_, By_, Bz_, p.ky), fmul(p.Sy, Bkz));
-  const float Cx = fsub(pick(Cx_, Cy_, Cz_, p.kx), fmul(p.Sx, Ckz));
-  const float Cy = fsub(pick(Cx_, Cy_, Cz_, p.ky), fmul(p.Sy, Ckz));
-  const float U = fsub(fmul(Cx, By), fmul(Cy, Bx));
-  const float V = fsub(fmul(Ax, Cy), fmul(Ay, Cx));
-  const float W = fsub(fmul(Bx, Ay), fmul(By, Ax));
-  const bool inside = ((U <= 0.f) && (V <= 0.f) && (W <= 0.f)) || ((U >= 0.f) && (V >= 0.f) && (W >= 0.f));
-  if (!inside) return false;
-  const float det = fadd(fadd(U, V), W);
-  if (!(det != 0.f)) return false;
-  const float inv_det = fdiv(1.f, det);
-  const float Az = fmul(p.Sz, Akz), Bz = fmul(p.Sz, Bkz), Cz = fmul(p.Sz, Ckz);
-  const float T = fadd(fadd(fmul(U, Az), fmul(V, Bz)), fmul(W, Cz));
-  t = fmul(T, inv_det);
-  if (!((t_far > t) && (t > t_near))) return false;
-  u = fmul(V, inv_det);
-  v = fmul(W, inv_det);
-  return true;
-}
 
 __device__ __forceinline__ float safe_rcp(float d) {
   // box tests only: keep the reciprocal finite so 0 * inf never produces NaN
@@ -92,218 +64,368 @@ __device__ __forceinline__ float safe_rcp(float d) {
   return 1.f / d;
 }
 
-// Byte i of w as a float without the quarter-rate I2F (XU pipe): PRMT builds the bit pattern of
-// 2^23 + q, the subtraction is exact.  Both instructions run on the full-rate ALU / FMA pipes.
-template <int I>
-__device__ __forceinline__ float ubyte(uint32_t w) {
-  return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)I)), 8388608.f);
-}
-
-// Per-thread traversal stack: the first SM_STACK entries in shared memory (column tid of a
-// [SM_STACK][BLOCK_THREADS] array: conflict-free), deeper entries in local memory.
-struct Stack {
-  uint2* sm;                          // &s_stack[threadIdx.x]
-  uint2 deep[STACK_SIZE - SM_STACK];
-  int sp;
-  __device__ __forceinline__ void push(uint32_t ref, float t, uint32_t* overflow_flag) {
-    const uint2 e = make_uint2(ref, __float_as_uint(t));
-    if (sp < SM_STACK) sm[sp * BLOCK_THREADS] = e;
-    else if (sp < STACK_SIZE) deep[sp - SM_STACK] = e;
-    else { *overflow_flag = 1u; return; }
-    ++sp;
-  }
-  __device__ __forceinline__ uint2 pop() {
-    --sp;
-    return sp < SM_STACK ? sm[sp * BLOCK_THREADS] : deep[sp - SM_STACK];
-  }
-};
-
-// Traverses one mesh.  GENERAL = qbvh semantics for arbitrary (also negative) t ranges:
-// closest = smallest |t|, bounds shrink on the side of the hit (qbvh.h:1812-1823).
-// ANY_HIT returns at the first accepted triangle (shadow rays only need `found`).
-// Control flow is "while-while": all lanes of a warp first descend inner nodes until each holds
-// a leaf (or is done), then all test their leaves — the two phases reconverge separately, so a
-// lane testing triangles never serialises against a lane decoding a node.
-template <bool ANY_HIT, bool GENERAL, bool STATS>
-__device__ __forceinline__ void traverse_mesh(const MeshDev& m, uint32_t mesh_index, float ox, float oy, float oz,
-                                              float dx, float dy, float dz, float& t_near, float& t_far, Best& best,
-                                              uint32_t& stat_nodes, uint32_t& stat_tris, uint32_t* overflow_flag, Stack& stk) {
-  if (m.nt == 0) return;
-  const RayPre pre = woop_precompute(dx, dy, dz);
-  const float idx = safe_rcp(dx), idy = safe_rcp(dy), idz = safe_rcp(dz);
-  const bool negx = idx < 0.f, negy = idy < 0.f, negz = idz < 0.f;
-
-  stk.sp = 0;
-  uint32_t cur = 0;  // root node; J3DG_EMPTY_CHILD (which has the leaf bit set) = nothing left
-  const WideNode* __restrict__ nodes = m.nodes;
-  const TriRec* __restrict__ tris = m.tris;
-
-  auto pop = [&]() -> uint32_t {
-    while (stk.sp > 0) {
-      const uint2 e = stk.pop();
-      // entry points of popped boxes that now lie beyond the shrunk interval are skipped
-      if (GENERAL || __uint_as_float(e.y) <= t_far) return e.x;
-    }
-    return J3DG_EMPTY_CHILD;
-  };
-
-  for (;;) {
-    // ---- phase 1: inner nodes, 8 quantised child boxes each ----
-    while (!(cur & J3DG_LEAF_BIT)) {
-      const uint4* np = reinterpret_cast<const uint4*>(nodes + cur);
-      const uint4 h0 = __ldg(np + 0);  // ox oy oz | ex ey ez n
-      const uint4 q0 = __ldg(np + 1);  // qlo x[0..7] | qlo y[0..7]
-      const uint4 q1 = __ldg(np + 2);  // qlo z[0..7] | qhi x[0..7]
-      const uint4 q2 = __ldg(np + 3);  // qhi y[0..7] | qhi z[0..7]
-      const uint4 c0 = __ldg(np + 4);
-      const uint4 c1 = __ldg(np + 5);
-      if (STATS) ++stat_nodes;
-      const float sx = __uint_as_float(__byte_perm(h0.w, 0u, 0x4440u) << 23) * idx;
-      const float sy = __uint_as_float(__byte_perm(h0.w, 0u, 0x4441u) << 23) * idy;
-      const float sz = __uint_as_float(__byte_perm(h0.w, 0u, 0x4442u) << 23) * idz;
-      const float bx = (__uint_as_float(h0.x) - ox) * idx;
-      const float by = (__uint_as_float(h0.y) - oy) * idy;
-      const float bz = (__uint_as_float(h0.z) - oz) * idz;
-      // near / far plane words per axis (two 32-bit words = 8 children)
-      const uint32_t nx0 = negx ? q1.z : q0.x, nx1 = negx ? q1.w : q0.y;
-      const uint32_t fx0 = negx ? q0.x : q1.z, fx1 = negx ? q0.y : q1.w;
-      const uint32_t ny0 = negy ? q2.x : q0.z, ny1 = negy ? q2.y : q0.w;
-      const uint32_t fy0 = negy ? q0.z : q2.x, fy1 = negy ? q0.w : q2.y;
-      const uint32_t nz0 = negz ? q2.z : q1.x, nz1 = negz ? q2.w : q1.y;
-      const uint32_t fz0 = negz ? q1.x : q2.z, fz1 = negz ? q1.y : q2.w;
-      uint32_t near_ref = J3DG_EMPTY_CHILD;
-      float near_t = FLT_MAX;
-      auto test_child = [&](auto IC, uint32_t wnx, uint32_t wfx, uint32_t wny, uint32_t wfy, uint32_t wnz, uint32_t wfz, uint32_t ref) {
-        constexpr int B = decltype(IC)::value;
-        const float tlx = fmaf(ubyte<B>(wnx), sx, bx);
-        const float thx = fmaf(ubyte<B>(wfx), sx, bx);
-        const float tly = fmaf(ubyte<B>(wny), sy, by);
-        const float thy = fmaf(ubyte<B>(wfy), sy, by);
-        const float tlz = fmaf(ubyte<B>(wnz), sz, bz);
-        const float thz = fmaf(ubyte<B>(wfz), sz, bz);
-        float tmin = fmaxf(fmaxf(tlx, tly), fmaxf(tlz, t_near));
-        float tmax = fminf(fminf(thx, thy), fminf(thz, t_far));
-        // conservative padding against rounding of the slab arithmetic
-        tmin = fmaf(-fabsf(tmin), 2e-6f, tmin);
-        tmax = fmaf(fabsf(tmax), 2e-6f, tmax);
-        if (tmin <= tmax) {  // empty slots have inverted boxes and never pass
-          float tt = tmin;
-          if (tt < near_t) {  // keep the nearest in registers, push the other one
-            const uint32_t r2 = near_ref; const float t2 = near_t;
-            near_ref = ref; near_t = tt;
-            ref = r2; tt = t2;
-          }
-          if (ref != J3DG_EMPTY_CHILD) stk.push(ref, tt, overflow_flag);
-        }
-      };
-      test_child(std::integral_constant<int, 0>{}, nx0, fx0, ny0, fy0, nz0, fz0, c0.x);
-      test_child(std::integral_constant<int, 1>{}, nx0, fx0, ny0, fy0, nz0, fz0, c0.y);
-      test_child(std::integral_constant<int, 2>{}, nx0, fx0, ny0, fy0, nz0, fz0, c0.z);
-      test_child(std::integral_constant<int, 3>{}, nx0, fx0, ny0, fy0, nz0, fz0, c0.w);
-      test_child(std::integral_constant<int, 0>{}, nx1, fx1, ny1, fy1, nz1, fz1, c1.x);
-      test_child(std::integral_constant<int, 1>{}, nx1, fx1, ny1, fy1, nz1, fz1, c1.y);
-      test_child(std::integral_constant<int, 2>{}, nx1, fx1, ny1, fy1, nz1, fz1, c1.z);
-      test_child(std::integral_constant<int, 3>{}, nx1, fx1, ny1, fy1, nz1, fz1, c1.w);
-      cur = (near_ref != J3DG_EMPTY_CHILD) ? near_ref : pop();
-    }
-    if (cur == J3DG_EMPTY_CHILD) return;
-    // ---- phase 2: leaves, 1..4 consecutive triangle records each ----
-    do {
-      const uint32_t first = cur & J3DG_LEAF_FIRST_MASK;
-      const uint32_t cnt = ((cur >> 29) & 3u) + 1u;
-      for (uint32_t k = 0; k < cnt; ++k) {
-        const float4* tp = reinterpret_cast<const float4*>(tris + first + k);
-        const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
-        if (STATS) ++stat_tris;
-        float t, u, v;
-        if (woop_test(v0, v1, v2, pre, ox, oy, oz, t_near, t_far, t, u, v)) {
-          const bool closer = GENERAL ? (fabsf(t) < fabsf(best.t)) : (t < best.t);
-          if (closer) {
-            best.found = true; best.t = t; best.u = u; best.v = v; best.slot = first + k; best.mesh = mesh_index;
-            if (!GENERAL || t > 0.f) t_far = t; else t_near = t;
-            if (ANY_HIT) return;
-          }
-        }
-      }
-      cur = pop();
-    } while (cur != J3DG_EMPTY_CHILD && (cur & J3DG_LEAF_BIT));
-    if (cur == J3DG_EMPTY_CHILD) return;
-  }
-}
-
-template <bool ANY_HIT, bool STATS>
-__device__ __forceinline__ void trace_scene(const MeshDev* __restrict__ meshes, uint32_t nm, float4 org, float4 dir,
-                                            float t_near, float t_far, Best& best, uint32_t& sn, uint32_t& st, uint32_t* ovf, Stack& stk) {
-  best.found = false;
-  best.t = FLT_MAX;
-  for (uint32_t o = 0; o < nm; ++o) {
-    const MeshDev& m = meshes[o];
-    // qbvh.h:3358-3359: the ray is taken into object space by the inverted object matrix
-    const float4 d2 = mat_vec(m.cs_inv, dir);
-    const float4 o2 = mat_vec(m.cs_inv, org);
-    traverse_mesh<ANY_HIT, false, STATS>(m, o, o2.x, o2.y, o2.z, d2.x, d2.y, d2.z, t_near, t_far, best, sn, st, ovf, stk);
-    if (ANY_HIT && best.found) return;
-  }
-}
-
 __device__ __forceinline__ float4 transform_point(const float* __restrict__ m, float4 p) {  // jtk::transform, qbvh.h:5140-5151
   float4 r = mat_vec(m, p);
   if (r.w != 1.f && r.w != 0.f) { r.x = fdiv(r.x, r.w); r.y = fdiv(r.y, r.w); r.z = fdiv(r.z, r.w); r.w = 1.f; }
   return r;
 }
 
-// stats layout (u64 each): [0] node visits, [1] triangle tests, [2] stack-overflow flag, [3] tile counter of the
-// running launch, [4] hit pixels of shadowed frames (accumulates until the timings are reset).
-//
-// Persistent threads: the grid is sized to fill the machine once (SMs x resident blocks); every WARP pulls the
-// next 8x4-pixel tile from a global counter, so a warp whose rays finish early (background, silhouette) never
-// waits for the slowest warp of its block, and there is no tail of half-empty blocks.  Tiles are numbered
-// super-tile by super-tile (32x32 pixels) so that warps running at the same time work on neighbouring pixels and
-// share the upper BVH levels in L1/L2.
-template <bool STATS>
-__global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) cast_kernel(const MeshDev* __restrict__ meshes, uint32_t nm, ViewDev vw,
-                                                              int x0, int y0, int x1, int y1, j3dg_pixel* __restrict__ out,
-                                                              uint32_t stride, unsigned long long* __restrict__ stats) {
-  __shared__ uint2 s_stack[SM_STACK * BLOCK_THREADS];
-  Stack stk;
-  stk.sm = s_stack + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const uint32_t tiles_x = (uint32_t)(x1 - x0 + TILE_W) / TILE_W, tiles_y = (uint32_t)(y1 - y0 + TILE_H) / TILE_H;
-  const uint32_t supers_x = (tiles_x + SUPER_W - 1) / SUPER_W, supers_y = (tiles_y + SUPER_H - 1) / SUPER_H;
-  const uint32_t total = supers_x * supers_y * (SUPER_W * SUPER_H);
-  uint32_t sn = 0, st = 0;
-  for (;;) {
-    uint32_t tile = 0;
-    if (lane == 0) tile = atomicAdd(reinterpret_cast<unsigned int*>(stats + 3), 1u);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= total) break;
-    const uint32_t sup = tile / (SUPER_W * SUPER_H), in = tile % (SUPER_W * SUPER_H);
-    const uint32_t tx = (sup % supers_x) * SUPER_W + (in % SUPER_W), ty = (sup / supers_x) * SUPER_H + (in / SUPER_W);
-    const int x = x0 + (int)tx * TILE_W + (lane & (TILE_W - 1));
-    const int y = y0 + (int)ty * TILE_H + (lane / TILE_W);
-    if (x > x1 || y > y1) continue;  // warp-uniform for whole tiles outside; lanes outside just skip
-    unsigned long long tile_t0 = 0;
-    if (STATS) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tile_t0));
-    // canvas.cpp:773-776
-    const float w = (float)vw.width, h = (float)vw.height;
+// min over the 8 lanes of a group (xor shuffles stay inside an aligned group of 8)
+__device__ __forceinline__ float group_min(uint32_t gmask, float v) {
+  v = fminf(v, __shfl_xor_sync(gmask, v, 1));
+  v = fminf(v, __shfl_xor_sync(gmask, v, 2));
+  v = fminf(v, __shfl_xor_sync(gmask, v, 4));
+  return v;
+}
+
+struct WorldRay { float4 org, dir; float t_near, t_far; };
+
+// The ray of slot `id` in world space.  PRIMARY: id = (y << 16) | x, canvas.cpp:773-782.
+template <int MODE>
+__device__ __forceinline__ WorldRay world_ray(const TraceParams& p, uint32_t id) {
+  WorldRay r;
+  if (MODE == PRIMARY) {
+    const int x = (int)(id & 0xffffu), y = (int)(id >> 16);
+    const float w = (float)p.vw.width, h = (float)p.vw.height;
     float4 sp;
     sp.x = fsub(fmul(2.f, fdiv(fadd((float)x, 0.5f), w)), 1.f);
     sp.y = fsub(fmul(2.f, fdiv(fadd((float)y, 0.5f), h)), 1.f);
-    sp.z = vw.near_plane;
+    sp.z = p.vw.near_plane;
     sp.w = 1.f;
-    float4 dir = mat_vec(vw.pinv, sp);
+    float4 dir = mat_vec(p.vw.pinv, sp);
     dir.w = 0.f;
-    dir = mat_vec(vw.cs, dir);
-    const float4 org = make_float4(vw.origin[0], vw.origin[1], vw.origin[2], vw.origin[3]);
-    Best best;
-    uint32_t pn = 0, pt = 0;  // this pixel's node visits / triangle tests (STATS only)
-    trace_scene<false, STATS>(meshes, nm, org, dir, fdiv(vw.diagonal, 100.f), FLT_MAX, best, pn, pt, (uint32_t*)(stats + 2), stk);
-    sn += pn; st += pt;
+    r.dir = mat_vec(p.vw.cs, dir);
+    r.org = make_float4(p.vw.origin[0], p.vw.origin[1], p.vw.origin[2], p.vw.origin[3]);
+    r.t_near = fdiv(p.vw.diagonal, 100.f);
+    r.t_far = FLT_MAX;
+  } else if (MODE == SHADOW) {  // canvas.cpp:849-854
+    const float4 pos = __ldg(p.shadow_pos + id);
+    r.org = pos;
+    r.dir.x = fsub(p.vw.light[0], pos.x); r.dir.y = fsub(p.vw.light[1], pos.y);
+    r.dir.z = fsub(p.vw.light[2], pos.z); r.dir.w = fsub(p.vw.light[3], pos.w);
+    r.t_near = 1e-3f;
+    r.t_far = FLT_MAX;
+  } else {
+    const float* q = p.rays + 8 * (size_t)id;
+    r.org = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 1.f);
+    r.dir = make_float4(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5), 0.f);
+    r.t_near = __ldg(q + 6);
+    r.t_far = __ldg(q + 7);
+  }
+  return r;
+}
 
-    uint4 lo, hi;  // the 32-byte pixel record as two 16-byte stores
-    if (best.found) {
-      const MeshDev& m = meshes[best.mesh];
-      const float4* tp = reinterpret_cast<const float4*>(m.tris + best.slot);
+// MODE PRIMARY: closest hit per pixel, raw result into the pixel buffer.
+// MODE SHADOW : any hit (first accepted triangle ends the ray), sets mark bit 0.
+// MODE RAYLIST: qbvh::find_closest_triangle semantics for arbitrary (also negative) t ranges:
+//               closest = smallest |t|, bounds shrink on the side of the hit (qbvh.h:1812-1823).
+template <int MODE, bool STATS>
+__global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) trace_kernel(const TraceParams p) {
+  constexpr bool ANY_HIT = MODE == SHADOW;
+  constexpr bool GENERAL = MODE == RAYLIST;
+  __shared__ uint2 s_stack[STACK_SIZE * GROUPS_PER_BLOCK];
+  const int lane = threadIdx.x & 31;
+  const int c = lane & 7;                               // my child / triangle slot
+  const int gshift = lane & 24;                         // first lane of my group
+  const uint32_t gmask = 0xFFu << gshift;
+  uint2* const stk = s_stack + (threadIdx.x >> 3);      // entry i at stk[i * GROUPS_PER_BLOCK]
+  const uint32_t below = (1u << c) - 1u;
+  uint32_t* const overflow_flag = reinterpret_cast<uint32_t*>(p.stats + 2);
+
+  // ---- number of ray slots ----
+  uint32_t total_pools;   // a pool = 32 consecutive slots
+  uint32_t supers_x = 1;
+  uint32_t list_n = 0;
+  if (MODE == PRIMARY) {
+    const uint32_t tiles_x = (uint32_t)(p.x1 - p.x0 + TILE_W) / TILE_W, tiles_y = (uint32_t)(p.y1 - p.y0 + TILE_H) / TILE_H;
+    supers_x = (tiles_x + SUPER_W - 1) / SUPER_W;
+    total_pools = supers_x * ((tiles_y + SUPER_H - 1) / SUPER_H) * (SUPER_W * SUPER_H);
+  } else {
+    list_n = MODE == SHADOW ? (uint32_t)p.stats[5] : p.nrays;
+    total_pools = (list_n + 31u) / 32u;
+    if (MODE == SHADOW && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.stats + 4, (unsigned long long)list_n);
+  }
+
+  // ---- per-ray state, replicated in the 8 lanes of the group ----
+  bool have_ray = false;
+  uint32_t ray_id = 0;          // PRIMARY: (y << 16) | x; otherwise index into the ray list
+  uint32_t mesh_k = 0;
+  const WideNode* __restrict__ nodes = nullptr;
+  const TriRec* __restrict__ tris = nullptr;
+  float ox = 0.f, oy = 0.f, oz = 0.f, idx = 0.f, idy = 0.f, idz = 0.f;
+  float Sx = 0.f, Sy = 0.f, Sz = 0.f;
+  int kx = 0, ky = 1, kz = 2;
+  uint32_t sel_nx = 0, sel_fx = 0, sel_ny = 0, sel_fy = 0, sel_nz = 0, sel_fz = 0;
+  float t_near = 0.f, t_far = 0.f;
+  float best_t = FLT_MAX, best_u = 0.f, best_v = 0.f;
+  uint32_t best_slot = 0xFFFFFFFFu, best_mesh = 0;
+  uint32_t cur = J3DG_EMPTY_CHILD;
+  int sp = 0;
+  uint32_t pn = 0, pt = 0;
+
+  // ---- warp-uniform pool state ----
+  uint32_t pool_next = 32, pool_id = 0;
+  bool exhausted = false;
+
+  auto pop = [&]() -> uint32_t {
+    while (sp > 0) {
+      --sp;
+      const uint2 e = stk[sp * GROUPS_PER_BLOCK];
+      // entry points of popped boxes that now lie beyond the shrunk interval are skipped
+      if (GENERAL || __uint_as_float(e.y) <= t_far) return e.x;
+    }
+    return J3DG_EMPTY_CHILD;
+  };
+
+  // object-space ray for mesh k (qbvh.h:3358-3359) + intersect_woop_precompute (qbvh.h:4793-4823)
+  auto enter_mesh = [&](const WorldRay& wr, uint32_t k) {
+    const MeshDev& m = p.meshes[k];
+    nodes = m.nodes;
+    tris = m.tris;
+    const float4 d2 = mat_vec(m.cs_inv, wr.dir);
+    const float4 o2 = mat_vec(m.cs_inv, wr.org);
+    ox = o2.x; oy = o2.y; oz = o2.z;
+    const float ax = fabsf(d2.x), ay = fabsf(d2.y), az = fabsf(d2.z);
+    kz = 2;
+    if (ax > ay) { if (ax > az) kz = 0; }
+    else { if (ay > az) kz = 1; }
+    kx = kz == 2 ? 0 : kz + 1;
+    ky = kx == 2 ? 0 : kx + 1;
+    const float dkz = pick(d2.x, d2.y, d2.z, kz);
+    if (dkz < 0.f) { const int t = kx; kx = ky; ky = t; }
+    Sz = fdiv(1.f, dkz);
+    Sx = fmul(pick(d2.x, d2.y, d2.z, kx), Sz);
+    Sy = fmul(pick(d2.x, d2.y, d2.z, ky), Sz);
+    idx = safe_rcp(d2.x); idy = safe_rcp(d2.y); idz = safe_rcp(d2.z);
+    // PRMT selectors: result bytes = {plane byte, 0x00 (byte 6), 0x00 (byte 6), 0x4B (byte 7)} = bits of 2^23 + q
+    sel_nx = 0x7660u | (idx < 0.f ? 3u : 0u); sel_fx = 0x7660u | (idx < 0.f ? 0u : 3u);
+    sel_ny = 0x7660u | (idy < 0.f ? 4u : 1u); sel_fy = 0x7660u | (idy < 0.f ? 1u : 4u);
+    sel_nz = 0x7660u | (idz < 0.f ? 5u : 2u); sel_fz = 0x7660u | (idz < 0.f ? 2u : 5u);
+    sp = 0;
+    cur = m.nt ? 0u : J3DG_EMPTY_CHILD;
+  };
+
+  for (;;) {
+    // =========================== (A) finish rays, move to the next mesh, refill ===========================
+    if (have_ray && cur == J3DG_EMPTY_CHILD) {
+      ++mesh_k;
+      const bool found = best_slot != 0xFFFFFFFFu;
+      if (mesh_k < p.nm && !(ANY_HIT && found)) {
+        const WorldRay wr = world_ray<MODE>(p, ray_id);
+        enter_mesh(wr, mesh_k);
+      } else {
+        // ---- write the result ----
+        if (MODE == PRIMARY) {
+          const int x = (int)(ray_id & 0xffffu), y = (int)(ray_id >> 16);
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)y * p.stride + x);
+          if (c == 0) {  // depth; misses already carry the final record (canvas.cpp:859-866)
+            uint4 lo = make_uint4(0u, 0u, 0u, __float_as_uint(found ? best_t : FLT_MAX));
+            if (STATS) { lo.y = pn; lo.z = pt; }  // the counting pass returns per-pixel costs in the u / v slots
+            dst[0] = lo;
+          } else if (c == 1) {  // raw hit: record slot, barycentrics, mesh index (resolve_kernel finishes it)
+            dst[1] = found ? make_uint4(best_slot, __float_as_uint(best_u), __float_as_uint(best_v), best_mesh) : make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+          }
+        } else if (MODE == SHADOW) {
+          if (found && c == 0) {
+            uint8_t* mark = reinterpret_cast<uint8_t*>(p.out + __ldg(p.shadow_pix + ray_id));
+            *mark = *mark | 1u;  // canvas.cpp:856
+          }
+        } else {
+          if (c == 0) {
+            float* h = p.hits + 4 * (size_t)ray_id;
+            h[0] = found ? best_u : 0.f;
+            h[1] = found ? best_v : 0.f;
+            h[2] = best_t;
+            h[3] = found ? 1.f : 0.f;
+            p.ids[ray_id] = found ? __float_as_uint(p.meshes[best_mesh].tris[best_slot].v0.w) : 0xFFFFFFFFu;
+          }
+        }
+        if (STATS && c == 0) {
+          atomicAdd(p.stats + 0, (unsigned long long)pn);
+          atomicAdd(p.stats + 1, (unsigned long long)pt);
+        }
+        have_ray = false;
+      }
+    }
+    // groups without a ray take the next slots of the warp's pool (warp-uniform loop)
+    uint32_t need = __ballot_sync(0xffffffffu, !have_ray) & 0x01010101u;
+    while (need && !exhausted) {
+      if (pool_next >= 32u) {
+        uint32_t id = 0;
+        if (lane == 0) id = atomicAdd(reinterpret_cast<unsigned int*>(p.stats + 3), 1u);
+        pool_id = __shfl_sync(0xffffffffu, id, 0);
+        pool_next = 0;
+        if (pool_id >= total_pools) { exhausted = true; break; }
+      }
+      const uint32_t rank = __popc(need & ((1u << gshift) - 1u));  // requesting groups before mine
+      const uint32_t slot = pool_next + rank;
+      const bool take = !have_ray && slot < 32u;
+      pool_next += __popc(need);
+      if (take) {
+        bool ok;
+        if (MODE == PRIMARY) {
+          const uint32_t sup = pool_id / (SUPER_W * SUPER_H), in = pool_id % (SUPER_W * SUPER_H);
+          const uint32_t tx = (sup % supers_x) * SUPER_W + (in % SUPER_W), ty = (sup / supers_x) * SUPER_H + (in / SUPER_W);
+          const int x = p.x0 + (int)tx * TILE_W + (int)(slot & (TILE_W - 1));
+          const int y = p.y0 + (int)ty * TILE_H + (int)(slot / TILE_W);
+          ok = x <= p.x1 && y <= p.y1;
+          ray_id = ((uint32_t)y << 16) | (uint32_t)x;
+        } else {
+          ray_id = pool_id * 32u + slot;
+          ok = ray_id < list_n;
+        }
+        if (ok && p.nm == 0u) {  // empty scene: every ray misses
+          if (MODE == PRIMARY) {
+            const int x = (int)(ray_id & 0xffffu), y = (int)(ray_id >> 16);
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)y * p.stride + x);
+            if (c == 0) dst[0] = make_uint4(0u, 0u, 0u, __float_as_uint(FLT_MAX));
+            else if (c == 1) dst[1] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+          } else if (MODE == RAYLIST && c == 0) {
+            float* h = p.hits + 4 * (size_t)ray_id;
+            h[0] = 0.f; h[1] = 0.f; h[2] = FLT_MAX; h[3] = 0.f;
+            p.ids[ray_id] = 0xFFFFFFFFu;
+          }
+          ok = false;
+        }
+        if (ok) {
+          const WorldRay wr = world_ray<MODE>(p, ray_id);
+          t_near = wr.t_near; t_far = wr.t_far;
+          best_t = FLT_MAX; best_u = 0.f; best_v = 0.f; best_slot = 0xFFFFFFFFu; best_mesh = 0;
+          mesh_k = 0;
+          pn = 0; pt = 0;
+          enter_mesh(wr, 0);
+          have_ray = true;
+        }
+      }
+      need = __ballot_sync(0xffffffffu, !have_ray) & 0x01010101u;
+    }
+    if (exhausted && !__any_sync(0xffffffffu, have_ray)) break;
+
+    // =========================== (B) inner node: lane c tests child c ===========================
+    if (have_ray && !(cur & J3DG_LEAF_BIT)) {
+      const char* np = reinterpret_cast<const char*>(nodes + cur);
+      const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(np));          // ox oy oz | nchild      (broadcast)
+      const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(np) + 1);      // sx sy sz | pad         (broadcast)
+      const uint2 q = __ldg(reinterpret_cast<const uint2*>(np + 32) + c);  // my child's quantised box
+      const uint32_t ref = __ldg(reinterpret_cast<const uint32_t*>(np + 96) + c);
+      if (STATS) ++pn;
+      const float sx = __uint_as_float(h1.x) * idx, sy = __uint_as_float(h1.y) * idy, sz = __uint_as_float(h1.z) * idz;
+      const float bx = (__uint_as_float(h0.x) - ox) * idx;
+      const float by = (__uint_as_float(h0.y) - oy) * idy;
+      const float bz = (__uint_as_float(h0.z) - oz) * idz;
+      // byte -> float without the quarter-rate I2F: PRMT builds the bits of 2^23 + q, the subtraction is exact
+      const float qnx = __fsub_rn(__uint_as_float(__byte_perm(q.x, q.y, sel_nx)), 8388608.f);
+      const float qfx = __fsub_rn(__uint_as_float(__byte_perm(q.x, q.y, sel_fx)), 8388608.f);
+      const float qny = __fsub_rn(__uint_as_float(__byte_perm(q.x, q.y, sel_ny)), 8388608.f);
+      const float qfy = __fsub_rn(__uint_as_float(__byte_perm(q.x, q.y, sel_fy)), 8388608.f);
+      const float qnz = __fsub_rn(__uint_as_float(__byte_perm(q.x, q.y, sel_nz)), 8388608.f);
+      const float qfz = __fsub_rn(__uint_as_float(__byte_perm(q.x, q.y, sel_fz)), 8388608.f);
+      float tmin = fmaxf(fmaxf(fmaf(qnx, sx, bx), fmaf(qny, sy, by)), fmaxf(fmaf(qnz, sz, bz), t_near));
+      float tmax = fminf(fminf(fmaf(qfx, sx, bx), fmaf(qfy, sy, by)), fminf(fmaf(qfz, sz, bz), t_far));
+      // conservative padding against rounding of the slab arithmetic
+      tmin = fmaf(-fabsf(tmin), 2e-6f, tmin);
+      tmax = fmaf(fabsf(tmax), 2e-6f, tmax);
+      const bool hit = tmin <= tmax;  // empty slots have inverted boxes and never pass
+      const uint32_t hm = (__ballot_sync(gmask, hit) >> gshift) & 0xFFu;
+      if (hm == 0u) {
+        cur = pop();
+      } else {
+        const float key = hit ? tmin : FLT_MAX;
+        const float nearest = group_min(gmask, key);
+        const uint32_t nm8 = (__ballot_sync(gmask, hit && key == nearest) >> gshift) & 0xFFu;
+        const int near_lane = __ffs(nm8) - 1;
+        const uint32_t others = hm & ~(1u << near_lane);
+        if (hit && c != near_lane) {
+          const int pos = sp + __popc(others & below);
+          if (pos < STACK_SIZE) stk[pos * GROUPS_PER_BLOCK] = make_uint2(ref, __float_as_uint(tmin));
+          else *overflow_flag = 1u;
+        }
+        sp = min(sp + __popc(others), STACK_SIZE);
+        cur = __shfl_sync(gmask, ref, gshift + near_lane);
+        __syncwarp(gmask);  // the pushes must be visible to whichever lane pops them
+      }
+    }
+
+    // =========================== (C) leaf: lane c tests triangle c ===========================
+    if (have_ray && (cur & J3DG_LEAF_BIT) && cur != J3DG_EMPTY_CHILD) {
+      const uint32_t first = cur & J3DG_LEAF_FIRST_MASK;
+      const float4* tp = reinterpret_cast<const float4*>(tris + first + c);
+      const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+      const uint32_t lm = (__ballot_sync(gmask, __float_as_uint(v1.w) != 0u) >> gshift) & 0xFFu;
+      const int last = lm ? __ffs(lm) - 1 : GROUP - 1;
+      bool hit = c <= last;
+      if (STATS) pt += (uint32_t)(last + 1);
+      float t = 0.f, u = 0.f, v = 0.f;
+      if (hit) {  // one lane of intersect_woop (qbvh.h:4825-4869); 1/det is correctly rounded instead of rcpps + NR
+        const float Ax_ = fsub(v0.x, ox), Ay_ = fsub(v0.y, oy), Az_ = fsub(v0.z, oz);
+        const float Bx_ = fsub(v1.x, ox), By_ = fsub(v1.y, oy), Bz_ = fsub(v1.z, oz);
+        const float Cx_ = fsub(v2.x, ox), Cy_ = fsub(v2.y, oy), Cz_ = fsub(v2.z, oz);
+        const float Akz = pick(Ax_, Ay_, Az_, kz), Bkz = pick(Bx_, By_, Bz_, kz), Ckz = pick(Cx_, Cy_, Cz_, kz);
+        const float Ax = fsub(pick(Ax_, Ay_, Az_, kx), fmul(Sx, Akz));
+        const float Ay = fsub(pick(Ax_, Ay_, Az_, ky), fmul(Sy, Akz));
+        const float Bx = fsub(pick(Bx_, By_, Bz_, kx), fmul(Sx, Bkz));
+        const float By = fsub(pick(Bx_, By_, Bz_, ky), fmul(Sy, Bkz));
+        const float Cx = fsub(pick(Cx_, Cy_, Cz_, kx), fmul(Sx, Ckz));
+        const float Cy = fsub(pick(Cx_, Cy_, Cz_, ky), fmul(Sy, Ckz));
+        const float U = fsub(fmul(Cx, By), fmul(Cy, Bx));
+        const float V = fsub(fmul(Ax, Cy), fmul(Ay, Cx));
+        const float W = fsub(fmul(Bx, Ay), fmul(By, Ax));
+        hit = ((U <= 0.f) && (V <= 0.f) && (W <= 0.f)) || ((U >= 0.f) && (V >= 0.f) && (W >= 0.f));
+        const float det = fadd(fadd(U, V), W);
+        hit = hit && (det != 0.f);
+        if (hit) {
+          const float inv_det = fdiv(1.f, det);
+          const float Az = fmul(Sz, Akz), Bz = fmul(Sz, Bkz), Cz = fmul(Sz, Ckz);
+          const float T = fadd(fadd(fmul(U, Az), fmul(V, Bz)), fmul(W, Cz));
+          t = fmul(T, inv_det);
+          hit = (t_far > t) && (t > t_near);
+          u = fmul(V, inv_det);
+          v = fmul(W, inv_det);
+        }
+      }
+      const float key = hit ? (GENERAL ? fabsf(t) : t) : FLT_MAX;
+      const uint32_t anyhit = __ballot_sync(gmask, hit) & gmask;
+      bool done = false;
+      if (anyhit) {
+        const float nearest = group_min(gmask, key);
+        const uint32_t wm = (__ballot_sync(gmask, hit && key == nearest) >> gshift) & 0xFFu;
+        const int win = __ffs(wm) - 1;  // lowest slot wins ties, like the sequential strict-less update
+        const float wt = __shfl_sync(gmask, t, gshift + win);
+        const float wu = __shfl_sync(gmask, u, gshift + win);
+        const float wv = __shfl_sync(gmask, v, gshift + win);
+        const bool closer = GENERAL ? (nearest < fabsf(best_t)) : (wt < best_t);
+        if (closer) {
+          best_t = wt; best_u = wu; best_v = wv; best_slot = first + (uint32_t)win; best_mesh = mesh_k;
+          if (!GENERAL || wt > 0.f) t_far = wt; else t_near = wt;
+          done = ANY_HIT;
+        }
+      }
+      if (done) { cur = J3DG_EMPTY_CHILD; sp = 0; }
+      else cur = pop();
+    }
+  }
+}
+
+// ---- hit -> pixel record (canvas.cpp:788-834) + shadow ray generation (836-854) --------------------------
+// One thread per pixel, one warp per 8x4 tile (the order the trace kernels use).  Misses already hold
+// their final record.  Shadow rays of hit pixels are appended to a list with one atomic per warp.
+__global__ void __launch_bounds__(256) resolve_kernel(const MeshDev* __restrict__ meshes, ViewDev vw, int x0, int y0, int x1, int y1,
+                                                       j3dg_pixel* __restrict__ out, uint32_t stride, float4* __restrict__ shadow_pos,
+                                                       uint32_t* __restrict__ shadow_pix, unsigned long long* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t tiles_x = (uint32_t)(x1 - x0 + TILE_W) / TILE_W;
+  const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int x = x0 + (int)(tile % tiles_x) * TILE_W + (lane & (TILE_W - 1));
+  const int y = y0 + (int)(tile / tiles_x) * TILE_H + (lane / TILE_W);
+  bool shadow_ray = false;
+  float4 pos = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (x <= x1 && y <= y1) {
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)y * stride + x);
+    const uint4 raw = dst[1];
+    if (raw.x != 0xFFFFFFFFu) {
+      const float t = __uint_as_float(dst[0].w);
+      const MeshDev& m = meshes[raw.w];
+      const float4* tp = reinterpret_cast<const float4*>(m.tris + raw.x);
       const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
       const uint32_t tri = __float_as_uint(v0.w);
       // compute_triangle_normals (geometry.h:2561-2578; vec.h:477-487, 531-536)
@@ -318,7 +440,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) cast_kern
       float4 n = mat_vec(vw.cs_inv, make_float4(nx, ny, nz, 0.f));
       n = mat_vec(m.cs, n);
       uint32_t mark = 0, r = 0, g = 0, b = 0;
-      const float bu = best.u, bv = best.v;
+      const float bu = __uint_as_float(raw.y), bv = __uint_as_float(raw.z);
       const float k = fsub(fsub(1.f, bu), bv);
       if ((vw.flags & J3DG_TEXTURED) && m.uv != nullptr && m.texture != nullptr) {  // canvas.cpp:803-820
         const float* uvc = m.uv + 6 * (size_t)tri;
@@ -346,89 +468,34 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) cast_kern
         b = (uint32_t)__float2int_rz(fmul(cb, 255.f)) & 0xffu;
         mark |= 2u;
       }
-      if (vw.flags & J3DG_SHADOW) {  // canvas.cpp:836-857
+      if (vw.flags & J3DG_SHADOW) {  // canvas.cpp:836-848
         const float4 V0 = transform_point(m.cs, make_float4(v0.x, v0.y, v0.z, 1.f));
         const float4 V1 = transform_point(m.cs, make_float4(v1.x, v1.y, v1.z, 1.f));
         const float4 V2 = transform_point(m.cs, make_float4(v2.x, v2.y, v2.z, 1.f));
-        float4 pos, ld;
         pos.x = fadd(fadd(fmul(V0.x, k), fmul(bu, V1.x)), fmul(bv, V2.x));
         pos.y = fadd(fadd(fmul(V0.y, k), fmul(bu, V1.y)), fmul(bv, V2.y));
         pos.z = fadd(fadd(fmul(V0.z, k), fmul(bu, V1.z)), fmul(bv, V2.z));
         pos.w = fadd(fadd(fmul(V0.w, k), fmul(bu, V1.w)), fmul(bv, V2.w));
-        ld.x = fsub(vw.light[0], pos.x); ld.y = fsub(vw.light[1], pos.y);
-        ld.z = fsub(vw.light[2], pos.z); ld.w = fsub(vw.light[3], pos.w);
-        Best sh;
-        uint32_t dn = 0, dt = 0;
-        trace_scene<true, false>(meshes, nm, pos, ld, 1e-3f, FLT_MAX, sh, dn, dt, (uint32_t*)(stats + 2), stk);
-        if (sh.found) mark |= 1u;
+        shadow_ray = true;
       }
-      lo.x = mark | (r << 8) | (g << 16) | (b << 24);
-      lo.y = __float_as_uint(n.x);
-      lo.z = __float_as_uint(n.y);
-      lo.w = __float_as_uint(best.t);
-      hi.x = tri;
-      hi.y = __float_as_uint(bu);
-      hi.z = __float_as_uint(bv);
-      hi.w = m.db_id;
-    } else {  // canvas.cpp:859-866
-      lo = make_uint4(0u, 0u, 0u, __float_as_uint(FLT_MAX));
-      hi = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
-    }
-    if (STATS) {  // the counting pass returns per-pixel costs in the u / v slots, tile start / end time (ns) in the barycentric slots
-      __syncwarp();
-      unsigned long long tile_t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tile_t1));
-      lo.y = pn; lo.z = pt; hi.y = (uint32_t)tile_t0; hi.z = (uint32_t)tile_t1;
-    }
-    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)y * stride + x);
-    dst[0] = lo;
-    dst[1] = hi;
-  }
-  if (STATS) {
-    for (int o = 16; o; o >>= 1) {
-      sn += __shfl_xor_sync(0xffffffffu, sn, o);
-      st += __shfl_xor_sync(0xffffffffu, st, o);
-    }
-    if (lane == 0) {
-      atomicAdd(stats + 0, (unsigned long long)sn);
-      atomicAdd(stats + 1, (unsigned long long)st);
+      dst[0] = make_uint4(mark | (r << 8) | (g << 16) | (b << 24), __float_as_uint(n.x), __float_as_uint(n.y), __float_as_uint(t));
+      dst[1] = make_uint4(tri, raw.y, raw.z, m.db_id);
     }
   }
-}
-
-// Counts hit pixels (rays accounting for shadow rays) — tiny reduction over the db_id field.
-__global__ void __launch_bounds__(256) count_hits_kernel(const j3dg_pixel* __restrict__ px, uint32_t stride, int x0, int y0, int w, int h,
-                                                          unsigned long long* __restrict__ counter) {
-  uint32_t c = 0;
-  const size_t total = (size_t)w * h;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int x = x0 + (int)(i % w), y = y0 + (int)(i / w);
-    c += px[(size_t)y * stride + x].object_id != 0xFFFFFFFFu;
+  if (vw.flags & J3DG_SHADOW) {  // warp-uniform
+    const uint32_t votes = __ballot_sync(0xffffffffu, shadow_ray);
+    if (votes) {
+      const int leader = __ffs(votes) - 1;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(stats + 5, (unsigned long long)__popc(votes));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (shadow_ray) {
+        const uint32_t i = (uint32_t)base + __popc(votes & ((1u << lane) - 1u));
+        shadow_pos[i] = pos;
+        shadow_pix[i] = (uint32_t)((size_t)y * stride + x);
+      }
+    }
   }
-  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(counter, (unsigned long long)c);
-}
-
-__global__ void __launch_bounds__(BLOCK_THREADS) find_closest_kernel(MeshDev m, const float* __restrict__ rays, uint32_t n,
-                                                            float* __restrict__ hits, uint32_t* __restrict__ ids, uint32_t* overflow) {
-  __shared__ uint2 s_stack[SM_STACK * BLOCK_THREADS];
-  Stack stk;
-  stk.sm = s_stack + threadIdx.x;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float* r = rays + 8 * (size_t)i;
-  float t_near = r[6], t_far = r[7];
-  Best best;
-  best.found = false;
-  best.t = FLT_MAX;
-  uint32_t sn = 0, st = 0;
-  traverse_mesh<false, true, false>(m, 0, r[0], r[1], r[2], r[3], r[4], r[5], t_near, t_far, best, sn, st, overflow, stk);
-  float* h = hits + 4 * (size_t)i;
-  h[0] = best.found ? best.u : 0.f;
-  h[1] = best.found ? best.v : 0.f;
-  h[2] = best.t;
-  h[3] = best.found ? 1.f : 0.f;
-  ids[i] = best.found ? __float_as_uint(m.tris[best.slot].v0.w) : 0xFFFFFFFFu;
 }
 
 void fill_mesh_dev(const j3dg_mesh* m, MeshDev& d) {
@@ -458,6 +525,17 @@ void host_mat_vec(const float* m, const float* v, float* out) {
   }
 }
 
+// persistent grid: fill every SM once, never more blocks than there is work
+template <class K>
+int persistent_grid(j3dg_ctx* ctx, K kernel, long long pools, int* grid) {
+  int nb = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, BLOCK_THREADS, 0);
+  if (e != cudaSuccess) return j3dg_cuda_fail(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor", __FILE__, __LINE__);
+  const int warps_per_block = BLOCK_THREADS / 32;
+  *grid = (int)std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * std::max(nb, 1), (pools + warps_per_block - 1) / warps_per_block));
+  return J3DG_OK;
+}
+
 }  // namespace
 
 void j3dg_make_view_dev(const j3dg_view* v, ViewDev& d) {
@@ -479,6 +557,7 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
                      int x0, int y0, int x1, int y1, j3dg_pixel* d_pixels, uint32_t stride, bool stats) {
   const int w = (int)view->width, h = (int)view->height;
   if (w <= 0 || h <= 0) return J3DG_OK;
+  if (w > 65535 || h > 65535) { j3dg_set_error(ctx, "j3dg_cast: canvas larger than 65535 pixels on a side"); return J3DG_EINVAL; }
   // canvas.cpp:682-698
   x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::max(x1, 0); y1 = std::max(y1, 0);
   if (x0 >= w) x0 = w - 1; if (y0 >= h) y0 = h - 1; if (x1 >= w) x1 = w - 1; if (y1 >= h) y1 = h - 1;
@@ -497,34 +576,54 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
     if (rc != J3DG_OK) return rc;
   }
   if (used) CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_meshes, host.data(), sizeof(MeshDev) * used, cudaMemcpyHostToDevice, ctx->stream));
-  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));  // [4] accumulates until reset
-  ViewDev vd;
-  j3dg_make_view_dev(view, vd);
+  const bool shadows = (view->flags & J3DG_SHADOW) && used && !stats;
   const int rw = x1 - x0 + 1, rh = y1 - y0 + 1;
-  // persistent grid: fill every SM once, never more blocks than there are tiles
-  static int blocks_per_sm[2] = {0, 0};
-  if (!blocks_per_sm[stats ? 1 : 0]) {
-    int nb = 0;
-    cudaError_t e = stats ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cast_kernel<true>, BLOCK_THREADS, 0)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cast_kernel<false>, BLOCK_THREADS, 0);
-    if (e != cudaSuccess) return j3dg_cuda_fail(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor", __FILE__, __LINE__);
-    blocks_per_sm[stats ? 1 : 0] = std::max(nb, 1);
+  const size_t shadow_pix_off = ((size_t)rw * rh * sizeof(float4) + 255) & ~(size_t)255;
+  if (shadows) {  // one shadow ray per hit pixel at most
+    int rc = j3dg_reserve(ctx, &ctx->d_shadow, &ctx->shadow_cap, shadow_pix_off + (size_t)rw * rh * sizeof(uint32_t));
+    if (rc != J3DG_OK) return rc;
   }
+  // [0..3] per-launch counters, [4] accumulates until the timings are reset, [5] shadow list length
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats + 5, 0, sizeof(unsigned long long), ctx->stream));
+  TraceParams tp = {};
+  tp.meshes = ctx->d_meshes;
+  tp.nm = used;
+  j3dg_make_view_dev(view, tp.vw);
+  if (!shadows) tp.vw.flags &= ~J3DG_SHADOW;
+  tp.x0 = x0; tp.y0 = y0; tp.x1 = x1; tp.y1 = y1;
+  tp.out = d_pixels;
+  tp.stride = stride;
+  tp.stats = ctx->d_stats;
+  tp.shadow_pos = (const float4*)ctx->d_shadow;
+  tp.shadow_pix = (const uint32_t*)((const char*)ctx->d_shadow + shadow_pix_off);
   const long long ntiles = (long long)((rw + TILE_W - 1) / TILE_W) * ((rh + TILE_H - 1) / TILE_H);
-  const int warps_per_block = BLOCK_THREADS / 32;
-  const int grid = (int)std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * blocks_per_sm[stats ? 1 : 0],
-                                                                   (ntiles + warps_per_block - 1) / warps_per_block));
+  int grid = 1;
   { int rc = j3dg_stage_begin(ctx, 0); if (rc != J3DG_OK) return rc; }
-  if (stats)
-    cast_kernel<true><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(ctx->d_meshes, used, vd, x0, y0, x1, y1, d_pixels, stride, ctx->d_stats);
-  else
-    cast_kernel<false><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(ctx->d_meshes, used, vd, x0, y0, x1, y1, d_pixels, stride, ctx->d_stats);
+  if (stats) {
+    int rc = persistent_grid(ctx, trace_kernel<PRIMARY, true>, ntiles, &grid);
+    if (rc != J3DG_OK) return rc;
+    trace_kernel<PRIMARY, true><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
+  } else {
+    int rc = persistent_grid(ctx, trace_kernel<PRIMARY, false>, ntiles, &grid);
+    if (rc != J3DG_OK) return rc;
+    trace_kernel<PRIMARY, false><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
+  }
   KERNEL_CHECK(ctx);
-  { int rc = j3dg_stage_end(ctx, 0); if (rc != J3DG_OK) return rc; }
-  if (ctx->profiling && (view->flags & J3DG_SHADOW)) {  // one shadow ray per hit pixel: count them
-    count_hits_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_pixels, stride, x0, y0, rw, rh, ctx->d_stats + 4);
+  if (used && !stats) {
+    const uint32_t warps = 256 / 32;
+    resolve_kernel<<<(uint32_t)((ntiles + warps - 1) / warps), 256, 0, ctx->stream>>>(ctx->d_meshes, tp.vw, x0, y0, x1, y1, d_pixels, stride,
+                                                                                     (float4*)tp.shadow_pos, (uint32_t*)tp.shadow_pix, ctx->d_stats);
     KERNEL_CHECK(ctx);
   }
+  if (shadows) {
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats + 3, 0, sizeof(unsigned long long), ctx->stream));  // pool counter of the second launch
+    int rc = persistent_grid(ctx, trace_kernel<SHADOW, false>, ((long long)rw * rh + 31) / 32, &grid);
+    if (rc != J3DG_OK) return rc;
+    trace_kernel<SHADOW, false><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
+    KERNEL_CHECK(ctx);
+  }
+  { int rc = j3dg_stage_end(ctx, 0); if (rc != J3DG_OK) return rc; }
   ctx->rays_primary += (uint64_t)rw * rh;  // shadow rays (d_stats[4]) are added when the timings are read
   return J3DG_OK;
 }
@@ -534,8 +633,24 @@ int j3dg_launch_find_closest(j3dg_mesh* m, const float* d_rays, uint32_t n, floa
   if (!n) return J3DG_OK;
   MeshDev d;
   fill_mesh_dev(m, d);
+  {
+    void* p = ctx->d_meshes;
+    int rc = j3dg_reserve(ctx, &p, &ctx->meshes_cap, sizeof(MeshDev));
+    ctx->d_meshes = (MeshDev*)p;
+    if (rc != J3DG_OK) return rc;
+  }
+  CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_meshes, &d, sizeof(MeshDev), cudaMemcpyHostToDevice, ctx->stream));
+  CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // `d` lives on this stack frame
   CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
-  find_closest_kernel<<<(n + BLOCK_THREADS - 1) / BLOCK_THREADS, BLOCK_THREADS, 0, ctx->stream>>>(d, d_rays, n, d_hits, d_ids, (uint32_t*)(ctx->d_stats + 2));
+  TraceParams tp = {};
+  tp.meshes = ctx->d_meshes;
+  tp.nm = (d.nodes && d.nt) ? 1u : 0u;
+  tp.stats = ctx->d_stats;
+  tp.rays = d_rays; tp.hits = d_hits; tp.ids = d_ids; tp.nrays = n;
+  int grid = 1;
+  int rc = persistent_grid(ctx, trace_kernel<RAYLIST, false>, ((long long)n + 31) / 32, &grid);
+  if (rc != J3DG_OK) return rc;
+  trace_kernel<RAYLIST, false><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
   KERNEL_CHECK(ctx);
   return J3DG_OK;
 }

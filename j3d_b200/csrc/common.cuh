@@ -15,33 +15,40 @@
 // Device data layout (DESIGN.md "Data layout in HBM")
 // ---------------------------------------------------------------------------------------
 
-// 8-wide BVH node, 96 bytes = exactly three 32-byte sectors, 32-byte aligned.
-// Child boxes are quantised to 8 bits per plane relative to (origin, 2^exp) — decoded box
-// fl(origin + q * 2^e) is guaranteed by the builder to contain the child's true box.
-// child[i]: bit31 = 0 -> index of an inner node; bit31 = 1 -> leaf:
-//           bits 29..30 = triangle count - 1 (1..4), bits 0..28 = first triangle record.
+// 8-wide BVH node, 128 bytes = exactly one L1/L2 cache line, 128-byte aligned.  The layout is
+// CHILD-MAJOR because the traversal kernel maps the 8 children of a node onto 8 lanes of a warp
+// (one ray per 8-lane group): lane c reads its own 8-byte quantised box and its own child
+// reference, the two 16-byte headers are broadcast loads.
+// Child boxes are quantised to 8 bits per plane relative to (origin, scale): the decoded plane
+// fl(origin + q * scale) is guaranteed by the builder to contain the child's true box (scale is a
+// power of two, so q * scale is exact).
+// box[c] = { qlo.x, qlo.y, qlo.z, qhi.x, qhi.y, qhi.z, 0x00, 0x4B }: the two constant bytes let a
+//          single PRMT assemble the float 2^23 + q from any plane byte (byte 7 -> exponent, byte 6 -> zeros).
+// child[c]: bit31 = 0 -> index of an inner node; bit31 = 1 -> leaf, bits 0..30 = first triangle
+//           record; a leaf is 1..8 consecutive records, the last one carries TriRec::last != 0.
 // Empty slots have an inverted box (qlo = 255, qhi = 0) and child = J3DG_EMPTY_CHILD.
-struct __align__(32) WideNode {
+struct __align__(128) WideNode {
   float ox, oy, oz;      // quantisation origin = node box minimum
-  uint8_t ex, ey, ez;    // biased float exponents: scale_axis = uint_as_float(e << 23)
-  uint8_t nchild;        // number of used slots (diagnostic)
-  uint8_t qlo[3][8];     // [axis][slot]
-  uint8_t qhi[3][8];
+  uint32_t nchild;       // number of used slots (diagnostic)
+  float sx, sy, sz;      // quantisation step per axis (a power of two)
+  uint32_t pad0;
+  uint8_t box[8][8];     // [slot][qlo.xyz, qhi.xyz, 0x00, 0x4B]
   uint32_t child[8];
 };
-static_assert(sizeof(WideNode) == 96, "WideNode must be 96 bytes");
+static_assert(sizeof(WideNode) == 128, "WideNode must be 128 bytes");
 
 #define J3DG_LEAF_BIT 0x80000000u
 #define J3DG_EMPTY_CHILD 0xFFFFFFFFu
-#define J3DG_MAX_LEAF 4
-#define J3DG_LEAF_FIRST_MASK 0x1FFFFFFFu
+#define J3DG_MAX_LEAF 8
+#define J3DG_LEAF_FIRST_MASK 0x7FFFFFFFu
+#define J3DG_TRI_PAD 8   // records allocated past the end: a group always loads 8 consecutive records
 
 // Pre-gathered triangle record, 48 bytes, in Morton-sorted order so that every BVH subtree
 // owns a contiguous range.  Raw vertex positions (the Woop test needs v - origin exactly as
-// the reference computes it); .w lanes carry the original triangle index.
+// the reference computes it); v0.w carries the original triangle index, v1.w the end-of-leaf flag.
 struct __align__(16) TriRec {
   float4 v0;  // xyz, w = __uint_as_float(original triangle index)
-  float4 v1;  // xyz, w unused (0)
+  float4 v1;  // xyz, w = __uint_as_float(1) on the last record of a leaf, else 0
   float4 v2;  // xyz, w unused (0)
 };
 static_assert(sizeof(TriRec) == 48, "TriRec must be 48 bytes");
@@ -125,6 +132,7 @@ struct j3dg_ctx {
   MeshDev* d_meshes = nullptr; size_t meshes_cap = 0;
   unsigned long long* d_stats = nullptr;
   void* d_misc = nullptr; size_t misc_cap = 0;
+  void* d_shadow = nullptr; size_t shadow_cap = 0;   // shadow ray list (origins + pixel offsets)
 };
 
 void j3dg_set_error(j3dg_ctx* ctx, const std::string& msg);
