@@ -110,6 +110,11 @@ int j3dg_ctx_timings(j3dg_ctx* ctx, j3dg_timings* out, int reset);
 /* Per-stage CUDA-event timing on/off (default on; off removes the event records). */
 int j3dg_ctx_set_profiling(j3dg_ctx* ctx, int enabled);
 
+/* Performance tuning of the ray cast; the rendered result does not depend on it (up to exact ties).
+ * lane_budget: node visits a ray may spend in the one-ray-per-lane kernel before it is handed to the
+ * one-ray-per-8-lanes kernel (0 = default); cast_algo: 0 = hybrid (default), 1 = 8-lane kernel only. */
+int j3dg_ctx_set_tuning(j3dg_ctx* ctx, uint32_t lane_budget, int cast_algo);
+
 /* ---- BVH build: replaces `new qbvh(triangles, vertices)` + compute_triangle_normals
  *      + compute_bb in add_object (j3d/scene.cpp:8-25; jtk/qbvh.h:1679-1686). -------
  * vertices: nv x 3 float (jtk::vec3<float>), triangles: nt x 3 uint32.

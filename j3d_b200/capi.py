@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
         L.j3dg_render_frame.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(_vp), _u32, C.POINTER(View),
                                         _vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp]
         L.j3dg_ctx_set_matcap.argtypes = [_vp, _vp, _u32, _u32, _u32, _u32]
+        L.j3dg_ctx_set_tuning.argtypes = [_vp, _u32, C.c_int]
         L.j3dg_cast_stats.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(View), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.j3dg_cast_cost_image.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(View), _vp, _vp]
         _lib = L
@@ -345,6 +346,9 @@ class Context:
         self._check(self._L.j3dg_render_frame(self._h, self._handles(meshes), len(meshes), self._handles(clouds), len(clouds),
                                               C.byref(view), _ptr(matcap), mw, mh, mw, cavity, bg_top, bg_bottom,
                                               _ptr(pixels_out), _ptr(rgba_out)), "j3dg_render_frame")
+
+    def set_tuning(self, lane_budget: int = 0, cast_algo: int = 0):
+        self._check(self._L.j3dg_ctx_set_tuning(self._h, lane_budget, cast_algo), "j3dg_ctx_set_tuning")
 
     def cast_stats(self, meshes, view: View):
         a, b = C.c_double(), C.c_double()

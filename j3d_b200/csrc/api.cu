@@ -142,12 +142,14 @@ J3DG_API int j3dg_ctx_create(int device, j3dg_ctx** out) {
   }
   ctx->stream = ctx->own_stream;
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
-  if (cudaMalloc((void**)&ctx->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+  if (cudaMalloc((void**)&ctx->d_stats, 16 * sizeof(unsigned long long)) != cudaSuccess) {
     j3dg_set_error(nullptr, "cannot allocate device memory");
     delete ctx;
     return J3DG_ENOMEM;
   }
-  cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long));
+  cudaMemset(ctx->d_stats, 0, 16 * sizeof(unsigned long long));
+  if (const char* e = getenv("J3DG_LANE_BUDGET")) ctx->lane_budget = (uint32_t)std::max(1, atoi(e));  // developer tuning knobs
+  if (const char* e = getenv("J3DG_CAST_ALGO")) ctx->cast_algo = strcmp(e, "group") == 0 ? 1 : 0;
   *out = ctx;
   return J3DG_OK;
 }
@@ -157,7 +159,7 @@ J3DG_API void j3dg_ctx_destroy(j3dg_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->d_pixels); cudaFree(ctx->d_pixels_in); cudaFree(ctx->d_rgba); cudaFree(ctx->d_bg); cudaFree(ctx->d_packed);
-  cudaFree(ctx->d_matcap); cudaFree(ctx->d_meshes); cudaFree(ctx->d_stats); cudaFree(ctx->d_misc); cudaFree(ctx->d_shadow);
+  cudaFree(ctx->d_matcap); cudaFree(ctx->d_meshes); cudaFree(ctx->d_stats); cudaFree(ctx->d_misc); cudaFree(ctx->d_shadow); cudaFree(ctx->d_hard);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   for (auto& r : ctx->ring) { for (auto e : r.a) cudaEventDestroy(e); for (auto e : r.b) cudaEventDestroy(e); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -188,6 +190,13 @@ J3DG_API int j3dg_ctx_synchronize(j3dg_ctx* ctx) {
 J3DG_API int j3dg_ctx_set_profiling(j3dg_ctx* ctx, int enabled) {
   if (!ctx) return J3DG_EINVAL;
   ctx->profiling = enabled != 0;
+  return J3DG_OK;
+}
+
+J3DG_API int j3dg_ctx_set_tuning(j3dg_ctx* ctx, uint32_t lane_budget, int cast_algo) {
+  if (!ctx || cast_algo < 0 || cast_algo > 1) return J3DG_EINVAL;
+  ctx->lane_budget = lane_budget ? lane_budget : 32u;
+  ctx->cast_algo = cast_algo;
   return J3DG_OK;
 }
 

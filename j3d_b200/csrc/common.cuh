@@ -133,6 +133,9 @@ struct j3dg_ctx {
   unsigned long long* d_stats = nullptr;
   void* d_misc = nullptr; size_t misc_cap = 0;
   void* d_shadow = nullptr; size_t shadow_cap = 0;   // shadow ray list (origins + pixel offsets)
+  void* d_hard = nullptr; size_t hard_cap = 0;       // hard-ray list handed from the lane kernel to the group kernel
+  uint32_t lane_budget = 32;                         // node visits per ray before the lane kernel evicts it (J3DG_LANE_BUDGET)
+  int cast_algo = 0;                                 // 0 hybrid (lane + group), 1 group kernel only (J3DG_CAST_ALGO=group)
 };
 
 void j3dg_set_error(j3dg_ctx* ctx, const std::string& msg);

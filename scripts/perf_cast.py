@@ -28,6 +28,7 @@ for k in range(nframes):
     tm = ctx.timings(reset=True)
     cast.append(tm.cast_ms)
 ctx.render_frame([m], [], j.orbit_view(v0, 30.0), pixels_out=px, rgba_out=rgba)
+ctx.synchronize()  # the library runs on its own stream
 p = px.cpu().numpy().view(j.PIXEL_DTYPE).reshape(H, W)
 hit = p["object_id"] != 0xFFFFFFFF
 chk = zlib.crc32(p["object_id"].tobytes()) ^ zlib.crc32(p["depth"].tobytes())

@@ -80,6 +80,32 @@ def test_cast_matches_oracle(ctx, oracle, f, w, h, flags, angle, colors):
     m.destroy(); om.destroy()
 
 
+@pytest.mark.parametrize("budget,algo", [(1, 0), (3, 0), (8, 0), (0, 1)])
+def test_cast_independent_of_tuning(ctx, oracle, budget, algo):
+    """Both traversal kernels and the hard-ray hand-over between them: a lane budget of 1 sends every ray
+    that meets the mesh through the 8-lanes-per-ray kernel; algo 1 uses that kernel alone.  Shadow rays
+    take the same two paths.  The result must match the oracle either way."""
+    verts, tris, vc, v = _scene(40, 640, 360, j.DEFAULT_FLAGS | j.SHADOW, 33.0, True)
+    m = ctx.mesh_create(verts, tris, vcolors=vc)
+    try:
+        ctx.set_tuning(1 << 30, 0)
+        base = ctx.cast([m], v)
+        ctx.set_tuning(budget, algo)
+        got = ctx.cast([m], v)
+    finally:
+        ctx.set_tuning(0, 0)
+    om = oracle.mesh(verts, tris, vcolors=vc)
+    want = oracle.cast([om], v)
+    st = compare_pixels(got, want, tag=f"budget={budget} algo={algo}")
+    assert st["hits"] > 0
+    # against the lane kernel alone: the same closest hits (exact ties may pick the other triangle)
+    assert (got["object_id"] == base["object_id"]).mean() >= 0.9999
+    same = got["object_id"] == base["object_id"]
+    assert (got["depth"][same] == base["depth"][same]).all()
+    assert (got["mark"][same] == base["mark"][same]).mean() >= 0.9999
+    m.destroy(); om.destroy()
+
+
 def test_cast_two_objects_textured(ctx, oracle):
     w, h = 640, 360
     verts, tris = j.icosphere(30)
