@@ -180,6 +180,17 @@ int j3dg_render_frame(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nr_of_me
                       const uint32_t* matcap, uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity_clr,
                       uint32_t bg_top, uint32_t bg_bottom,
                       j3dg_pixel* pixels_out, uint32_t* rgba_out);
+/* Pipelined variant for sweeps (orbit renders, turntables): submit enqueues the frame and returns;
+ * the device->host copies run on a second stream, the device canvases are double-buffered, so the
+ * copy of frame k overlaps the kernels of frame k+1.  pixels_out / rgba_out are HOST buffers
+ * (page-locked for real overlap), nullable; each must stay untouched until the matching
+ * j3dg_frame_wait returns.  At most two frames may be in flight; wait completes them in order. */
+int j3dg_frame_submit(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nr_of_meshes,
+                      j3dg_cloud* const* clouds, uint32_t nr_of_clouds, const j3dg_view* view,
+                      const uint32_t* matcap, uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity_clr,
+                      uint32_t bg_top, uint32_t bg_bottom,
+                      j3dg_pixel* pixels_out, uint32_t* rgba_out);
+int j3dg_frame_wait(j3dg_ctx* ctx);
 /* Upload a matcap once and reuse it (frames then pass matcap == NULL). */
 int j3dg_ctx_set_matcap(j3dg_ctx* ctx, const uint32_t* matcap, uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity_clr);
 

@@ -112,6 +112,8 @@ def lib() -> C.CDLL:
         L.j3dg_splat.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(View), _vp, _vp, _u32, _vp, _u32]
         L.j3dg_render_frame.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(_vp), _u32, C.POINTER(View),
                                         _vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp]
+        L.j3dg_frame_submit.argtypes = L.j3dg_render_frame.argtypes
+        L.j3dg_frame_wait.argtypes = [_vp]
         L.j3dg_ctx_set_matcap.argtypes = [_vp, _vp, _u32, _u32, _u32, _u32]
         L.j3dg_ctx_set_tuning.argtypes = [_vp, _u32, C.c_int]
         L.j3dg_cast_stats.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(View), C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -346,6 +348,19 @@ class Context:
         self._check(self._L.j3dg_render_frame(self._h, self._handles(meshes), len(meshes), self._handles(clouds), len(clouds),
                                               C.byref(view), _ptr(matcap), mw, mh, mw, cavity, bg_top, bg_bottom,
                                               _ptr(pixels_out), _ptr(rgba_out)), "j3dg_render_frame")
+
+    def frame_submit(self, meshes, clouds, view: View, matcap=None, cavity: int = 0, bg_top=0xFF000000, bg_bottom=0xFF404040,
+                     pixels_out=None, rgba_out=None):
+        """Pipelined render_frame: returns at once; the host buffers are complete after the matching frame_wait()."""
+        mw = mh = 0
+        if matcap is not None:
+            mh, mw = matcap.shape
+        self._check(self._L.j3dg_frame_submit(self._h, self._handles(meshes), len(meshes), self._handles(clouds), len(clouds),
+                                              C.byref(view), _ptr(matcap), mw, mh, mw, cavity, bg_top, bg_bottom,
+                                              _ptr(pixels_out), _ptr(rgba_out)), "j3dg_frame_submit")
+
+    def frame_wait(self):
+        self._check(self._L.j3dg_frame_wait(self._h), "j3dg_frame_wait")
 
     def set_tuning(self, lane_budget: int = 0, cast_algo: int = 0):
         self._check(self._L.j3dg_ctx_set_tuning(self._h, lane_budget, cast_algo), "j3dg_ctx_set_tuning")

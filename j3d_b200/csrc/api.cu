@@ -160,6 +160,13 @@ J3DG_API void j3dg_ctx_destroy(j3dg_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->d_pixels); cudaFree(ctx->d_pixels_in); cudaFree(ctx->d_rgba); cudaFree(ctx->d_bg); cudaFree(ctx->d_packed);
   cudaFree(ctx->d_matcap); cudaFree(ctx->d_meshes); cudaFree(ctx->d_stats); cudaFree(ctx->d_misc); cudaFree(ctx->d_shadow); cudaFree(ctx->d_hard);
+  for (auto& sl : ctx->slot) {
+    cudaFree(sl.d_px); cudaFree(sl.d_rgba);
+    if (sl.kernels_done) cudaEventDestroy(sl.kernels_done);
+    if (sl.copy_done) cudaEventDestroy(sl.copy_done);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->h_overflow) cudaFreeHost(ctx->h_overflow);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   for (auto& r : ctx->ring) { for (auto e : r.a) cudaEventDestroy(e); for (auto e : r.b) cudaEventDestroy(e); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -195,7 +202,7 @@ J3DG_API int j3dg_ctx_set_profiling(j3dg_ctx* ctx, int enabled) {
 
 J3DG_API int j3dg_ctx_set_tuning(j3dg_ctx* ctx, uint32_t lane_budget, int cast_algo) {
   if (!ctx || cast_algo < 0 || cast_algo > 1) return J3DG_EINVAL;
-  ctx->lane_budget = lane_budget ? lane_budget : 32u;
+  ctx->lane_budget = lane_budget ? lane_budget : 24u;
   ctx->cast_algo = cast_algo;
   return J3DG_OK;
 }
@@ -590,6 +597,68 @@ J3DG_API int j3dg_render_frame(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t
   if (pixels_out && !px_dev) { CU_CHECK(ctx, cudaMemcpyAsync(pixels_out, d_px, (size_t)w * h * sizeof(j3dg_pixel), cudaMemcpyDeviceToHost, ctx->stream)); copied = true; }
   if (rgba_out && !rgba_dev) { CU_CHECK(ctx, cudaMemcpyAsync(rgba_out, d_rgba, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->stream)); copied = true; }
   if (copied) return check_overflow(ctx);
+  return J3DG_OK;
+}
+
+// ---- pipelined frames ---------------------------------------------------------------------------
+// j3dg_render_frame with host outputs costs kernels + PCIe copy back to back.  For sweeps (orbit
+// renders, turntables) j3dg_frame_submit enqueues the kernels on the context stream and the
+// device->host copies on a second stream, double-buffering the device canvases, so the copy of
+// frame k overlaps the kernels of frame k+1; j3dg_frame_wait returns when the oldest frame's host
+// buffers are complete.
+J3DG_API int j3dg_frame_submit(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, j3dg_cloud* const* clouds, uint32_t nc,
+                               const j3dg_view* view, const uint32_t* matcap, uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity_clr,
+                               uint32_t bg_top, uint32_t bg_bottom, j3dg_pixel* pixels_out, uint32_t* rgba_out) {
+  if (!ctx || !view || (nm && !meshes) || (nc && !clouds)) { j3dg_set_error(ctx, "j3dg_frame_submit: bad argument"); return J3DG_EINVAL; }
+  if (j3dg_is_device_ptr(pixels_out) || j3dg_is_device_ptr(rgba_out)) { j3dg_set_error(ctx, "j3dg_frame_submit: outputs must be host buffers"); return J3DG_EINVAL; }
+  if (ctx->frames_submitted - ctx->frames_waited >= 2) { j3dg_set_error(ctx, "j3dg_frame_submit: two frames already in flight, call j3dg_frame_wait"); return J3DG_EINVAL; }
+  cudaSetDevice(ctx->device);
+  const uint32_t w = view->width, h = view->height;
+  if (!w || !h) { j3dg_set_error(ctx, "j3dg_frame_submit: empty canvas"); return J3DG_EINVAL; }
+  if (!ctx->copy_stream) {
+    CU_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CU_CHECK(ctx, cudaHostAlloc((void**)&ctx->h_overflow, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+    for (auto& sl : ctx->slot) {
+      CU_CHECK(ctx, cudaEventCreateWithFlags(&sl.kernels_done, cudaEventDisableTiming));
+      CU_CHECK(ctx, cudaEventCreateWithFlags(&sl.copy_done, cudaEventDisableTiming));
+    }
+  }
+  const int si = (int)(ctx->frames_submitted & 1);
+  j3dg_ctx::FrameSlot& sl = ctx->slot[si];
+  const uint32_t* d_mc; uint32_t dmw, dmh, dms, dcav;
+  int rc = stage_matcap(ctx, matcap, mw, mh, mstride, cavity_clr, &d_mc, &dmw, &dmh, &dms, &dcav);
+  if (rc != J3DG_OK) return rc;
+  if ((rc = ensure_background(ctx, w, h, bg_top, bg_bottom)) != J3DG_OK) return rc;
+  if ((rc = j3dg_reserve(ctx, &sl.d_px, &sl.px_cap, (size_t)w * h * sizeof(j3dg_pixel))) != J3DG_OK) return rc;
+  if ((rc = j3dg_reserve(ctx, &sl.d_rgba, &sl.rgba_cap, (size_t)w * h * 4)) != J3DG_OK) return rc;
+  j3dg_pixel* d_px = (j3dg_pixel*)sl.d_px;
+  uint32_t* d_rgba = (uint32_t*)sl.d_rgba;
+  // the kernels of this frame may overwrite the slot only after the copy of the frame before last left it
+  if (sl.busy) CU_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, sl.copy_done, 0));
+  if ((rc = j3dg_launch_cast(ctx, meshes, nm, view, 0, 0, (int)w - 1, (int)h - 1, d_px, w, false)) != J3DG_OK) return rc;
+  if ((rc = j3dg_launch_shade(ctx, d_px, w, view, d_mc, dmw, dmh, dms, dcav, ctx->d_bg, w, d_rgba, w)) != J3DG_OK) return rc;
+  if (nc && (rc = j3dg_launch_splat(ctx, clouds, nc, view, d_px, d_px, w, d_rgba, w)) != J3DG_OK) return rc;
+  CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_overflow + si, reinterpret_cast<uint32_t*>(ctx->d_stats + 2), sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_CHECK(ctx, cudaEventRecord(sl.kernels_done, ctx->stream));
+  CU_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, sl.kernels_done, 0));
+  if (pixels_out) CU_CHECK(ctx, cudaMemcpyAsync(pixels_out, d_px, (size_t)w * h * sizeof(j3dg_pixel), cudaMemcpyDeviceToHost, ctx->copy_stream));
+  if (rgba_out) CU_CHECK(ctx, cudaMemcpyAsync(rgba_out, d_rgba, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  CU_CHECK(ctx, cudaEventRecord(sl.copy_done, ctx->copy_stream));
+  sl.busy = true;
+  ctx->frames_submitted++;
+  return J3DG_OK;
+}
+
+J3DG_API int j3dg_frame_wait(j3dg_ctx* ctx) {
+  if (!ctx) return J3DG_EINVAL;
+  if (ctx->frames_waited == ctx->frames_submitted) { j3dg_set_error(ctx, "j3dg_frame_wait: no frame in flight"); return J3DG_EINVAL; }
+  const int si = (int)(ctx->frames_waited & 1);
+  CU_CHECK(ctx, cudaEventSynchronize(ctx->slot[si].copy_done));
+  ctx->frames_waited++;
+  if (ctx->h_overflow[si]) {
+    j3dg_set_error(ctx, "traversal stack overflow (BVH deeper than the kernel's stack)");
+    return J3DG_ECUDA;
+  }
   return J3DG_OK;
 }
 

@@ -31,6 +31,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstring>
 
 namespace {
 
@@ -39,7 +40,7 @@ constexpr int BLOCK_THREADS = 128;
 constexpr int LANE_SM_STACK = 12;                         // lane kernel: stack entries per ray in shared memory (12 * 8 B * 128 = 12 KB per block) ...
 constexpr int LANE_STACK = 96;                            // ... of this many in total (the rest in local memory, rarely touched)
 #ifndef J3DG_LANE_MIN_BLOCKS
-#define J3DG_LANE_MIN_BLOCKS 6
+#define J3DG_LANE_MIN_BLOCKS 8
 #endif
 constexpr int GROUPS_PER_BLOCK = BLOCK_THREADS / GROUP;   // 16 rays in flight per block
 constexpr int STACK_SIZE = 96;                            // entries per ray; 96 * 8 B * 16 = 12 KB shared memory per block
@@ -862,7 +863,12 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
     ctx->d_meshes = (MeshDev*)p;
     if (rc != J3DG_OK) return rc;
   }
-  if (used) CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_meshes, host.data(), sizeof(MeshDev) * used, cudaMemcpyHostToDevice, ctx->stream));
+  host.resize(used);
+  if (used && (ctx->meshes_uploaded.size() != used || memcmp(ctx->meshes_uploaded.data(), host.data(), sizeof(MeshDev) * used) != 0)) {
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_meshes, host.data(), sizeof(MeshDev) * used, cudaMemcpyHostToDevice, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // pageable source
+    ctx->meshes_uploaded = host;
+  }
   const bool shadows = (view->flags & J3DG_SHADOW) && used && !stats;
   const int rw = x1 - x0 + 1, rh = y1 - y0 + 1;
   const size_t npx = (size_t)rw * rh;
@@ -965,6 +971,7 @@ int j3dg_launch_find_closest(j3dg_mesh* m, const float* d_rays, uint32_t n, floa
   }
   CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_meshes, &d, sizeof(MeshDev), cudaMemcpyHostToDevice, ctx->stream));
   CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // `d` lives on this stack frame
+  ctx->meshes_uploaded.clear();
   CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
   TraceParams tp = {};
   tp.meshes = ctx->d_meshes;

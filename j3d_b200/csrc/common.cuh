@@ -133,8 +133,19 @@ struct j3dg_ctx {
   unsigned long long* d_stats = nullptr;
   void* d_misc = nullptr; size_t misc_cap = 0;
   void* d_shadow = nullptr; size_t shadow_cap = 0;   // shadow ray list (origins + pixel offsets)
+  // pipelined frames (j3dg_frame_submit / j3dg_frame_wait): double-buffered device canvases, a copy stream
+  struct FrameSlot {
+    void* d_px = nullptr; size_t px_cap = 0;
+    void* d_rgba = nullptr; size_t rgba_cap = 0;
+    cudaEvent_t kernels_done = nullptr, copy_done = nullptr;
+    bool busy = false;
+  } slot[2];
+  cudaStream_t copy_stream = nullptr;
+  uint64_t frames_submitted = 0, frames_waited = 0;
+  uint32_t* h_overflow = nullptr;                    // pinned: stack-overflow flag of each in-flight frame
+  std::vector<MeshDev> meshes_uploaded;              // last mesh table sent to d_meshes (re-uploaded only when it changes)
   void* d_hard = nullptr; size_t hard_cap = 0;       // hard-ray list handed from the lane kernel to the group kernel
-  uint32_t lane_budget = 32;                         // node visits per ray before the lane kernel evicts it (J3DG_LANE_BUDGET)
+  uint32_t lane_budget = 24;                         // node visits per ray before the lane kernel evicts it (J3DG_LANE_BUDGET)
   int cast_algo = 0;                                 // 0 hybrid (lane + group), 1 group kernel only (J3DG_CAST_ALGO=group)
 };
 

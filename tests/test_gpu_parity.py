@@ -279,6 +279,32 @@ def test_render_frame_equals_stages(ctx, oracle):
     m.destroy(); cl.destroy(); om.destroy()
 
 
+def test_pipelined_frames_equal_synchronous(ctx):
+    """j3dg_frame_submit / j3dg_frame_wait: every frame of a sweep equals the synchronous j3dg_render_frame."""
+    verts, tris, vc, v0 = _scene(25, 320, 180, j.DEFAULT_FLAGS | j.SHADOW, 0.0, True)
+    m = ctx.mesh_create(verts, tris, vcolors=vc)
+    mc, cav = j.make_matcap(0)
+    ctx.set_matcap(mc, cav)
+    views = [j.orbit_view(v0, 17.0 * k) for k in range(5)]
+    want = []
+    for v in views:
+        px = np.zeros((180, 320), j.PIXEL_DTYPE); rgba = np.zeros((180, 320), np.uint32)
+        ctx.render_frame([m], [], v, pixels_out=px, rgba_out=rgba)
+        want.append((px, rgba))
+    got = [(np.zeros((180, 320), j.PIXEL_DTYPE), np.zeros((180, 320), np.uint32)) for _ in views]
+    for k, v in enumerate(views):
+        ctx.frame_submit([m], [], v, pixels_out=got[k][0], rgba_out=got[k][1])
+        if k >= 1:
+            ctx.frame_wait()
+    ctx.frame_wait()
+    for (gp, gr), (wp, wr) in zip(got, want):
+        assert gp.tobytes() == wp.tobytes()
+        assert (gr == wr).all()
+    with pytest.raises(j.J3dgError):
+        ctx.frame_wait()  # nothing in flight
+    m.destroy()
+
+
 def test_degenerate_inputs(ctx, oracle):
     """Edge cases: single triangle, duplicated triangles, zero-area triangles, unreferenced vertices."""
     w, h = 160, 120
