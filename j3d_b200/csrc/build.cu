@@ -212,7 +212,7 @@ __device__ __forceinline__ uint32_t pick_exponent(float extent) {
   uint32_t e = (bits >> 23) & 0xffu;
   if (bits & 0x7fffffu) e += 1;
   if (e < 1) e = 1;
-  if (e > 254) e = 254;
+  if (e > 230) e = 230;  // the node stores step * 2^15 and the fit loop may still raise e
   return e;
 }
 
@@ -299,8 +299,8 @@ __global__ void __launch_bounds__(128) collapse_kernel(BinTree t, int n, const W
       }
       for (int i = nc; i < 8; ++i) { node.box[i][ax] = 255; node.box[i][3 + ax] = 0; }
     }
-    for (int i = 0; i < 8; ++i) { node.box[i][6] = 0x00; node.box[i][7] = 0x4B; }
-    node.sx = __uint_as_float(e[0] << 23); node.sy = __uint_as_float(e[1] << 23); node.sz = __uint_as_float(e[2] << 23);
+    for (int i = 0; i < 8; ++i) { node.box[i][6] = 0x80; node.box[i][7] = 0x3F; }
+    node.sx = __uint_as_float((e[0] + 15u) << 23); node.sy = __uint_as_float((e[1] + 15u) << 23); node.sz = __uint_as_float((e[2] + 15u) << 23);  // step * 2^15
     node.nchild = (uint32_t)nc;
     for (int i = 0; i < 8; ++i) node.child[i] = J3DG_EMPTY_CHILD;
     for (int i = 0; i < nc; ++i) {
@@ -336,13 +336,13 @@ __global__ void single_triangle_root_kernel(BinTree t, WideNode* nodes, TriRec* 
   const float ext[3] = {mx.x - mn.x, mx.y - mn.y, mx.z - mn.z};
   uint32_t e[3];
   for (int ax = 0; ax < 3; ++ax) {
-    e[ax] = min(254u, pick_exponent(ext[ax]) + 1);
+    e[ax] = pick_exponent(ext[ax]) + 1;
     for (int i = 0; i < 8; ++i) { node.box[i][ax] = 255; node.box[i][3 + ax] = 0; }
     node.box[0][ax] = 0;
     node.box[0][3 + ax] = 255;
   }
-  for (int i = 0; i < 8; ++i) { node.box[i][6] = 0x00; node.box[i][7] = 0x4B; }
-  node.sx = __uint_as_float(e[0] << 23); node.sy = __uint_as_float(e[1] << 23); node.sz = __uint_as_float(e[2] << 23);
+  for (int i = 0; i < 8; ++i) { node.box[i][6] = 0x80; node.box[i][7] = 0x3F; }
+  node.sx = __uint_as_float((e[0] + 15u) << 23); node.sy = __uint_as_float((e[1] + 15u) << 23); node.sz = __uint_as_float((e[2] + 15u) << 23);  // step * 2^15
   node.nchild = 1;
   for (int i = 0; i < 8; ++i) node.child[i] = J3DG_EMPTY_CHILD;
   node.child[0] = J3DG_LEAF_BIT | 0u;

@@ -32,15 +32,17 @@
 
 #include <algorithm>
 #include <cstring>
+#include <cstdio>
 
 namespace {
 
 constexpr int GROUP = 8;                                  // group kernel: lanes per ray = children per node = max triangles per leaf
 constexpr int BLOCK_THREADS = 128;
-constexpr int LANE_SM_STACK = 12;                         // lane kernel: stack entries per ray in shared memory (12 * 8 B * 128 = 12 KB per block) ...
-constexpr int LANE_STACK = 96;                            // ... of this many in total (the rest in local memory, rarely touched)
 #ifndef J3DG_LANE_MIN_BLOCKS
 #define J3DG_LANE_MIN_BLOCKS 8
+#endif
+#ifndef J3DG_LANE_REFILL_MIN
+#define J3DG_LANE_REFILL_MIN 4                            // lane kernel: idle lanes that trigger a refill from the pool
 #endif
 constexpr int GROUPS_PER_BLOCK = BLOCK_THREADS / GROUP;   // 16 rays in flight per block
 constexpr int STACK_SIZE = 96;                            // entries per ray; 96 * 8 B * 16 = 12 KB shared memory per block
@@ -65,8 +67,13 @@ struct TraceParams {
   // hard-ray hand-over between the two kernels
   uint32_t budget;               // lane kernel: node visits a ray may spend before it is evicted
   unsigned int* pool_ctr;        // pool counter of THIS launch
-  unsigned int* hard_count;      // lane kernel: append position; group kernel (list mode): number of entries
-  uint2* hard_id;                // {ray id, mesh of the best hit so far}
+  // hard-ray queue (single launch: lane warps produce, group warps consume)
+  unsigned int* hard_count;      // producers: append position
+  unsigned int* hard_taken;      // consumers: next entry to claim
+  unsigned int* done_blocks;     // lane blocks that have finished producing
+  uint32_t hard_capacity;        // entries the queue arrays hold
+  uint32_t consumer_blocks;      // blocks [0, consumer_blocks) consume from the start; the others trace tiles first
+  uint2* hard_id;                // {ray id (0xFFFFFFFF = entry not written yet), mesh of the best hit so far}
   float4* hard_best;             // {t, u, v, record slot bits} of the best hit so far (slot 0xFFFFFFFF: none)
   const float* rays;             // RAYLIST: n x 8 floats
   float* hits;                   // RAYLIST: n x 4 floats
@@ -98,10 +105,29 @@ __device__ __forceinline__ float group_min(float v) {
   return v;
 }
 
-// byte -> float without the quarter-rate I2F (XU pipe): PRMT builds the bits of 2^23 + q from the child's
-// 8-byte box record (bytes 6 and 7 hold 0x00 and 0x4B), the subtraction is exact.
+// Quantised plane byte -> float without an I2F (quarter-rate XU pipe) and without any arithmetic: one PRMT
+// assembles the bits 0x3F80_qq_00 = 1 + q * 2^-15 from the child's 8-byte box record, whose bytes 6 and 7 hold
+// 0x80 and 0x3F (selector nibble 0xF = byte 7 with sign replication = 0x00).  The node stores its quantisation
+// step pre-multiplied by 2^15, so  t = fma(m, S, B)  with  S = step * 2^15 / d  and  B = (origin - o) / d - S
+// equals q * step / d + (origin - o) / d.  The cancellation of S costs at most |S| * 2^-24 (1/512 of a quantum);
+// B is widened by |S| * 2^-22 on the near and far side to stay conservative.
 __device__ __forceinline__ float plane(uint32_t lo, uint32_t hi, uint32_t sel) {
-  return __fsub_rn(__uint_as_float(__byte_perm(lo, hi, sel)), 8388608.f);
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sel));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ uint32_t plane_sel(uint32_t byte_index) { return 0x760Fu | (byte_index << 4); }
+
+// Per node and axis: S and the widened near / far offsets.
+struct Slab { float S, Bn, Bf; };
+__device__ __forceinline__ Slab slab(float step32k, float origin, float o, float inv_d) {
+  Slab r;
+  r.S = step32k * inv_d;
+  const float B = fmaf(origin - o, inv_d, -r.S);
+  const float pad = fabsf(r.S) * 2.384185791015625e-07f;  // 2^-22
+  r.Bn = B - pad;
+  r.Bf = B + pad;
+  return r;
 }
 
 struct WorldRay { float4 org, dir; float t_near, t_far; };
@@ -145,12 +171,18 @@ __device__ __forceinline__ WorldRay world_ray(const TraceParams& p, uint32_t id)
 // MODE SHADOW : any hit (first accepted triangle ends the ray), sets mark bit 0.
 // MODE RAYLIST: qbvh::find_closest_triangle semantics for arbitrary (also negative) t ranges:
 //               closest = smallest |t|, bounds shrink on the side of the hit (qbvh.h:1812-1823).
-// LIST: the rays are the entries of the hard-ray list the lane kernel left behind.
-template <int MODE, bool LIST>
-__global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) group_kernel(const TraceParams p) {
+// SRC POOLS: rays come in pools of 32 slots (a pixel tile / 32 consecutive list entries) from p.pool_ctr.
+// SRC QUEUE: rays are the entries of the hard-ray queue the lane warps of the same launch fill; an entry
+//            is claimed with an atomic, polled until its ray id is written (the producer writes the seed,
+//            fences, then the id; the consumer restores the empty marker), and a group retires when its
+//            claimed index lies past the final length after every producer block has signed off.
+enum Source { POOLS = 0, QUEUE = 1 };
+constexpr uint32_t QUEUE_EMPTY = 0xFFFFFFFFu;
+
+template <int MODE, int SRC>
+__device__ __forceinline__ void group_loop(const TraceParams& p, uint2* s_stack) {
   constexpr bool ANY_HIT = MODE == SHADOW;
   constexpr bool GENERAL = MODE == RAYLIST;
-  __shared__ uint2 s_stack[STACK_SIZE * GROUPS_PER_BLOCK];
   const int lane = threadIdx.x & 31;
   const int c = lane & 7;                               // my child / triangle slot
   const int gshift = lane & 24;                         // first lane of my group
@@ -162,9 +194,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) group_ker
   uint32_t total_pools;   // a pool = 32 consecutive slots
   uint32_t supers_x = 1;
   uint32_t list_n = 0;
-  if (LIST) {
-    list_n = *p.hard_count;
-    total_pools = (list_n + 3u) / 4u;
+  if (SRC == QUEUE) {
+    total_pools = 0;
   } else if (MODE == PRIMARY) {
     const uint32_t tiles_x = (uint32_t)(p.x1 - p.x0 + TILE_W) / TILE_W, tiles_y = (uint32_t)(p.y1 - p.y0 + TILE_H) / TILE_H;
     supers_x = (tiles_x + SUPER_W - 1) / SUPER_W;
@@ -190,12 +221,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) group_ker
   uint32_t cur = J3DG_EMPTY_CHILD;
   int sp = 0;
 
-  // ---- warp-uniform pool state ----
-  // A pool is what one warp fetches at a time: a 32-pixel tile, or — for the few, long hard rays — just
-  // one ray per group, so that they spread over every resident warp instead of queueing in a few.
-  constexpr uint32_t POOL = LIST ? 4u : 32u;
-  uint32_t pool_next = POOL, pool_id = 0;
+  // ---- warp-uniform pool state (POOLS) / per-group queue state (QUEUE) ----
+  uint32_t pool_next = 32u, pool_id = 0;
   bool exhausted = false;
+  uint32_t claimed = QUEUE_EMPTY;   // QUEUE: entry this group has claimed and waits for
+  bool retired = false;             // QUEUE: nothing left for this group
+  const uint32_t producer_blocks = gridDim.x - p.consumer_blocks;
 
   auto pop = [&]() -> uint32_t {
     while (sp > 0) {
@@ -227,10 +258,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) group_ker
     Sx = fmul(pick(d2.x, d2.y, d2.z, kx), Sz);
     Sy = fmul(pick(d2.x, d2.y, d2.z, ky), Sz);
     idx = safe_rcp(d2.x); idy = safe_rcp(d2.y); idz = safe_rcp(d2.z);
-    // PRMT selectors: result bytes = {plane byte, 0x00 (byte 6), 0x00 (byte 6), 0x4B (byte 7)} = bits of 2^23 + q
-    sel_nx = 0x7660u | (idx < 0.f ? 3u : 0u); sel_fx = 0x7660u | (idx < 0.f ? 0u : 3u);
-    sel_ny = 0x7660u | (idy < 0.f ? 4u : 1u); sel_fy = 0x7660u | (idy < 0.f ? 1u : 4u);
-    sel_nz = 0x7660u | (idz < 0.f ? 5u : 2u); sel_fz = 0x7660u | (idz < 0.f ? 2u : 5u);
+    sel_nx = plane_sel(idx < 0.f ? 3u : 0u); sel_fx = plane_sel(idx < 0.f ? 0u : 3u);
+    sel_ny = plane_sel(idy < 0.f ? 4u : 1u); sel_fy = plane_sel(idy < 0.f ? 1u : 4u);
+    sel_nz = plane_sel(idz < 0.f ? 5u : 2u); sel_fz = plane_sel(idz < 0.f ? 2u : 5u);
     sp = 0;
     cur = m.nt ? 0u : J3DG_EMPTY_CHILD;
   };
@@ -271,10 +301,48 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) group_ker
         have_ray = false;
       }
     }
+    if (SRC == QUEUE) {
+      // groups without a ray claim the next queue entry and poll it (once per round: never a spin inside a warp
+      // whose other groups are traversing)
+      if (!have_ray && !retired) {
+        if (claimed == QUEUE_EMPTY) {
+          uint32_t i = 0;
+          if (c == 0) i = atomicAdd(p.hard_taken, 1u);
+          claimed = __shfl_sync(0xFFu << gshift, i, gshift);
+        }
+        uint2 e = make_uint2(QUEUE_EMPTY, 0u);
+        if (claimed < p.hard_capacity)  // claims run past the end of the queue while it drains
+          asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "l"(p.hard_id + claimed));
+        if (e.x != QUEUE_EMPTY) {
+          __threadfence();  // the seed was written before the id
+          const float4 seed = __ldcg(p.hard_best + claimed);
+          __syncwarp(0xFFu << gshift);
+          if (c == 0) p.hard_id[claimed].x = QUEUE_EMPTY;  // leave the queue clean for the next launch
+          claimed = QUEUE_EMPTY;
+          ray_id = e.x;
+          const WorldRay wr = world_ray<MODE>(p, ray_id);
+          t_near = wr.t_near; t_far = wr.t_far;
+          best_t = seed.x; best_u = seed.y; best_v = seed.z; best_slot = __float_as_uint(seed.w); best_mesh = e.y;
+          if (best_slot != 0xFFFFFFFFu) t_far = best_t;  // the lane warp's best hit so far prunes the restart
+          mesh_k = 0;
+          enter_mesh(wr, 0);
+          have_ray = true;
+        } else if (*reinterpret_cast<volatile unsigned int*>(p.done_blocks) >= producer_blocks) {
+          // every producer has signed off (after fencing its writes): the queue length is final
+          if (claimed >= *reinterpret_cast<volatile unsigned int*>(p.hard_count)) retired = true;
+        }
+      }
+      const uint32_t busy = __ballot_sync(0xffffffffu, have_ray);
+      if (!busy) {
+        if (__all_sync(0xffffffffu, retired)) break;
+        __nanosleep(200);  // nothing to do yet: do not hammer the queue
+        continue;
+      }
+    } else {
     // groups without a ray take the next slots of the warp's pool (warp-uniform loop)
     uint32_t need = __ballot_sync(0xffffffffu, !have_ray) & 0x01010101u;
     while (need && !exhausted) {
-      if (pool_next >= POOL) {
+      if (pool_next >= 32u) {
         uint32_t id = 0;
         if (lane == 0) id = atomicAdd(p.pool_ctr, 1u);
         pool_id = __shfl_sync(0xffffffffu, id, 0);
@@ -283,22 +351,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) group_ker
       }
       const uint32_t rank = __popc(need & ((1u << gshift) - 1u));  // requesting groups before mine
       const uint32_t slot = pool_next + rank;
-      const bool take = !have_ray && slot < POOL;
+      const bool take = !have_ray && slot < 32u;
       pool_next += __popc(need);
       if (take) {
         bool ok;
-        float4 seed = make_float4(FLT_MAX, 0.f, 0.f, __uint_as_float(0xFFFFFFFFu));
-        uint32_t seed_mesh = 0;
-        if (LIST) {
-          const uint32_t i = pool_id * POOL + slot;
-          ok = i < list_n;
-          if (ok) {
-            const uint2 e = p.hard_id[i];
-            ray_id = e.x;
-            seed_mesh = e.y;
-            seed = p.hard_best[i];
-          }
-        } else if (MODE == PRIMARY) {
+        if (MODE == PRIMARY) {
           const uint32_t sup = pool_id / (SUPER_W * SUPER_H), in = pool_id % (SUPER_W * SUPER_H);
           const uint32_t tx = (sup % supers_x) * SUPER_W + (in % SUPER_W), ty = (sup / supers_x) * SUPER_H + (in / SUPER_W);
           const int x = p.x0 + (int)tx * TILE_W + (int)(slot & (TILE_W - 1));
@@ -325,8 +382,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) group_ker
         if (ok) {
           const WorldRay wr = world_ray<MODE>(p, ray_id);
           t_near = wr.t_near; t_far = wr.t_far;
-          best_t = seed.x; best_u = seed.y; best_v = seed.z; best_slot = __float_as_uint(seed.w); best_mesh = seed_mesh;
-          if (best_slot != 0xFFFFFFFFu) t_far = best_t;  // the lane kernel's best hit so far prunes the restart
+          best_t = FLT_MAX; best_u = 0.f; best_v = 0.f; best_slot = 0xFFFFFFFFu; best_mesh = 0;
           mesh_k = 0;
           enter_mesh(wr, 0);
           have_ray = true;
@@ -335,6 +391,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) group_ker
       need = __ballot_sync(0xffffffffu, !have_ray) & 0x01010101u;
     }
     if (exhausted && !__any_sync(0xffffffffu, have_ray)) break;
+    }
 
     // Phases (B) and (C) are entered by the WHOLE warp whenever any of its four groups needs them, and every
     // collective uses the full mask: the groups stay in lockstep and ballot / shuffle compile to single
@@ -352,12 +409,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) group_ker
         q = __ldg(reinterpret_cast<const uint2*>(np + 32) + c);  // my child's quantised box
         ref = __ldg(reinterpret_cast<const uint32_t*>(np + 96) + c);
       }
-      const float sx = __uint_as_float(h1.x) * idx, sy = __uint_as_float(h1.y) * idy, sz = __uint_as_float(h1.z) * idz;
-      const float bx = (__uint_as_float(h0.x) - ox) * idx;
-      const float by = (__uint_as_float(h0.y) - oy) * idy;
-      const float bz = (__uint_as_float(h0.z) - oz) * idz;
-      float tmin = fmaxf(fmaxf(fmaf(plane(q.x, q.y, sel_nx), sx, bx), fmaf(plane(q.x, q.y, sel_ny), sy, by)), fmaxf(fmaf(plane(q.x, q.y, sel_nz), sz, bz), t_near));
-      float tmax = fminf(fminf(fmaf(plane(q.x, q.y, sel_fx), sx, bx), fmaf(plane(q.x, q.y, sel_fy), sy, by)), fminf(fmaf(plane(q.x, q.y, sel_fz), sz, bz), t_far));
+      const Slab X = slab(__uint_as_float(h1.x), __uint_as_float(h0.x), ox, idx);
+      const Slab Y = slab(__uint_as_float(h1.y), __uint_as_float(h0.y), oy, idy);
+      const Slab Z = slab(__uint_as_float(h1.z), __uint_as_float(h0.z), oz, idz);
+      float tmin = fmaxf(fmaxf(fmaf(plane(q.x, q.y, sel_nx), X.S, X.Bn), fmaf(plane(q.x, q.y, sel_ny), Y.S, Y.Bn)), fmaxf(fmaf(plane(q.x, q.y, sel_nz), Z.S, Z.Bn), t_near));
+      float tmax = fminf(fminf(fmaf(plane(q.x, q.y, sel_fx), X.S, X.Bf), fmaf(plane(q.x, q.y, sel_fy), Y.S, Y.Bf)), fminf(fmaf(plane(q.x, q.y, sel_fz), Z.S, Z.Bf), t_far));
       // conservative padding against rounding of the slab arithmetic
       tmin = fmaf(-fabsf(tmin), 2e-6f, tmin);
       tmax = fmaf(fabsf(tmax), 2e-6f, tmax);
@@ -449,175 +505,70 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) group_ker
   }
 }
 
-// =====================================================================================================
-// lane kernel: one ray per lane
-// =====================================================================================================
-
-// Per-thread traversal stack: the first LANE_SM_STACK entries in shared memory (column tid of a
-// [LANE_SM_STACK][BLOCK_THREADS] array: conflict-free), deeper entries in local memory.
-struct LaneStack {
-  uint2* sm;  // &s_stack[threadIdx.x]
-  uint2 deep[LANE_STACK - LANE_SM_STACK];
-  int sp;
-  __device__ __forceinline__ void push(uint32_t ref, float t, uint32_t* overflow_flag) {
-    const uint2 e = make_uint2(ref, __float_as_uint(t));
-    if (sp < LANE_SM_STACK) sm[sp * BLOCK_THREADS] = e;
-    else if (sp < LANE_STACK) deep[sp - LANE_SM_STACK] = e;
-    else { *overflow_flag = 1u; return; }
-    ++sp;
-  }
-  __device__ __forceinline__ uint2 pop() {
-    --sp;
-    return sp < LANE_SM_STACK ? sm[sp * BLOCK_THREADS] : deep[sp - LANE_SM_STACK];
-  }
-};
-
-struct LaneBest {
-  float t, u, v;
-  uint32_t slot, mesh;
-};
-
-// Traverses one mesh with one lane.  Returns false when the ray ran out of budget (the caller evicts it).
-// Control flow is "while-while": all lanes of the warp first descend inner nodes until each holds a leaf
-// (or is done), then all test their leaves — the two phases reconverge separately.
-template <bool ANY_HIT, bool STATS>
-__device__ __forceinline__ bool lane_traverse(const MeshDev& m, uint32_t mesh_index, float ox, float oy, float oz, float dx, float dy, float dz,
-                                              float t_near, float& t_far, LaneBest& best, uint32_t& visits, uint32_t budget,
-                                              uint32_t& stat_tris, uint32_t* overflow_flag, LaneStack& stk) {
-  if (m.nt == 0) return true;
-  // intersect_woop_precompute, qbvh.h:4793-4823
-  int kz = 2;
-  {
-    const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
-    if (ax > ay) { if (ax > az) kz = 0; }
-    else { if (ay > az) kz = 1; }
-  }
-  int kx = kz == 2 ? 0 : kz + 1;
-  int ky = kx == 2 ? 0 : kx + 1;
-  const float dkz = pick(dx, dy, dz, kz);
-  if (dkz < 0.f) { const int t = kx; kx = ky; ky = t; }
-  const float Sz = fdiv(1.f, dkz);
-  const float Sx = fmul(pick(dx, dy, dz, kx), Sz);
-  const float Sy = fmul(pick(dx, dy, dz, ky), Sz);
-  const float idx = safe_rcp(dx), idy = safe_rcp(dy), idz = safe_rcp(dz);
-  const uint32_t sel_nx = 0x7660u | (idx < 0.f ? 3u : 0u), sel_fx = 0x7660u | (idx < 0.f ? 0u : 3u);
-  const uint32_t sel_ny = 0x7660u | (idy < 0.f ? 4u : 1u), sel_fy = 0x7660u | (idy < 0.f ? 1u : 4u);
-  const uint32_t sel_nz = 0x7660u | (idz < 0.f ? 5u : 2u), sel_fz = 0x7660u | (idz < 0.f ? 2u : 5u);
-
-  stk.sp = 0;
-  uint32_t cur = 0;  // root node; J3DG_EMPTY_CHILD (which has the leaf bit set) = nothing left
-  const WideNode* __restrict__ nodes = m.nodes;
-  const TriRec* __restrict__ tris = m.tris;
-
-  auto pop = [&]() -> uint32_t {
-    while (stk.sp > 0) {
-      const uint2 e = stk.pop();
-      // entry points of popped boxes that now lie beyond the shrunk interval are skipped
-      if (__uint_as_float(e.y) <= t_far) return e.x;
-    }
-    return J3DG_EMPTY_CHILD;
-  };
-
-  for (;;) {
-    // ---- phase 1: inner nodes, 8 quantised child boxes each ----
-    while (!(cur & J3DG_LEAF_BIT)) {
-      if (visits >= budget) return false;
-      ++visits;
-      const uint4* np = reinterpret_cast<const uint4*>(nodes + cur);
-      const uint4 h0 = __ldg(np + 0);  // ox oy oz | nchild
-      const uint4 h1 = __ldg(np + 1);  // sx sy sz | pad
-      const uint4 b0 = __ldg(np + 2);  // boxes of children 0, 1
-      const uint4 b1 = __ldg(np + 3);
-      const uint4 b2 = __ldg(np + 4);
-      const uint4 b3 = __ldg(np + 5);
-      const uint4 c0 = __ldg(np + 6);
-      const uint4 c1 = __ldg(np + 7);
-      const float sx = __uint_as_float(h1.x) * idx, sy = __uint_as_float(h1.y) * idy, sz = __uint_as_float(h1.z) * idz;
-      const float bx = (__uint_as_float(h0.x) - ox) * idx;
-      const float by = (__uint_as_float(h0.y) - oy) * idy;
-      const float bz = (__uint_as_float(h0.z) - oz) * idz;
-      uint32_t near_ref = J3DG_EMPTY_CHILD;
-      float near_t = FLT_MAX;
-      auto test_child = [&](uint32_t lo, uint32_t hi, uint32_t ref) {
-        float tmin = fmaxf(fmaxf(fmaf(plane(lo, hi, sel_nx), sx, bx), fmaf(plane(lo, hi, sel_ny), sy, by)), fmaxf(fmaf(plane(lo, hi, sel_nz), sz, bz), t_near));
-        float tmax = fminf(fminf(fmaf(plane(lo, hi, sel_fx), sx, bx), fmaf(plane(lo, hi, sel_fy), sy, by)), fminf(fmaf(plane(lo, hi, sel_fz), sz, bz), t_far));
-        // conservative padding against rounding of the slab arithmetic
-        tmin = fmaf(-fabsf(tmin), 2e-6f, tmin);
-        tmax = fmaf(fabsf(tmax), 2e-6f, tmax);
-        if (tmin <= tmax) {  // empty slots have inverted boxes and never pass
-          float tt = tmin;
-          if (tt < near_t) {  // keep the nearest in registers, push the other one
-            const uint32_t r2 = near_ref; const float t2 = near_t;
-            near_ref = ref; near_t = tt;
-            ref = r2; tt = t2;
-          }
-          if (ref != J3DG_EMPTY_CHILD) stk.push(ref, tt, overflow_flag);
-        }
-      };
-      test_child(b0.x, b0.y, c0.x);
-      test_child(b0.z, b0.w, c0.y);
-      test_child(b1.x, b1.y, c0.z);
-      test_child(b1.z, b1.w, c0.w);
-      test_child(b2.x, b2.y, c1.x);
-      test_child(b2.z, b2.w, c1.y);
-      test_child(b3.x, b3.y, c1.z);
-      test_child(b3.z, b3.w, c1.w);
-      cur = (near_ref != J3DG_EMPTY_CHILD) ? near_ref : pop();
-    }
-    if (cur == J3DG_EMPTY_CHILD) return true;
-    // ---- phase 2: leaves, 1..8 consecutive triangle records each, the last one flagged ----
-    do {
-      uint32_t slot = cur & J3DG_LEAF_FIRST_MASK;
-      for (;;) {
-        const float4* tp = reinterpret_cast<const float4*>(tris + slot);
-        const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
-        if (STATS) ++stat_tris;
-        // one lane of intersect_woop (qbvh.h:4825-4869); 1/det is correctly rounded instead of rcpps + NR
-        const float Ax_ = fsub(v0.x, ox), Ay_ = fsub(v0.y, oy), Az_ = fsub(v0.z, oz);
-        const float Bx_ = fsub(v1.x, ox), By_ = fsub(v1.y, oy), Bz_ = fsub(v1.z, oz);
-        const float Cx_ = fsub(v2.x, ox), Cy_ = fsub(v2.y, oy), Cz_ = fsub(v2.z, oz);
-        const float Akz = pick(Ax_, Ay_, Az_, kz), Bkz = pick(Bx_, By_, Bz_, kz), Ckz = pick(Cx_, Cy_, Cz_, kz);
-        const float Ax = fsub(pick(Ax_, Ay_, Az_, kx), fmul(Sx, Akz));
-        const float Ay = fsub(pick(Ax_, Ay_, Az_, ky), fmul(Sy, Akz));
-        const float Bx = fsub(pick(Bx_, By_, Bz_, kx), fmul(Sx, Bkz));
-        const float By = fsub(pick(Bx_, By_, Bz_, ky), fmul(Sy, Bkz));
-        const float Cx = fsub(pick(Cx_, Cy_, Cz_, kx), fmul(Sx, Ckz));
-        const float Cy = fsub(pick(Cx_, Cy_, Cz_, ky), fmul(Sy, Ckz));
-        const float U = fsub(fmul(Cx, By), fmul(Cy, Bx));
-        const float V = fsub(fmul(Ax, Cy), fmul(Ay, Cx));
-        const float W = fsub(fmul(Bx, Ay), fmul(By, Ax));
-        const bool inside = ((U <= 0.f) && (V <= 0.f) && (W <= 0.f)) || ((U >= 0.f) && (V >= 0.f) && (W >= 0.f));
-        const float det = fadd(fadd(U, V), W);
-        if (inside && det != 0.f) {
-          const float inv_det = fdiv(1.f, det);
-          const float Az = fmul(Sz, Akz), Bz = fmul(Sz, Bkz), Cz = fmul(Sz, Ckz);
-          const float T = fadd(fadd(fmul(U, Az), fmul(V, Bz)), fmul(W, Cz));
-          const float t = fmul(T, inv_det);
-          if ((t_far > t) && (t > t_near) && (t < best.t)) {
-            best.t = t; best.u = fmul(V, inv_det); best.v = fmul(W, inv_det); best.slot = slot; best.mesh = mesh_index;
-            t_far = t;
-            if (ANY_HIT) return true;
-          }
-        }
-        if (__float_as_uint(v1.w) != 0u) break;  // end of leaf
-        ++slot;
-      }
-      cur = pop();
-    } while (cur != J3DG_EMPTY_CHILD && (cur & J3DG_LEAF_BIT));
-    if (cur == J3DG_EMPTY_CHILD) return true;
-  }
+template <int MODE>
+__global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) group_kernel(const TraceParams p) {
+  __shared__ uint2 s_stack[STACK_SIZE * GROUPS_PER_BLOCK];
+  group_loop<MODE, POOLS>(p, s_stack);
 }
 
-// Persistent warps; lane L of a warp owns slot L of the warp's current pool (an 8x4 pixel tile, or 32
-// consecutive entries of the shadow-ray list).
+// =====================================================================================================
+// lane kernel: one ray per lane, persistent lanes
+// =====================================================================================================
+// Every lane runs its own ray through a small state machine (at a node / at a leaf / done); the warp
+// alternates a node phase and a leaf phase ("while-while") so that lanes decoding a node never serialise
+// against lanes testing triangles.  A lane whose ray is done writes its pixel and — as soon as
+// LANE_REFILL_MIN lanes are idle — takes the next ray of the warp's pool, so the 32 lanes stay busy instead
+// of waiting for the slowest ray of a tile (dynamic ray fetch, Aila & Laine 2009).  A pool is one 8x4
+// pixel tile (or 32 shadow rays); when the warp fetches a pool its 32 lanes set up the 32 rays in
+// parallel — ray generation, object-space transform, Woop shear constants, reciprocals — and park them
+// in shared memory, so a refill costs a few shared-memory loads.
+// The traversal stack is LANE_STACK entries per lane, all in shared memory, pushed without branches.
+// A ray that spends more than `budget` node visits, or would overflow the stack, is evicted to the
+// hard-ray list with its best hit so far (group_kernel finishes it).
+constexpr int LANE_STACK = 12;        // 13 rows (one scratch row) * 8 B * 128 lanes = 13 KB shared memory per block
+constexpr int LANE_REFILL_MIN = J3DG_LANE_REFILL_MIN;
+constexpr int RAY_WORDS = 12;         // parked ray: ox oy oz | idx idy idz | Sx Sy Sz | kx,ky,kz packed | t_far | ray id
+
+// Object-space traversal constants of a ray for one mesh (qbvh.h:3358-3359, 4793-4823).
+struct LaneRay {
+  float ox, oy, oz, idx, idy, idz, Sx, Sy, Sz;
+  uint32_t kpack;  // kx | ky << 2 | kz << 4
+};
+
+__device__ __forceinline__ LaneRay lane_ray_setup(const MeshDev& m, const WorldRay& wr) {
+  LaneRay r;
+  const float4 d2 = mat_vec(m.cs_inv, wr.dir);
+  const float4 o2 = mat_vec(m.cs_inv, wr.org);
+  r.ox = o2.x; r.oy = o2.y; r.oz = o2.z;
+  int kz = 2;
+  const float ax = fabsf(d2.x), ay = fabsf(d2.y), az = fabsf(d2.z);
+  if (ax > ay) { if (ax > az) kz = 0; }
+  else { if (ay > az) kz = 1; }
+  int kx = kz == 2 ? 0 : kz + 1;
+  int ky = kx == 2 ? 0 : kx + 1;
+  const float dkz = pick(d2.x, d2.y, d2.z, kz);
+  if (dkz < 0.f) { const int t = kx; kx = ky; ky = t; }
+  r.Sz = fdiv(1.f, dkz);
+  r.Sx = fmul(pick(d2.x, d2.y, d2.z, kx), r.Sz);
+  r.Sy = fmul(pick(d2.x, d2.y, d2.z, ky), r.Sz);
+  r.idx = safe_rcp(d2.x); r.idy = safe_rcp(d2.y); r.idz = safe_rcp(d2.z);
+  r.kpack = (uint32_t)kx | ((uint32_t)ky << 2) | ((uint32_t)kz << 4);
+  return r;
+}
+
+constexpr size_t LANE_SMEM_STACK = (size_t)(LANE_STACK + 1) * BLOCK_THREADS * sizeof(uint2);
+constexpr size_t LANE_SMEM_RAYS = (size_t)(BLOCK_THREADS / 32) * RAY_WORDS * 32 * sizeof(uint32_t);
+constexpr size_t GROUP_SMEM = (size_t)STACK_SIZE * GROUPS_PER_BLOCK * sizeof(uint2);
+constexpr size_t CAST_SMEM = LANE_SMEM_STACK + LANE_SMEM_RAYS > GROUP_SMEM ? LANE_SMEM_STACK + LANE_SMEM_RAYS : GROUP_SMEM;
+
 template <int MODE, bool STATS>
-__global__ void __launch_bounds__(BLOCK_THREADS, J3DG_LANE_MIN_BLOCKS) lane_kernel(const TraceParams p) {
+__device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* s_stack, uint32_t* s_rays) {
   constexpr bool ANY_HIT = MODE == SHADOW;
-  __shared__ uint2 s_stack[LANE_SM_STACK * BLOCK_THREADS];
-  LaneStack stk;
-  stk.sm = s_stack + threadIdx.x;
+  uint2* const stk = s_stack + threadIdx.x;                                           // row i at stk[i * BLOCK_THREADS]
+  uint32_t* const park = s_rays + (threadIdx.x >> 5) * (RAY_WORDS * 32);              // word w of slot s at park[w * 32 + s]
   const int lane = threadIdx.x & 31;
-  uint32_t* const overflow_flag = reinterpret_cast<uint32_t*>(p.stats + 2);
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const float t_near = MODE == PRIMARY ? fdiv(p.vw.diagonal, 100.f) : 1e-3f;          // canvas.cpp:781 / 853
   uint32_t total_pools, supers_x = 1, list_n = 0;
   if (MODE == PRIMARY) {
     const uint32_t tiles_x = (uint32_t)(p.x1 - p.x0 + TILE_W) / TILE_W, tiles_y = (uint32_t)(p.y1 - p.y0 + TILE_H) / TILE_H;
@@ -628,58 +579,238 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_LANE_MIN_BLOCKS) lane_kern
     total_pools = (list_n + 31u) / 32u;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.stats + 4, (unsigned long long)list_n);  // shadow rays traced
   }
+
+  // ---- per-lane ray state ----
+  bool have = false;
+  uint32_t ray_id = 0, mesh_k = 0, visits = 0, ntris = 0;
+  const WideNode* __restrict__ nodes = nullptr;
+  const TriRec* __restrict__ tris = nullptr;
+  LaneRay r = {};
+  uint32_t sel_nx = 0, sel_fx = 0, sel_ny = 0, sel_fy = 0, sel_nz = 0, sel_fz = 0;
+  float t_far = 0.f;
+  float best_t = FLT_MAX, best_u = 0.f, best_v = 0.f;
+  uint32_t best_slot = 0xFFFFFFFFu, best_mesh = 0;
+  uint32_t cur = J3DG_EMPTY_CHILD;
+  int sp = 0;
+  bool evict = false;
   uint32_t sum_nodes = 0, sum_tris = 0;
+  // ---- warp-uniform pool state ----
+  uint32_t pool_next = 0, pool_count = 0;
+  bool exhausted = false;
+
+  auto enter = [&](const LaneRay& lr, uint32_t k) {
+    const MeshDev& m = p.meshes[k];
+    nodes = m.nodes; tris = m.tris;
+    r = lr;
+    sel_nx = plane_sel(r.idx < 0.f ? 3u : 0u); sel_fx = plane_sel(r.idx < 0.f ? 0u : 3u);
+    sel_ny = plane_sel(r.idy < 0.f ? 4u : 1u); sel_fy = plane_sel(r.idy < 0.f ? 1u : 4u);
+    sel_nz = plane_sel(r.idz < 0.f ? 5u : 2u); sel_fz = plane_sel(r.idz < 0.f ? 2u : 5u);
+    sp = 0;
+    cur = m.nt ? 0u : J3DG_EMPTY_CHILD;
+  };
+  auto pop = [&]() -> uint32_t {
+    while (sp > 0) {
+      --sp;
+      const uint2 e = stk[sp * BLOCK_THREADS];
+      // entry points of popped boxes that now lie beyond the shrunk interval are skipped
+      if (__uint_as_float(e.y & ~7u) <= t_far) return e.x;
+    }
+    return J3DG_EMPTY_CHILD;
+  };
+
   for (;;) {
-    uint32_t pool = 0;
-    if (lane == 0) pool = atomicAdd(p.pool_ctr, 1u);
-    pool = __shfl_sync(0xffffffffu, pool, 0);
-    if (pool >= total_pools) break;
-    uint32_t ray_id;
-    bool ok;
-    if (MODE == PRIMARY) {
-      const uint32_t sup = pool / (SUPER_W * SUPER_H), in = pool % (SUPER_W * SUPER_H);
-      const uint32_t tx = (sup % supers_x) * SUPER_W + (in % SUPER_W), ty = (sup / supers_x) * SUPER_H + (in / SUPER_W);
-      const int x = p.x0 + (int)tx * TILE_W + (lane & (TILE_W - 1));
-      const int y = p.y0 + (int)ty * TILE_H + (lane / TILE_W);
-      ok = x <= p.x1 && y <= p.y1;
-      ray_id = ((uint32_t)y << 16) | (uint32_t)x;
-    } else {
-      ray_id = pool * 32u + (uint32_t)lane;
-      ok = ray_id < list_n;
+    // =========================== (A) rays that are done or evicted ===========================
+    if (have && (cur == J3DG_EMPTY_CHILD || evict)) {
+      const bool found = best_slot != 0xFFFFFFFFu;
+      if (!evict && mesh_k + 1 < p.nm && !(ANY_HIT && found)) {  // next object (qbvh.h:3340-3385)
+        ++mesh_k;
+        enter(lane_ray_setup(p.meshes[mesh_k], world_ray<MODE>(p, ray_id)), mesh_k);
+      } else {
+        if (evict) {  // a group of 8 lanes finishes this ray, starting from the best hit so far
+          const uint32_t i = atomicAdd(p.hard_count, 1u);
+          __stcg(p.hard_best + i, make_float4(best_t, best_u, best_v, __uint_as_float(best_slot)));
+          __threadfence();  // the consumer reads the seed after it has seen the id
+          asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" :: "l"(p.hard_id + i), "r"(ray_id), "r"(best_mesh) : "memory");
+        } else if (MODE == PRIMARY) {
+          const int x = (int)(ray_id & 0xffffu), y = (int)(ray_id >> 16);
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)y * p.stride + x);
+          uint4 lo = make_uint4(0u, 0u, 0u, __float_as_uint(found ? best_t : FLT_MAX));  // misses already carry the final record (canvas.cpp:859-866)
+          if (STATS) { lo.y = visits; lo.z = ntris; }  // the counting pass returns per-pixel costs in the u / v slots
+          dst[0] = lo;
+          // raw hit: record slot, barycentrics, mesh index (resolve_kernel finishes it)
+          dst[1] = found ? make_uint4(best_slot, __float_as_uint(best_u), __float_as_uint(best_v), best_mesh) : make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+        } else if (found) {
+          uint8_t* mark = reinterpret_cast<uint8_t*>(p.out + __ldg(p.shadow_pix + ray_id));
+          *mark = *mark | 1u;  // canvas.cpp:856
+        }
+        if (STATS) { sum_nodes += visits; sum_tris += ntris; }
+        have = false;
+      }
     }
-    if (!ok) continue;
-    const WorldRay wr = world_ray<MODE>(p, ray_id);
-    float t_far = wr.t_far;
-    LaneBest best;
-    best.t = FLT_MAX; best.u = 0.f; best.v = 0.f; best.slot = 0xFFFFFFFFu; best.mesh = 0;
-    uint32_t visits = 0, ntris = 0;
-    bool finished = true;
-    for (uint32_t k = 0; k < p.nm; ++k) {
-      const MeshDev& m = p.meshes[k];
-      // qbvh.h:3358-3359: the ray is taken into object space by the inverted object matrix
-      const float4 d2 = mat_vec(m.cs_inv, wr.dir);
-      const float4 o2 = mat_vec(m.cs_inv, wr.org);
-      finished = lane_traverse<ANY_HIT, STATS>(m, k, o2.x, o2.y, o2.z, d2.x, d2.y, d2.z, wr.t_near, t_far, best, visits, p.budget, ntris,
-                                               overflow_flag, stk);
-      if (!finished || (ANY_HIT && best.slot != 0xFFFFFFFFu)) break;
+    // =========================== (B) refill idle lanes from the warp's pool ===========================
+    uint32_t idle = __ballot_sync(0xffffffffu, !have);
+    if (idle && !exhausted && ((int)__popc(idle) >= LANE_REFILL_MIN || idle == 0xffffffffu || !__any_sync(0xffffffffu, have && cur != J3DG_EMPTY_CHILD))) {
+      while (idle && !exhausted) {
+        if (pool_next >= pool_count) {  // fetch the next pool; its 32 rays are set up by the 32 lanes in parallel
+          uint32_t pool = 0;
+          if (lane == 0) pool = atomicAdd(p.pool_ctr, 1u);
+          pool = __shfl_sync(0xffffffffu, pool, 0);
+          if (pool >= total_pools) { exhausted = true; break; }
+          uint32_t id;
+          bool ok;
+          if (MODE == PRIMARY) {
+            const uint32_t sup = pool / (SUPER_W * SUPER_H), in = pool % (SUPER_W * SUPER_H);
+            const uint32_t tx = (sup % supers_x) * SUPER_W + (in % SUPER_W), ty = (sup / supers_x) * SUPER_H + (in / SUPER_W);
+            const int x = p.x0 + (int)tx * TILE_W + (lane & (TILE_W - 1));
+            const int y = p.y0 + (int)ty * TILE_H + (lane / TILE_W);
+            ok = x <= p.x1 && y <= p.y1;
+            id = ((uint32_t)y << 16) | (uint32_t)x;
+          } else {
+            id = pool * 32u + (uint32_t)lane;
+            ok = id < list_n;
+          }
+          if (ok && p.nm == 0u) {  // empty scene: every ray misses
+            if (MODE == PRIMARY) {
+              uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)(id >> 16) * p.stride + (id & 0xffffu));
+              dst[0] = make_uint4(0u, 0u, 0u, __float_as_uint(FLT_MAX));
+              dst[1] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+            }
+            ok = false;
+          }
+          const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+          __syncwarp();  // every lane is past its reads of the previous pool
+          if (ok) {
+            const WorldRay wr = world_ray<MODE>(p, id);
+            const LaneRay lr = lane_ray_setup(p.meshes[0], wr);
+            const uint32_t s = __popc(okmask & lt_mask);  // dense slots
+            park[0 * 32 + s] = __float_as_uint(lr.ox); park[1 * 32 + s] = __float_as_uint(lr.oy); park[2 * 32 + s] = __float_as_uint(lr.oz);
+            park[3 * 32 + s] = __float_as_uint(lr.idx); park[4 * 32 + s] = __float_as_uint(lr.idy); park[5 * 32 + s] = __float_as_uint(lr.idz);
+            park[6 * 32 + s] = __float_as_uint(lr.Sx); park[7 * 32 + s] = __float_as_uint(lr.Sy); park[8 * 32 + s] = __float_as_uint(lr.Sz);
+            park[9 * 32 + s] = lr.kpack; park[10 * 32 + s] = __float_as_uint(wr.t_far); park[11 * 32 + s] = id;
+          }
+          __syncwarp();
+          pool_next = 0;
+          pool_count = __popc(okmask);
+          if (pool_count == 0) continue;
+        }
+        const uint32_t s = pool_next + __popc(idle & lt_mask);  // the r-th idle lane takes the r-th parked ray
+        if (!have && s < pool_count) {
+          LaneRay lr;
+          lr.ox = __uint_as_float(park[0 * 32 + s]); lr.oy = __uint_as_float(park[1 * 32 + s]); lr.oz = __uint_as_float(park[2 * 32 + s]);
+          lr.idx = __uint_as_float(park[3 * 32 + s]); lr.idy = __uint_as_float(park[4 * 32 + s]); lr.idz = __uint_as_float(park[5 * 32 + s]);
+          lr.Sx = __uint_as_float(park[6 * 32 + s]); lr.Sy = __uint_as_float(park[7 * 32 + s]); lr.Sz = __uint_as_float(park[8 * 32 + s]);
+          lr.kpack = park[9 * 32 + s];
+          t_far = __uint_as_float(park[10 * 32 + s]);
+          ray_id = park[11 * 32 + s];
+          best_t = FLT_MAX; best_u = 0.f; best_v = 0.f; best_slot = 0xFFFFFFFFu; best_mesh = 0;
+          mesh_k = 0; visits = 0; ntris = 0; evict = false;
+          enter(lr, 0);
+          have = true;
+        }
+        pool_next += __popc(idle);
+        idle = __ballot_sync(0xffffffffu, !have);
+      }
     }
-    if (STATS) { sum_nodes += visits; sum_tris += ntris; }
-    const bool found = best.slot != 0xFFFFFFFFu;
-    if (!finished) {  // out of budget: the group kernel finishes this ray, starting from the best hit so far
-      const uint32_t i = atomicAdd(p.hard_count, 1u);
-      p.hard_id[i] = make_uint2(ray_id, best.mesh);
-      p.hard_best[i] = make_float4(best.t, best.u, best.v, __uint_as_float(best.slot));
-    } else if (MODE == PRIMARY) {
-      const int x = (int)(ray_id & 0xffffu), y = (int)(ray_id >> 16);
-      uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)y * p.stride + x);
-      uint4 lo = make_uint4(0u, 0u, 0u, __float_as_uint(found ? best.t : FLT_MAX));  // misses already carry the final record (canvas.cpp:859-866)
-      if (STATS) { lo.y = visits; lo.z = ntris; }  // the counting pass returns per-pixel costs in the u / v slots
-      dst[0] = lo;
-      // raw hit: record slot, barycentrics, mesh index (resolve_kernel finishes it)
-      dst[1] = found ? make_uint4(best.slot, __float_as_uint(best.u), __float_as_uint(best.v), best.mesh) : make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
-    } else if (found) {
-      uint8_t* mark = reinterpret_cast<uint8_t*>(p.out + __ldg(p.shadow_pix + ray_id));
-      *mark = *mark | 1u;  // canvas.cpp:856
+    if (exhausted && !__any_sync(0xffffffffu, have)) break;
+
+    // =========================== (C) node phase: 8 quantised child boxes per visit ===========================
+    while (__any_sync(0xffffffffu, have && !evict && !(cur & J3DG_LEAF_BIT))) {
+      if (have && !evict && !(cur & J3DG_LEAF_BIT)) {
+        if (visits >= p.budget) {
+          evict = true;
+        } else {
+          ++visits;
+          const uint4* np = reinterpret_cast<const uint4*>(nodes + cur);
+          const uint4 h0 = __ldg(np + 0);  // ox oy oz | nchild
+          const uint4 h1 = __ldg(np + 1);  // sx sy sz | pad
+          const uint4 b0 = __ldg(np + 2);  // boxes of children 0, 1
+          const uint4 b1 = __ldg(np + 3);
+          const uint4 b2 = __ldg(np + 4);
+          const uint4 b3 = __ldg(np + 5);
+          const uint4 c0 = __ldg(np + 6);
+          const uint4 c1 = __ldg(np + 7);
+          const Slab X = slab(__uint_as_float(h1.x), __uint_as_float(h0.x), r.ox, r.idx);
+          const Slab Y = slab(__uint_as_float(h1.y), __uint_as_float(h0.y), r.oy, r.idy);
+          const Slab Z = slab(__uint_as_float(h1.z), __uint_as_float(h0.z), r.oz, r.idz);
+          // Entry distance of child i, low 3 bits replaced by i (distances are positive, so their bit patterns
+          // order like integers); missed children get +inf.  Empty slots have inverted boxes and never pass.
+          constexpr uint32_t MISS_KEY = 0x7F800000u;
+          auto child_key = [&](uint32_t lo, uint32_t hi, uint32_t i) -> uint32_t {
+            float tmin = fmaxf(fmaxf(fmaf(plane(lo, hi, sel_nx), X.S, X.Bn), fmaf(plane(lo, hi, sel_ny), Y.S, Y.Bn)), fmaxf(fmaf(plane(lo, hi, sel_nz), Z.S, Z.Bn), t_near));
+            float tmax = fminf(fminf(fmaf(plane(lo, hi, sel_fx), X.S, X.Bf), fmaf(plane(lo, hi, sel_fy), Y.S, Y.Bf)), fminf(fmaf(plane(lo, hi, sel_fz), Z.S, Z.Bf), t_far));
+            // conservative padding against rounding of the slab arithmetic
+            tmin = fmaf(-fabsf(tmin), 2e-6f, tmin);
+            tmax = fmaf(fabsf(tmax), 2e-6f, tmax);
+            return tmin <= tmax ? ((__float_as_uint(tmin) & ~7u) | i) : (MISS_KEY | i);
+          };
+          const uint32_t k0 = child_key(b0.x, b0.y, 0u), k1 = child_key(b0.z, b0.w, 1u), k2 = child_key(b1.x, b1.y, 2u), k3 = child_key(b1.z, b1.w, 3u);
+          const uint32_t k4 = child_key(b2.x, b2.y, 4u), k5 = child_key(b2.z, b2.w, 5u), k6 = child_key(b3.x, b3.y, 6u), k7 = child_key(b3.z, b3.w, 7u);
+          const int nearest = min(min(min((int)k0, (int)k1), min((int)k2, (int)k3)), min(min((int)k4, (int)k5), min((int)k6, (int)k7)));
+          const uint32_t ni = (uint32_t)nearest & 7u;
+          uint32_t near_ref = c0.x;
+          near_ref = ni == 1u ? c0.y : near_ref; near_ref = ni == 2u ? c0.z : near_ref; near_ref = ni == 3u ? c0.w : near_ref;
+          near_ref = ni == 4u ? c1.x : near_ref; near_ref = ni == 5u ? c1.y : near_ref; near_ref = ni == 6u ? c1.z : near_ref;
+          near_ref = ni == 7u ? c1.w : near_ref;
+          if ((uint32_t)nearest >= MISS_KEY) near_ref = J3DG_EMPTY_CHILD;
+          // branch-free pushes of the other hit children (row LANE_STACK is scratch; the low key bits are cleared at pop)
+          int wanted = sp;
+          auto push = [&](uint32_t key, uint32_t ref) {
+            stk[sp * BLOCK_THREADS] = make_uint2(ref, key);
+            const int go = (key < MISS_KEY && (int)key != nearest) ? 1 : 0;
+            wanted += go;
+            sp = min(sp + go, LANE_STACK);
+          };
+          push(k0, c0.x); push(k1, c0.y); push(k2, c0.z); push(k3, c0.w);
+          push(k4, c1.x); push(k5, c1.y); push(k6, c1.z); push(k7, c1.w);
+          evict = wanted > LANE_STACK;  // stack full: the group kernel (96 entries) takes the ray
+          cur = (near_ref != J3DG_EMPTY_CHILD) ? near_ref : pop();
+        }
+      }
+      // leave for a refill when enough lanes ran dry
+      if ((int)__popc(__ballot_sync(0xffffffffu, !have || evict || cur == J3DG_EMPTY_CHILD)) >= LANE_REFILL_MIN) break;
+    }
+
+    // =========================== (D) leaf phase: 1..8 consecutive triangle records, the last one flagged ===========================
+    if (have && !evict && (cur & J3DG_LEAF_BIT) && cur != J3DG_EMPTY_CHILD) {
+      const int kx = (int)(r.kpack & 3u), ky = (int)((r.kpack >> 2) & 3u), kz = (int)(r.kpack >> 4);
+      do {
+        uint32_t slot = cur & J3DG_LEAF_FIRST_MASK;
+        for (;;) {
+          const float4* tp = reinterpret_cast<const float4*>(tris + slot);
+          const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+          if (STATS) ++ntris;
+          // one lane of intersect_woop (qbvh.h:4825-4869); 1/det is correctly rounded instead of rcpps + NR
+          const float Ax_ = fsub(v0.x, r.ox), Ay_ = fsub(v0.y, r.oy), Az_ = fsub(v0.z, r.oz);
+          const float Bx_ = fsub(v1.x, r.ox), By_ = fsub(v1.y, r.oy), Bz_ = fsub(v1.z, r.oz);
+          const float Cx_ = fsub(v2.x, r.ox), Cy_ = fsub(v2.y, r.oy), Cz_ = fsub(v2.z, r.oz);
+          const float Akz = pick(Ax_, Ay_, Az_, kz), Bkz = pick(Bx_, By_, Bz_, kz), Ckz = pick(Cx_, Cy_, Cz_, kz);
+          const float Ax = fsub(pick(Ax_, Ay_, Az_, kx), fmul(r.Sx, Akz));
+          const float Ay = fsub(pick(Ax_, Ay_, Az_, ky), fmul(r.Sy, Akz));
+          const float Bx = fsub(pick(Bx_, By_, Bz_, kx), fmul(r.Sx, Bkz));
+          const float By = fsub(pick(Bx_, By_, Bz_, ky), fmul(r.Sy, Bkz));
+          const float Cx = fsub(pick(Cx_, Cy_, Cz_, kx), fmul(r.Sx, Ckz));
+          const float Cy = fsub(pick(Cx_, Cy_, Cz_, ky), fmul(r.Sy, Ckz));
+          const float U = fsub(fmul(Cx, By), fmul(Cy, Bx));
+          const float V = fsub(fmul(Ax, Cy), fmul(Ay, Cx));
+          const float W = fsub(fmul(Bx, Ay), fmul(By, Ax));
+          const bool inside = ((U <= 0.f) && (V <= 0.f) && (W <= 0.f)) || ((U >= 0.f) && (V >= 0.f) && (W >= 0.f));
+          const float det = fadd(fadd(U, V), W);
+          if (inside && det != 0.f) {
+            const float inv_det = fdiv(1.f, det);
+            const float Az = fmul(r.Sz, Akz), Bz = fmul(r.Sz, Bkz), Cz = fmul(r.Sz, Ckz);
+            const float T = fadd(fadd(fmul(U, Az), fmul(V, Bz)), fmul(W, Cz));
+            const float t = fmul(T, inv_det);
+            if ((t_far > t) && (t > t_near) && (t < best_t)) {
+              best_t = t; best_u = fmul(V, inv_det); best_v = fmul(W, inv_det); best_slot = slot; best_mesh = mesh_k;
+              t_far = t;
+            }
+          }
+          if (__float_as_uint(v1.w) != 0u) break;  // end of leaf
+          ++slot;
+        }
+        if (ANY_HIT && best_slot != 0xFFFFFFFFu) { cur = J3DG_EMPTY_CHILD; sp = 0; }
+        else cur = pop();
+      } while (cur != J3DG_EMPTY_CHILD && (cur & J3DG_LEAF_BIT));
     }
   }
   if (STATS) {
@@ -692,6 +823,42 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_LANE_MIN_BLOCKS) lane_kern
       atomicAdd(p.stats + 1, (unsigned long long)sum_tris);
     }
   }
+}
+
+// The cast kernel proper: one launch, two kinds of warps.  Blocks [0, consumer_blocks) consume the hard-ray
+// queue from the start; all other blocks first trace tiles (one ray per lane, evicting long rays into the
+// queue), sign off, and then help to drain the queue.  The launch is cooperative, so every block is resident
+// and the consumers may wait for the producers.
+template <int MODE, bool STATS>
+__global__ void __launch_bounds__(BLOCK_THREADS, J3DG_LANE_MIN_BLOCKS) cast_kernel(const TraceParams p) {
+  __shared__ __align__(16) unsigned char smem[CAST_SMEM];
+#ifdef J3DG_TIMELINE
+  unsigned long long tl0, tl1, tl2;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl0));
+#endif
+  if (blockIdx.x >= p.consumer_blocks) {
+    lane_loop<MODE, STATS>(p, reinterpret_cast<uint2*>(smem), reinterpret_cast<uint32_t*>(smem + LANE_SMEM_STACK));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(p.done_blocks, 1u);
+    }
+  }
+#ifdef J3DG_TIMELINE
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl1));
+#endif
+  group_loop<MODE, QUEUE>(p, reinterpret_cast<uint2*>(smem));
+#ifdef J3DG_TIMELINE
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl2));
+  if (MODE == PRIMARY && threadIdx.x == 0) {  // [13] first start, [14] last end of the lane phase, [15] last end; + sums for means
+    atomicMin(p.stats + 13, tl0);
+    atomicMax(p.stats + 14, tl1);
+    atomicMax(p.stats + 15, tl2);
+    atomicAdd(p.stats + 16, tl1 - tl0);
+    atomicAdd(p.stats + 17, tl2 - tl1);
+    atomicAdd(p.stats + 18, 1ull);
+  }
+#endif
 }
 
 // ---- hit -> pixel record (canvas.cpp:788-834) + shadow ray generation (836-854) --------------------------
@@ -878,15 +1045,23 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
     if (rc != J3DG_OK) return rc;
   }
   const size_t hard_id_off = (npx * sizeof(float4) + 255) & ~(size_t)255;
-  {  // hard-ray list: worst case every ray is evicted
+  if (ctx->hard_cap < hard_id_off + npx * sizeof(uint2)) {  // hard-ray queue: worst case every ray is evicted
     int rc = j3dg_reserve(ctx, &ctx->d_hard, &ctx->hard_cap, hard_id_off + npx * sizeof(uint2));
     if (rc != J3DG_OK) return rc;
+    // every id = "not written yet"; consumers restore the marker, so the queue stays clean between launches
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->d_hard, 0xFF, ctx->hard_cap, ctx->stream));
+    ctx->hard_id_off = hard_id_off;
   }
-  // stats slots (u64 each): [0] node visits [1] triangle tests [2] stack overflow flag [3] pool counter lane<PRIMARY>
-  // [4] shadow rays traced (accumulates until the timings are reset) [5] shadow list length [6] hard rays PRIMARY
-  // [7] pool counter group<PRIMARY> [8] pool counter lane<SHADOW> [9] hard rays SHADOW [10] pool counter group<SHADOW>
+  // stats slots (u64 each): [0] node visits [1] triangle tests [2] stack overflow flag [3] pool counter PRIMARY
+  // [4] shadow rays traced (accumulates until the timings are reset) [5] shadow list length [6] queue length PRIMARY
+  // [7] queue claims PRIMARY [8] pool counter SHADOW [9] queue length SHADOW [10] queue claims SHADOW
+  // [11] producer blocks done PRIMARY [12] producer blocks done SHADOW
   CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
-  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats + 5, 0, 6 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats + 5, 0, 8 * sizeof(unsigned long long), ctx->stream));
+#ifdef J3DG_TIMELINE
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats + 13, 0xFF, sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats + 14, 0, 5 * sizeof(unsigned long long), ctx->stream));
+#endif
   TraceParams tp = {};
   tp.meshes = ctx->d_meshes;
   tp.nm = used;
@@ -899,33 +1074,40 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   tp.shadow_pos = (const float4*)ctx->d_shadow;
   tp.shadow_pix = (const uint32_t*)((const char*)ctx->d_shadow + shadow_pix_off);
   tp.hard_best = (float4*)ctx->d_hard;
-  tp.hard_id = (uint2*)((char*)ctx->d_hard + hard_id_off);
+  tp.hard_id = (uint2*)((char*)ctx->d_hard + ctx->hard_id_off);
+  tp.hard_capacity = (uint32_t)std::min<size_t>((ctx->hard_cap - ctx->hard_id_off) / sizeof(uint2), ctx->hard_id_off / sizeof(float4));
   tp.budget = stats ? 0xFFFFFFFFu : ctx->lane_budget;
   auto ctr = [&](int slot) { return reinterpret_cast<unsigned int*>(ctx->d_stats + slot); };
   const long long ntiles = (long long)((rw + TILE_W - 1) / TILE_W) * ((rh + TILE_H - 1) / TILE_H);
+  // One cooperative launch of the hybrid kernel: the grid fills the machine once, every block is resident.
+  auto launch_hybrid = [&](auto kernel, long long pools) -> int {
+    int nb = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, BLOCK_THREADS, 0);
+    if (e != cudaSuccess) return j3dg_cuda_fail(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor", __FILE__, __LINE__);
+    const int full = ctx->sm_count * std::max(nb, 1);
+    // dedicated consumer blocks only when the machine is full anyway; small jobs just run producers that convert
+    tp.consumer_blocks = (stats || pools * 32 < (long long)full * BLOCK_THREADS * 4) ? 0u : (uint32_t)std::min<long long>(ctx->consumer_blocks, full / 2);
+    const long long producers = std::max<long long>(1, std::min<long long>((long long)full - tp.consumer_blocks, (pools + 3) / 4));
+    const int grid = (int)(producers + tp.consumer_blocks);
+    void* args[] = {(void*)&tp};
+    e = cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(BLOCK_THREADS), args, 0, ctx->stream);
+    if (e != cudaSuccess) return j3dg_cuda_fail(ctx, e, "cudaLaunchCooperativeKernel", __FILE__, __LINE__);
+    ctx->launches++;
+    return J3DG_OK;
+  };
   int grid = 1, rc;
   rc = j3dg_stage_begin(ctx, 0);
   if (rc != J3DG_OK) return rc;
   // ---- primary rays ----
+  tp.pool_ctr = ctr(3); tp.hard_count = ctr(6); tp.hard_taken = ctr(7); tp.done_blocks = ctr(11);
   if (stats) {
-    tp.pool_ctr = ctr(3); tp.hard_count = ctr(6);
-    if ((rc = persistent_grid(ctx, lane_kernel<PRIMARY, true>, ntiles, &grid)) != J3DG_OK) return rc;
-    lane_kernel<PRIMARY, true><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
-    KERNEL_CHECK(ctx);
-  } else if (ctx->cast_algo == 1) {  // group kernel only (A/B testing)
-    tp.pool_ctr = ctr(7);
-    if ((rc = persistent_grid(ctx, group_kernel<PRIMARY, false>, ntiles, &grid)) != J3DG_OK) return rc;
-    group_kernel<PRIMARY, false><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
+    if ((rc = launch_hybrid(cast_kernel<PRIMARY, true>, ntiles)) != J3DG_OK) return rc;
+  } else if (ctx->cast_algo == 1) {  // 8-lanes-per-ray kernel only (A/B testing)
+    if ((rc = persistent_grid(ctx, group_kernel<PRIMARY>, ntiles, &grid)) != J3DG_OK) return rc;
+    group_kernel<PRIMARY><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
     KERNEL_CHECK(ctx);
   } else {
-    tp.pool_ctr = ctr(3); tp.hard_count = ctr(6);
-    if ((rc = persistent_grid(ctx, lane_kernel<PRIMARY, false>, ntiles, &grid)) != J3DG_OK) return rc;
-    lane_kernel<PRIMARY, false><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
-    KERNEL_CHECK(ctx);
-    tp.pool_ctr = ctr(7);
-    if ((rc = persistent_grid(ctx, group_kernel<PRIMARY, true>, ((long long)npx + 3) / 4, &grid)) != J3DG_OK) return rc;
-    group_kernel<PRIMARY, true><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
-    KERNEL_CHECK(ctx);
+    if ((rc = launch_hybrid(cast_kernel<PRIMARY, false>, ntiles)) != J3DG_OK) return rc;
   }
   if (used && !stats) {
     const uint32_t warps = 256 / 32;
@@ -936,25 +1118,27 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   // ---- shadow rays of the hit pixels ----
   if (shadows) {
     const long long pools = ((long long)npx + 31) / 32;
+    tp.pool_ctr = ctr(8); tp.hard_count = ctr(9); tp.hard_taken = ctr(10); tp.done_blocks = ctr(12);
     if (ctx->cast_algo == 1) {
-      tp.pool_ctr = ctr(10);
-      if ((rc = persistent_grid(ctx, group_kernel<SHADOW, false>, pools, &grid)) != J3DG_OK) return rc;
-      group_kernel<SHADOW, false><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
+      if ((rc = persistent_grid(ctx, group_kernel<SHADOW>, pools, &grid)) != J3DG_OK) return rc;
+      group_kernel<SHADOW><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
       KERNEL_CHECK(ctx);
     } else {
-      tp.pool_ctr = ctr(8); tp.hard_count = ctr(9);
-      if ((rc = persistent_grid(ctx, lane_kernel<SHADOW, false>, pools, &grid)) != J3DG_OK) return rc;
-      lane_kernel<SHADOW, false><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
-      KERNEL_CHECK(ctx);
-      tp.pool_ctr = ctr(10);
-      if ((rc = persistent_grid(ctx, group_kernel<SHADOW, true>, ((long long)npx + 3) / 4, &grid)) != J3DG_OK) return rc;
-      group_kernel<SHADOW, true><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
-      KERNEL_CHECK(ctx);
+      if ((rc = launch_hybrid(cast_kernel<SHADOW, false>, pools)) != J3DG_OK) return rc;
     }
   }
   rc = j3dg_stage_end(ctx, 0);
   if (rc != J3DG_OK) return rc;
   ctx->rays_primary += (uint64_t)rw * rh;  // shadow rays (d_stats[4]) are added when the timings are read
+#ifdef J3DG_TIMELINE
+  if (!stats) {
+    unsigned long long t[20];
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(t, ctx->d_stats, sizeof(t), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "timeline: lane phase ends by %.0f us, kernel ends %.0f us; per block mean lane %.0f us, mean drain %.0f us; hard rays %llu\n",
+            (t[14] - t[13]) * 1e-3, (t[15] - t[13]) * 1e-3, t[16] * 1e-3 / t[18], t[17] * 1e-3 / t[18], t[6]);
+  }
+#endif
   return J3DG_OK;
 }
 
@@ -980,9 +1164,9 @@ int j3dg_launch_find_closest(j3dg_mesh* m, const float* d_rays, uint32_t n, floa
   tp.rays = d_rays; tp.hits = d_hits; tp.ids = d_ids; tp.nrays = n;
   tp.pool_ctr = reinterpret_cast<unsigned int*>(ctx->d_stats + 3);
   int grid = 1;
-  int rc = persistent_grid(ctx, group_kernel<RAYLIST, false>, ((long long)n + 31) / 32, &grid);
+  int rc = persistent_grid(ctx, group_kernel<RAYLIST>, ((long long)n + 31) / 32, &grid);
   if (rc != J3DG_OK) return rc;
-  group_kernel<RAYLIST, false><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
+  group_kernel<RAYLIST><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
   KERNEL_CHECK(ctx);
   return J3DG_OK;
 }

@@ -22,24 +22,26 @@
 // Child boxes are quantised to 8 bits per plane relative to (origin, scale): the decoded plane
 // fl(origin + q * scale) is guaranteed by the builder to contain the child's true box (scale is a
 // power of two, so q * scale is exact).
-// box[c] = { qlo.x, qlo.y, qlo.z, qhi.x, qhi.y, qhi.z, 0x00, 0x4B }: the two constant bytes let a
-//          single PRMT assemble the float 2^23 + q from any plane byte (byte 7 -> exponent, byte 6 -> zeros).
+// box[c] = { qlo.x, qlo.y, qlo.z, qhi.x, qhi.y, qhi.z, 0x80, 0x3F }: the two constant bytes let a
+//          single PRMT assemble the float 0x3F80_qq_00 = 1 + q * 2^-15 from any plane byte (cast.cu, plane()).
 // child[c]: bit31 = 0 -> index of an inner node; bit31 = 1 -> leaf, bits 0..30 = first triangle
 //           record; a leaf is 1..8 consecutive records, the last one carries TriRec::last != 0.
 // Empty slots have an inverted box (qlo = 255, qhi = 0) and child = J3DG_EMPTY_CHILD.
 struct __align__(128) WideNode {
   float ox, oy, oz;      // quantisation origin = node box minimum
   uint32_t nchild;       // number of used slots (diagnostic)
-  float sx, sy, sz;      // quantisation step per axis (a power of two)
+  float sx, sy, sz;      // quantisation step per axis (a power of two) times 2^15
   uint32_t pad0;
-  uint8_t box[8][8];     // [slot][qlo.xyz, qhi.xyz, 0x00, 0x4B]
+  uint8_t box[8][8];     // [slot][qlo.xyz, qhi.xyz, 0x80, 0x3F]
   uint32_t child[8];
 };
 static_assert(sizeof(WideNode) == 128, "WideNode must be 128 bytes");
 
 #define J3DG_LEAF_BIT 0x80000000u
 #define J3DG_EMPTY_CHILD 0xFFFFFFFFu
-#define J3DG_MAX_LEAF 8
+#ifndef J3DG_MAX_LEAF
+#define J3DG_MAX_LEAF 8       // triangles per leaf, at most 8 (the group kernel tests a leaf with 8 lanes)
+#endif
 #define J3DG_LEAF_FIRST_MASK 0x7FFFFFFFu
 #define J3DG_TRI_PAD 8   // records allocated past the end: a group always loads 8 consecutive records
 
@@ -145,6 +147,8 @@ struct j3dg_ctx {
   uint32_t* h_overflow = nullptr;                    // pinned: stack-overflow flag of each in-flight frame
   std::vector<MeshDev> meshes_uploaded;              // last mesh table sent to d_meshes (re-uploaded only when it changes)
   void* d_hard = nullptr; size_t hard_cap = 0;       // hard-ray list handed from the lane kernel to the group kernel
+  size_t hard_id_off = 0;                            // offset of the id array inside d_hard
+  uint32_t consumer_blocks = 0;                      // blocks of the cast kernel that consume the hard-ray queue from the start (J3DG_CONSUMER_BLOCKS)
   uint32_t lane_budget = 24;                         // node visits per ray before the lane kernel evicts it (J3DG_LANE_BUDGET)
   int cast_algo = 0;                                 // 0 hybrid (lane + group), 1 group kernel only (J3DG_CAST_ALGO=group)
 };
