@@ -205,9 +205,9 @@ static inline size_t scratch_bytes(uint32_t n) {
 
 // Sorts by bits [0, key_bits) of the keys.  Result ends in (keys_a, vals_a) if the number of
 // passes is even, else in (keys_b, vals_b); returns which through *result_in_b.
-// vals_a need not be initialised: the first pass generates 0..n-1.
+// iota_values: vals_a need not be initialised, the first pass generates 0..n-1.
 static inline int sort_pairs(j3dg_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t n,
-                             int key_bits, uint32_t* scratch, bool* result_in_b) {
+                             int key_bits, uint32_t* scratch, bool* result_in_b, bool iota_values = true) {
   static bool attr_set = false;
   if (!attr_set) {
     CU_CHECK(ctx, cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM));
@@ -233,7 +233,7 @@ static inline int sort_pairs(j3dg_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, 
     KERNEL_CHECK(ctx);
     scan_apply<<<nchunks, SCAN_THREADS, 0, ctx->stream>>>(table, table_n, sums);
     KERNEL_CHECK(ctx);
-    scatter_kernel<<<ntiles, THREADS, SCATTER_SMEM, ctx->stream>>>(kin, vin, kout, vout, n, shift, table, ntiles, pass == 0 ? 1 : 0);
+    scatter_kernel<<<ntiles, THREADS, SCATTER_SMEM, ctx->stream>>>(kin, vin, kout, vout, n, shift, table, ntiles, (pass == 0 && iota_values) ? 1 : 0);
     KERNEL_CHECK(ctx);
     in_b = !in_b;
   }

@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(256) seed_kernel(const j3dg_pixel* __restrict_
 __device__ __forceinline__ int cvt_rne(float x) { return (fabsf(x) < 2147483648.f) ? __float2int_rn(x) : (int)0x80000000; }
 __device__ __forceinline__ int cvt_trunc(float x) { return (fabsf(x) < 2147483648.f) ? __float2int_rz(x) : (int)0x80000000; }
 
+constexpr uint32_t REPLAY_MASKED = 0xFFFFFFFFu;  // a NaN pattern: like a masked lane, a NaN depth never passes the test
+
 struct Lane {
   int idx;       // clamped pixel index (render.h:779-781)
   bool masked;   // outside the canvas (render.h:729-732)
@@ -112,7 +114,7 @@ __device__ __forceinline__ void load_packet(const float* __restrict__ pos, uint3
 template <bool COLLECT>
 __global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ pos, SplatParams s, unsigned long long* __restrict__ packed,
                                                        uint8_t* __restrict__ dirty, uint32_t* __restrict__ counters,
-                                                       unsigned long long* __restrict__ list) {
+                                                       unsigned long long* __restrict__ list, uint32_t* __restrict__ list_depth) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t npackets = s.tail_start >> 2;
   if (t < npackets) {
@@ -141,7 +143,11 @@ __global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ 
     } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (dirty[l[k].idx]) list[atomicAdd(&counters[1], 1u)] = ((unsigned long long)(uint32_t)l[k].idx << 32) | (unsigned long long)(4u * t + k);
+        if (dirty[l[k].idx]) {  // the replay needs the lane's depth, or that it is masked (then it only writes the old value back)
+          const uint32_t e = atomicAdd(&counters[1], 1u);
+          list[e] = ((unsigned long long)(uint32_t)l[k].idx << 32) | (unsigned long long)(4u * t + k);
+          list_depth[e] = l[k].masked ? REPLAY_MASKED : __float_as_uint(l[k].depth);
+        }
     }
   } else {
     const uint32_t i = s.tail_start + (t - npackets);
@@ -154,7 +160,9 @@ __global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ 
       unsigned long long* cell = packed + l.idx;
       if (word > *((volatile unsigned long long*)cell)) atomicMax(cell, word);
     } else if (dirty[l.idx]) {
-      list[atomicAdd(&counters[1], 1u)] = ((unsigned long long)(uint32_t)l.idx << 32) | (unsigned long long)i;
+      const uint32_t e = atomicAdd(&counters[1], 1u);
+      list[e] = ((unsigned long long)(uint32_t)l.idx << 32) | (unsigned long long)i;
+      list_depth[e] = __float_as_uint(l.depth);
     }
   }
 }
@@ -183,10 +191,12 @@ __device__ __forceinline__ uint32_t shade_point(const SplatParams& s, const floa
   return color;
 }
 
-// Sequential replay of every dirty pixel with the reference's packet semantics.  `list` is sorted
-// by (pixel, point index); the thread at the first entry of a pixel walks that pixel's entries.
-__global__ void __launch_bounds__(128) replay_kernel(SplatParams s, const float* __restrict__ pos, const float* __restrict__ nrm,
-                                                      const uint32_t* __restrict__ clr, const unsigned long long* __restrict__ list, uint32_t count,
+// Sequential replay of every dirty pixel with the reference's packet semantics.  `list` is sorted by
+// (pixel, point index) and carries each entry's projected depth (REPLAY_MASKED for lanes outside the canvas),
+// so the fold over a pixel's entries touches no point data; the thread at the first entry of a pixel walks
+// that pixel's entries and shades the surviving point once at the end.
+__global__ void __launch_bounds__(128) replay_kernel(SplatParams s, const float* __restrict__ nrm, const uint32_t* __restrict__ clr,
+                                                      const unsigned long long* __restrict__ list, const uint32_t* __restrict__ list_depth, uint32_t count,
                                                       unsigned long long* __restrict__ packed, float* __restrict__ zprev,
                                                       j3dg_pixel* __restrict__ px, uint32_t pstride, uint32_t* __restrict__ rgba, uint32_t rstride) {
   const uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -194,46 +204,52 @@ __global__ void __launch_bounds__(128) replay_kernel(SplatParams s, const float*
   const uint32_t q = (uint32_t)(list[k0] >> 32);
   if (k0 > 0 && (uint32_t)(list[k0 - 1] >> 32) == q) return;  // not the first entry of its pixel
   float z = zprev[q];
-  const int qx = (int)(q % (uint32_t)s.w), qy = (int)(q / (uint32_t)s.w);
-  uint32_t* out_rgba = rgba + (size_t)qy * rstride + qx;
-  j3dg_pixel* out_px = px + (size_t)qy * pstride + qx;
+  constexpr uint32_t NONE = 0xFFFFFFFFu;
+  uint32_t color_point = NONE;  // the point whose colour the pixel ends up with
+  uint32_t id_point = NONE;     // the point the pixel record ends up naming, and the z-buffer value at that moment
+  float id_z = 0.f;
   uint32_t k = k0;
-  while (k < count && (uint32_t)(list[k] >> 32) == q) {
-    const uint32_t i = (uint32_t)list[k];
-    if (i >= s.tail_start) {  // scalar tail point, render.h:847-862
-      const Lane l = project_tail(s, __ldg(pos + 3 * (size_t)i), __ldg(pos + 3 * (size_t)i + 1), __ldg(pos + 3 * (size_t)i + 2));
-      if (!l.masked && l.depth > z) {
-        z = l.depth;
-        *out_rgba = shade_point(s, nrm, clr, i);
-        out_px->object_id = i; out_px->depth = fdiv(1.f, z); out_px->db_id = s.db_id;
-      }
+  while (k < count) {
+    unsigned long long e = list[k];
+    if ((uint32_t)(e >> 32) != q) break;
+    const uint32_t i = (uint32_t)e;
+    if (i >= s.tail_start) {  // scalar tail point, render.h:847-862 (clipped ones were never collected)
+      const float d = __uint_as_float(list_depth[k]);
+      if (d > z) { z = d; color_point = i; id_point = i; id_z = z; }
       ++k;
       continue;
     }
     // all lanes of this packet that touch the pixel: every test sees the pre-packet depth
     const uint32_t packet = i >> 2;
     const float z_old = z;
-    int last_pass_index = -1;
+    uint32_t last_pass_point = NONE;
     bool last_lane_pass = false;
     uint32_t last_lane_point = i;
     float last_lane_depth = 0.f;
-    while (k < count && (uint32_t)(list[k] >> 32) == q && (((uint32_t)list[k]) >> 2) == packet && (uint32_t)list[k] < s.tail_start) {
-      const uint32_t pi = (uint32_t)list[k];
-      const Lane l = project_simd(s, __ldg(pos + 3 * (size_t)pi), __ldg(pos + 3 * (size_t)pi + 1), __ldg(pos + 3 * (size_t)pi + 2));
-      const bool pass = !l.masked && (z_old < l.depth);  // render.h:791-792
-      if (pass) last_pass_index = (int)pi;                // the last passing lane's callback wins (canvas.cpp:999-1026)
-      last_lane_pass = pass; last_lane_point = pi; last_lane_depth = l.depth;
+    while (k < count) {
+      e = list[k];
+      const uint32_t pi = (uint32_t)e;
+      if ((uint32_t)(e >> 32) != q || (pi >> 2) != packet || pi >= s.tail_start) break;
+      const uint32_t bits = list_depth[k];
+      const float d = __uint_as_float(bits);
+      const bool pass = bits != REPLAY_MASKED && (z_old < d);  // render.h:791-792
+      if (pass) last_pass_point = pi;                           // the last passing lane's callback wins (canvas.cpp:999-1026)
+      last_lane_pass = pass; last_lane_point = pi; last_lane_depth = d;
       ++k;
     }
     if (last_lane_pass) {  // the highest lane's write is the one that sticks (render.h:797-805)
       z = last_lane_depth;
-      *out_rgba = shade_point(s, nrm, clr, last_lane_point);
+      color_point = last_lane_point;
     }  // else: it wrote the pre-packet depth and colour back
-    if (last_pass_index >= 0) {
-      out_px->object_id = (uint32_t)last_pass_index;
-      out_px->depth = fdiv(1.f, z);  // 1 / zbuffer after the packet's writes
-      out_px->db_id = s.db_id;
-    }
+    if (last_pass_point != NONE) { id_point = last_pass_point; id_z = z; }  // 1 / zbuffer after the packet's writes
+  }
+  const int qx = (int)(q % (uint32_t)s.w), qy = (int)(q / (uint32_t)s.w);
+  if (color_point != NONE) rgba[(size_t)qy * rstride + qx] = shade_point(s, nrm, clr, color_point);
+  if (id_point != NONE) {
+    j3dg_pixel* out_px = px + (size_t)qy * pstride + qx;
+    out_px->object_id = id_point;
+    out_px->depth = fdiv(1.f, id_z);
+    out_px->db_id = s.db_id;
   }
   zprev[q] = z;
   packed[q] = ((unsigned long long)__float_as_uint(z) << 32) | 0xFFFFFFFFull;  // resolved: resolve_kernel skips it
@@ -343,7 +359,7 @@ int j3dg_launch_splat(j3dg_ctx* ctx, j3dg_cloud* const* clouds, uint32_t nc, con
       const uint32_t blocks = (threads + 255) / 256;
       CU_CHECK(ctx, cudaMemsetAsync(dirty, 0, npx, ctx->stream));
       CU_CHECK(ctx, cudaMemsetAsync(counters, 0, 16, ctx->stream));
-      project_kernel<false><<<blocks, 256, 0, ctx->stream>>>(cl->d_pos, s, packed, dirty, counters, nullptr);
+      project_kernel<false><<<blocks, 256, 0, ctx->stream>>>(cl->d_pos, s, packed, dirty, counters, nullptr, nullptr);
       KERNEL_CHECK(ctx);
       uint32_t h_cnt[2] = {0, 0};
       CU_CHECK(ctx, cudaMemcpyAsync(h_cnt, counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
@@ -361,7 +377,7 @@ int j3dg_launch_splat(j3dg_ctx* ctx, j3dg_cloud* const* clouds, uint32_t nc, con
         uint32_t* vals_a = (uint32_t*)take(nn * 4);
         uint32_t* vals_b = (uint32_t*)take(nn * 4);
         uint32_t* scratch = (uint32_t*)take(rsort::scratch_bytes(cl->n));
-        project_kernel<true><<<blocks, 256, 0, ctx->stream>>>(cl->d_pos, s, packed, dirty, counters, (unsigned long long*)keys_a);
+        project_kernel<true><<<blocks, 256, 0, ctx->stream>>>(cl->d_pos, s, packed, dirty, counters, (unsigned long long*)keys_a, vals_a);
         KERNEL_CHECK(ctx);
         CU_CHECK(ctx, cudaMemcpyAsync(h_cnt, counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
         CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -369,10 +385,10 @@ int j3dg_launch_splat(j3dg_ctx* ctx, j3dg_cloud* const* clouds, uint32_t nc, con
         if (count) {
           bool in_b = false;
           const int key_bits = 32 + bits_for(npx - 1);
-          rc = rsort::sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, count, key_bits, scratch, &in_b);
+          rc = rsort::sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, count, key_bits, scratch, &in_b, false);
           if (rc != J3DG_OK) return rc;
           const unsigned long long* sorted = (const unsigned long long*)(in_b ? keys_b : keys_a);
-          replay_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(s, cl->d_pos, cl->d_nrm, cl->d_clr, sorted, count, packed, zprev,
+          replay_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(s, cl->d_nrm, cl->d_clr, sorted, in_b ? vals_b : vals_a, count, packed, zprev,
                                                                        d_px_inout, pstride, d_rgba, rstride);
           KERNEL_CHECK(ctx);
         }
