@@ -344,7 +344,7 @@ def run_b200(args, f, rank, world, local_rank):
             traffic = json.loads(tp.read_text()).get("cast_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "cast stage = lane_kernel + group_kernel + resolve_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "cast stage = cast_kernel (one cooperative launch: lane warps + 8-lane hard-ray groups) + resolve_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
                 "tris_per_ray": tris_per_ray, "kernel_ms": cast_ms, "kernel_mrays_s": W * H / cast_ms / 1e3}
     cpu = cpu_baseline(j, f, verts, tris, v0) if (world == 1 and not args.no_cpu_baseline) else None

@@ -115,6 +115,17 @@ int j3dg_ctx_set_profiling(j3dg_ctx* ctx, int enabled);
  * one-ray-per-8-lanes kernel (0 = default); cast_algo: 0 = hybrid (default), 1 = 8-lane kernel only. */
 int j3dg_ctx_set_tuning(j3dg_ctx* ctx, uint32_t lane_budget, int cast_algo);
 
+/* Screen sharding for one frame rendered by several GPUs (BASELINE configs[2]): the canvas is cut
+ * into bands of J3DG_SHARD_BAND_ROWS rows, band b belongs to rank b mod world.  With world > 1, j3dg_cast /
+ * j3dg_render_frame trace only this rank's bands plus the single pixel row above each of them (the edge
+ * shader's up neighbour, canvas.cpp:625-640 — recomputed instead of exchanged), and j3dg_shade writes only
+ * this rank's rows; everything else in the output buffers is left untouched.  The result in the owned rows
+ * is identical to the unsharded frame.  Gathering the bands (NCCL) happens above this ABI
+ * (j3d_b200/dist.py::gather_bands).  world = 1 (default) switches sharding off.  Point-cloud splats are not
+ * sharded.  Bands are counted from the first row of the cast rectangle (row 0 for whole frames). */
+#define J3DG_SHARD_BAND_ROWS 32
+int j3dg_ctx_set_screen_shard(j3dg_ctx* ctx, uint32_t rank, uint32_t world);
+
 /* ---- BVH build: replaces `new qbvh(triangles, vertices)` + compute_triangle_normals
  *      + compute_bb in add_object (j3d/scene.cpp:8-25; jtk/qbvh.h:1679-1686). -------
  * vertices: nv x 3 float (jtk::vec3<float>), triangles: nt x 3 uint32.

@@ -116,6 +116,7 @@ def lib() -> C.CDLL:
         L.j3dg_frame_wait.argtypes = [_vp]
         L.j3dg_ctx_set_matcap.argtypes = [_vp, _vp, _u32, _u32, _u32, _u32]
         L.j3dg_ctx_set_tuning.argtypes = [_vp, _u32, C.c_int]
+        L.j3dg_ctx_set_screen_shard.argtypes = [_vp, _u32, _u32]
         L.j3dg_cast_stats.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(View), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.j3dg_cast_cost_image.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(View), _vp, _vp]
         _lib = L
@@ -364,6 +365,10 @@ class Context:
 
     def set_tuning(self, lane_budget: int = 0, cast_algo: int = 0):
         self._check(self._L.j3dg_ctx_set_tuning(self._h, lane_budget, cast_algo), "j3dg_ctx_set_tuning")
+
+    def set_screen_shard(self, rank: int = 0, world: int = 1):
+        """Band b (J3DG_SHARD_BAND_ROWS = 32 rows) of every frame belongs to rank b mod world; world = 1: off."""
+        self._check(self._L.j3dg_ctx_set_screen_shard(self._h, rank, world), "j3dg_ctx_set_screen_shard")
 
     def cast_stats(self, meshes, view: View):
         a, b = C.c_double(), C.c_double()

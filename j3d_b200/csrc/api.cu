@@ -208,6 +208,13 @@ J3DG_API int j3dg_ctx_set_tuning(j3dg_ctx* ctx, uint32_t lane_budget, int cast_a
   return J3DG_OK;
 }
 
+J3DG_API int j3dg_ctx_set_screen_shard(j3dg_ctx* ctx, uint32_t rank, uint32_t world) {
+  if (!ctx || world == 0 || rank >= world) { j3dg_set_error(ctx, "j3dg_ctx_set_screen_shard: need rank < world"); return J3DG_EINVAL; }
+  ctx->shard_rank = rank;
+  ctx->shard_world = world;
+  return J3DG_OK;
+}
+
 J3DG_API int j3dg_ctx_timings(j3dg_ctx* ctx, j3dg_timings* out, int reset) {
   if (!ctx || !out) return J3DG_EINVAL;
   CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -54,11 +54,56 @@ constexpr int SUPER_W = 4, SUPER_H = 8;                   // tiles are numbered 
 
 enum Mode { PRIMARY = 0, SHADOW = 1, RAYLIST = 2 };
 
+// Enumeration of the 8x4-pixel tiles of a rectangle as "pools" (one pool = one tile = 32 rays).  Tiles are
+// numbered super-tile by super-tile (32x32 pixels), super-tile rows = BANDS of J3DG_SHARD_BAND_ROWS rows.
+// Screen sharding (j3dg_ctx_set_screen_shard): band b belongs to rank b mod world, so the pools
+// of a rank are the tiles of its own bands, followed by HALO pools: the tile row directly above each owned
+// band, of which only the bottom pixel row is traced — the edge shader reads the up neighbour
+// (canvas.cpp:625-640), the right neighbour lies in the same band.  world == 1: every band, no halo.
+struct TileGrid {
+  uint32_t supers_x;      // super-tiles per band
+  uint32_t main_pools;    // own_bands * supers_x * 32
+  uint32_t total_pools;   // main_pools + halo pools
+  uint32_t rank, world;
+};
+static_assert(SUPER_H * TILE_H == J3DG_SHARD_BAND_ROWS, "a band is one super-tile row");
+
+TileGrid make_tile_grid(int x0, int y0, int x1, int y1, uint32_t rank, uint32_t world) {
+  TileGrid g;
+  const uint32_t tiles_x = (uint32_t)(x1 - x0 + TILE_W) / TILE_W, tiles_y = (uint32_t)(y1 - y0 + TILE_H) / TILE_H;
+  g.supers_x = (tiles_x + SUPER_W - 1) / SUPER_W;
+  const uint32_t bands = (tiles_y + SUPER_H - 1) / SUPER_H;
+  g.rank = rank; g.world = world ? world : 1u;
+  const uint32_t own = rank < bands ? (bands - rank + g.world - 1) / g.world : 0u;
+  g.main_pools = own * g.supers_x * (SUPER_W * SUPER_H);
+  g.total_pools = g.main_pools + (g.world > 1 ? own * g.supers_x * SUPER_W : 0u);
+  return g;
+}
+
+// pool -> tile coordinates; false: nothing to trace.  `halo`: only the tile's bottom pixel row is wanted.
+__device__ __forceinline__ bool tile_of_pool(const TileGrid& g, uint32_t pool, uint32_t& tx, uint32_t& ty, bool& halo) {
+  if (pool < g.main_pools) {
+    const uint32_t sup = pool / (SUPER_W * SUPER_H), in = pool % (SUPER_W * SUPER_H);
+    const uint32_t band = g.rank + (sup / g.supers_x) * g.world;
+    tx = (sup % g.supers_x) * SUPER_W + (in % SUPER_W);
+    ty = band * SUPER_H + (in / SUPER_W);
+    halo = false;
+    return true;
+  }
+  const uint32_t h = pool - g.main_pools, per = g.supers_x * SUPER_W;
+  const uint32_t band = g.rank + (h / per) * g.world;
+  tx = h % per;
+  ty = band * SUPER_H - 1u;
+  halo = true;
+  return band != 0u;
+}
+
 struct TraceParams {
   const MeshDev* meshes;
   uint32_t nm;
   ViewDev vw;
   int x0, y0, x1, y1;
+  TileGrid grid;                 // PRIMARY: the pools of this launch
   j3dg_pixel* out;               // PRIMARY: raw hits are written here; SHADOW: mark bit 0 is set here
   uint32_t stride;
   unsigned long long* stats;     // [0] node rounds [1] triangle tests [2] overflow flag [3] pool counter [4] shadow rays (accumulating) [5] shadow list length
@@ -192,14 +237,11 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* s_stack)
 
   // ---- number of ray slots ----
   uint32_t total_pools;   // a pool = 32 consecutive slots
-  uint32_t supers_x = 1;
   uint32_t list_n = 0;
   if (SRC == QUEUE) {
     total_pools = 0;
   } else if (MODE == PRIMARY) {
-    const uint32_t tiles_x = (uint32_t)(p.x1 - p.x0 + TILE_W) / TILE_W, tiles_y = (uint32_t)(p.y1 - p.y0 + TILE_H) / TILE_H;
-    supers_x = (tiles_x + SUPER_W - 1) / SUPER_W;
-    total_pools = supers_x * ((tiles_y + SUPER_H - 1) / SUPER_H) * (SUPER_W * SUPER_H);
+    total_pools = p.grid.total_pools;
   } else {
     list_n = MODE == SHADOW ? (uint32_t)p.stats[5] : p.nrays;
     total_pools = (list_n + 31u) / 32u;
@@ -226,6 +268,7 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* s_stack)
   bool exhausted = false;
   uint32_t claimed = QUEUE_EMPTY;   // QUEUE: entry this group has claimed and waits for
   bool retired = false;             // QUEUE: nothing left for this group
+  uint32_t backoff = 250u;          // QUEUE: nanoseconds an idle warp sleeps before it polls again (doubles up to 4 us)
   const uint32_t producer_blocks = gridDim.x - p.consumer_blocks;
 
   auto pop = [&]() -> uint32_t {
@@ -335,9 +378,11 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* s_stack)
       const uint32_t busy = __ballot_sync(0xffffffffu, have_ray);
       if (!busy) {
         if (__all_sync(0xffffffffu, retired)) break;
-        __nanosleep(200);  // nothing to do yet: do not hammer the queue
+        __nanosleep(backoff);  // nothing to do yet: do not hammer the queue (nor the issue slots of the lane warps)
+        backoff = min(backoff * 2u, 4000u);
         continue;
       }
+      backoff = 250u;
     } else {
     // groups without a ray take the next slots of the warp's pool (warp-uniform loop)
     uint32_t need = __ballot_sync(0xffffffffu, !have_ray) & 0x01010101u;
@@ -356,11 +401,12 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* s_stack)
       if (take) {
         bool ok;
         if (MODE == PRIMARY) {
-          const uint32_t sup = pool_id / (SUPER_W * SUPER_H), in = pool_id % (SUPER_W * SUPER_H);
-          const uint32_t tx = (sup % supers_x) * SUPER_W + (in % SUPER_W), ty = (sup / supers_x) * SUPER_H + (in / SUPER_W);
+          uint32_t tx, ty;
+          bool halo;
+          const bool tile_ok = tile_of_pool(p.grid, pool_id, tx, ty, halo);
           const int x = p.x0 + (int)tx * TILE_W + (int)(slot & (TILE_W - 1));
           const int y = p.y0 + (int)ty * TILE_H + (int)(slot / TILE_W);
-          ok = x <= p.x1 && y <= p.y1;
+          ok = tile_ok && x <= p.x1 && y <= p.y1 && (!halo || slot / TILE_W == TILE_H - 1);
           ray_id = ((uint32_t)y << 16) | (uint32_t)x;
         } else {
           ray_id = pool_id * 32u + slot;
@@ -433,6 +479,12 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* s_stack)
             const int pos = sp + __popc(others & below);
             if (pos < STACK_SIZE) stk[pos * GROUPS_PER_BLOCK] = make_uint2(ref, __float_as_uint(tmin));
             else *overflow_flag = 1u;
+#ifdef J3DG_GROUP_PUSH_PREFETCH
+            {  // pull the postponed child towards L2 while the nearer one is traversed
+              const char* a = (ref & J3DG_LEAF_BIT) ? reinterpret_cast<const char*>(tris + (ref & J3DG_LEAF_FIRST_MASK)) : reinterpret_cast<const char*>(nodes + ref);
+              asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
+            }
+#endif
           }
           sp = min(sp + __popc(others), STACK_SIZE);
           cur = next;
@@ -527,6 +579,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) group_ker
 // hard-ray list with its best hit so far (group_kernel finishes it).
 constexpr int LANE_STACK = 12;        // 13 rows (one scratch row) * 8 B * 128 lanes = 13 KB shared memory per block
 constexpr int LANE_REFILL_MIN = J3DG_LANE_REFILL_MIN;
+#ifndef J3DG_LANE_TRI_WEIGHT
+#define J3DG_LANE_TRI_WEIGHT 1                            // lane kernel: a triangle step is taken when tri lanes * weight >= node lanes
+#endif
+constexpr int LANE_TRI_WEIGHT = J3DG_LANE_TRI_WEIGHT;
+#ifndef J3DG_TRI_PREFETCH
+#define J3DG_TRI_PREFETCH 5                               // lane kernel: L1 prefetch distance of a triangle step in float4 units (0 = off)
+#endif
+constexpr int LANE_TRI_PREFETCH = J3DG_TRI_PREFETCH;
 constexpr int RAY_WORDS = 12;         // parked ray: ox oy oz | idx idy idz | Sx Sy Sz | kx,ky,kz packed | t_far | ray id
 
 // Object-space traversal constants of a ray for one mesh (qbvh.h:3358-3359, 4793-4823).
@@ -569,11 +629,9 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* s_stack, 
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const float t_near = MODE == PRIMARY ? fdiv(p.vw.diagonal, 100.f) : 1e-3f;          // canvas.cpp:781 / 853
-  uint32_t total_pools, supers_x = 1, list_n = 0;
+  uint32_t total_pools, list_n = 0;
   if (MODE == PRIMARY) {
-    const uint32_t tiles_x = (uint32_t)(p.x1 - p.x0 + TILE_W) / TILE_W, tiles_y = (uint32_t)(p.y1 - p.y0 + TILE_H) / TILE_H;
-    supers_x = (tiles_x + SUPER_W - 1) / SUPER_W;
-    total_pools = supers_x * ((tiles_y + SUPER_H - 1) / SUPER_H) * (SUPER_W * SUPER_H);
+    total_pools = p.grid.total_pools;
   } else {
     list_n = (uint32_t)p.stats[5];
     total_pools = (list_n + 31u) / 32u;
@@ -659,11 +717,12 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* s_stack, 
           uint32_t id;
           bool ok;
           if (MODE == PRIMARY) {
-            const uint32_t sup = pool / (SUPER_W * SUPER_H), in = pool % (SUPER_W * SUPER_H);
-            const uint32_t tx = (sup % supers_x) * SUPER_W + (in % SUPER_W), ty = (sup / supers_x) * SUPER_H + (in / SUPER_W);
+            uint32_t tx, ty;
+            bool halo;
+            const bool tile_ok = tile_of_pool(p.grid, pool, tx, ty, halo);
             const int x = p.x0 + (int)tx * TILE_W + (lane & (TILE_W - 1));
             const int y = p.y0 + (int)ty * TILE_H + (lane / TILE_W);
-            ok = x <= p.x1 && y <= p.y1;
+            ok = tile_ok && x <= p.x1 && y <= p.y1 && (!halo || lane / TILE_W == TILE_H - 1);
             id = ((uint32_t)y << 16) | (uint32_t)x;
           } else {
             id = pool * 32u + (uint32_t)lane;
@@ -713,10 +772,65 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* s_stack, 
     }
     if (exhausted && !__any_sync(0xffffffffu, have)) break;
 
-    // =========================== (C) node phase: 8 quantised child boxes per visit ===========================
-    while (__any_sync(0xffffffffu, have && !evict && !(cur & J3DG_LEAF_BIT))) {
-      if (have && !evict && !(cur & J3DG_LEAF_BIT)) {
+    // =========================== (C) steps ===========================
+    // Every lane with a ray is either AT A NODE (cur = inner node) or AT A TRIANGLE (cur = leaf bit | record slot).
+    // The warp takes one step at a time — a node step (8 quantised child boxes) or a triangle step (ONE record) —
+    // and votes which: a step of one kind idles the lanes waiting for the other kind, so the warp takes the
+    // kind whose idle lanes cost less (a node step is ~TRI_WEIGHT times longer than a triangle step).  Rays leave
+    // a leaf after its flagged last record, so leaves of different sizes do not hold each other up.
+    const int kx = (int)(r.kpack & 3u), ky = (int)((r.kpack >> 2) & 3u), kz = (int)(r.kpack >> 4);
+    for (;;) {
+      const bool at_node = have && !evict && !(cur & J3DG_LEAF_BIT);
+      const bool at_tri = have && !evict && (cur & J3DG_LEAF_BIT) && cur != J3DG_EMPTY_CHILD;
+      const int nn = __popc(__ballot_sync(0xffffffffu, at_node)), nt = __popc(__ballot_sync(0xffffffffu, at_tri));
+      if (nn + nt == 0) break;
+      // leave for (A) / (B) when enough lanes ran dry and there is something to refill them with
+      if (32 - nn - nt >= LANE_REFILL_MIN && !(exhausted && pool_next >= pool_count)) break;
+      if (nn == 0 || nt * LANE_TRI_WEIGHT >= nn) {
+        // ---------------- triangle step: one record per lane ----------------
+        if (at_tri) {
+          const uint32_t slot = cur & J3DG_LEAF_FIRST_MASK;
+          const float4* tp = reinterpret_cast<const float4*>(tris + slot);
+          const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+          if (LANE_TRI_PREFETCH) asm volatile("prefetch.global.L1 [%0];" :: "l"(tp + LANE_TRI_PREFETCH));  // the line the leaf's next record ends in
+          if (STATS) ++ntris;
+          // one lane of intersect_woop (qbvh.h:4825-4869); 1/det is correctly rounded instead of rcpps + NR
+          const float Ax_ = fsub(v0.x, r.ox), Ay_ = fsub(v0.y, r.oy), Az_ = fsub(v0.z, r.oz);
+          const float Bx_ = fsub(v1.x, r.ox), By_ = fsub(v1.y, r.oy), Bz_ = fsub(v1.z, r.oz);
+          const float Cx_ = fsub(v2.x, r.ox), Cy_ = fsub(v2.y, r.oy), Cz_ = fsub(v2.z, r.oz);
+          const float Akz = pick(Ax_, Ay_, Az_, kz), Bkz = pick(Bx_, By_, Bz_, kz), Ckz = pick(Cx_, Cy_, Cz_, kz);
+          const float Ax = fsub(pick(Ax_, Ay_, Az_, kx), fmul(r.Sx, Akz));
+          const float Ay = fsub(pick(Ax_, Ay_, Az_, ky), fmul(r.Sy, Akz));
+          const float Bx = fsub(pick(Bx_, By_, Bz_, kx), fmul(r.Sx, Bkz));
+          const float By = fsub(pick(Bx_, By_, Bz_, ky), fmul(r.Sy, Bkz));
+          const float Cx = fsub(pick(Cx_, Cy_, Cz_, kx), fmul(r.Sx, Ckz));
+          const float Cy = fsub(pick(Cx_, Cy_, Cz_, ky), fmul(r.Sy, Ckz));
+          const float U = fsub(fmul(Cx, By), fmul(Cy, Bx));
+          const float V = fsub(fmul(Ax, Cy), fmul(Ay, Cx));
+          const float W = fsub(fmul(Bx, Ay), fmul(By, Ax));
+          const bool inside = ((U <= 0.f) && (V <= 0.f) && (W <= 0.f)) || ((U >= 0.f) && (V >= 0.f) && (W >= 0.f));
+          const float det = fadd(fadd(U, V), W);
+          if (inside && det != 0.f) {
+            const float inv_det = fdiv(1.f, det);
+            const float Az = fmul(r.Sz, Akz), Bz = fmul(r.Sz, Bkz), Cz = fmul(r.Sz, Ckz);
+            const float T = fadd(fadd(fmul(U, Az), fmul(V, Bz)), fmul(W, Cz));
+            const float t = fmul(T, inv_det);
+            if ((t_far > t) && (t > t_near) && (t < best_t)) {
+              best_t = t; best_u = fmul(V, inv_det); best_v = fmul(W, inv_det); best_slot = slot; best_mesh = mesh_k;
+              t_far = t;
+            }
+          }
+          if (ANY_HIT && best_slot != 0xFFFFFFFFu) { cur = J3DG_EMPTY_CHILD; sp = 0; }
+          else if (__float_as_uint(v1.w) != 0u) cur = pop();  // end of leaf
+          else cur = cur + 1u;
+        }
+      } else if (at_node) {
+        // ---------------- node step: 8 quantised child boxes ----------------
+#ifdef J3DG_TAIL_BUDGET_DIV
+        if (visits >= (exhausted ? p.budget / J3DG_TAIL_BUDGET_DIV : p.budget)) {  // no rays left to hide a long one behind
+#else
         if (visits >= p.budget) {
+#endif
           evict = true;
         } else {
           ++visits;
@@ -757,6 +871,12 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* s_stack, 
           auto push = [&](uint32_t key, uint32_t ref) {
             stk[sp * BLOCK_THREADS] = make_uint2(ref, key);
             const int go = (key < MISS_KEY && (int)key != nearest) ? 1 : 0;
+#ifdef J3DG_PUSH_PREFETCH
+            if (go) {  // pull the postponed child towards L2 while the nearer one is traversed
+              const char* a = (ref & J3DG_LEAF_BIT) ? reinterpret_cast<const char*>(tris + (ref & J3DG_LEAF_FIRST_MASK)) : reinterpret_cast<const char*>(nodes + ref);
+              asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
+            }
+#endif
             wanted += go;
             sp = min(sp + go, LANE_STACK);
           };
@@ -766,51 +886,6 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* s_stack, 
           cur = (near_ref != J3DG_EMPTY_CHILD) ? near_ref : pop();
         }
       }
-      // leave for a refill when enough lanes ran dry
-      if ((int)__popc(__ballot_sync(0xffffffffu, !have || evict || cur == J3DG_EMPTY_CHILD)) >= LANE_REFILL_MIN) break;
-    }
-
-    // =========================== (D) leaf phase: 1..8 consecutive triangle records, the last one flagged ===========================
-    if (have && !evict && (cur & J3DG_LEAF_BIT) && cur != J3DG_EMPTY_CHILD) {
-      const int kx = (int)(r.kpack & 3u), ky = (int)((r.kpack >> 2) & 3u), kz = (int)(r.kpack >> 4);
-      do {
-        uint32_t slot = cur & J3DG_LEAF_FIRST_MASK;
-        for (;;) {
-          const float4* tp = reinterpret_cast<const float4*>(tris + slot);
-          const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
-          if (STATS) ++ntris;
-          // one lane of intersect_woop (qbvh.h:4825-4869); 1/det is correctly rounded instead of rcpps + NR
-          const float Ax_ = fsub(v0.x, r.ox), Ay_ = fsub(v0.y, r.oy), Az_ = fsub(v0.z, r.oz);
-          const float Bx_ = fsub(v1.x, r.ox), By_ = fsub(v1.y, r.oy), Bz_ = fsub(v1.z, r.oz);
-          const float Cx_ = fsub(v2.x, r.ox), Cy_ = fsub(v2.y, r.oy), Cz_ = fsub(v2.z, r.oz);
-          const float Akz = pick(Ax_, Ay_, Az_, kz), Bkz = pick(Bx_, By_, Bz_, kz), Ckz = pick(Cx_, Cy_, Cz_, kz);
-          const float Ax = fsub(pick(Ax_, Ay_, Az_, kx), fmul(r.Sx, Akz));
-          const float Ay = fsub(pick(Ax_, Ay_, Az_, ky), fmul(r.Sy, Akz));
-          const float Bx = fsub(pick(Bx_, By_, Bz_, kx), fmul(r.Sx, Bkz));
-          const float By = fsub(pick(Bx_, By_, Bz_, ky), fmul(r.Sy, Bkz));
-          const float Cx = fsub(pick(Cx_, Cy_, Cz_, kx), fmul(r.Sx, Ckz));
-          const float Cy = fsub(pick(Cx_, Cy_, Cz_, ky), fmul(r.Sy, Ckz));
-          const float U = fsub(fmul(Cx, By), fmul(Cy, Bx));
-          const float V = fsub(fmul(Ax, Cy), fmul(Ay, Cx));
-          const float W = fsub(fmul(Bx, Ay), fmul(By, Ax));
-          const bool inside = ((U <= 0.f) && (V <= 0.f) && (W <= 0.f)) || ((U >= 0.f) && (V >= 0.f) && (W >= 0.f));
-          const float det = fadd(fadd(U, V), W);
-          if (inside && det != 0.f) {
-            const float inv_det = fdiv(1.f, det);
-            const float Az = fmul(r.Sz, Akz), Bz = fmul(r.Sz, Bkz), Cz = fmul(r.Sz, Ckz);
-            const float T = fadd(fadd(fmul(U, Az), fmul(V, Bz)), fmul(W, Cz));
-            const float t = fmul(T, inv_det);
-            if ((t_far > t) && (t > t_near) && (t < best_t)) {
-              best_t = t; best_u = fmul(V, inv_det); best_v = fmul(W, inv_det); best_slot = slot; best_mesh = mesh_k;
-              t_far = t;
-            }
-          }
-          if (__float_as_uint(v1.w) != 0u) break;  // end of leaf
-          ++slot;
-        }
-        if (ANY_HIT && best_slot != 0xFFFFFFFFu) { cur = J3DG_EMPTY_CHILD; sp = 0; }
-        else cur = pop();
-      } while (cur != J3DG_EMPTY_CHILD && (cur & J3DG_LEAF_BIT));
     }
   }
   if (STATS) {
@@ -864,17 +939,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_LANE_MIN_BLOCKS) cast_kern
 // ---- hit -> pixel record (canvas.cpp:788-834) + shadow ray generation (836-854) --------------------------
 // One thread per pixel, one warp per 8x4 tile (the order the trace kernels use).  Misses already hold
 // their final record.  Shadow rays of hit pixels are appended to a list with one atomic per warp.
-__global__ void __launch_bounds__(256) resolve_kernel(const MeshDev* __restrict__ meshes, ViewDev vw, int x0, int y0, int x1, int y1,
+__global__ void __launch_bounds__(256) resolve_kernel(const MeshDev* __restrict__ meshes, ViewDev vw, int x0, int y0, int x1, int y1, TileGrid grid,
                                                        j3dg_pixel* __restrict__ out, uint32_t stride, float4* __restrict__ shadow_pos,
                                                        uint32_t* __restrict__ shadow_pix, unsigned long long* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
-  const uint32_t tiles_x = (uint32_t)(x1 - x0 + TILE_W) / TILE_W;
-  const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int x = x0 + (int)(tile % tiles_x) * TILE_W + (lane & (TILE_W - 1));
-  const int y = y0 + (int)(tile / tiles_x) * TILE_H + (lane / TILE_W);
+  const uint32_t pool = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  uint32_t tx = 0, ty = 0;
+  bool halo = false;
+  const bool tile_ok = pool < grid.total_pools && tile_of_pool(grid, pool, tx, ty, halo);
+  const int x = x0 + (int)tx * TILE_W + (lane & (TILE_W - 1));
+  const int y = y0 + (int)ty * TILE_H + (lane / TILE_W);
   bool shadow_ray = false;
   float4 pos = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (x <= x1 && y <= y1) {
+  if (tile_ok && x <= x1 && y <= y1 && (!halo || lane / TILE_W == TILE_H - 1)) {
     uint4* dst = reinterpret_cast<uint4*>(out + (size_t)y * stride + x);
     const uint4 raw = dst[1];
     if (raw.x != 0xFFFFFFFFu) {
@@ -923,7 +1000,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const MeshDev* __restrict_
         b = (uint32_t)__float2int_rz(fmul(cb, 255.f)) & 0xffu;
         mark |= 2u;
       }
-      if (vw.flags & J3DG_SHADOW) {  // canvas.cpp:836-848
+      if ((vw.flags & J3DG_SHADOW) && !halo) {  // canvas.cpp:836-848; halo pixels serve the edge shader only (u, v, depth, id)
         const float4 V0 = transform_point(m.cs, make_float4(v0.x, v0.y, v0.z, 1.f));
         const float4 V1 = transform_point(m.cs, make_float4(v1.x, v1.y, v1.z, 1.f));
         const float4 V2 = transform_point(m.cs, make_float4(v2.x, v2.y, v2.z, 1.f));
@@ -1078,7 +1155,9 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   tp.hard_capacity = (uint32_t)std::min<size_t>((ctx->hard_cap - ctx->hard_id_off) / sizeof(uint2), ctx->hard_id_off / sizeof(float4));
   tp.budget = stats ? 0xFFFFFFFFu : ctx->lane_budget;
   auto ctr = [&](int slot) { return reinterpret_cast<unsigned int*>(ctx->d_stats + slot); };
-  const long long ntiles = (long long)((rw + TILE_W - 1) / TILE_W) * ((rh + TILE_H - 1) / TILE_H);
+  const bool sharded = ctx->shard_world > 1 && !stats;
+  tp.grid = make_tile_grid(x0, y0, x1, y1, sharded ? ctx->shard_rank : 0u, sharded ? ctx->shard_world : 1u);
+  const long long ntiles = tp.grid.total_pools;
   // One cooperative launch of the hybrid kernel: the grid fills the machine once, every block is resident.
   auto launch_hybrid = [&](auto kernel, long long pools) -> int {
     int nb = 0;
@@ -1111,7 +1190,7 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   }
   if (used && !stats) {
     const uint32_t warps = 256 / 32;
-    resolve_kernel<<<(uint32_t)((ntiles + warps - 1) / warps), 256, 0, ctx->stream>>>(ctx->d_meshes, tp.vw, x0, y0, x1, y1, d_pixels, stride,
+    resolve_kernel<<<(uint32_t)((ntiles + warps - 1) / warps), 256, 0, ctx->stream>>>(ctx->d_meshes, tp.vw, x0, y0, x1, y1, tp.grid, d_pixels, stride,
                                                                                      (float4*)tp.shadow_pos, (uint32_t*)tp.shadow_pix, ctx->d_stats);
     KERNEL_CHECK(ctx);
   }
@@ -1129,7 +1208,13 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   }
   rc = j3dg_stage_end(ctx, 0);
   if (rc != J3DG_OK) return rc;
-  ctx->rays_primary += (uint64_t)rw * rh;  // shadow rays (d_stats[4]) are added when the timings are read
+  if (!sharded) {
+    ctx->rays_primary += (uint64_t)rw * rh;  // shadow rays (d_stats[4]) are added when the timings are read
+  } else {  // own bands + one halo row above each (except the first band of the rectangle)
+    const int bands = (rh + J3DG_SHARD_BAND_ROWS - 1) / J3DG_SHARD_BAND_ROWS;
+    for (int b = (int)ctx->shard_rank; b < bands; b += (int)ctx->shard_world)
+      ctx->rays_primary += (uint64_t)rw * (std::min(rh, (b + 1) * J3DG_SHARD_BAND_ROWS) - b * J3DG_SHARD_BAND_ROWS + (b ? 1 : 0));
+  }
 #ifdef J3DG_TIMELINE
   if (!stats) {
     unsigned long long t[20];

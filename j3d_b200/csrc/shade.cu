@@ -14,6 +14,7 @@ struct ShadeParams {
   float pinv[16];
   const uint32_t* matcap;
   uint32_t mw, mh, mstride, cavity;
+  uint32_t shard_rank, shard_world;  // screen sharding: only rows of this rank's bands are shaded
 };
 
 struct Px {  // the fields shading reads
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(256) shade_kernel(const j3dg_pixel* __restrict
   const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31);
   const uint32_t y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= s.w || y >= s.h) return;
+  if (s.shard_world > 1u && (y / J3DG_SHARD_BAND_ROWS) % s.shard_world != s.shard_rank) return;  // another rank's band
   const j3dg_pixel* pp = px + (size_t)y * pstride + x;
   const Px p = load_px(pp);
   uint32_t* o = rgba + (size_t)y * rstride + x;
@@ -216,6 +218,7 @@ int j3dg_launch_shade(j3dg_ctx* ctx, const j3dg_pixel* d_pixels, uint32_t pstrid
   s.w = view->width; s.h = view->height; s.flags = view->flags; s.near_plane = view->near_plane;
   memcpy(s.pinv, view->projection_inv, 64);
   s.matcap = d_matcap; s.mw = mw; s.mh = mh; s.mstride = mstride; s.cavity = cavity;
+  s.shard_rank = ctx->shard_rank; s.shard_world = ctx->shard_world;
   dim3 grid((s.w + 31) / 32, (s.h + 7) / 8);
   { int rc = j3dg_stage_begin(ctx, 1); if (rc != J3DG_OK) return rc; }
   shade_kernel<<<grid, 256, 0, ctx->stream>>>(d_pixels, pstride, s, d_bg, bg_stride, d_rgba, rstride);

@@ -102,3 +102,42 @@ def allreduce_max_u64(t: torch.Tensor) -> torch.Tensor:
     signed int64 max is identical."""
     dist.all_reduce(t.view(torch.int64), op=dist.ReduceOp.MAX)
     return t
+
+
+# ---- screen sharding of ONE frame (BASELINE configs[2]; j3dg_ctx_set_screen_shard) -----------
+BAND_ROWS = 32  # = J3DG_SHARD_BAND_ROWS
+
+
+def bands_for_rank(height: int, rank: int, world: int) -> list[tuple[int, int]]:
+    """Inclusive row ranges [y0, y1] of the bands rank owns: band b belongs to rank b mod world."""
+    nb = (height + BAND_ROWS - 1) // BAND_ROWS
+    return [(b * BAND_ROWS, min((b + 1) * BAND_ROWS, height) - 1) for b in range(rank, nb, world)]
+
+
+def pack_bands(img: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """This rank's bands of `img` ([H, ...]) as one [per, BAND_ROWS, ...] tensor (per = bands per rank,
+    rounded up; missing rows are zero)."""
+    h = img.shape[0]
+    nb = (h + BAND_ROWS - 1) // BAND_ROWS
+    per = (nb + world - 1) // world
+    if h == nb * BAND_ROWS and nb == per * world:
+        return img.view((per, world, BAND_ROWS) + tuple(img.shape[1:]))[:, rank].contiguous()
+    out = img.new_zeros((per, BAND_ROWS) + tuple(img.shape[1:]))
+    for l, (y0, y1) in enumerate(bands_for_rank(h, rank, world)):
+        out[l, : y1 - y0 + 1] = img[y0: y1 + 1]
+    return out
+
+
+def gather_bands(img: torch.Tensor, dst: int = 0) -> torch.Tensor | None:
+    """Every rank holds a frame whose own bands are valid (a frame rendered with set_screen_shard(rank, world));
+    returns the complete frame on `dst`.  One gather of 1/world of the frame per rank; on `dst` the gathered
+    [world, per, 32, ...] block is the frame with the two leading axes swapped."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    mine = pack_bands(img, rank, world)
+    parts = [torch.empty_like(mine) for _ in range(world)] if rank == dst else None
+    dist.gather(mine, parts, dst=dst)
+    if rank != dst:
+        return None
+    g = torch.stack(parts, dim=0)  # [world, per, 32, ...]
+    g = g.transpose(0, 1).reshape((-1,) + tuple(img.shape[1:]))
+    return g[: img.shape[0]]

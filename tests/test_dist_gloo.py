@@ -18,6 +18,8 @@ def test_partitions_cover_exactly_once():
         assert frames == list(range(360))
         bands = jd.row_bands(1080, world)
         assert bands[0][0] == 0 and bands[-1][1] == 1079 and all(bands[i][1] + 1 == bands[i + 1][0] for i in range(world - 1))
+        rows = sorted(y for r in range(world) for (a, b) in jd.bands_for_rank(1080, r, world) for y in range(a, b + 1))
+        assert rows == list(range(1080))
         cover = np.zeros((270, 480), np.int32)
         for r in range(world):
             for (x0, y0, x1, y1) in jd.tiles_for_rank(480, 270, r, world, tile=64):
@@ -46,6 +48,15 @@ def _worker(rank, world, port, out):
         frames = jd.gather_frames(torch.full((4, 4), rank, dtype=torch.int32), dst=0)
         packed = torch.tensor([(10 + rank) << 32 | 5, (20 - rank) << 32 | rank], dtype=torch.int64)
         jd.allreduce_max_u64(packed)
+        # screen sharding of one frame: every rank holds a frame with only its own 32-row bands valid
+        for hh in (37, 64, 200):
+            truth = torch.arange(hh * w, dtype=torch.int32).reshape(hh, w)
+            mine = torch.full_like(truth, -1)
+            for (b0, b1) in jd.bands_for_rank(hh, rank, world):
+                mine[b0:b1 + 1] = truth[b0:b1 + 1]
+            whole = jd.gather_bands(mine, dst=0)
+            if rank == 0:
+                assert torch.equal(whole, truth)
         if rank == 0:
             assert torch.equal(got, full)
             assert [int(f[0, 0]) for f in frames] == list(range(world))

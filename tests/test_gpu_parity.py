@@ -279,6 +279,58 @@ def test_render_frame_equals_stages(ctx, oracle):
     m.destroy(); cl.destroy(); om.destroy()
 
 
+@pytest.mark.parametrize("w,h,world,flags", [
+    (400, 240, 2, j.DEFAULT_FLAGS | j.SHADOW),
+    (333, 201, 3, j.DEFAULT_FLAGS),                       # ragged: 6.3 bands over 3 ranks
+    (640, 360, 8, j.DEFAULT_FLAGS | j.SHADOW),            # more ranks than some ranks have bands for
+    (320, 200, 4, (j.DEFAULT_FLAGS | j.WIREFRAME) & ~j.EDGES),
+])
+def test_screen_shards_reassemble_to_the_full_frame(ctx, w, h, world, flags):
+    """BASELINE configs[2] on one GPU: render the frame once unsharded and once per rank with
+    j3dg_ctx_set_screen_shard(rank, world) into poisoned device buffers.  Every rank's own 32-row bands must be
+    bit-identical to the unsharded frame (pixel records and RGBA — the halo row above each band feeds the edge
+    shader), rows of other ranks must stay untouched except that halo row, and the bands of all ranks cover
+    the frame exactly once (dist.bands_for_rank is what gather_bands ships)."""
+    import torch
+    from j3d_b200 import dist as jd
+    verts, tris, vc, v = _scene(30, w, h, flags, 40.0, True)
+    m = ctx.mesh_create(verts, tris, vcolors=vc)
+    mc, cav = j.make_matcap(0)
+    ctx.set_matcap(mc, cav)
+    POISON = 0x5A
+    def render():
+        px = torch.full((h, w, 32), POISON, dtype=torch.uint8, device="cuda")
+        rgba = torch.full((h, w, 4), POISON, dtype=torch.uint8, device="cuda")
+        ctx.render_frame([m], [], v, pixels_out=px, rgba_out=rgba)
+        ctx.synchronize()
+        return px.cpu().numpy(), rgba.cpu().numpy()
+    full_px, full_rgba = render()
+    assert (full_px.view(j.PIXEL_DTYPE)["object_id"] != MISS).any()
+    covered = np.zeros(h, np.int32)
+    try:
+        for rank in range(world):
+            ctx.set_screen_shard(rank, world)
+            px, rgba = render()
+            own = np.zeros(h, bool)
+            for (y0, y1) in jd.bands_for_rank(h, rank, world):
+                own[y0:y1 + 1] = True
+                covered[y0:y1 + 1] += 1
+            assert px[own].tobytes() == full_px[own].tobytes()
+            assert rgba[own].tobytes() == full_rgba[own].tobytes()
+            halo = np.zeros(h, bool)
+            halo[:-1] = own[1:] & ~own[:-1]
+            untouched = ~own & ~halo
+            assert (px[untouched] == POISON).all() and (rgba[~own] == POISON).all()
+            tm = ctx.timings(reset=True)
+            assert tm.kernel_launches > 0
+    finally:
+        ctx.set_screen_shard(0, 1)
+    assert (covered == 1).all()
+    with pytest.raises(j.J3dgError):
+        ctx.set_screen_shard(2, 2)
+    m.destroy()
+
+
 def test_pipelined_frames_equal_synchronous(ctx):
     """j3dg_frame_submit / j3dg_frame_wait: every frame of a sweep equals the synchronous j3dg_render_frame."""
     verts, tris, vc, v0 = _scene(25, 320, 180, j.DEFAULT_FLAGS | j.SHADOW, 0.0, True)
