@@ -9,7 +9,7 @@
 //   4. binary radix tree over the sorted codes (Karras 2012)      radix_tree_kernel
 //   5. leaf boxes + pre-gathered 48-byte triangle records,
 //      bottom-up box fit                                          refit_kernel
-//   6. top-down collapse into 8-wide quantised 96-byte nodes,
+//   6. top-down collapse into 8-wide quantised 128-byte nodes,
 //      opening the largest-area child first (SAH-greedy)          collapse_kernel (one launch per level)
 // Every subtree of the radix tree owns a contiguous range of the sorted triangle records, so a
 // leaf reference is just (first, count).
