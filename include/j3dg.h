@@ -205,6 +205,28 @@ int j3dg_frame_wait(j3dg_ctx* ctx);
 /* Upload a matcap once and reuse it (frames then pass matcap == NULL). */
 int j3dg_ctx_set_matcap(j3dg_ctx* ctx, const uint32_t* matcap, uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity_clr);
 
+/* ---- picking on the device: the consumers of the pixel buffer that j3d runs on the
+ *      host copy — canvas::get_pixel (j3d/canvas.cpp:141-153), view::get_id (j3d/view.cpp:483-492),
+ *      view::get_world_position (view.cpp:439-469), view::get_index -> get_closest_vertex (view.cpp:471-481,
+ *      j3d/pixel.cpp:6-33) and the pivot pick of canvas::do_mouse (canvas.cpp:157-179) — answered from the
+ *      canvas that is still resident in HBM, so an interactive host reads back RGBA only (4 B/px instead
+ *      of 36 B/px) plus 64 bytes per query.  Outside the canvas or on a miss pixel: db_id = 0,
+ *      closest_vertex = 0xFFFFFFFF, world_pos = pivot = NaN (the reference's invalid_vertex / (uint32_t)-1 / 0).
+ *      For a point-cloud pixel world_pos = cloud cs * point and closest_vertex = the point index. ---------- */
+typedef struct j3dg_pick_result {
+  j3dg_pixel pixel;        /* the record at (x, y) */
+  float world_pos[3];      /* view::get_world_position */
+  uint32_t closest_vertex; /* view::get_index */
+  float pivot[3];          /* scene::pivot after a click on (x, y): ray origin + depth * ray dir */
+  uint32_t db_id;          /* view::get_id */
+} j3dg_pick_result;        /* 64 bytes */
+/* pixels: DEVICE buffer to read, or NULL = the canvas of the last j3dg_render_frame / j3dg_frame_submit /
+ * host-destination j3dg_cast of this context (it must have view->width x view->height pixels).
+ * xy: n x {x, y} int32 (host or device); out: n records (host or device).  Synchronous on return. */
+int j3dg_pick(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nr_of_meshes,
+              j3dg_cloud* const* clouds, uint32_t nr_of_clouds, const j3dg_view* view,
+              const j3dg_pixel* pixels, uint32_t pixel_stride, const int32_t* xy, uint32_t n, j3dg_pick_result* out);
+
 /* Traversal statistics of the device BVH for the given view (a counting pass, not the
  * timed kernel): mean wide-node visits and triangle tests per primary ray.  SURVEY §8d. */
 int j3dg_cast_stats(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nr_of_meshes, const j3dg_view* view,

@@ -4,7 +4,7 @@ include/j3dg.h.  See DESIGN.md.  There is no CPU fallback: the CUDA library must
 (`python -m j3d_b200.build`) and a B200 must be present to render.
 """
 from .capi import (  # noqa: F401
-    DEFAULT_FLAGS, EDGES, ONE_BIT, PIXEL_DTYPE, SHADING, SHADOW, TEXTURED, VERTEXCOLORS, WIREFRAME,
+    DEFAULT_FLAGS, EDGES, ONE_BIT, PICK_DTYPE, PIXEL_DTYPE, SHADING, SHADOW, TEXTURED, VERTEXCOLORS, WIREFRAME,
     Cloud, Context, J3dgError, Mesh, MeshInfo, Timings, View,
     cloud, compute_bb, fill_background, icosphere, make_matcap, make_view, orbit_view, vertex_colors,
 )

@@ -23,6 +23,9 @@ PIXEL_DTYPE = np.dtype(
      ("object_id", "<u4"), ("barycentric_u", "<f4"), ("barycentric_v", "<f4"), ("db_id", "<u4")]
 )
 assert PIXEL_DTYPE.itemsize == 32
+# j3dg_pick (include/j3dg.h)
+PICK_DTYPE = np.dtype([("pixel", PIXEL_DTYPE), ("world_pos", "<f4", (3,)), ("closest_vertex", "<u4"), ("pivot", "<f4", (3,)), ("db_id", "<u4")])
+assert PICK_DTYPE.itemsize == 64
 
 
 class View(C.Structure):
@@ -119,6 +122,7 @@ def lib() -> C.CDLL:
         L.j3dg_ctx_set_screen_shard.argtypes = [_vp, _u32, _u32]
         L.j3dg_cast_stats.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(View), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.j3dg_cast_cost_image.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(View), _vp, _vp]
+        L.j3dg_pick.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(_vp), _u32, C.POINTER(View), _vp, _u32, _vp, _u32, _vp]
         _lib = L
     return _lib
 
@@ -375,6 +379,15 @@ class Context:
         self._check(self._L.j3dg_cast_stats(self._h, self._handles(meshes), len(meshes), C.byref(view), C.byref(a), C.byref(b)),
                     "j3dg_cast_stats")
         return a.value, b.value
+
+    def pick(self, meshes, clouds, view: View, xy, pixels=None, pixel_stride: int | None = None) -> np.ndarray:
+        """Device-side picking (canvas::get_pixel, view::get_id / get_world_position / get_index, pivot pick) for n
+        query pixels xy [n,2] int32; pixels None = the resident canvas of the last frame.  Returns PICK_DTYPE [n]."""
+        xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+        out = np.zeros((xy.shape[0],), PICK_DTYPE)
+        self._check(self._L.j3dg_pick(self._h, self._handles(meshes), len(meshes), self._handles(clouds), len(clouds), C.byref(view),
+                                      _ptr(pixels), pixel_stride or 0, _ptr(xy), xy.shape[0], _ptr(out)), "j3dg_pick")
+        return out
 
     def cast_cost_image(self, meshes, view: View):
         """Per-pixel (node visits, triangle tests) of the counting pass — diagnostic."""

@@ -41,6 +41,7 @@ int j3dg_reserve(j3dg_ctx* ctx, void** ptr, size_t* cap, size_t bytes) {
   if (*cap >= bytes && *ptr) return J3DG_OK;
   if (*ptr) {
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->last_canvas == *ptr) ctx->last_canvas = nullptr;  // j3dg_pick must not read a freed canvas
     cudaFree(*ptr);
     *ptr = nullptr;
     *cap = 0;
@@ -472,6 +473,7 @@ J3DG_API int j3dg_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, con
   if (rc != J3DG_OK) return rc;
   rc = j3dg_launch_cast(ctx, meshes, nm, view, x0, y0, x1, y1, (j3dg_pixel*)ctx->d_pixels, w, false);
   if (rc != J3DG_OK) return rc;
+  ctx->last_canvas = ctx->d_pixels; ctx->last_w = w; ctx->last_h = h;
   int cx0 = std::min(std::max(x0, 0), (int)w - 1), cy0 = std::min(std::max(y0, 0), (int)h - 1);
   int cx1 = std::min(std::max(x1, 0), (int)w - 1), cy1 = std::min(std::max(y1, 0), (int)h - 1);
   if (cx1 >= cx0 && cy1 >= cy0) {
@@ -601,6 +603,7 @@ J3DG_API int j3dg_render_frame(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t
   if ((rc = j3dg_launch_cast(ctx, meshes, nm, view, 0, 0, (int)w - 1, (int)h - 1, d_px, w, false)) != J3DG_OK) return rc;
   if ((rc = j3dg_launch_shade(ctx, d_px, w, view, d_mc, dmw, dmh, dms, dcav, ctx->d_bg, w, d_rgba, w)) != J3DG_OK) return rc;
   if (nc && (rc = j3dg_launch_splat(ctx, clouds, nc, view, d_px, d_px, w, d_rgba, w)) != J3DG_OK) return rc;
+  ctx->last_canvas = d_px; ctx->last_w = w; ctx->last_h = h;
   bool copied = false;
   if (pixels_out && !px_dev) { CU_CHECK(ctx, cudaMemcpyAsync(pixels_out, d_px, (size_t)w * h * sizeof(j3dg_pixel), cudaMemcpyDeviceToHost, ctx->stream)); copied = true; }
   if (rgba_out && !rgba_dev) { CU_CHECK(ctx, cudaMemcpyAsync(rgba_out, d_rgba, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->stream)); copied = true; }
@@ -646,6 +649,7 @@ J3DG_API int j3dg_frame_submit(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t
   if ((rc = j3dg_launch_cast(ctx, meshes, nm, view, 0, 0, (int)w - 1, (int)h - 1, d_px, w, false)) != J3DG_OK) return rc;
   if ((rc = j3dg_launch_shade(ctx, d_px, w, view, d_mc, dmw, dmh, dms, dcav, ctx->d_bg, w, d_rgba, w)) != J3DG_OK) return rc;
   if (nc && (rc = j3dg_launch_splat(ctx, clouds, nc, view, d_px, d_px, w, d_rgba, w)) != J3DG_OK) return rc;
+  ctx->last_canvas = d_px; ctx->last_w = w; ctx->last_h = h;
   CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_overflow + si, reinterpret_cast<uint32_t*>(ctx->d_stats + 2), sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU_CHECK(ctx, cudaEventRecord(sl.kernels_done, ctx->stream));
   CU_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, sl.kernels_done, 0));
@@ -682,6 +686,7 @@ J3DG_API int j3dg_cast_stats(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t n
   const bool prof = ctx->profiling;
   ctx->profiling = false;
   rc = j3dg_launch_cast(ctx, meshes, nm, &v, 0, 0, (int)w - 1, (int)h - 1, (j3dg_pixel*)ctx->d_pixels, w, true);
+  if (ctx->last_canvas == ctx->d_pixels) ctx->last_canvas = nullptr;  // the counting pass leaves costs, not records
   ctx->profiling = prof;
   if (rc != J3DG_OK) return rc;
   unsigned long long st[4];

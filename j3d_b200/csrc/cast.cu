@@ -115,7 +115,7 @@ struct TraceParams {
   // hard-ray queue (single launch: lane warps produce, group warps consume)
   unsigned int* hard_count;      // producers: append position
   unsigned int* hard_taken;      // consumers: next entry to claim
-  unsigned int* done_blocks;     // lane blocks that have finished producing
+  unsigned int* done_blocks;     // lane WARPS that have finished producing
   uint32_t hard_capacity;        // entries the queue arrays hold
   uint32_t consumer_blocks;      // blocks [0, consumer_blocks) consume from the start; the others trace tiles first
   uint2* hard_id;                // {ray id (0xFFFFFFFF = entry not written yet), mesh of the best hit so far}
@@ -224,14 +224,14 @@ __device__ __forceinline__ WorldRay world_ray(const TraceParams& p, uint32_t id)
 enum Source { POOLS = 0, QUEUE = 1 };
 constexpr uint32_t QUEUE_EMPTY = 0xFFFFFFFFu;
 
-template <int MODE, int SRC>
-__device__ __forceinline__ void group_loop(const TraceParams& p, uint2* s_stack) {
+// `stk` = entry 0 of this group's stack, entry i at stk[i * GSTRIDE] (GSTRIDE groups are interleaved).
+template <int MODE, int SRC, int GSTRIDE>
+__device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const stk) {
   constexpr bool ANY_HIT = MODE == SHADOW;
   constexpr bool GENERAL = MODE == RAYLIST;
   const int lane = threadIdx.x & 31;
   const int c = lane & 7;                               // my child / triangle slot
   const int gshift = lane & 24;                         // first lane of my group
-  uint2* const stk = s_stack + (threadIdx.x >> 3);      // entry i at stk[i * GROUPS_PER_BLOCK]
   const uint32_t below = (1u << c) - 1u;
   uint32_t* const overflow_flag = reinterpret_cast<uint32_t*>(p.stats + 2);
 
@@ -269,12 +269,12 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* s_stack)
   uint32_t claimed = QUEUE_EMPTY;   // QUEUE: entry this group has claimed and waits for
   bool retired = false;             // QUEUE: nothing left for this group
   uint32_t backoff = 250u;          // QUEUE: nanoseconds an idle warp sleeps before it polls again (doubles up to 4 us)
-  const uint32_t producer_blocks = gridDim.x - p.consumer_blocks;
+  const uint32_t producer_warps = (gridDim.x - p.consumer_blocks) * (BLOCK_THREADS / 32);  // producers sign off warp by warp
 
   auto pop = [&]() -> uint32_t {
     while (sp > 0) {
       --sp;
-      const uint2 e = stk[sp * GROUPS_PER_BLOCK];
+      const uint2 e = stk[sp * GSTRIDE];
       // entry points of popped boxes that now lie beyond the shrunk interval are skipped
       if (GENERAL || __uint_as_float(e.y) <= t_far) return e.x;
     }
@@ -370,7 +370,7 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* s_stack)
           mesh_k = 0;
           enter_mesh(wr, 0);
           have_ray = true;
-        } else if (*reinterpret_cast<volatile unsigned int*>(p.done_blocks) >= producer_blocks) {
+        } else if (*reinterpret_cast<volatile unsigned int*>(p.done_blocks) >= producer_warps) {
           // every producer has signed off (after fencing its writes): the queue length is final
           if (claimed >= *reinterpret_cast<volatile unsigned int*>(p.hard_count)) retired = true;
         }
@@ -470,6 +470,12 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* s_stack)
       const uint32_t nm8 = (__ballot_sync(0xffffffffu, hit && key == nearest) >> gshift) & 0xFFu;
       const int near_lane = __ffs(nm8) - 1;  // -1 when nothing was hit
       const uint32_t next = __shfl_sync(0xffffffffu, ref, gshift + (near_lane & 7));
+#ifdef J3DG_NEXT_PREFETCH
+      if (at_node && hm != 0u) {  // lane c pulls in line c % 4 of the next node's / leaf's 384 bytes (a node is one line)
+        const char* a = (next & J3DG_LEAF_BIT) ? reinterpret_cast<const char*>(tris + (next & J3DG_LEAF_FIRST_MASK)) + 128 * (c & 3) : reinterpret_cast<const char*>(nodes + next);
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(a));
+      }
+#endif
       if (at_node) {
         if (hm == 0u) {
           cur = pop();
@@ -477,7 +483,7 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* s_stack)
           const uint32_t others = hm & ~(1u << near_lane);
           if (hit && c != near_lane) {
             const int pos = sp + __popc(others & below);
-            if (pos < STACK_SIZE) stk[pos * GROUPS_PER_BLOCK] = make_uint2(ref, __float_as_uint(tmin));
+            if (pos < STACK_SIZE) stk[pos * GSTRIDE] = make_uint2(ref, __float_as_uint(tmin));
             else *overflow_flag = 1u;
 #ifdef J3DG_GROUP_PUSH_PREFETCH
             {  // pull the postponed child towards L2 while the nearer one is traversed
@@ -560,7 +566,7 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* s_stack)
 template <int MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_CAST_MIN_BLOCKS) group_kernel(const TraceParams p) {
   __shared__ uint2 s_stack[STACK_SIZE * GROUPS_PER_BLOCK];
-  group_loop<MODE, POOLS>(p, s_stack);
+  group_loop<MODE, POOLS, GROUPS_PER_BLOCK>(p, s_stack + (threadIdx.x >> 3));
 }
 
 // =====================================================================================================
@@ -587,6 +593,10 @@ constexpr int LANE_TRI_WEIGHT = J3DG_LANE_TRI_WEIGHT;
 #define J3DG_TRI_PREFETCH 5                               // lane kernel: L1 prefetch distance of a triangle step in float4 units (0 = off)
 #endif
 constexpr int LANE_TRI_PREFETCH = J3DG_TRI_PREFETCH;
+// every warp owns a contiguous (LANE_STACK + 1) x 32 slice of the stack area: when its tiles run out it turns into
+// four 8-lane groups that reuse the same slice ((LANE_STACK + 1) * 32 / 4 = 104 >= STACK_SIZE entries per group),
+// so no block-wide barrier separates the two phases
+constexpr int LANE_STRIDE = 32;
 constexpr int RAY_WORDS = 12;         // parked ray: ox oy oz | idx idy idz | Sx Sy Sz | kx,ky,kz packed | t_far | ray id
 
 // Object-space traversal constants of a ray for one mesh (qbvh.h:3358-3359, 4793-4823).
@@ -622,9 +632,8 @@ constexpr size_t GROUP_SMEM = (size_t)STACK_SIZE * GROUPS_PER_BLOCK * sizeof(uin
 constexpr size_t CAST_SMEM = LANE_SMEM_STACK + LANE_SMEM_RAYS > GROUP_SMEM ? LANE_SMEM_STACK + LANE_SMEM_RAYS : GROUP_SMEM;
 
 template <int MODE, bool STATS>
-__device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* s_stack, uint32_t* s_rays) {
+__device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* const stk, uint32_t* s_rays) {  // stk: row i of this lane at stk[i * LANE_STRIDE]
   constexpr bool ANY_HIT = MODE == SHADOW;
-  uint2* const stk = s_stack + threadIdx.x;                                           // row i at stk[i * BLOCK_THREADS]
   uint32_t* const park = s_rays + (threadIdx.x >> 5) * (RAY_WORDS * 32);              // word w of slot s at park[w * 32 + s]
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -669,7 +678,7 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* s_stack, 
   auto pop = [&]() -> uint32_t {
     while (sp > 0) {
       --sp;
-      const uint2 e = stk[sp * BLOCK_THREADS];
+      const uint2 e = stk[sp * LANE_STRIDE];
       // entry points of popped boxes that now lie beyond the shrunk interval are skipped
       if (__uint_as_float(e.y & ~7u) <= t_far) return e.x;
     }
@@ -866,10 +875,16 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* s_stack, 
           near_ref = ni == 4u ? c1.x : near_ref; near_ref = ni == 5u ? c1.y : near_ref; near_ref = ni == 6u ? c1.z : near_ref;
           near_ref = ni == 7u ? c1.w : near_ref;
           if ((uint32_t)nearest >= MISS_KEY) near_ref = J3DG_EMPTY_CHILD;
+#ifdef J3DG_NEXT_PREFETCH
+          if (near_ref != J3DG_EMPTY_CHILD) {  // start fetching the next node / first record while the other children are pushed
+            const char* a = (near_ref & J3DG_LEAF_BIT) ? reinterpret_cast<const char*>(tris + (near_ref & J3DG_LEAF_FIRST_MASK)) : reinterpret_cast<const char*>(nodes + near_ref);
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(a));
+          }
+#endif
           // branch-free pushes of the other hit children (row LANE_STACK is scratch; the low key bits are cleared at pop)
           int wanted = sp;
           auto push = [&](uint32_t key, uint32_t ref) {
-            stk[sp * BLOCK_THREADS] = make_uint2(ref, key);
+            stk[sp * LANE_STRIDE] = make_uint2(ref, key);
             const int go = (key < MISS_KEY && (int)key != nearest) ? 1 : 0;
 #ifdef J3DG_PUSH_PREFETCH
             if (go) {  // pull the postponed child towards L2 while the nearer one is traversed
@@ -911,10 +926,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_LANE_MIN_BLOCKS) cast_kern
   unsigned long long tl0, tl1, tl2;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl0));
 #endif
+  static_assert((LANE_STACK + 1) * 32 / 4 >= STACK_SIZE, "a warp's stack slice must hold four group stacks");
+  uint2* const warp_stack = reinterpret_cast<uint2*>(smem) + (threadIdx.x >> 5) * ((LANE_STACK + 1) * 32);
   if (blockIdx.x >= p.consumer_blocks) {
-    lane_loop<MODE, STATS>(p, reinterpret_cast<uint2*>(smem), reinterpret_cast<uint32_t*>(smem + LANE_SMEM_STACK));
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    lane_loop<MODE, STATS>(p, warp_stack + (threadIdx.x & 31), reinterpret_cast<uint32_t*>(smem + LANE_SMEM_STACK));
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
       __threadfence();
       atomicAdd(p.done_blocks, 1u);
     }
@@ -922,7 +939,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_LANE_MIN_BLOCKS) cast_kern
 #ifdef J3DG_TIMELINE
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl1));
 #endif
-  group_loop<MODE, QUEUE>(p, reinterpret_cast<uint2*>(smem));
+  group_loop<MODE, QUEUE, 4>(p, warp_stack + ((threadIdx.x & 31) >> 3));
 #ifdef J3DG_TIMELINE
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl2));
   if (MODE == PRIMARY && threadIdx.x == 0) {  // [13] first start, [14] last end of the lane phase, [15] last end; + sums for means

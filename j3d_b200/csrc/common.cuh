@@ -151,6 +151,7 @@ struct j3dg_ctx {
   uint32_t consumer_blocks = 0;                      // blocks of the cast kernel that consume the hard-ray queue from the start (J3DG_CONSUMER_BLOCKS)
   uint32_t lane_budget = 24;                         // node visits per ray before the lane kernel evicts it (J3DG_LANE_BUDGET)
   int cast_algo = 0;                                 // 0 hybrid (lane + group), 1 group kernel only (J3DG_CAST_ALGO=group)
+  void* last_canvas = nullptr; uint32_t last_w = 0, last_h = 0;  // device canvas of the most recent frame (j3dg_pick reads it)
   uint32_t shard_rank = 0, shard_world = 1;          // screen sharding (j3dg_ctx_set_screen_shard): band b of 32 rows belongs to rank b mod world
 };
 

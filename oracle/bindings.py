@@ -17,7 +17,7 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE.parent))
-from j3d_b200.capi import PIXEL_DTYPE, View  # noqa: E402  (struct layouts only)
+from j3d_b200.capi import PICK_DTYPE, PIXEL_DTYPE, View  # noqa: E402  (struct layouts only)
 
 _vp, _u32, _fp = C.c_void_p, C.c_uint32, C.POINTER(C.c_float)
 
@@ -56,6 +56,8 @@ class Oracle:
         L.orc_shade.argtypes = [_vp, _u32, C.POINTER(View), _vp, _u32, _u32, _u32, _vp, _u32]
         L.orc_splat.argtypes = [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_u32), C.POINTER(_vp),
                                 C.POINTER(_u32), _u32, C.POINTER(View), _vp, _vp, _u32, _vp, _u32]
+        L.orc_pick.argtypes = [_vp, _u32, C.POINTER(View), C.POINTER(_vp), _u32, C.POINTER(_vp), C.POINTER(_u32), C.POINTER(_vp),
+                               C.POINTER(_u32), _u32, _vp, _u32, _vp]
         self.L = L
 
     def make_view(self, w, h, bb_min, bb_max, flags) -> View:
@@ -119,6 +121,22 @@ class Oracle:
         self.L.orc_splat(pos, nrm, clr, cnt, css, ids, n, C.byref(view), _p(pixels_in), _p(pixels_inout), view.width, _p(rgba), view.width)
 
 
+    def pick(self, pixels, view: View, meshes, clouds, xy):
+        """clouds: list of (pos, cs|None, db_id).  Returns PICK_DTYPE [n]."""
+        xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+        out = np.zeros((xy.shape[0],), PICK_DTYPE)
+        marr = (_vp * max(1, len(meshes)))(*[m.h for m in meshes])
+        n = len(clouds)
+        ident = np.eye(4, dtype=np.float32)
+        keep = [ident if c[1] is None else np.ascontiguousarray(c[1], np.float32) for c in clouds]
+        pos = (_vp * max(1, n))(*[_p(c[0]) for c in clouds])
+        cnt = (_u32 * max(1, n))(*[c[0].shape[0] for c in clouds])
+        css = (_vp * max(1, n))(*[_p(k) for k in keep])
+        ids = (_u32 * max(1, n))(*[c[2] for c in clouds])
+        self.L.orc_pick(_p(pixels), view.width, C.byref(view), marr, len(meshes), pos, cnt, css, ids, n, _p(xy), xy.shape[0], _p(out))
+        return out
+
+
 class OracleMesh:
     def __init__(self, orc: Oracle, h, nt):
         self.orc, self.h, self.nt = orc, h, nt
@@ -174,6 +192,7 @@ class Ref:
         L.ref_time_qbvh.argtypes = [_vp, _u32, _vp, _u32, C.POINTER(_u32)]
         L.ref_find_closest.argtypes = [_vp, _u32, _vp, _u32, _u32, _vp, _u32, _vp, _vp]
         L.ref_hardware_concurrency.restype = C.c_int
+        L.ref_pick.argtypes = [_vp, _vp, _u32, _vp]
         self.L, self.w, self.h = L, w, h
         self.s = L.ref_create(w, h)
 
@@ -195,6 +214,13 @@ class Ref:
     def add_cloud(self, pos, nrm=None, clr=None, cs=None):
         csb = None if cs is None else np.ascontiguousarray(cs, np.float32)
         return self.L.ref_add_cloud(self.s, _p(pos), _p(nrm), _p(clr), pos.shape[0], _p(csb))
+
+    def pick(self, xy):
+        """Picking through the reference's own code on canvas::_canvas of the last render.  PICK_DTYPE [n]."""
+        xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+        out = np.zeros((xy.shape[0],), PICK_DTYPE)
+        self.L.ref_pick(self.s, _p(xy), xy.shape[0], _p(out))
+        return out
 
     def unzoom(self):
         self.L.ref_unzoom(self.s)

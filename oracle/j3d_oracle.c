@@ -846,3 +846,71 @@ void orc_splat(const float* const* pos, const float* const* nrm, const uint32_t*
 #undef PX_AT
   free(zbuf);
 }
+
+/* ---- picking ---------------------------------------------------------------
+ * canvas::get_pixel (canvas.cpp:148-153), view::get_id (view.cpp:483-492), view::get_world_position
+ * (view.cpp:439-469), get_closest_vertex (pixel.cpp:6-33), pivot pick of canvas::do_mouse
+ * (canvas.cpp:157-179).  Plain C without contraction: every product / sum rounds separately like
+ * the reference's SSE build.  Cloud pixels: world position = cloud cs * point, closest vertex =
+ * the point index (pixel.cpp:28-32). */
+void orc_pick(const j3dg_pixel* px, uint32_t stride, const j3dg_view* v, orc_mesh* const* meshes, uint32_t nm,
+              const float* const* cloud_pos, const uint32_t* cloud_counts, const float* const* cloud_cs,
+              const uint32_t* cloud_db_ids, uint32_t nclouds, const int32_t* xy, uint32_t n, j3dg_pick_result* out)
+{
+  union { uint32_t u; float f; } qn; qn.u = 0x7fc00000u;
+  for (uint32_t i = 0; i < n; ++i) {
+    j3dg_pick_result r;
+    memset(&r, 0, sizeof(r));
+    for (int k = 0; k < 3; ++k) { r.world_pos[k] = qn.f; r.pivot[k] = qn.f; }
+    r.closest_vertex = 0xFFFFFFFFu;
+    const int x = xy[2 * i], y = xy[2 * i + 1];
+    if (x >= 0 && y >= 0 && x < (int)v->width && y < (int)v->height) {
+      const j3dg_pixel p = px[(size_t)y * stride + x];
+      r.pixel = p;
+      r.db_id = p.db_id;
+      if (p.db_id) {
+        /* canvas.cpp:165-177 */
+        const float w = (float)v->width, h = (float)v->height;
+        float sp[4], dir[4], d2[4], o4[4] = {0.f, 0.f, 0.f, 1.f}, org[4];
+        sp[0] = 2.f * (((float)x + 0.5f) / w) - 1.f;
+        sp[1] = 2.f * (((float)y + 0.5f) / h) - 1.f;
+        sp[2] = v->near_plane; sp[3] = 1.f;
+        mat_vec(v->projection_inv, sp, dir);
+        dir[3] = 0.f;
+        mat_vec(v->cs, dir, d2);
+        mat_vec(v->cs, o4, org);
+        for (int k = 0; k < 3; ++k) { float t = p.depth * d2[k]; r.pivot[k] = org[k] + t; }
+        int done = 0;
+        for (uint32_t k = 0; k < nm && !done; ++k) {
+          const orc_mesh* m = meshes[k];
+          if (m->db_id != p.db_id || p.object_id >= m->nt) continue;
+          const uint32_t v0 = m->tris[3 * (size_t)p.object_id], v1 = m->tris[3 * (size_t)p.object_id + 1], v2 = m->tris[3 * (size_t)p.object_id + 2];
+          const float* A = m->verts + 3 * (size_t)v0; const float* B = m->verts + 3 * (size_t)v1; const float* Cc = m->verts + 3 * (size_t)v2;
+          const float kk = 1.f - p.barycentric_u - p.barycentric_v;
+          float pos[4];
+          for (int j = 0; j < 3; ++j) { float a = A[j] * kk, b = p.barycentric_u * B[j], c = p.barycentric_v * Cc[j]; float s = a + b; pos[j] = s + c; }
+          { float a = 1.f * kk, b = p.barycentric_u * 1.f, c = p.barycentric_v * 1.f; float s = a + b; pos[3] = s + c; }
+          float wp[4];
+          mat_vec(m->cs, pos, wp);
+          for (int j = 0; j < 3; ++j) r.world_pos[j] = wp[j];
+          float dA = 0.f, dB = 0.f, dC = 0.f;
+          { float e0 = pos[0] - A[0], e1 = pos[1] - A[1], e2 = pos[2] - A[2]; float s = e0 * e0; float t = e1 * e1; s = s + t; t = e2 * e2; dA = s + t; }
+          { float e0 = pos[0] - B[0], e1 = pos[1] - B[1], e2 = pos[2] - B[2]; float s = e0 * e0; float t = e1 * e1; s = s + t; t = e2 * e2; dB = s + t; }
+          { float e0 = pos[0] - Cc[0], e1 = pos[1] - Cc[1], e2 = pos[2] - Cc[2]; float s = e0 * e0; float t = e1 * e1; s = s + t; t = e2 * e2; dC = s + t; }
+          r.closest_vertex = (dA < dB) ? ((dA < dC) ? v0 : v2) : ((dB < dC) ? v1 : v2);
+          done = 1;
+        }
+        for (uint32_t k = 0; k < nclouds && !done; ++k) {
+          if (cloud_db_ids[k] != p.db_id || p.object_id >= cloud_counts[k]) continue;
+          const float* q = cloud_pos[k] + 3 * (size_t)p.object_id;
+          float pos[4] = {q[0], q[1], q[2], 1.f}, wp[4];
+          mat_vec(cloud_cs[k], pos, wp);
+          for (int j = 0; j < 3; ++j) r.world_pos[j] = wp[j];
+          r.closest_vertex = p.object_id;
+          done = 1;
+        }
+      }
+    }
+    out[i] = r;
+  }
+}

@@ -15,6 +15,8 @@
 #include "mesh.h"
 #include "pc.h"
 #include "matcap.h"
+#include "mouse.h"
+#include "pixel.h"
 
 // Implementation sections of the stb-style jtk headers, in the order j3d/main.cpp:15-36
 // instantiates them (they are not include-guarded, so order matters).
@@ -30,6 +32,7 @@
 #include "jtk/image.h"
 
 #include <chrono>
+#include <limits>
 #include <cstring>
 #include <thread>
 
@@ -344,6 +347,69 @@ void ref_find_closest(const float* verts, uint32_t nv, const uint32_t* tris, uin
     hits[4 * i + 2] = h.distance;
     hits[4 * i + 3] = h.found ? 1.f : 0.f;
     ids[i] = h.found ? id : (uint32_t)-1;
+    }
+  }
+
+// Picking through the reference's own code: canvas::get_pixel (canvas.cpp:148-153), get_closest_vertex
+// (pixel.cpp:6-33), the pivot pick of canvas::do_mouse (canvas.cpp:157-179; a click without movement only
+// sets scene::pivot, which is restored afterwards) and the expression of view::get_world_position
+// (view.cpp:439-469; view.cpp itself needs SDL, so its four arithmetic lines are evaluated here with the
+// reference's float4 operators).  Reads canvas::_canvas, i.e. the buffer after the splat.
+void ref_pick(void* p, const int32_t* xy, uint32_t n, j3dg_pick_result* out)
+  {
+  ref_state* st = (ref_state*)p;
+  static_assert(sizeof(j3dg_pick_result) == 64, "pick layout");
+  const float qnan = std::numeric_limits<float>::quiet_NaN();
+  for (uint32_t i = 0; i < n; ++i)
+    {
+    j3dg_pick_result r;
+    std::memset(&r, 0, sizeof(r));
+    r.world_pos[0] = r.world_pos[1] = r.world_pos[2] = qnan;
+    r.pivot[0] = r.pivot[1] = r.pivot[2] = qnan;
+    r.closest_vertex = (uint32_t)-1;
+    const int x = xy[2 * i], y = xy[2 * i + 1];
+    if (x >= 0 && y >= 0 && x < (int)st->cnv.width() && y < (int)st->cnv.height())
+      {
+      pixel px;
+      st->cnv.get_pixel(px, (float)x, (float)y, 0.f, 0.f);
+      std::memcpy(&r.pixel, &px, sizeof(px));
+      r.db_id = px.db_id;
+      if (px.db_id)
+        {
+        float saved[3] = { st->scn.pivot[0], st->scn.pivot[1], st->scn.pivot[2] };
+        mouse_data md;
+        std::memset(&md, 0, sizeof(md));
+        md.mouse_x = md.prev_mouse_x = (float)x;
+        md.mouse_y = md.prev_mouse_y = (float)y;
+        md.left_button_down = true;
+        bool refresh = false;
+        st->cnv.do_mouse(refresh, md, st->scn, 0.f, 0.f);
+        for (int k = 0; k < 3; ++k) { r.pivot[k] = st->scn.pivot[k]; st->scn.pivot[k] = saved[k]; }
+        mesh* m = st->database.get_mesh(px.db_id);
+        if (m)
+          {
+          const uint32_t v0 = m->triangles[px.object_id][0];
+          const uint32_t v1 = m->triangles[px.object_id][1];
+          const uint32_t v2 = m->triangles[px.object_id][2];
+          const float4 V0(m->vertices[v0][0], m->vertices[v0][1], m->vertices[v0][2], 1.f);
+          const float4 V1(m->vertices[v1][0], m->vertices[v1][1], m->vertices[v1][2], 1.f);
+          const float4 V2(m->vertices[v2][0], m->vertices[v2][1], m->vertices[v2][2], 1.f);
+          const float4 pos = V0 * (1.f - px.barycentric_u - px.barycentric_v) + px.barycentric_u * V1 + px.barycentric_v * V2;
+          auto world_pos = matrix_vector_multiply(m->cs, pos);
+          for (int k = 0; k < 3; ++k) r.world_pos[k] = world_pos[k];
+          r.closest_vertex = get_closest_vertex(px, &m->vertices, &m->triangles);
+          }
+        else if (pc* ptcl = st->database.get_pc(px.db_id))
+          {
+          // view.cpp:462-467 dereferences the (null) mesh pointer here; the evident intent is the cloud's own cs
+          const float4 pos(ptcl->vertices[px.object_id][0], ptcl->vertices[px.object_id][1], ptcl->vertices[px.object_id][2], 1.f);
+          auto world_pos = matrix_vector_multiply(ptcl->cs, pos);
+          for (int k = 0; k < 3; ++k) r.world_pos[k] = world_pos[k];
+          r.closest_vertex = get_closest_vertex(px, &ptcl->vertices, (const std::vector<vec3<uint32_t>>*)nullptr);
+          }
+        }
+      }
+    out[i] = r;
     }
   }
 

@@ -40,5 +40,8 @@ def load(name):
     after = None
     if "pixels_after_splat" in z.files:
         after = np.ascontiguousarray(z["pixels_after_splat"]).view(j.PIXEL_DTYPE).reshape(c["h"], c["w"])
+    pz = np.load(HERE / "golden" / "picks.npz")
+    picks = np.ascontiguousarray(pz[name]).view(j.PICK_DTYPE).reshape(-1)
     return dict(case=c, view=view_from_dict(meta["view"]), verts=verts, tris=tris, vc=vc, cloud=cl,
-                pixels=px, rgba=np.ascontiguousarray(z["rgba"]), pixels_after_splat=after)
+                pixels=px, rgba=np.ascontiguousarray(z["rgba"]), pixels_after_splat=after,
+                pick_xy=mg.pick_queries(c["w"], c["h"]), picks=picks)

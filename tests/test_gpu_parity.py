@@ -433,6 +433,54 @@ def test_cuda_matches_golden(ctx, name):
         c.destroy()
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_pick_matches_golden(ctx, name):
+    """j3dg_pick on the reference's own pixel buffer (uploaded to the device) answers every query — record,
+    db id, world position, closest vertex, pivot — bit for bit like the reference's host functions."""
+    import torch
+    g = load(name)
+    v = g["view"]
+    m = ctx.mesh_create(g["verts"], g["tris"], vcolors=g["vc"])
+    clouds = [ctx.cloud_create(*g["cloud"])] if g["cloud"] is not None else []
+    canvas = g["pixels_after_splat"] if g["pixels_after_splat"] is not None else g["pixels"]
+    d_canvas = torch.from_numpy(canvas.view(np.uint8).reshape(v.height, v.width, 32).copy()).cuda()
+    got = ctx.pick([m], clouds, v, g["pick_xy"], pixels=d_canvas)
+    assert got.tobytes() == g["picks"].tobytes()
+    m.destroy()
+    for c in clouds:
+        c.destroy()
+
+
+def test_pick_on_resident_canvas(ctx, oracle):
+    """RGBA-only readback: render a frame without downloading the pixel records, then pick from the canvas that
+    stayed in HBM; the answers equal the oracle's on the (separately downloaded) records."""
+    w, h = 320, 200
+    verts, tris = j.icosphere(16)
+    pos, nrm, clr = j.cloud(20001)
+    pos = (pos * 1.25).astype(np.float32)
+    mn, mx = j.compute_bb(np.concatenate([verts, pos]))
+    v = j.orbit_view(j.make_view(w, h, mn, mx, j.DEFAULT_FLAGS | j.SHADOW), 20.0)
+    mc, cav = j.make_matcap(0)
+    cs = np.eye(4, dtype=np.float32); cs[3, 0] = 0.05  # column-major: translation x
+    m = ctx.mesh_create(verts, tris, cs=cs.reshape(-1))
+    cl = ctx.cloud_create(pos, nrm, clr)
+    rgba = np.zeros((h, w), np.uint32)
+    ctx.render_frame([m], [cl], v, mc, cav, pixels_out=None, rgba_out=rgba)
+    xy = np.stack(np.meshgrid(np.arange(-3, w + 4, 3), np.arange(-2, h + 3, 2)), -1).reshape(-1, 2).astype(np.int32)
+    got = ctx.pick([m], [cl], v, xy)
+    px = np.zeros((h, w), j.PIXEL_DTYPE)
+    ctx.render_frame([m], [cl], v, mc, cav, pixels_out=px, rgba_out=rgba)
+    om = oracle.mesh(verts, tris, cs=cs.reshape(-1))
+    want = oracle.pick(px, v, [om], [(pos, None, 0x40000000)], xy)
+    assert got.tobytes() == want.tobytes()
+    assert (got["db_id"] == 0x20000000).sum() > 100 and (got["db_id"] == 0x40000000).sum() > 100
+    # a canvas of another size is not silently reused
+    v2 = j.make_view(64, 48, mn, mx)
+    with pytest.raises(j.J3dgError):
+        ctx.pick([m], [cl], v2, xy[:4])
+    m.destroy(); cl.destroy(); om.destroy()
+
+
 # ---- BASELINE.json full size (config B: 28 037 120 triangles, 1080p): size-independent properties ----
 def _numpy_closest(verts, tris, org, d, t_near):
     """Brute-force restatement of the Woop test over ALL triangles for one ray (float32, unfused)."""

@@ -57,6 +57,20 @@ def test_oracle_matches_golden(oracle, name):
     om.destroy()
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_pick_matches_golden(oracle, name):
+    """Picking (get_pixel / get_id / get_world_position / get_closest_vertex / pivot pick) on the reference's own
+    pixel buffer: the restatement must reproduce the reference's answers bit for bit (NaNs included)."""
+    g = load(name)
+    om = oracle.mesh(g["verts"], g["tris"], vcolors=g["vc"])
+    canvas = g["pixels_after_splat"] if g["pixels_after_splat"] is not None else g["pixels"]
+    clouds = [(g["cloud"][0], None, 0x40000000)] if g["cloud"] is not None else []
+    got = oracle.pick(canvas, g["view"], [om], clouds, g["pick_xy"])
+    assert got.tobytes() == g["picks"].tobytes()
+    assert (g["picks"]["db_id"] != 0).sum() > 10  # the fixture does exercise hit pixels
+    om.destroy()
+
+
 def test_views_match_golden(oracle):
     """camera.cpp / scene.cpp numbers: oracle and the product's host library vs the reference's."""
     for key, d in META["cameras"].items():
@@ -113,6 +127,10 @@ def test_oracle_equals_reference_live(oracle):
         want1 = ref.pixels(1)
         for f in ("object_id", "depth", "db_id"):
             assert (after[f] == want1[f]).all(), f
+        # picking on canvas::_canvas through the reference's own functions
+        xy = np.stack(np.meshgrid(np.arange(-2, w + 3, 5), np.arange(-1, h + 2, 3)), -1).reshape(-1, 2).astype(np.int32)
+        got = oracle.pick(after, v, [om], [(pos, None, 0x40000000)], xy)
+        assert got.tobytes() == ref.pick(xy).tobytes()
         ref.close(); om.destroy()
 
 
