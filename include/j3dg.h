@@ -227,6 +227,28 @@ int j3dg_pick(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nr_of_meshes,
               j3dg_cloud* const* clouds, uint32_t nr_of_clouds, const j3dg_view* view,
               const j3dg_pixel* pixels, uint32_t pixel_stride, const int32_t* xy, uint32_t n, j3dg_pick_result* out);
 
+/* ---- all hits along a ray: qbvh::find_all_triangles (jtk/qbvh.h:1854-2000), the query
+ *      j3d's voxel export is built on.  rays: n x 8 floats as in j3dg_mesh_find_closest; a triangle is
+ *      reported when the reference's Woop test accepts it with t_near < t < t_far (the interval never shrinks).
+ *      Results in CSR form: offsets has n + 1 entries (offsets[n] = *total = number of hits); hits are
+ *      total x 4 floats {u, v, distance, 0} and triangle_ids total x uint32, grouped per ray, in traversal
+ *      order within a ray (the reference's order is an artefact of its own tree as well).
+ *      hits / triangle_ids NULL: only offsets and *total are produced (size query).  If capacity < *total the
+ *      call fails with J3DG_EINVAL after writing offsets and *total.  Buffers all host or all device. ----- */
+int j3dg_mesh_find_all(j3dg_mesh* mesh, const float* rays, uint32_t n, uint32_t* offsets, float* hits,
+                       uint32_t* triangle_ids, uint32_t capacity, uint32_t* total);
+
+/* ---- voxel export: the grid-filling loop of _write_vox (j3d/vox.cpp:270-377).  dims = the reference's
+ *      (max_dim scaled by the bbox extents, vox.cpp:274-289); three axis-aligned ray grids (one ray per
+ *      voxel column, through the column centre, direction +x, +y, +2z); every hit writes the palette index
+ *      color_to_index (vox.cpp:154-172) of the texture / vertex colour / white at the hit point into the
+ *      voxel containing it: data[x + (y + z * dims[1]) * dims[0]], 0 = empty.  Where several hits with
+ *      different colours fall into one voxel the reference keeps whichever of its worker threads wrote last;
+ *      here the largest palette index wins (deterministic).  data NULL: only dims_out is produced.
+ *      data: host or device, capacity in bytes >= dims[0] * dims[1] * dims[2]. ------------------------------ */
+int j3dg_mesh_voxel_dims(const j3dg_mesh* mesh, uint32_t max_dim, uint32_t dims_out[3]);
+int j3dg_mesh_voxelize(j3dg_mesh* mesh, uint32_t max_dim, uint32_t dims_out[3], uint8_t* data, size_t capacity);
+
 /* Traversal statistics of the device BVH for the given view (a counting pass, not the
  * timed kernel): mean wide-node visits and triangle tests per primary ray.  SURVEY §8d. */
 int j3dg_cast_stats(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nr_of_meshes, const j3dg_view* view,

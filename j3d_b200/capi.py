@@ -122,6 +122,9 @@ def lib() -> C.CDLL:
         L.j3dg_ctx_set_screen_shard.argtypes = [_vp, _u32, _u32]
         L.j3dg_cast_stats.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(View), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.j3dg_cast_cost_image.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(View), _vp, _vp]
+        L.j3dg_mesh_find_all.argtypes = [_vp, _vp, _u32, _vp, _vp, _vp, _u32, C.POINTER(_u32)]
+        L.j3dg_mesh_voxel_dims.argtypes = [_vp, _u32, C.POINTER(_u32)]
+        L.j3dg_mesh_voxelize.argtypes = [_vp, _u32, C.POINTER(_u32), _vp, C.c_size_t]
         L.j3dg_pick.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(_vp), _u32, C.POINTER(View), _vp, _u32, _vp, _u32, _vp]
         _lib = L
     return _lib
@@ -431,6 +434,31 @@ class Mesh:
         ids = np.zeros((n,), np.uint32)
         self.ctx._check(self.ctx._L.j3dg_mesh_find_closest(self._h, _ptr(rays), n, _ptr(hits), _ptr(ids)), "j3dg_mesh_find_closest")
         return hits, ids
+
+
+    def find_all(self, rays: np.ndarray):
+        """qbvh::find_all_triangles for a ray batch: (offsets [n+1], hits [total,4] {u,v,t,0}, triangle ids [total])."""
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        offsets = np.zeros((n + 1,), np.uint32)
+        total = C.c_uint32()
+        L = self.ctx._L
+        self.ctx._check(L.j3dg_mesh_find_all(self._h, _ptr(rays), n, _ptr(offsets), None, None, 0, C.byref(total)), "j3dg_mesh_find_all")
+        hits = np.zeros((max(total.value, 1), 4), np.float32)
+        ids = np.zeros((max(total.value, 1),), np.uint32)
+        self.ctx._check(L.j3dg_mesh_find_all(self._h, _ptr(rays), n, _ptr(offsets), _ptr(hits), _ptr(ids), total.value, C.byref(total)),
+                        "j3dg_mesh_find_all")
+        return offsets, hits[:total.value], ids[:total.value]
+
+    def voxelize(self, max_dim: int, out=None) -> np.ndarray:
+        """_write_vox's voxel grid (palette indices, 0 = empty) as [Z,Y,X] u8; out: optional device pointer / tensor."""
+        dims = (C.c_uint32 * 3)()
+        L = self.ctx._L
+        self.ctx._check(L.j3dg_mesh_voxel_dims(self._h, max_dim, dims), "j3dg_mesh_voxel_dims")
+        if out is None:
+            out = np.zeros((dims[2], dims[1], dims[0]), np.uint8)
+        self.ctx._check(L.j3dg_mesh_voxelize(self._h, max_dim, dims, _ptr(out), dims[0] * dims[1] * dims[2]), "j3dg_mesh_voxelize")
+        return out
 
 
 class Cloud:

@@ -29,6 +29,7 @@
 // reference's operation order.  Only the box tests use FMA — they are conservative and do not
 // influence which triangle is the closest hit.
 #include "common.cuh"
+#include "traverse.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -126,15 +127,6 @@ struct TraceParams {
   uint32_t nrays;
 };
 
-__device__ __forceinline__ float pick(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
-
-__device__ __forceinline__ float safe_rcp(float d) {
-  // box tests only: keep the reciprocal finite so 0 * inf never produces NaN
-  const float big = 1e18f;
-  if (fabsf(d) < 1e-18f) return d < 0.f ? -big : big;
-  return 1.f / d;
-}
-
 __device__ __forceinline__ float4 transform_point(const float* __restrict__ m, float4 p) {  // jtk::transform, qbvh.h:5140-5151
   float4 r = mat_vec(m, p);
   if (r.w != 1.f && r.w != 0.f) { r.x = fdiv(r.x, r.w); r.y = fdiv(r.y, r.w); r.z = fdiv(r.z, r.w); r.w = 1.f; }
@@ -148,31 +140,6 @@ __device__ __forceinline__ float group_min(float v) {
   v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 2));
   v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 4));
   return v;
-}
-
-// Quantised plane byte -> float without an I2F (quarter-rate XU pipe) and without any arithmetic: one PRMT
-// assembles the bits 0x3F80_qq_00 = 1 + q * 2^-15 from the child's 8-byte box record, whose bytes 6 and 7 hold
-// 0x80 and 0x3F (selector nibble 0xF = byte 7 with sign replication = 0x00).  The node stores its quantisation
-// step pre-multiplied by 2^15, so  t = fma(m, S, B)  with  S = step * 2^15 / d  and  B = (origin - o) / d - S
-// equals q * step / d + (origin - o) / d.  The cancellation of S costs at most |S| * 2^-24 (1/512 of a quantum);
-// B is widened by |S| * 2^-22 on the near and far side to stay conservative.
-__device__ __forceinline__ float plane(uint32_t lo, uint32_t hi, uint32_t sel) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sel));
-  return __uint_as_float(r);
-}
-__device__ __forceinline__ uint32_t plane_sel(uint32_t byte_index) { return 0x760Fu | (byte_index << 4); }
-
-// Per node and axis: S and the widened near / far offsets.
-struct Slab { float S, Bn, Bf; };
-__device__ __forceinline__ Slab slab(float step32k, float origin, float o, float inv_d) {
-  Slab r;
-  r.S = step32k * inv_d;
-  const float B = fmaf(origin - o, inv_d, -r.S);
-  const float pad = fabsf(r.S) * 2.384185791015625e-07f;  // 2^-22
-  r.Bn = B - pad;
-  r.Bf = B + pad;
-  return r;
 }
 
 struct WorldRay { float4 org, dir; float t_near, t_far; };

@@ -106,6 +106,20 @@ static __global__ void __launch_bounds__(SCAN_THREADS) scan_apply(uint32_t* __re
   }
 }
 
+// In-place exclusive prefix sum of n uint32 (sums: scratch of ceil(n / SCAN_CHUNK) uint32).
+static inline uint32_t scan_scratch_count(size_t n) { return (uint32_t)((n + SCAN_CHUNK - 1) / SCAN_CHUNK); }
+static inline int exclusive_scan_u32(j3dg_ctx* ctx, uint32_t* data, size_t n, uint32_t* sums) {
+  if (!n) return J3DG_OK;
+  const uint32_t nchunks = scan_scratch_count(n);
+  scan_chunk_sums<<<nchunks, SCAN_THREADS, 0, ctx->stream>>>(data, n, sums);
+  KERNEL_CHECK(ctx);
+  scan_sums_serial<<<1, SCAN_THREADS, 0, ctx->stream>>>(sums, nchunks);
+  KERNEL_CHECK(ctx);
+  scan_apply<<<nchunks, SCAN_THREADS, 0, ctx->stream>>>(data, n, sums);
+  KERNEL_CHECK(ctx);
+  return J3DG_OK;
+}
+
 // ---- stable scatter ------------------------------------------------------------------
 static __global__ void __launch_bounds__(THREADS) scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                            uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,

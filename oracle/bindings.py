@@ -56,6 +56,9 @@ class Oracle:
         L.orc_shade.argtypes = [_vp, _u32, C.POINTER(View), _vp, _u32, _u32, _u32, _vp, _u32]
         L.orc_splat.argtypes = [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_u32), C.POINTER(_vp),
                                 C.POINTER(_u32), _u32, C.POINTER(View), _vp, _vp, _u32, _vp, _u32]
+        L.orc_find_all.restype = _u32
+        L.orc_find_all.argtypes = [_vp, _vp, _u32, _vp, _vp, _vp, _u32]
+        L.orc_voxelize.argtypes = [_vp, _u32, C.POINTER(_u32), _vp, _vp]
         L.orc_pick.argtypes = [_vp, _u32, C.POINTER(View), C.POINTER(_vp), _u32, C.POINTER(_vp), C.POINTER(_u32), C.POINTER(_vp),
                                C.POINTER(_u32), _u32, _vp, _u32, _vp]
         self.L = L
@@ -158,6 +161,26 @@ class OracleMesh:
         self.orc.L.orc_find_closest(self.h, _p(rays), n, _p(hits), _p(ids))
         return hits, ids
 
+    def find_all(self, rays):
+        """qbvh::find_all_triangles: (offsets [n+1], hits [total,4] {u,v,t,0}, ids [total])."""
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        offsets = np.zeros((n + 1,), np.uint32)
+        total = self.orc.L.orc_find_all(self.h, _p(rays), n, _p(offsets), None, None, 0)
+        hits = np.zeros((max(total, 1), 4), np.float32)
+        ids = np.zeros((max(total, 1),), np.uint32)
+        self.orc.L.orc_find_all(self.h, _p(rays), n, _p(offsets), _p(hits), _p(ids), total)
+        return offsets, hits[:total], ids[:total]
+
+    def voxelize(self, max_dim):
+        """_write_vox's grid: (vmax [Z,Y,X] u8, vmin [Z,Y,X] u8)."""
+        dims = (_u32 * 3)()
+        self.orc.L.orc_voxelize(self.h, max_dim, dims, None, None)
+        shape = (dims[2], dims[1], dims[0])
+        vmax, vmin = np.zeros(shape, np.uint8), np.zeros(shape, np.uint8)
+        self.orc.L.orc_voxelize(self.h, max_dim, dims, _p(vmax), _p(vmin))
+        return vmax, vmin
+
     def destroy(self):
         if self.h:
             self.orc.L.orc_mesh_destroy(self.h)
@@ -193,6 +216,9 @@ class Ref:
         L.ref_find_closest.argtypes = [_vp, _u32, _vp, _u32, _u32, _vp, _u32, _vp, _vp]
         L.ref_hardware_concurrency.restype = C.c_int
         L.ref_pick.argtypes = [_vp, _vp, _u32, _vp]
+        L.ref_find_all.restype = _u32
+        L.ref_find_all.argtypes = [_vp, _u32, _vp, _u32, _vp, _u32, _vp, _vp, _vp, _u32]
+        L.ref_voxelize.argtypes = [_vp, _u32, _vp, _u32, _vp, _vp, _vp, _u32, _u32, _u32, C.POINTER(_u32), _vp, C.c_uint64]
         self.L, self.w, self.h = L, w, h
         self.s = L.ref_create(w, h)
 
@@ -221,6 +247,32 @@ class Ref:
         out = np.zeros((xy.shape[0],), PICK_DTYPE)
         self.L.ref_pick(self.s, _p(xy), xy.shape[0], _p(out))
         return out
+
+    def find_all(self, verts, tris, rays):
+        """The reference's qbvh::find_all_triangles: (offsets [n+1], hits [total,4], ids [total])."""
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        offsets = np.zeros((n + 1,), np.uint32)
+        total = self.L.ref_find_all(_p(verts), verts.shape[0], _p(tris), tris.shape[0], _p(rays), n, _p(offsets), None, None, 0)
+        hits = np.zeros((max(total, 1), 4), np.float32)
+        ids = np.zeros((max(total, 1),), np.uint32)
+        self.L.ref_find_all(_p(verts), verts.shape[0], _p(tris), tris.shape[0], _p(rays), n, _p(offsets), _p(hits), _p(ids), total)
+        return offsets, hits[:total], ids[:total]
+
+    def voxelize(self, verts, tris, max_dim, vcolors=None, uv=None, texture=None):
+        """The reference's write_vox end to end (through a temporary .vox file): grid [Z,Y,X] u8."""
+        tw = th = 0
+        if texture is not None:
+            th, tw = texture.shape
+        dims = (_u32 * 3)()
+        rc = self.L.ref_voxelize(_p(verts), verts.shape[0], _p(tris), tris.shape[0], _p(vcolors), _p(uv), _p(texture), tw, th, max_dim, dims, None, 0)
+        if rc != 0:
+            raise RuntimeError(f"ref_voxelize failed: {rc}")
+        grid = np.zeros((dims[2], dims[1], dims[0]), np.uint8)
+        rc = self.L.ref_voxelize(_p(verts), verts.shape[0], _p(tris), tris.shape[0], _p(vcolors), _p(uv), _p(texture), tw, th, max_dim, dims, _p(grid), grid.size)
+        if rc != 0:
+            raise RuntimeError(f"ref_voxelize failed: {rc}")
+        return grid
 
     def unzoom(self):
         self.L.ref_unzoom(self.s)

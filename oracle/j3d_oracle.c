@@ -914,3 +914,161 @@ void orc_pick(const j3dg_pixel* px, uint32_t stride, const j3dg_view* v, orc_mes
     out[i] = r;
   }
 }
+
+/* ---- all hits + voxel export ------------------------------------------------
+ * qbvh::find_all_triangles, qbvh.h:1854-2000: every triangle the Woop test accepts inside the
+ * ORIGINAL interval (t_near, t_far); nothing shrinks.  Traversal order is this file's own. */
+typedef void (*hit_sink)(void* user, uint32_t tri, float t, float u, float v);
+
+static void mesh_find_all(const orc_mesh* m, const float org[3], const float dir[3], float t_near, float t_far, hit_sink sink, void* user)
+{
+  if (!m->nt) return;
+  woop_pre pre = woop_precompute(dir);
+  double inv[3];
+  for (int j = 0; j < 3; ++j) inv[j] = 1.0 / (double)dir[j];
+  uint32_t stack[128]; int sp = 0;
+  stack[sp++] = 0;
+  while (sp) {
+    const bnode* n = &m->nodes[stack[--sp]];
+    double lo = (double)t_near, hi = (double)t_far;
+    int miss = 0;
+    for (int j = 0; j < 3 && !miss; ++j) {
+      if (dir[j] == 0.f) { if (org[j] < n->mn[j] || org[j] > n->mx[j]) miss = 1; continue; }
+      double a = ((double)n->mn[j] - (double)org[j]) * inv[j], b = ((double)n->mx[j] - (double)org[j]) * inv[j];
+      if (a > b) { double t = a; a = b; b = t; }
+      double pad = 1e-6 * (fabs(a) + fabs(b)) + 1e-30;
+      a -= pad; b += pad;
+      if (a > lo) lo = a;
+      if (b < hi) hi = b;
+      if (lo > hi) miss = 1;
+    }
+    if (miss) continue;
+    if (n->count) {
+      for (uint32_t i = 0; i < n->count; ++i) {
+        uint32_t t = m->order[n->first + i];
+        const uint32_t* tr = m->tris + 3 * (size_t)t;
+        float tt, uu, vv;
+        if (woop_intersect(m->verts + 3 * (size_t)tr[0], m->verts + 3 * (size_t)tr[1], m->verts + 3 * (size_t)tr[2], &pre, org, t_near, t_far, &tt, &uu, &vv))
+          sink(user, t, tt, uu, vv);
+      }
+    } else {
+      stack[sp++] = n->left; stack[sp++] = n->right;
+    }
+  }
+}
+
+typedef struct { uint32_t total, capacity; float* hits; uint32_t* ids; } csr_sink_t;
+static void csr_sink(void* user, uint32_t tri, float t, float u, float v)
+{
+  csr_sink_t* s = (csr_sink_t*)user;
+  if (s->total < s->capacity && s->hits) {
+    s->hits[4 * (size_t)s->total + 0] = u; s->hits[4 * (size_t)s->total + 1] = v;
+    s->hits[4 * (size_t)s->total + 2] = t; s->hits[4 * (size_t)s->total + 3] = 0.f;
+    s->ids[s->total] = tri;
+  }
+  s->total++;
+}
+
+uint32_t orc_find_all(const orc_mesh* m, const float* rays, uint32_t n, uint32_t* offsets, float* hits, uint32_t* ids, uint32_t capacity)
+{
+  csr_sink_t s; s.total = 0; s.capacity = capacity; s.hits = hits; s.ids = ids;
+  for (uint32_t i = 0; i < n; ++i) {
+    offsets[i] = s.total;
+    mesh_find_all(m, rays + 8 * (size_t)i, rays + 8 * (size_t)i + 3, rays[8 * (size_t)i + 6], rays[8 * (size_t)i + 7], csr_sink, &s);
+  }
+  offsets[n] = s.total;
+  return s.total;
+}
+
+/* vox.cpp:154-172 */
+static uint8_t color_to_index(uint8_t r, uint8_t g, uint8_t b)
+{
+  if (r < 16) r = 0; else r -= 16;
+  if (g < 16) g = 0; else g -= 16;
+  if (b < 32) b = 0; else b -= 32;
+  uint8_t ret = (uint8_t)(((r >> 5) << 5) | ((g >> 5) << 2) | (b >> 6));
+  return ret == 0 ? 1 : ret;
+}
+
+/* vox.cpp:274-289 */
+void orc_voxel_dims(const orc_mesh* m, uint32_t max_dim, uint32_t dims[3])
+{
+  int largest = 0;
+  if ((m->bb_max[1] - m->bb_min[1]) > (m->bb_max[largest] - m->bb_min[largest])) largest = 1;
+  if ((m->bb_max[2] - m->bb_min[2]) > (m->bb_max[largest] - m->bb_min[largest])) largest = 2;
+  for (int j = 0; j < 3; ++j) {
+    float a = (float)max_dim * (m->bb_max[j] - m->bb_min[j]);
+    float b = a / (m->bb_max[largest] - m->bb_min[largest]);
+    dims[j] = (uint32_t)b;
+    if (dims[j] == 0) dims[j] = 1;
+  }
+}
+
+typedef struct { const orc_mesh* m; uint32_t dim[3]; uint8_t* vmax; uint8_t* vmin; } vox_sink_t;
+static void vox_sink(void* user, uint32_t tri, float t, float u, float v)
+{ /* vox.cpp:336-375 */
+  (void)t;
+  vox_sink_t* s = (vox_sink_t*)user;
+  const orc_mesh* m = s->m;
+  const uint32_t* tr = m->tris + 3 * (size_t)tri;
+  const float* V0 = m->verts + 3 * (size_t)tr[0]; const float* V1 = m->verts + 3 * (size_t)tr[1]; const float* V2 = m->verts + 3 * (size_t)tr[2];
+  const float k = 1.f - u - v;
+  float pos[3];
+  for (int j = 0; j < 3; ++j) { float a = V0[j] * k, b = u * V1[j], c = v * V2[j]; float q = a + b; pos[j] = q + c; }
+  float clr[3] = {1.f, 1.f, 1.f};
+  if (m->uv && m->tex && m->tw > 0 && m->th > 0) {
+    const float* uvc = m->uv + 6 * (size_t)tri;
+    float cx, cy;
+    { float a = k * uvc[0], b = u * uvc[2], c = v * uvc[4]; float q = a + b; cx = q + c; }
+    { float a = k * uvc[1], b = u * uvc[3], c = v * uvc[5]; float q = a + b; cy = q + c; }
+    cx = cx < 1.f ? cx : 1.f; cx = cx > 0.f ? cx : 0.f;   /* std::max(std::min(c, 1.f), 0.f) */
+    cy = cy < 1.f ? cy : 1.f; cy = cy > 0.f ? cy : 0.f;
+    int x = (int)(cx * (float)(m->tw - 1)), y = (int)(cy * (float)(m->th - 1));
+    uint32_t color = m->tex[(size_t)y * m->tw + x];
+    clr[0] = (float)(color & 255) / 255.f; clr[1] = (float)((color >> 8) & 255) / 255.f; clr[2] = (float)((color >> 16) & 255) / 255.f;
+  } else if (m->vcolors) {
+    const float* c0 = m->vcolors + 3 * (size_t)tr[0]; const float* c1 = m->vcolors + 3 * (size_t)tr[1]; const float* c2 = m->vcolors + 3 * (size_t)tr[2];
+    for (int j = 0; j < 3; ++j) { float a = c0[j] * k, b = u * c1[j], c = v * c2[j]; float q = a + b; clr[j] = q + c; }
+  }
+  uint32_t X[3];
+  for (int j = 0; j < 3; ++j) {
+    float x = (pos[j] - m->bb_min[j]) / (m->bb_max[j] - m->bb_min[j]);
+    float xs = x * (float)s->dim[j];
+    X[j] = xs > 0.f ? (uint32_t)xs : 0u;   /* cvttss2si of a small negative value truncates to 0 */
+    if (X[j] == s->dim[j]) X[j] = s->dim[j] - 1;
+    if (X[j] >= s->dim[j]) return;
+  }
+  float r255 = clr[0] * 255.f, g255 = clr[1] * 255.f, b255 = clr[2] * 255.f;
+  uint8_t ci = color_to_index((uint8_t)r255, (uint8_t)g255, (uint8_t)b255);
+  size_t idx = (size_t)X[0] + ((size_t)X[1] + (size_t)X[2] * s->dim[1]) * s->dim[0];
+  if (ci > s->vmax[idx]) s->vmax[idx] = ci;
+  if (s->vmin && (s->vmin[idx] == 0 || ci < s->vmin[idx])) s->vmin[idx] = ci;
+}
+
+/* The grid-filling loop of _write_vox (vox.cpp:300-379).  vmax: largest palette index written into each voxel
+ * (what the CUDA path stores); vmin (nullable): smallest — the reference's own result (last writer among its
+ * threads) lies between the two, and equals both wherever only one colour fell into the voxel. */
+void orc_voxelize(const orc_mesh* m, uint32_t max_dim, uint32_t dims[3], uint8_t* vmax, uint8_t* vmin)
+{
+  vox_sink_t s;
+  s.m = m; s.vmax = vmax; s.vmin = vmin;
+  orc_voxel_dims(m, max_dim, s.dim);
+  for (int j = 0; j < 3; ++j) dims[j] = s.dim[j];
+  if (!vmax) return;
+  size_t nvox = (size_t)s.dim[0] * s.dim[1] * s.dim[2];
+  memset(vmax, 0, nvox);
+  if (vmin) memset(vmin, 0, nvox);
+  for (int dd = 0; dd < 3; ++dd) {
+    float dir[3] = {0.f, 0.f, 0.f};
+    dir[dd] = dd == 2 ? 2.f : 1.f;
+    const int d1i = (dd + 1) % 3, d2i = (dd + 2) % 3;
+    for (uint32_t d1 = 0; d1 < s.dim[d1i]; ++d1)
+      for (uint32_t d2 = 0; d2 < s.dim[d2i]; ++d2) {
+        float org[3];
+        org[dd] = m->bb_min[dd];
+        { float a = ((float)d1 + 0.5f) / (float)s.dim[d1i]; float b = a * (m->bb_max[d1i] - m->bb_min[d1i]); org[d1i] = b + m->bb_min[d1i]; }
+        { float a = ((float)d2 + 0.5f) / (float)s.dim[d2i]; float b = a * (m->bb_max[d2i] - m->bb_min[d2i]); org[d2i] = b + m->bb_min[d2i]; }
+        mesh_find_all(m, org, dir, 0.f, FLT_MAX, vox_sink, &s);
+      }
+  }
+}

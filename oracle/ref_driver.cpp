@@ -17,6 +17,11 @@
 #include "matcap.h"
 #include "mouse.h"
 #include "pixel.h"
+#include "vox.h"
+#include "ogt/ogt_vox.h"
+#include <unistd.h>
+#include <cstdio>
+#include <cstdlib>
 
 // Implementation sections of the stb-style jtk headers, in the order j3d/main.cpp:15-36
 // instantiates them (they are not include-guarded, so order matters).
@@ -411,6 +416,104 @@ void ref_pick(void* p, const int32_t* xy, uint32_t n, j3dg_pick_result* out)
       }
     out[i] = r;
     }
+  }
+
+// qbvh::find_all_triangles (qbvh.h:1854-2000) on a ray batch, on the tree vox.cpp:308 builds
+// (`new qbvh(triangles, vertices)`).  CSR output: offsets[n + 1]; hits total x {u, v, distance, 0}; ids.
+// Returns the total number of hits (nothing beyond `capacity` is written).
+uint32_t ref_find_all(const float* verts, uint32_t nv, const uint32_t* tris, uint32_t nt, const float* rays, uint32_t n,
+  uint32_t* offsets, float* hits, uint32_t* ids, uint32_t capacity)
+  {
+  (void)nv;
+  std::vector<vec3<uint32_t>> triangles(nt);
+  std::memcpy((void*)triangles.data(), tris, sizeof(uint32_t) * 3 * nt);
+  qbvh bvh(triangles, (const vec3<float>*)verts);
+  uint32_t total = 0;
+  for (uint32_t i = 0; i < n; ++i)
+    {
+    offsets[i] = total;
+    ray r;
+    r.orig = float4(rays[8 * i + 0], rays[8 * i + 1], rays[8 * i + 2], 1.f);
+    r.dir = float4(rays[8 * i + 3], rays[8 * i + 4], rays[8 * i + 5], 0.f);
+    r.t_near = rays[8 * i + 6];
+    r.t_far = rays[8 * i + 7];
+    std::vector<uint32_t> triangle_ids;
+    std::vector<hit> all_hits = bvh.find_all_triangles(triangle_ids, r, triangles.data(), (const vec3<float>*)verts);
+    for (size_t k = 0; k < all_hits.size(); ++k, ++total)
+      {
+      if (total < capacity)
+        {
+        hits[4 * (size_t)total + 0] = all_hits[k].u;
+        hits[4 * (size_t)total + 1] = all_hits[k].v;
+        hits[4 * (size_t)total + 2] = all_hits[k].distance;
+        hits[4 * (size_t)total + 3] = 0.f;
+        ids[total] = triangle_ids[k];
+        }
+      }
+    }
+  offsets[n] = total;
+  return total;
+  }
+
+// The reference's voxel export end to end: write_vox (j3d/vox.cpp:270-440, compiled unmodified) into a
+// temporary .vox file, read back with the reference's own ogt_vox reader.  Returns 0 on success; dims_out
+// always receives the grid size; the grid (x + (y + z * dims[1]) * dims[0]) is copied if it fits capacity.
+int ref_voxelize(const float* verts, uint32_t nv, const uint32_t* tris, uint32_t nt, const float* vcolors,
+  const float* uv, const uint32_t* tex, uint32_t tw, uint32_t th, uint32_t max_dim, uint32_t* dims_out, uint8_t* data, uint64_t capacity)
+  {
+  std::vector<vec3<float>> vertices(nv), clrs;
+  std::memcpy((void*)vertices.data(), verts, sizeof(float) * 3 * nv);
+  std::vector<vec3<uint32_t>> triangles(nt);
+  std::memcpy((void*)triangles.data(), tris, sizeof(uint32_t) * 3 * nt);
+  if (vcolors)
+    {
+    clrs.resize(nv);
+    std::memcpy((void*)clrs.data(), vcolors, sizeof(float) * 3 * nv);
+    }
+  std::vector<vec3<vec2<float>>> uvs;
+  image<uint32_t> texture;
+  if (uv && tex && tw && th)
+    {
+    uvs.resize(nt);
+    std::memcpy((void*)uvs.data(), uv, sizeof(float) * 6 * nt);
+    texture = image<uint32_t>(tw, th);
+    for (uint32_t y = 0; y < th; ++y)
+      std::memcpy(texture.row(y), tex + (size_t)y * tw, sizeof(uint32_t) * tw);
+    }
+  char path[] = "/tmp/j3d_ref_vox_XXXXXX";
+  int fd = mkstemp(path);
+  if (fd < 0)
+    return -1;
+  close(fd);
+  bool ok = write_vox(path, vertices, clrs, triangles, uvs, texture, max_dim);
+  int rc = -2;
+  if (ok)
+    {
+    FILE* fp = fopen(path, "rb");
+    if (fp)
+      {
+      fseek(fp, 0, SEEK_END);
+      uint32_t size = (uint32_t)ftell(fp);
+      fseek(fp, 0, SEEK_SET);
+      std::vector<uint8_t> buffer(size);
+      size_t got = fread(buffer.data(), 1, size, fp);
+      fclose(fp);
+      const ogt_vox_scene* scene = got == size ? ogt_vox_read_scene(buffer.data(), size) : nullptr;
+      if (scene && scene->num_models >= 1)
+        {
+        const ogt_vox_model* m = scene->models[0];
+        dims_out[0] = m->size_x; dims_out[1] = m->size_y; dims_out[2] = m->size_z;
+        const uint64_t nvox = (uint64_t)m->size_x * m->size_y * m->size_z;
+        if (data && capacity >= nvox)
+          std::memcpy(data, m->voxel_data, nvox);
+        rc = 0;
+        }
+      if (scene)
+        ogt_vox_destroy_scene(scene);
+      }
+    }
+  remove(path);
+  return rc;
   }
 
 // Traversal statistics of the reference QBVH are not exposed by the reference; none here.

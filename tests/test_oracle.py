@@ -71,6 +71,45 @@ def test_oracle_pick_matches_golden(oracle, name):
     om.destroy()
 
 
+def test_oracle_find_all_matches_golden(oracle):
+    """qbvh::find_all_triangles: the restatement returns the reference's hit sets, bit for bit."""
+    import zlib
+    import make_golden as mg
+    verts, tris, rays = mg.allhits_inputs()
+    assert mg.crc(verts, tris, rays) == META["allhits"]["input_crc"]
+    z = np.load(mg.HERE / "allhits.npz")
+    om = oracle.mesh(verts, tris)
+    off, hits, ids = om.find_all(rays)
+    hits, ids = mg.canonical_hits(off, hits, ids)
+    assert (off == z["offsets"]).all() and int(off[-1]) == META["allhits"]["total"] > 2500
+    assert (ids == z["ids"]).all()
+    assert hits.tobytes() == z["hits"].tobytes()
+    counts = np.diff(off.astype(np.int64))
+    assert (counts[500:] % 2 == 0).mean() > 0.99  # closed surface: a full ray enters as often as it leaves
+    om.destroy()
+
+
+@pytest.mark.parametrize("name", ["vox_white", "vox_colors", "vox_texture"])
+def test_oracle_voxelize_matches_golden(oracle, name):
+    """_write_vox's grid: same dimensions and occupancy as the reference's .vox output; where one colour fell into a
+    voxel the palette index is the reference's, elsewhere the reference's (thread-order dependent) value lies
+    between the smallest and the largest candidate."""
+    import make_golden as mg
+    verts, tris, vc, uv, tex, max_dim = mg.voxel_inputs(name)
+    assert mg.crc(verts, tris, *[x for x in (vc, uv, tex) if x is not None]) == META[name]["input_crc"]
+    want = np.load(mg.HERE / "voxels.npz")[name]
+    om = oracle.mesh(verts, tris, vcolors=vc, uv=uv, texture=tex)
+    vmax, vmin = om.voxelize(max_dim)
+    assert vmax.shape == want.shape == tuple(META[name]["dims"][::-1])
+    assert ((vmax != 0) == (want != 0)).all()
+    assert ((want >= vmin) & (want <= vmax)).all()
+    single = vmin == vmax
+    assert single.mean() > 0.9 and (want[single] == vmax[single]).all()
+    if name == "vox_white":
+        assert (want[want != 0] == 255).all()
+    om.destroy()
+
+
 def test_views_match_golden(oracle):
     """camera.cpp / scene.cpp numbers: oracle and the product's host library vs the reference's."""
     for key, d in META["cameras"].items():
@@ -132,6 +171,20 @@ def test_oracle_equals_reference_live(oracle):
         got = oracle.pick(after, v, [om], [(pos, None, 0x40000000)], xy)
         assert got.tobytes() == ref.pick(xy).tobytes()
         ref.close(); om.destroy()
+    # the ray queries and the voxel export of vox.cpp, live
+    import make_golden as mg
+    verts, tris, rays = mg.allhits_inputs()
+    ref = Ref(32, 18)
+    om = oracle.mesh(verts, tris)
+    a, b = om.find_all(rays), ref.find_all(verts, tris, rays)
+    assert (a[0] == b[0]).all()
+    ha, ia = mg.canonical_hits(*a)
+    hb, ib = mg.canonical_hits(*b)
+    assert (ia == ib).all() and ha.tobytes() == hb.tobytes()
+    vmax, vmin = om.voxelize(21)
+    got = ref.voxelize(verts, tris, 21)
+    assert (got == vmax).all() and (vmin == vmax).all()
+    ref.close(); om.destroy()
 
 
 def test_empty_and_ragged_inputs(oracle):
