@@ -251,19 +251,40 @@ def run_b200(args, f, rank, world, local_rank):
 
     # ---- device-resident frame buffers ----
     px = torch.empty((H, W, 32), dtype=torch.uint8, device=dev)
-    rgba = torch.empty((H, W), dtype=torch.int32, device=dev)
-    gather_list = [torch.empty_like(rgba) for _ in range(world)] if (world > 1 and rank == 0) else None
+    rgba2 = [torch.empty((H, W), dtype=torch.int32, device=dev) for _ in range(2)]
+    rgba = rgba2[0]
+    # N > 1: the NCCL gather of frame k runs on its own stream and overlaps the kernels of frame k + 1
+    # (double-buffered RGBA); the timed region ends only after the last gather has completed.
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    gather_lists = [[torch.empty_like(rgba) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
+    ev_render = [torch.cuda.Event() for _ in range(2)]
+    ev_gather = [torch.cuda.Event() for _ in range(2)]
 
     total = args.warmup + args.steps
     views = frame_views(j, v0, rank, total, world)  # rank r renders frames r, r+N, r+2N ...
+    state = {"k": 0}
 
     def step(v):
-        ctx.render_frame([mesh], [], v, pixels_out=px, rgba_out=rgba)
+        k = state["k"]
+        state["k"] = k + 1
+        b = k & 1
+        if world > 1 and k >= 2:
+            stream.wait_event(ev_gather[b])  # the gather of frame k - 2 has left this buffer
+        ctx.render_frame([mesh], [], v, pixels_out=px, rgba_out=rgba2[b])
         if world > 1:
-            dist.gather(rgba, gather_list, dst=0)
+            ev_render[b].record(stream)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev_render[b])
+                dist.gather(rgba2[b], gather_lists[b], dst=0)
+                ev_gather[b].record(comm)
+
+    def drain():
+        if world > 1:
+            stream.wait_stream(comm)
 
     for v in views[: args.warmup]:
         step(v)
+    drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -276,6 +297,7 @@ def run_b200(args, f, rank, world, local_rank):
     e0.record()
     for v in views[args.warmup:]:
         step(v)
+    drain()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -313,6 +335,8 @@ def run_b200(args, f, rank, world, local_rank):
     sweep(views[args.warmup:])
     e2e_s = time.perf_counter() - t0
     # the same frames one by one through the synchronous j3dg_render_frame (kernels, then copy)
+    for v in views[:3]:  # untimed: the first call allocates the context's own canvas
+        ctx.render_frame([mesh], [], v, pixels_out=hpx[0], rgba_out=hrgba[0])
     t0 = time.perf_counter()
     for v in views[args.warmup: args.warmup + min(args.steps, 20)]:
         ctx.render_frame([mesh], [], v, pixels_out=hpx[0], rgba_out=hrgba[0])
@@ -325,6 +349,45 @@ def run_b200(args, f, rank, world, local_rank):
     import ctypes
     h2d_bytes = ctypes.sizeof(j.View) + 256  # the view (kernel parameters) + the per-mesh table
     d2h_bytes = W * H * 32 + W * H * 4
+
+    # ---- interactive-host mode: RGBA-only readback, the pixel records stay in HBM and the host
+    # asks for the record under the cursor with j3dg_pick (64 bytes per query) ----
+    e2e_rgba = None
+    extras = None
+    if world == 1:
+        def sweep_rgba(vs):
+            for k, v in enumerate(vs):
+                ctx.frame_submit([mesh], [], v, pixels_out=None, rgba_out=hrgba[k & 1])
+                if k >= 1:
+                    ctx.frame_wait()
+            if vs:
+                ctx.frame_wait()
+                ctx.pick([mesh], [], vs[-1], np.array([[W // 2, H // 2]], np.int32))
+        sweep_rgba(views[: args.warmup])
+        t0 = time.perf_counter()
+        sweep_rgba(views[args.warmup:])
+        dt = time.perf_counter() - t0
+        e2e_rgba = {"value": rays_total / dt / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * dt / args.steps, "d2h_bytes_per_step": W * H * 4,
+                    "api": "j3dg_frame_submit(pixels_out=NULL)/j3dg_frame_wait + j3dg_pick: pixel records stay resident, RGBA only crosses PCIe"}
+        # ---- the other query clients of the same BVH, timed through the C ABI ----
+        qxy = np.stack(np.meshgrid(np.arange(0, W, 8), np.arange(0, H, 8)), -1).reshape(-1, 2).astype(np.int32)
+        ctx.pick([mesh], [], views[-1], qxy)
+        t0 = time.perf_counter()
+        picks = ctx.pick([mesh], [], views[-1], qxy)
+        pick_ms = 1e3 * (time.perf_counter() - t0)
+        vox_dim = 512
+        grid = torch.empty((vox_dim ** 3 + 64,), dtype=torch.uint8, device=dev)
+        mesh.voxelize(vox_dim, out=grid)
+        t0 = time.perf_counter()
+        mesh.voxelize(vox_dim, out=grid)
+        vox_ms = 1e3 * (time.perf_counter() - t0)
+        occupied = int((grid != 0).sum().item())
+        del grid
+        extras = {"pick": {"queries": int(qxy.shape[0]), "hits": int((picks["db_id"] != 0).sum()), "ms": pick_ms,
+                           "note": "j3dg_pick on the resident canvas, host xy in / host records out (64 B per query)"},
+                  "voxelize": {"max_dim": vox_dim, "rays": 3 * vox_dim * vox_dim, "occupied_voxels": occupied, "ms": vox_ms,
+                               "mrays_s": 3 * vox_dim * vox_dim / vox_ms / 1e3,
+                               "note": "j3dg_mesh_voxelize into a device grid: memset + 3 all-hits ray grids (vox.cpp:300-379)"}}
 
     if rank != 0:
         if world > 1:
@@ -348,13 +411,20 @@ def run_b200(args, f, rank, world, local_rank):
                 "traffic": traffic, "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
                 "tris_per_ray": tris_per_ray, "kernel_ms": cast_ms, "kernel_mrays_s": W * H / cast_ms / 1e3}
     cpu = cpu_baseline(j, f, verts, tris, v0) if (world == 1 and not args.no_cpu_baseline) else None
+    # the other stages against the same HBM roofline (algorithmic bytes per unit)
+    nv = verts.shape[0]
+    bvh_bytes = int(info.nr_of_nodes) * info.node_bytes + nt * info.triangle_bytes
+    shade_ms = tm.shade_ms / max(1, tm.shade_count)
+    stages = {"build": {"ms": build_ms, "algorithmic_bytes": 12 * nt + 12 * nv + bvh_bytes, "mtris_s": nt / build_ms / 1e3 if build_ms else None,
+                        "roofline_frac": (12 * nt + 12 * nv + bvh_bytes) / (build_ms * 1e-3) / 1e9 / peak if build_ms else None},
+              "shade": {"ms": shade_ms, "algorithmic_bytes": 40 * W * H, "roofline_frac": 40 * W * H / (shade_ms * 1e-3) / 1e9 / peak if shade_ms else None}}
 
     line = {
         "metric": "primary Mrays/s @1080p (ray cast + shading per frame)", "value": value, "unit": "Mrays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(f, nt), "l2": "inputs_larger_than_l2",
-                   "sharding": "replicas only" if world == 1 else f"orbit frames round-robin over {world} ranks, BVH NCCL-broadcast from rank 0, RGBA NCCL-gathered on rank 0 every step",
+                   "sharding": "replicas only" if world == 1 else f"orbit frames round-robin over {world} ranks, BVH NCCL-broadcast from rank 0, RGBA NCCL-gathered on rank 0 every step (gather of frame k on a second stream, overlapping the kernels of frame k+1)",
                    "bvh_bytes": int(info.nr_of_nodes) * info.node_bytes + nt * info.triangle_bytes},
         "bvh_build_ms": build_ms, "bvh_nodes": int(info.nr_of_nodes), "frames_per_s": 1e3 * args.steps * world / ms,
         "cast_ms": cast_ms, "shade_ms": tm.shade_ms / max(1, tm.shade_count),
@@ -362,8 +432,12 @@ def run_b200(args, f, rank, world, local_rank):
                 "ms_per_step": 1e3 * e2e_s / args.steps, "api": "j3dg_frame_submit/j3dg_frame_wait (pipelined, pinned host buffers)",
                 "sync_render_frame_ms_per_step": e2e_sync_ms, "mesh_create_ms": e2e_build_ms},
         "gpu_launches": int(tm.kernel_launches),
-        "clocks": clocks, "roofline": roofline,
+        "clocks": clocks, "roofline": roofline, "stages": stages,
     }
+    if e2e_rgba is not None:
+        line["e2e_rgba_only"] = e2e_rgba
+    if extras is not None:
+        line["queries"] = extras
     if bcast_ms is not None:
         line["bvh_broadcast_ms"] = bcast_ms
     if cpu is not None:

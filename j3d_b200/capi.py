@@ -457,7 +457,8 @@ class Mesh:
         self.ctx._check(L.j3dg_mesh_voxel_dims(self._h, max_dim, dims), "j3dg_mesh_voxel_dims")
         if out is None:
             out = np.zeros((dims[2], dims[1], dims[0]), np.uint8)
-        self.ctx._check(L.j3dg_mesh_voxelize(self._h, max_dim, dims, _ptr(out), dims[0] * dims[1] * dims[2]), "j3dg_mesh_voxelize")
+        cap = out.size if isinstance(out, np.ndarray) else (out.numel() if hasattr(out, "numel") else dims[0] * dims[1] * dims[2])
+        self.ctx._check(L.j3dg_mesh_voxelize(self._h, max_dim, dims, _ptr(out), cap), "j3dg_mesh_voxelize")
         return out
 
 
