@@ -253,25 +253,37 @@ def run_b200(args, f, rank, world, local_rank):
     px = torch.empty((H, W, 32), dtype=torch.uint8, device=dev)
     rgba2 = [torch.empty((H, W), dtype=torch.int32, device=dev) for _ in range(2)]
     rgba = rgba2[0]
-    # N > 1: the NCCL gather of frame k runs on its own stream and overlaps the kernels of frame k + 1
-    # (double-buffered RGBA); the timed region ends only after the last gather has completed.
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
-    gather_lists = [[torch.empty_like(rgba) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
+    # N > 1: every rank's frame must end up on rank 0 each step.
+    #   --exchange peer (default): the shade kernel of every rank stores its RGBA straight into rank 0's HBM over
+    #       NVLink peer memory (CUDA-IPC mapping, stream-ordered arrival / release flags; j3d_b200/dist.py::PeerFrames)
+    #       — no collective kernel has to find room beside the cooperative cast kernel, which owns every SM.
+    #   --exchange nccl: dist.gather on a second stream, double-buffered RGBA.
+    comm = torch.cuda.Stream(device=dev) if (world > 1 and args.exchange == "nccl") else None
+    gather_lists = [[torch.empty_like(rgba) for _ in range(world)] for _ in range(2)] if (comm is not None and rank == 0) else [None, None]
     ev_render = [torch.cuda.Event() for _ in range(2)]
     ev_gather = [torch.cuda.Event() for _ in range(2)]
+    pf = None
+    if world > 1 and args.exchange == "peer":
+        from j3d_b200.dist import PeerFrames
+        pf = PeerFrames(ctx, H, W, dev, dst=0)
 
     total = args.warmup + args.steps
     views = frame_views(j, v0, rank, total, world)  # rank r renders frames r, r+N, r+2N ...
     state = {"k": 0}
 
     def step(v):
+        if pf is not None:
+            k = pf.begin()
+            ctx.render_frame([mesh], [], v, pixels_out=px, rgba_out=pf.target(k))
+            pf.end(k)
+            return
         k = state["k"]
         state["k"] = k + 1
         b = k & 1
-        if world > 1 and k >= 2:
+        if comm is not None and k >= 2:
             stream.wait_event(ev_gather[b])  # the gather of frame k - 2 has left this buffer
         ctx.render_frame([mesh], [], v, pixels_out=px, rgba_out=rgba2[b])
-        if world > 1:
+        if comm is not None:
             ev_render[b].record(stream)
             with torch.cuda.stream(comm):
                 comm.wait_event(ev_render[b])
@@ -279,7 +291,7 @@ def run_b200(args, f, rank, world, local_rank):
                 ev_gather[b].record(comm)
 
     def drain():
-        if world > 1:
+        if comm is not None:
             stream.wait_stream(comm)
 
     for v in views[: args.warmup]:
@@ -303,6 +315,18 @@ def run_b200(args, f, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
+    exchange_ok = True
+    if pf is not None:
+        # the exchanged frame of the last step equals what this rank rendered (rank 0 checks its own slot and the
+        # arrival of everybody else's), and no flag wait ran into its time-out
+        exchange_ok = not ctx.stream_wait_timed_out()
+        if rank == 0:
+            last = pf.frames(pf.k - 1)
+            ctx.render_frame([mesh], [], views[-1], pixels_out=px, rgba_out=rgba2[0])
+            torch.cuda.synchronize()
+            exchange_ok = exchange_ok and bool(torch.equal(last[0], rgba2[0])) and all(int(last[r].abs().sum().item()) != 0 for r in range(world))
+    if pf is not None:
+        pf.close()
     clocks = sampler.stop() if rank == 0 else None
     tm = ctx.timings(reset=True)
     if world > 1:
@@ -424,7 +448,7 @@ def run_b200(args, f, rank, world, local_rank):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(f, nt), "l2": "inputs_larger_than_l2",
-                   "sharding": "replicas only" if world == 1 else f"orbit frames round-robin over {world} ranks, BVH NCCL-broadcast from rank 0, RGBA NCCL-gathered on rank 0 every step (gather of frame k on a second stream, overlapping the kernels of frame k+1)",
+                   "sharding": "replicas only" if world == 1 else f"orbit frames round-robin over {world} ranks, BVH NCCL-broadcast from rank 0, " + ("every rank's shade kernel stores its RGBA into rank 0's HBM over NVLink peer memory (CUDA IPC), stream-ordered arrival/release flags" if args.exchange == "peer" else "RGBA NCCL-gathered on rank 0 every step (second stream, overlapping the kernels of frame k+1)"),
                    "bvh_bytes": int(info.nr_of_nodes) * info.node_bytes + nt * info.triangle_bytes},
         "bvh_build_ms": build_ms, "bvh_nodes": int(info.nr_of_nodes), "frames_per_s": 1e3 * args.steps * world / ms,
         "cast_ms": cast_ms, "shade_ms": tm.shade_ms / max(1, tm.shade_count),
@@ -440,6 +464,7 @@ def run_b200(args, f, rank, world, local_rank):
         line["queries"] = extras
     if bcast_ms is not None:
         line["bvh_broadcast_ms"] = bcast_ms
+        line["exchange"] = {"kind": args.exchange, "verified": exchange_ok, "bytes_per_step_into_rank0": (world - 1) * W * H * 4}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))
@@ -457,6 +482,7 @@ def main():
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
     ap.add_argument("--f", type=int, default=0, help="override the icosphere frequency (T = 20 f^2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: how every rank's RGBA frame reaches rank 0")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     f = args.f or WORKLOADS[args.workload]

@@ -126,6 +126,25 @@ int j3dg_ctx_set_tuning(j3dg_ctx* ctx, uint32_t lane_budget, int cast_algo);
 #define J3DG_SHARD_BAND_ROWS 32
 int j3dg_ctx_set_screen_shard(j3dg_ctx* ctx, uint32_t rank, uint32_t world);
 
+/* ---- result exchange over NVLink peer memory (BASELINE configs[2], [4]).  The ray-cast kernel is a
+ *      cooperative launch that owns every SM, so a collective kernel cannot run beside it; instead every rank's
+ *      shade kernel stores its RGBA straight into a buffer that rank 0 owns and the others map through CUDA IPC
+ *      (pass the mapped address as rgba_out of j3dg_render_frame / j3dg_shade), and frames are handed over with
+ *      stream-ordered flags.  j3dg_peer_alloc: zeroed device buffer + its 64-byte IPC handle (ship the handle to
+ *      the other processes, e.g. with torch.distributed); j3dg_peer_open maps it in another process (peer access
+ *      is enabled lazily); j3dg_stream_signal writes `value` to *flag after everything enqueued before it on the
+ *      context stream is complete and visible system-wide; j3dg_stream_wait_geq blocks the STREAM (not the host)
+ *      until flags[0..n) >= value (n <= 32; gives up after 5 s and records it: j3dg_stream_wait_status).  Flags
+ *      may live in local or in peer-mapped memory.  j3d_b200/dist.py::PeerFrames is the protocol built on them. */
+#define J3DG_IPC_HANDLE_BYTES 64
+int j3dg_peer_alloc(j3dg_ctx* ctx, size_t bytes, void** dev_ptr, unsigned char* handle_out /* 64 bytes, nullable */);
+int j3dg_peer_free(j3dg_ctx* ctx, void* dev_ptr);
+int j3dg_peer_open(j3dg_ctx* ctx, const unsigned char* handle, void** dev_ptr);
+int j3dg_peer_close(j3dg_ctx* ctx, void* dev_ptr);
+int j3dg_stream_signal(j3dg_ctx* ctx, uint32_t* flag, uint32_t value);
+int j3dg_stream_wait_geq(j3dg_ctx* ctx, const uint32_t* flags, uint32_t n, uint32_t value);
+int j3dg_stream_wait_status(j3dg_ctx* ctx, int* timed_out);
+
 /* ---- BVH build: replaces `new qbvh(triangles, vertices)` + compute_triangle_normals
  *      + compute_bb in add_object (j3d/scene.cpp:8-25; jtk/qbvh.h:1679-1686). -------
  * vertices: nv x 3 float (jtk::vec3<float>), triangles: nt x 3 uint32.

@@ -125,6 +125,13 @@ def lib() -> C.CDLL:
         L.j3dg_mesh_find_all.argtypes = [_vp, _vp, _u32, _vp, _vp, _vp, _u32, C.POINTER(_u32)]
         L.j3dg_mesh_voxel_dims.argtypes = [_vp, _u32, C.POINTER(_u32)]
         L.j3dg_mesh_voxelize.argtypes = [_vp, _u32, C.POINTER(_u32), _vp, C.c_size_t]
+        L.j3dg_peer_alloc.argtypes = [_vp, C.c_size_t, C.POINTER(_vp), _vp]
+        L.j3dg_peer_free.argtypes = [_vp, _vp]
+        L.j3dg_peer_open.argtypes = [_vp, _vp, C.POINTER(_vp)]
+        L.j3dg_peer_close.argtypes = [_vp, _vp]
+        L.j3dg_stream_signal.argtypes = [_vp, _vp, _u32]
+        L.j3dg_stream_wait_geq.argtypes = [_vp, _vp, _u32, _u32]
+        L.j3dg_stream_wait_status.argtypes = [_vp, C.POINTER(C.c_int)]
         L.j3dg_pick.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(_vp), _u32, C.POINTER(View), _vp, _u32, _vp, _u32, _vp]
         _lib = L
     return _lib
@@ -391,6 +398,37 @@ class Context:
         self._check(self._L.j3dg_pick(self._h, self._handles(meshes), len(meshes), self._handles(clouds), len(clouds), C.byref(view),
                                       _ptr(pixels), pixel_stride or 0, _ptr(xy), xy.shape[0], _ptr(out)), "j3dg_pick")
         return out
+
+    # -- result exchange over NVLink peer memory (include/j3dg.h; protocol: j3d_b200/dist.py::PeerFrames) ----------
+    def peer_alloc(self, nbytes: int):
+        """Zeroed device buffer + its CUDA-IPC handle (bytes).  Returns (device pointer, handle)."""
+        p = _vp()
+        h = (C.c_ubyte * 64)()
+        self._check(self._L.j3dg_peer_alloc(self._h, nbytes, C.byref(p), C.cast(h, _vp)), "j3dg_peer_alloc")
+        return p.value, bytes(h)
+
+    def peer_free(self, ptr: int):
+        self._check(self._L.j3dg_peer_free(self._h, _vp(ptr)), "j3dg_peer_free")
+
+    def peer_open(self, handle: bytes) -> int:
+        p = _vp()
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self._L.j3dg_peer_open(self._h, C.cast(h, _vp), C.byref(p)), "j3dg_peer_open")
+        return p.value
+
+    def peer_close(self, ptr: int):
+        self._check(self._L.j3dg_peer_close(self._h, _vp(ptr)), "j3dg_peer_close")
+
+    def stream_signal(self, flag_ptr: int, value: int):
+        self._check(self._L.j3dg_stream_signal(self._h, _vp(flag_ptr), value), "j3dg_stream_signal")
+
+    def stream_wait_geq(self, flags_ptr: int, n: int, value: int):
+        self._check(self._L.j3dg_stream_wait_geq(self._h, _vp(flags_ptr), n, value), "j3dg_stream_wait_geq")
+
+    def stream_wait_timed_out(self) -> bool:
+        t = C.c_int()
+        self._check(self._L.j3dg_stream_wait_status(self._h, C.byref(t)), "j3dg_stream_wait_status")
+        return bool(t.value)
 
     def cast_cost_image(self, meshes, view: View):
         """Per-pixel (node visits, triangle tests) of the counting pass — diagnostic."""

@@ -141,3 +141,81 @@ def gather_bands(img: torch.Tensor, dst: int = 0) -> torch.Tensor | None:
     g = torch.stack(parts, dim=0)  # [world, per, 32, ...]
     g = g.transpose(0, 1).reshape((-1,) + tuple(img.shape[1:]))
     return g[: img.shape[0]]
+
+
+# ---- frames handed to rank 0 through NVLink peer memory instead of a collective (include/j3dg.h, csrc/peer.cu) ----
+def peer_slot_offset(slot: int, rank: int, world: int, frame_bytes: int) -> int:
+    """Byte offset of (slot, rank)'s frame inside the exchange buffer: [2 slots][world][frame]."""
+    return (slot * world + rank) * frame_bytes
+
+
+def peer_flags_offset(world: int, frame_bytes: int) -> int:
+    """The flag words follow the frames: arrived[0..world) then `released`, 256-byte aligned."""
+    return (2 * world * frame_bytes + 255) & ~255
+
+
+class PeerFrames:
+    """Every rank renders its frame STRAIGHT INTO rank `dst`'s HBM (the shade kernel's stores travel over NVLink);
+    no gather kernel competes with the cooperative cast kernel for SMs.  Double-buffered:
+
+        k = pf.begin()                 # stream waits until slot k & 1 has been released by dst
+        ctx.render_frame(..., rgba_out=pf.target(k))
+        pf.end(k)                      # signal arrival; dst's stream waits for all ranks, then releases the slot
+
+    On `dst`, pf.frames(k) are the world frames of step k ([world, H, W] int32 view of the buffer), valid between
+    end(k) and end(k + 1)... of the same slot parity, i.e. until end(k + 2) is enqueued."""
+
+    def __init__(self, ctx, height: int, width: int, device, dst: int = 0):
+        self.ctx, self.h, self.w, self.device, self.dst = ctx, height, width, device, dst
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.frame_bytes = height * width * 4
+        self.flags_off = peer_flags_offset(self.world, self.frame_bytes)
+        self.nbytes = self.flags_off + 256
+        handle = [None]
+        if self.rank == dst:
+            self.base, h = ctx.peer_alloc(self.nbytes)
+            handle[0] = h
+        dist.broadcast_object_list(handle, src=dst)
+        if self.rank != dst:
+            self.base = ctx.peer_open(handle[0])
+        self.k = 0
+        dist.barrier()
+
+    def _arrived(self, r: int) -> int:
+        return self.base + self.flags_off + 4 * r
+
+    def _released(self) -> int:
+        return self.base + self.flags_off + 4 * self.world
+
+    def begin(self) -> int:
+        k = self.k
+        if k >= 2:  # frame k - 2 lived in this slot: dst must have released it (released counts consumed frames)
+            self.ctx.stream_wait_geq(self._released(), 1, k - 1)
+        return k
+
+    def target(self, k: int) -> int:
+        return self.base + peer_slot_offset(k & 1, self.rank, self.world, self.frame_bytes)
+
+    def end(self, k: int):
+        self.ctx.stream_signal(self._arrived(self.rank), k + 1)
+        if self.rank == self.dst:
+            self.ctx.stream_wait_geq(self._arrived(0), self.world, k + 1)
+            self.ctx.stream_signal(self._released(), k + 1)
+        self.k = k + 1
+
+    def frames(self, k: int) -> torch.Tensor:
+        assert self.rank == self.dst
+        off = peer_slot_offset(k & 1, 0, self.world, self.frame_bytes)
+        t = device_bytes(self.base + off, self.world * self.frame_bytes, self.device)
+        return t.view(torch.int32).view(self.world, self.h, self.w)
+
+    def close(self):
+        self.ctx.synchronize()
+        dist.barrier()
+        if self.rank == self.dst:
+            dist.barrier()  # the others unmap first
+            self.ctx.peer_free(self.base)
+        else:
+            self.ctx.peer_close(self.base)
+            dist.barrier()
+        self.base = 0

@@ -187,6 +187,14 @@ inline void unzoom(scene& s) {
   j3dgh_unzoom(s.min_bb, s.max_bb, &d, s.pivot, s.coordinate_system.f, s.coordinate_system_inv.f);
 }
 
+// The grid-filling part of write_vox (j3d/vox.cpp:270-379) for an object that is already resident: dim and the
+// x + (y + z * dim[1]) * dim[0] palette-index grid the reference hands to ogt_vox (file writing stays on the host).
+inline void voxelize(context& ctx, const scene_object& obj, uint32_t max_dim, uint32_t dim[3], std::vector<uint8_t>& data) {
+  ctx.check(j3dg_mesh_voxelize(obj.bvh, max_dim, dim, nullptr, 0), "j3dg_mesh_voxelize");
+  data.assign((size_t)dim[0] * dim[1] * dim[2], 0);
+  ctx.check(j3dg_mesh_voxelize(obj.bvh, max_dim, dim, data.data(), data.size()), "j3dg_mesh_voxelize");
+}
+
 // canvas (j3d/canvas.h:11-102): same public surface for the render path.
 class canvas {
  public:
@@ -259,6 +267,37 @@ class canvas {
     _ctx.check(j3dg_splat(_ctx.get(), clouds.data(), (uint32_t)clouds.size(), &v, pix.data(), _canvas.data(), _w, im.data(), _stride),
                "j3dg_splat");
   }
+
+  // ---- picking, answered on the device from the canvas that is still resident after the last
+  //      render_scene / update_canvas: canvas::get_pixel (canvas.cpp:141-153), the pivot pick of canvas::do_mouse
+  //      (canvas.cpp:157-179) and, for `view`, get_world_position / get_index / get_id (view.cpp:439-492) ----
+  j3dg_pick_result pick(const scene& s, int x, int y) {
+    std::vector<j3dg_mesh*> meshes;
+    std::vector<j3dg_cloud*> clouds;
+    for (const auto& o : s.objects) if (o.bvh) meshes.push_back(o.bvh);
+    for (const auto& o : s.pointclouds) if (o.cloud) clouds.push_back(o.cloud);
+    j3dg_view v = make_view(s);
+    const int32_t xy[2] = {x, y};
+    j3dg_pick_result r;
+    _ctx.check(j3dg_pick(_ctx.get(), meshes.data(), (uint32_t)meshes.size(), clouds.data(), (uint32_t)clouds.size(), &v, nullptr, 0, xy, 1, &r),
+               "j3dg_pick");
+    return r;
+  }
+  void get_pixel(pixel& p, const scene& s, float pos_x, float pos_y, float mouse_offset_x, float mouse_offset_y) {
+    p = pick(s, (int)(uint32_t)(pos_x - mouse_offset_x), (int)(uint32_t)(pos_y - mouse_offset_y)).pixel;
+  }
+  // do_mouse, button-down part: a click on an object moves the scene pivot under the cursor
+  void pick_pivot(scene& s, float mouse_x, float mouse_y, float mouse_offset_x, float mouse_offset_y) {
+    const j3dg_pick_result r = pick(s, (int)(uint32_t)(mouse_x - mouse_offset_x), (int)(uint32_t)(mouse_y - mouse_offset_y));
+    if (r.db_id) std::memcpy(s.pivot, r.pivot, 12);
+  }
+  bool get_world_position(const scene& s, int x, int y, float out[3]) {  // false: invalid_vertex (NaN)
+    const j3dg_pick_result r = pick(s, x, y);
+    std::memcpy(out, r.world_pos, 12);
+    return r.db_id != 0 && r.closest_vertex != (uint32_t)-1;
+  }
+  uint32_t get_index(const scene& s, int x, int y) { return pick(s, x, y).closest_vertex; }
+  uint32_t get_id(const scene& s, int x, int y) { return pick(s, x, y).db_id; }
 
   j3dg_view make_view(const scene& s) const {
     j3dg_view v;

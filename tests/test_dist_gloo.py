@@ -79,3 +79,15 @@ def test_gather_world2_gloo():
         p.join(100)
         assert p.exitcode == 0
     assert sorted(out.keys()) == [0, 1]
+
+
+def test_peer_exchange_layout():
+    """Slot / flag arithmetic of the NVLink peer-memory frame exchange (dist.PeerFrames): frames never overlap,
+    both slots of every rank are distinct, the flag words lie behind the frames."""
+    from j3d_b200.dist import peer_flags_offset, peer_slot_offset
+    fb = 1920 * 1080 * 4
+    for world in (1, 2, 8):
+        offs = sorted(peer_slot_offset(s, r, world, fb) for s in (0, 1) for r in range(world))
+        assert offs == [i * fb for i in range(2 * world)]
+        fo = peer_flags_offset(world, fb)
+        assert fo >= 2 * world * fb and fo % 256 == 0

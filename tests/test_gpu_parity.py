@@ -563,6 +563,45 @@ def test_voxelize_matches_golden(ctx, oracle, name):
     m.destroy(); om.destroy()
 
 
+def test_peer_frames_protocol_single_gpu(ctx):
+    """The NVLink peer-memory frame exchange (csrc/peer.cu, dist.PeerFrames) with one rank: the shade kernel renders
+    into the exchange buffer, arrival / release flags order the steps, and the exchanged frame equals a direct render."""
+    import torch
+    import torch.distributed as dist
+    from j3d_b200.dist import PeerFrames
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29577", rank=0, world_size=1)
+        created = True
+    try:
+        w, h = 256, 160
+        verts, tris = j.icosphere(10)
+        mn, mx = j.compute_bb(verts)
+        v0 = j.make_view(w, h, mn, mx)
+        mc, cav = j.make_matcap(0)
+        ctx.set_matcap(mc, cav)
+        m = ctx.mesh_create(verts, tris)
+        pf = PeerFrames(ctx, h, w, torch.device("cuda", 0))
+        px = torch.empty((h, w, 32), dtype=torch.uint8, device="cuda")
+        for step in range(5):
+            v = j.orbit_view(v0, 10.0 * step)
+            k = pf.begin()
+            assert k == step
+            ctx.render_frame([m], [], v, pixels_out=px, rgba_out=pf.target(k))
+            pf.end(k)
+            ctx.synchronize()
+            want = np.zeros((h, w), np.uint32)
+            ctx.render_frame([m], [], v, rgba_out=want)
+            got = pf.frames(k)[0].cpu().numpy().view(np.uint32)
+            assert (got == want).all()
+        assert not ctx.stream_wait_timed_out()
+        pf.close()
+        m.destroy()
+    finally:
+        if created:
+            dist.destroy_process_group()
+
+
 # ---- BASELINE.json full size (config B: 28 037 120 triangles, 1080p): size-independent properties ----
 def _numpy_closest(verts, tris, org, d, t_near):
     """Brute-force restatement of the Woop test over ALL triangles for one ray (float32, unfused)."""
