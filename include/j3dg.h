@@ -221,6 +221,16 @@ int j3dg_frame_submit(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nr_of_me
                       uint32_t bg_top, uint32_t bg_bottom,
                       j3dg_pixel* pixels_out, uint32_t* rgba_out);
 int j3dg_frame_wait(j3dg_ctx* ctx);
+/* Dirty-rectangle readback (off by default).  When on, the HOST output buffers of j3dg_render_frame / j3dg_frame_submit
+ * are assumed to be persistent per-canvas buffers that nobody else writes between frames (like view::_pixels and
+ * canvas::im in j3d): the first frame a buffer receives is copied whole, afterwards only the bounding rectangle of the
+ * hit pixels of the current frame united with the rectangle that buffer received last time crosses PCIe — outside it the
+ * buffer already holds the identical miss records (canvas.cpp:859-866) / background pixels.  The host buffers end up
+ * byte-identical to a full copy.  Frames with point clouds or screen sharding are always copied whole.
+ * With pipelined frames the copies of frame k are enqueued by j3dg_frame_submit(k + 1) or j3dg_frame_wait(k). */
+int j3dg_ctx_set_dirty_rect(j3dg_ctx* ctx, int enabled);
+/* Device->host bytes the frame entry points (j3dg_render_frame / j3dg_frame_submit) have copied since the last reset. */
+int j3dg_ctx_readback_bytes(j3dg_ctx* ctx, uint64_t* bytes, int reset);
 /* Upload a matcap once and reuse it (frames then pass matcap == NULL). */
 int j3dg_ctx_set_matcap(j3dg_ctx* ctx, const uint32_t* matcap, uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity_clr);
 

@@ -125,6 +125,8 @@ def lib() -> C.CDLL:
         L.j3dg_mesh_find_all.argtypes = [_vp, _vp, _u32, _vp, _vp, _vp, _u32, C.POINTER(_u32)]
         L.j3dg_mesh_voxel_dims.argtypes = [_vp, _u32, C.POINTER(_u32)]
         L.j3dg_mesh_voxelize.argtypes = [_vp, _u32, C.POINTER(_u32), _vp, C.c_size_t]
+        L.j3dg_ctx_set_dirty_rect.argtypes = [_vp, C.c_int]
+        L.j3dg_ctx_readback_bytes.argtypes = [_vp, C.POINTER(C.c_uint64), C.c_int]
         L.j3dg_peer_alloc.argtypes = [_vp, C.c_size_t, C.POINTER(_vp), _vp]
         L.j3dg_peer_free.argtypes = [_vp, _vp]
         L.j3dg_peer_open.argtypes = [_vp, _vp, C.POINTER(_vp)]
@@ -376,6 +378,15 @@ class Context:
 
     def frame_wait(self):
         self._check(self._L.j3dg_frame_wait(self._h), "j3dg_frame_wait")
+
+    def set_dirty_rect(self, on: bool):
+        """Host output buffers are persistent per-canvas buffers: copy only the rectangle that changed (include/j3dg.h)."""
+        self._check(self._L.j3dg_ctx_set_dirty_rect(self._h, int(on)), "j3dg_ctx_set_dirty_rect")
+
+    def readback_bytes(self, reset: bool = False) -> int:
+        b = C.c_uint64()
+        self._check(self._L.j3dg_ctx_readback_bytes(self._h, C.byref(b), int(reset)), "j3dg_ctx_readback_bytes")
+        return b.value
 
     def set_tuning(self, lane_budget: int = 0, cast_algo: int = 0):
         self._check(self._L.j3dg_ctx_set_tuning(self._h, lane_budget, cast_algo), "j3dg_ctx_set_tuning")

@@ -574,6 +574,80 @@ J3DG_API int j3dg_splat(j3dg_ctx* ctx, j3dg_cloud* const* clouds, uint32_t nc, c
   return J3DG_OK;
 }
 
+// ---- dirty-rectangle readback (j3dg_ctx_set_dirty_rect) -------------------------------------------------------
+// Outside the bounding rectangle of the hit pixels a frame holds nothing but miss records and background, which a
+// host buffer that received an earlier frame of the same canvas already contains.  Only the union of the rectangle
+// this host buffer received last time and the current one crosses PCIe.
+namespace {
+
+struct Rect { int x0, y0, x1, y1; bool empty() const { return x1 < x0 || y1 < y0; } };
+
+Rect rect_union(Rect a, Rect b) {
+  if (a.empty()) return b;
+  if (b.empty()) return a;
+  return Rect{std::min(a.x0, b.x0), std::min(a.y0, b.y0), std::max(a.x1, b.x1), std::max(a.y1, b.y1)};
+}
+
+// Copies what `host` needs of the device image `dev` (elem bytes per pixel, both w pixels per row) on `stream`.
+int copy_dirty(j3dg_ctx* ctx, void* host, const void* dev, uint32_t w, uint32_t h, size_t elem, uint32_t key0, uint32_t key1, Rect cur, cudaStream_t stream) {
+  j3dg_ctx::DirtyBuf* e = nullptr;
+  for (auto& d : ctx->dirty_bufs)
+    if (d.ptr == host) { e = &d; break; }
+  Rect todo;
+  if (e && e->w == w && e->h == h && e->key0 == key0 && e->key1 == key1) {
+    todo = rect_union(Rect{e->x0, e->y0, e->x1, e->y1}, cur);
+  } else {
+    todo = Rect{0, 0, (int)w - 1, (int)h - 1};
+    if (!e) {
+      if (ctx->dirty_bufs.size() >= 16) ctx->dirty_bufs.erase(ctx->dirty_bufs.begin());
+      ctx->dirty_bufs.push_back({});
+      e = &ctx->dirty_bufs.back();
+    }
+  }
+  *e = j3dg_ctx::DirtyBuf{host, w, h, key0, key1, cur.x0, cur.y0, cur.x1, cur.y1};
+  if (todo.empty()) return J3DG_OK;
+  ctx->readback_bytes += (uint64_t)(todo.x1 - todo.x0 + 1) * (todo.y1 - todo.y0 + 1) * elem;
+  const size_t pitch = (size_t)w * elem, off = ((size_t)todo.y0 * w + todo.x0) * elem;
+  CU_CHECK(ctx, cudaMemcpy2DAsync((char*)host + off, pitch, (const char*)dev + off, pitch, (size_t)(todo.x1 - todo.x0 + 1) * elem,
+                                  (size_t)(todo.y1 - todo.y0 + 1), cudaMemcpyDeviceToHost, stream));
+  return J3DG_OK;
+}
+
+Rect bbox_rect(const uint32_t* bb, uint32_t w, uint32_t h) {  // {min x, min y, max x, max y} as the resolve kernel left them
+  if (bb[0] > bb[2] || bb[1] > bb[3]) return Rect{0, 0, -1, -1};
+  return Rect{(int)std::min(bb[0], w - 1), (int)std::min(bb[1], h - 1), (int)std::min(bb[2], w - 1), (int)std::min(bb[3], h - 1)};
+}
+
+// Enqueue the device->host copies of a submitted frame whose kernels have finished (pipelined path).
+int flush_slot_copies(j3dg_ctx* ctx, int si) {
+  j3dg_ctx::FrameSlot& sl = ctx->slot[si];
+  if (!sl.copies_pending) return J3DG_OK;
+  CU_CHECK(ctx, cudaEventSynchronize(sl.kernels_done));  // the hit bbox of this frame is on the host now
+  const Rect cur = bbox_rect(ctx->h_overflow + 8 * si + 1, sl.w, sl.h);
+  int rc;
+  if (sl.host_px && (rc = copy_dirty(ctx, sl.host_px, sl.d_px, sl.w, sl.h, sizeof(j3dg_pixel), 0u, 0u, cur, ctx->copy_stream)) != J3DG_OK) return rc;
+  if (sl.host_rgba && (rc = copy_dirty(ctx, sl.host_rgba, sl.d_rgba, sl.w, sl.h, 4, sl.bg_top, sl.bg_bottom, cur, ctx->copy_stream)) != J3DG_OK) return rc;
+  CU_CHECK(ctx, cudaEventRecord(sl.copy_done, ctx->copy_stream));
+  sl.copies_pending = false;
+  return J3DG_OK;
+}
+
+}  // namespace
+
+J3DG_API int j3dg_ctx_readback_bytes(j3dg_ctx* ctx, uint64_t* bytes, int reset) {
+  if (!ctx || !bytes) return J3DG_EINVAL;
+  *bytes = ctx->readback_bytes;
+  if (reset) ctx->readback_bytes = 0;
+  return J3DG_OK;
+}
+
+J3DG_API int j3dg_ctx_set_dirty_rect(j3dg_ctx* ctx, int enabled) {
+  if (!ctx) return J3DG_EINVAL;
+  ctx->dirty_rect = enabled != 0;
+  ctx->dirty_bufs.clear();
+  return J3DG_OK;
+}
+
 J3DG_API int j3dg_render_frame(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, j3dg_cloud* const* clouds, uint32_t nc,
                                const j3dg_view* view, const uint32_t* matcap, uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity_clr,
                                uint32_t bg_top, uint32_t bg_bottom, j3dg_pixel* pixels_out, uint32_t* rgba_out) {
@@ -605,8 +679,20 @@ J3DG_API int j3dg_render_frame(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t
   if (nc && (rc = j3dg_launch_splat(ctx, clouds, nc, view, d_px, d_px, w, d_rgba, w)) != J3DG_OK) return rc;
   ctx->last_canvas = d_px; ctx->last_w = w; ctx->last_h = h;
   bool copied = false;
-  if (pixels_out && !px_dev) { CU_CHECK(ctx, cudaMemcpyAsync(pixels_out, d_px, (size_t)w * h * sizeof(j3dg_pixel), cudaMemcpyDeviceToHost, ctx->stream)); copied = true; }
-  if (rgba_out && !rgba_dev) { CU_CHECK(ctx, cudaMemcpyAsync(rgba_out, d_rgba, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->stream)); copied = true; }
+  if (ctx->dirty_rect && !nc && ctx->shard_world == 1 && ((pixels_out && !px_dev) || (rgba_out && !rgba_dev))) {
+    uint32_t info[5];
+    CU_CHECK(ctx, cudaMemcpyAsync(info, reinterpret_cast<uint32_t*>(ctx->d_stats + 2), sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaMemcpyAsync(info + 1, ctx->d_stats + 20, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    const Rect cur = bbox_rect(info + 1, w, h);
+    if (pixels_out && !px_dev && (rc = copy_dirty(ctx, pixels_out, d_px, w, h, sizeof(j3dg_pixel), 0u, 0u, cur, ctx->stream)) != J3DG_OK) return rc;
+    if (rgba_out && !rgba_dev && (rc = copy_dirty(ctx, rgba_out, d_rgba, w, h, 4, bg_top, bg_bottom, cur, ctx->stream)) != J3DG_OK) return rc;
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (info[0]) { j3dg_set_error(ctx, "traversal stack overflow (BVH deeper than the kernel's stack)"); return J3DG_ECUDA; }
+    return J3DG_OK;
+  }
+  if (pixels_out && !px_dev) { CU_CHECK(ctx, cudaMemcpyAsync(pixels_out, d_px, (size_t)w * h * sizeof(j3dg_pixel), cudaMemcpyDeviceToHost, ctx->stream)); copied = true; ctx->readback_bytes += (uint64_t)w * h * sizeof(j3dg_pixel); }
+  if (rgba_out && !rgba_dev) { CU_CHECK(ctx, cudaMemcpyAsync(rgba_out, d_rgba, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->stream)); copied = true; ctx->readback_bytes += (uint64_t)w * h * 4; }
   if (copied) return check_overflow(ctx);
   return J3DG_OK;
 }
@@ -628,7 +714,7 @@ J3DG_API int j3dg_frame_submit(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t
   if (!w || !h) { j3dg_set_error(ctx, "j3dg_frame_submit: empty canvas"); return J3DG_EINVAL; }
   if (!ctx->copy_stream) {
     CU_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    CU_CHECK(ctx, cudaHostAlloc((void**)&ctx->h_overflow, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+    CU_CHECK(ctx, cudaHostAlloc((void**)&ctx->h_overflow, 16 * sizeof(uint32_t), cudaHostAllocDefault));
     for (auto& sl : ctx->slot) {
       CU_CHECK(ctx, cudaEventCreateWithFlags(&sl.kernels_done, cudaEventDisableTiming));
       CU_CHECK(ctx, cudaEventCreateWithFlags(&sl.copy_done, cudaEventDisableTiming));
@@ -650,12 +736,23 @@ J3DG_API int j3dg_frame_submit(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t
   if ((rc = j3dg_launch_shade(ctx, d_px, w, view, d_mc, dmw, dmh, dms, dcav, ctx->d_bg, w, d_rgba, w)) != J3DG_OK) return rc;
   if (nc && (rc = j3dg_launch_splat(ctx, clouds, nc, view, d_px, d_px, w, d_rgba, w)) != J3DG_OK) return rc;
   ctx->last_canvas = d_px; ctx->last_w = w; ctx->last_h = h;
-  CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_overflow + si, reinterpret_cast<uint32_t*>(ctx->d_stats + 2), sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_overflow + 8 * si, reinterpret_cast<uint32_t*>(ctx->d_stats + 2), sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_overflow + 8 * si + 1, ctx->d_stats + 20, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU_CHECK(ctx, cudaEventRecord(sl.kernels_done, ctx->stream));
-  CU_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, sl.kernels_done, 0));
-  if (pixels_out) CU_CHECK(ctx, cudaMemcpyAsync(pixels_out, d_px, (size_t)w * h * sizeof(j3dg_pixel), cudaMemcpyDeviceToHost, ctx->copy_stream));
-  if (rgba_out) CU_CHECK(ctx, cudaMemcpyAsync(rgba_out, d_rgba, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
-  CU_CHECK(ctx, cudaEventRecord(sl.copy_done, ctx->copy_stream));
+  if (ctx->dirty_rect && !nc && ctx->shard_world == 1 && (pixels_out || rgba_out)) {
+    // the copies wait until the frame's hit bbox is known: they are enqueued by the next submit (after ITS kernels, so
+    // the kernel stream never idles) or by the matching wait
+    sl.copies_pending = true;
+    sl.host_px = pixels_out; sl.host_rgba = rgba_out;
+    sl.w = w; sl.h = h; sl.bg_top = bg_top; sl.bg_bottom = bg_bottom;
+  } else {
+    sl.copies_pending = false;
+    CU_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, sl.kernels_done, 0));
+    if (pixels_out) { CU_CHECK(ctx, cudaMemcpyAsync(pixels_out, d_px, (size_t)w * h * sizeof(j3dg_pixel), cudaMemcpyDeviceToHost, ctx->copy_stream)); ctx->readback_bytes += (uint64_t)w * h * sizeof(j3dg_pixel); }
+    if (rgba_out) { CU_CHECK(ctx, cudaMemcpyAsync(rgba_out, d_rgba, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->copy_stream)); ctx->readback_bytes += (uint64_t)w * h * 4; }
+    CU_CHECK(ctx, cudaEventRecord(sl.copy_done, ctx->copy_stream));
+  }
+  if ((rc = flush_slot_copies(ctx, si ^ 1)) != J3DG_OK) return rc;  // the frame before this one
   sl.busy = true;
   ctx->frames_submitted++;
   return J3DG_OK;
@@ -665,9 +762,11 @@ J3DG_API int j3dg_frame_wait(j3dg_ctx* ctx) {
   if (!ctx) return J3DG_EINVAL;
   if (ctx->frames_waited == ctx->frames_submitted) { j3dg_set_error(ctx, "j3dg_frame_wait: no frame in flight"); return J3DG_EINVAL; }
   const int si = (int)(ctx->frames_waited & 1);
+  int rc = flush_slot_copies(ctx, si);
+  if (rc != J3DG_OK) return rc;
   CU_CHECK(ctx, cudaEventSynchronize(ctx->slot[si].copy_done));
   ctx->frames_waited++;
-  if (ctx->h_overflow[si]) {
+  if (ctx->h_overflow[8 * si]) {
     j3dg_set_error(ctx, "traversal stack overflow (BVH deeper than the kernel's stack)");
     return J3DG_ECUDA;
   }

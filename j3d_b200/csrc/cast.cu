@@ -927,6 +927,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const MeshDev* __restrict_
                                                        j3dg_pixel* __restrict__ out, uint32_t stride, float4* __restrict__ shadow_pos,
                                                        uint32_t* __restrict__ shadow_pix, unsigned long long* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
+  bool is_hit = false;
   const uint32_t pool = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   uint32_t tx = 0, ty = 0;
   bool halo = false;
@@ -939,6 +940,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const MeshDev* __restrict_
     uint4* dst = reinterpret_cast<uint4*>(out + (size_t)y * stride + x);
     const uint4 raw = dst[1];
     if (raw.x != 0xFFFFFFFFu) {
+      is_hit = !halo;
       const float t = __uint_as_float(dst[0].w);
       const MeshDev& m = meshes[raw.w];
       const float4* tp = reinterpret_cast<const float4*>(m.tris + raw.x);
@@ -996,6 +998,18 @@ __global__ void __launch_bounds__(256) resolve_kernel(const MeshDev* __restrict_
       }
       dst[0] = make_uint4(mark | (r << 8) | (g << 16) | (b << 24), __float_as_uint(n.x), __float_as_uint(n.y), __float_as_uint(t));
       dst[1] = make_uint4(tri, raw.y, raw.z, m.db_id);
+    }
+  }
+  // bounding rectangle of the hit pixels of this frame (stats slots 20, 21 = min x, min y, max x, max y): everything
+  // outside it is a miss record / background, which lets the host copy skip it (j3dg_ctx_set_dirty_rect)
+  if (__any_sync(0xffffffffu, is_hit)) {
+    uint32_t mnx = is_hit ? (uint32_t)x : 0xFFFFFFFFu, mny = is_hit ? (uint32_t)y : 0xFFFFFFFFu;
+    uint32_t mxx = is_hit ? (uint32_t)x : 0u, mxy = is_hit ? (uint32_t)y : 0u;
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+    mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    if (lane == 0) {
+      uint32_t* bb = reinterpret_cast<uint32_t*>(stats + 20);
+      atomicMin(bb + 0, mnx); atomicMin(bb + 1, mny); atomicMax(bb + 2, mxx); atomicMax(bb + 3, mxy);
     }
   }
   if (vw.flags & J3DG_SHADOW) {  // warp-uniform
@@ -1119,6 +1133,8 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   // [11] producer blocks done PRIMARY [12] producer blocks done SHADOW
   CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
   CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats + 5, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats + 20, 0xFF, sizeof(unsigned long long), ctx->stream));  // hit bbox: min x, min y
+  CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats + 21, 0, sizeof(unsigned long long), ctx->stream));     //           max x, max y
 #ifdef J3DG_TIMELINE
   CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats + 13, 0xFF, sizeof(unsigned long long), ctx->stream));
   CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats + 14, 0, 5 * sizeof(unsigned long long), ctx->stream));

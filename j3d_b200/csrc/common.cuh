@@ -141,10 +141,18 @@ struct j3dg_ctx {
     void* d_rgba = nullptr; size_t rgba_cap = 0;
     cudaEvent_t kernels_done = nullptr, copy_done = nullptr;
     bool busy = false;
+    // dirty-rectangle readback: the copies of a frame are enqueued once its hit bbox is known on the host
+    bool copies_pending = false;
+    void* host_px = nullptr; void* host_rgba = nullptr;
+    uint32_t w = 0, h = 0, bg_top = 0, bg_bottom = 0;
   } slot[2];
+  uint64_t readback_bytes = 0;                       // device->host bytes of frame outputs since the last reset (j3dg_ctx_readback_bytes)
+  bool dirty_rect = false;                           // j3dg_ctx_set_dirty_rect
+  struct DirtyBuf { void* ptr; uint32_t w, h, key0, key1; int x0, y0, x1, y1; };  // what a host buffer holds outside-of-miss
+  std::vector<DirtyBuf> dirty_bufs;
   cudaStream_t copy_stream = nullptr;
   uint64_t frames_submitted = 0, frames_waited = 0;
-  uint32_t* h_overflow = nullptr;                    // pinned: stack-overflow flag of each in-flight frame
+  uint32_t* h_overflow = nullptr;                    // pinned, 8 words per in-flight frame: [0] stack-overflow flag, [1..4] hit bbox
   std::vector<MeshDev> meshes_uploaded;              // last mesh table sent to d_meshes (re-uploaded only when it changes)
   void* d_hard = nullptr; size_t hard_cap = 0;       // hard-ray list handed from the lane kernel to the group kernel
   size_t hard_id_off = 0;                            // offset of the id array inside d_hard

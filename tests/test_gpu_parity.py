@@ -357,6 +357,65 @@ def test_pipelined_frames_equal_synchronous(ctx):
     m.destroy()
 
 
+def test_dirty_rect_readback_is_byte_identical(ctx):
+    """j3dg_ctx_set_dirty_rect: persistent host buffers that receive only the changed rectangle end up byte-identical
+    to full copies — object moving across the canvas, two alternating host buffers, pipelined and synchronous calls,
+    a settings change, an empty scene and a background change in between."""
+    w, h = 320, 180
+    verts, tris = j.icosphere(12)
+    verts = (verts * 0.35).astype(np.float32)
+    mn, mx = np.array([-1.5, -1, -1], np.float32), np.array([1.5, 1, 1], np.float32)  # scene bbox larger than the object
+    v0 = j.make_view(w, h, mn, mx, j.DEFAULT_FLAGS)
+    mc, cav = j.make_matcap(0)
+    ctx.set_matcap(mc, cav)
+    m = ctx.mesh_create(verts, tris)
+
+    def place(k):
+        cs = np.eye(4, dtype=np.float32)
+        cs[3, 0] = -1.2 + 0.45 * k  # column-major translation: the object walks from left to right
+        cs[3, 1] = 0.3 * ((k % 3) - 1)
+        m.set_cs(cs.reshape(-1))
+
+    frames = []
+    for k in range(7):
+        v = v0.copy()
+        if k == 4:
+            v.flags = j.DEFAULT_FLAGS | j.WIREFRAME
+        frames.append(v)
+
+    def full(k, meshes, bg):
+        place(k)
+        px = np.zeros((h, w), j.PIXEL_DTYPE); rgba = np.zeros((h, w), np.uint32)
+        ctx.render_frame(meshes, [], frames[k], pixels_out=px, rgba_out=rgba, bg_bottom=bg)
+        return px, rgba
+
+    ctx.set_dirty_rect(False)
+    want = [full(k, [m] if k != 5 else [], 0xFF404040 if k != 6 else 0xFF804020) for k in range(7)]
+    ctx.set_dirty_rect(True)
+    try:
+        bufs = [(np.zeros((h, w), j.PIXEL_DTYPE), np.zeros((h, w), np.uint32)) for _ in range(2)]
+        # pipelined, buffers alternate
+        for k in range(5):
+            place(k)
+            ctx.frame_submit([m], [], frames[k], pixels_out=bufs[k & 1][0], rgba_out=bufs[k & 1][1])
+            if k >= 1:
+                ctx.frame_wait()
+                assert bufs[(k - 1) & 1][0].tobytes() == want[k - 1][0].tobytes(), k
+                assert (bufs[(k - 1) & 1][1] == want[k - 1][1]).all(), k
+        ctx.frame_wait()
+        assert bufs[0][0].tobytes() == want[4][0].tobytes() and (bufs[0][1] == want[4][1]).all()
+        # synchronous calls into the same buffers: empty scene (everything the buffer held must be erased), new background
+        place(5)
+        ctx.render_frame([], [], frames[5], pixels_out=bufs[1][0], rgba_out=bufs[1][1])
+        assert bufs[1][0].tobytes() == want[5][0].tobytes() and (bufs[1][1] == want[5][1]).all()
+        place(6)
+        ctx.render_frame([m], [], frames[6], pixels_out=bufs[1][0], rgba_out=bufs[1][1], bg_bottom=0xFF804020)
+        assert bufs[1][0].tobytes() == want[6][0].tobytes() and (bufs[1][1] == want[6][1]).all()
+    finally:
+        ctx.set_dirty_rect(False)
+    m.destroy()
+
+
 def test_degenerate_inputs(ctx, oracle):
     """Edge cases: single triangle, duplicated triangles, zero-area triangles, unreferenced vertices."""
     w, h = 160, 120
