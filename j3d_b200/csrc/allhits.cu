@@ -115,10 +115,12 @@ __global__ void __launch_bounds__(AH_THREADS) allhits_kernel(const AllParams p) 
   while (cur != J3DG_EMPTY_CHILD) {
     if (!(cur & J3DG_LEAF_BIT)) {
       // ---- inner node: push every child box the ray pierces ----
-      const uint4* np = reinterpret_cast<const uint4*>(p.nodes + cur);
-      const uint4 h0 = __ldg(np + 0), h1 = __ldg(np + 1);
-      const uint4 b[4] = {__ldg(np + 2), __ldg(np + 3), __ldg(np + 4), __ldg(np + 5)};
-      const uint4 c[2] = {__ldg(np + 6), __ldg(np + 7)};
+      const char* np = reinterpret_cast<const char*>(p.nodes + cur);
+      const U32x8 q0 = ldg256(np), q1 = ldg256(np + 32), q2 = ldg256(np + 64), q3 = ldg256(np + 96);
+      const uint4 h0 = make_uint4(q0.v[0], q0.v[1], q0.v[2], q0.v[3]), h1 = make_uint4(q0.v[4], q0.v[5], q0.v[6], q0.v[7]);
+      const uint4 b[4] = {make_uint4(q1.v[0], q1.v[1], q1.v[2], q1.v[3]), make_uint4(q1.v[4], q1.v[5], q1.v[6], q1.v[7]),
+                          make_uint4(q2.v[0], q2.v[1], q2.v[2], q2.v[3]), make_uint4(q2.v[4], q2.v[5], q2.v[6], q2.v[7])};
+      const uint4 c[2] = {make_uint4(q3.v[0], q3.v[1], q3.v[2], q3.v[3]), make_uint4(q3.v[4], q3.v[5], q3.v[6], q3.v[7])};
       const Slab X = slab(__uint_as_float(h1.x), __uint_as_float(h0.x), ox, idx);
       const Slab Y = slab(__uint_as_float(h1.y), __uint_as_float(h0.y), oy, idy);
       const Slab Z = slab(__uint_as_float(h1.z), __uint_as_float(h0.z), oz, idz);

@@ -417,8 +417,9 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const st
       uint32_t ref = J3DG_EMPTY_CHILD;
       if (at_node) {
         const char* np = reinterpret_cast<const char*>(nodes + cur);
-        h0 = __ldg(reinterpret_cast<const uint4*>(np));          // ox oy oz | nchild      (broadcast)
-        h1 = __ldg(reinterpret_cast<const uint4*>(np) + 1);      // sx sy sz | pad         (broadcast)
+        const U32x8 hh = ldg256(np);                             // ox oy oz | nchild | sx sy sz | pad   (broadcast)
+        h0 = make_uint4(hh.v[0], hh.v[1], hh.v[2], hh.v[3]);
+        h1 = make_uint4(hh.v[4], hh.v[5], hh.v[6], hh.v[7]);
         q = __ldg(reinterpret_cast<const uint2*>(np + 32) + c);  // my child's quantised box
         ref = __ldg(reinterpret_cast<const uint32_t*>(np + 96) + c);
       }
@@ -810,15 +811,16 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* const stk
           evict = true;
         } else {
           ++visits;
-          const uint4* np = reinterpret_cast<const uint4*>(nodes + cur);
-          const uint4 h0 = __ldg(np + 0);  // ox oy oz | nchild
-          const uint4 h1 = __ldg(np + 1);  // sx sy sz | pad
-          const uint4 b0 = __ldg(np + 2);  // boxes of children 0, 1
-          const uint4 b1 = __ldg(np + 3);
-          const uint4 b2 = __ldg(np + 4);
-          const uint4 b3 = __ldg(np + 5);
-          const uint4 c0 = __ldg(np + 6);
-          const uint4 c1 = __ldg(np + 7);
+          const char* np = reinterpret_cast<const char*>(nodes + cur);
+          const U32x8 q0 = ldg256(np), q1 = ldg256(np + 32), q2 = ldg256(np + 64), q3 = ldg256(np + 96);
+          const uint4 h0 = make_uint4(q0.v[0], q0.v[1], q0.v[2], q0.v[3]);  // ox oy oz | nchild
+          const uint4 h1 = make_uint4(q0.v[4], q0.v[5], q0.v[6], q0.v[7]);  // sx sy sz | pad
+          const uint4 b0 = make_uint4(q1.v[0], q1.v[1], q1.v[2], q1.v[3]);  // boxes of children 0, 1
+          const uint4 b1 = make_uint4(q1.v[4], q1.v[5], q1.v[6], q1.v[7]);
+          const uint4 b2 = make_uint4(q2.v[0], q2.v[1], q2.v[2], q2.v[3]);
+          const uint4 b3 = make_uint4(q2.v[4], q2.v[5], q2.v[6], q2.v[7]);
+          const uint4 c0 = make_uint4(q3.v[0], q3.v[1], q3.v[2], q3.v[3]);
+          const uint4 c1 = make_uint4(q3.v[4], q3.v[5], q3.v[6], q3.v[7]);
           const Slab X = slab(__uint_as_float(h1.x), __uint_as_float(h0.x), r.ox, r.idx);
           const Slab Y = slab(__uint_as_float(h1.y), __uint_as_float(h0.y), r.oy, r.idy);
           const Slab Z = slab(__uint_as_float(h1.z), __uint_as_float(h0.z), r.oz, r.idz);
@@ -1007,9 +1009,13 @@ __global__ void __launch_bounds__(256) resolve_kernel(const MeshDev* __restrict_
     uint32_t mxx = is_hit ? (uint32_t)x : 0u, mxy = is_hit ? (uint32_t)y : 0u;
     mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
     mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
-    if (lane == 0) {
+    if (lane == 0) {  // plain reads first: after the first few warps almost nobody still widens the rectangle
       uint32_t* bb = reinterpret_cast<uint32_t*>(stats + 20);
-      atomicMin(bb + 0, mnx); atomicMin(bb + 1, mny); atomicMax(bb + 2, mxx); atomicMax(bb + 3, mxy);
+      const uint4 now = __ldcg(reinterpret_cast<const uint4*>(bb));
+      if (mnx < now.x) atomicMin(bb + 0, mnx);
+      if (mny < now.y) atomicMin(bb + 1, mny);
+      if (mxx > now.z) atomicMax(bb + 2, mxx);
+      if (mxy > now.w) atomicMax(bb + 3, mxy);
     }
   }
   if (vw.flags & J3DG_SHADOW) {  // warp-uniform

@@ -165,9 +165,13 @@ class PeerFrames:
     On `dst`, pf.frames(k) are the world frames of step k ([world, H, W] int32 view of the buffer), valid between
     end(k) and end(k + 1)... of the same slot parity, i.e. until end(k + 2) is enqueued."""
 
-    def __init__(self, ctx, height: int, width: int, device, dst: int = 0):
+    def __init__(self, ctx, height: int, width: int, device, dst: int = 0, shared_frame: bool = False):
+        """shared_frame = False: one frame per rank and slot (orbit sweep: every rank renders its own frame).
+        shared_frame = True : ONE frame per slot that all ranks write disjoint rows of (screen sharding,
+        j3dg_ctx_set_screen_shard: each rank's shade kernel writes only its own bands) — the gather disappears."""
         self.ctx, self.h, self.w, self.device, self.dst = ctx, height, width, device, dst
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.shared = shared_frame
         self.frame_bytes = height * width * 4
         self.flags_off = peer_flags_offset(self.world, self.frame_bytes)
         self.nbytes = self.flags_off + 256
@@ -194,7 +198,7 @@ class PeerFrames:
         return k
 
     def target(self, k: int) -> int:
-        return self.base + peer_slot_offset(k & 1, self.rank, self.world, self.frame_bytes)
+        return self.base + peer_slot_offset(k & 1, 0 if self.shared else self.rank, self.world, self.frame_bytes)
 
     def end(self, k: int):
         self.ctx.stream_signal(self._arrived(self.rank), k + 1)
@@ -206,8 +210,9 @@ class PeerFrames:
     def frames(self, k: int) -> torch.Tensor:
         assert self.rank == self.dst
         off = peer_slot_offset(k & 1, 0, self.world, self.frame_bytes)
-        t = device_bytes(self.base + off, self.world * self.frame_bytes, self.device)
-        return t.view(torch.int32).view(self.world, self.h, self.w)
+        n = 1 if self.shared else self.world
+        t = device_bytes(self.base + off, n * self.frame_bytes, self.device)
+        return t.view(torch.int32).view(n, self.h, self.w)
 
     def close(self):
         self.ctx.synchronize()

@@ -20,6 +20,8 @@ ap.add_argument("--size", default="3840x2160")
 ap.add_argument("--frames", type=int, default=8)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--no-shadow", action="store_true")
+ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                help="peer: every rank's shade kernel writes its bands straight into ONE frame in rank 0's HBM (NVLink peer memory); nccl: gather_bands")
 args = ap.parse_args()
 W, H = (int(t) for t in args.size.split("x"))
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
@@ -68,7 +70,14 @@ views = [j.orbit_view(v0, 25.0 * k) for k in range(args.warmup + args.frames)]
 px = torch.zeros((H, W, 32), dtype=torch.uint8, device=dev)
 rgba = torch.zeros((H, W), dtype=torch.int32, device=dev)
 
+pf = jd.PeerFrames(ctx, H, W, dev, dst=0, shared_frame=True) if (world > 1 and args.exchange == "peer") else None
+
 def frame(v):
+    if pf is not None:
+        k = pf.begin()
+        ctx.render_frame([mesh], [], v, pixels_out=px, rgba_out=pf.target(k))
+        pf.end(k)
+        return pf.frames(k)[0] if rank == 0 else None
     ctx.render_frame([mesh], [], v, pixels_out=px, rgba_out=rgba)
     return jd.gather_bands(rgba, dst=0) if world > 1 else rgba
 
@@ -93,6 +102,7 @@ if world > 1:
 # parity of the sharded path: rank 0 renders the last frame alone, unsharded
 identical = None
 if rank == 0:
+    torch.cuda.synchronize()
     got = whole.clone()
     ctx.set_screen_shard(0, 1)
     ctx.render_frame([mesh], [], views[-1], pixels_out=px, rgba_out=rgba)
@@ -106,7 +116,10 @@ if rank == 0:
                       "cast_ms_max_rank": stage[0].item() / args.frames, "shade_ms_max_rank": stage[1].item() / args.frames,
                       "bvh_build_ms": build_ms, "bvh_broadcast_ms": bcast_ms, "bvh_bytes": int(info.nr_of_nodes) * info.node_bytes + nt * info.triangle_bytes,
                       "gathered_equals_unsharded": identical, "hit_pixels": int(hit.sum()), "shadowed": int((p["mark"][hit] & 1).sum()),
-                      "mesh_generate_s": gen_s}))
+                      "mesh_generate_s": gen_s, "exchange": args.exchange if world > 1 else None,
+                      "exchange_timed_out": bool(ctx.stream_wait_timed_out()) if pf is not None else None}))
+if pf is not None:
+    pf.close()
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
