@@ -54,3 +54,18 @@ def ctx(native):
     c = j.Context(0)  # raises loudly without a B200: there is no fallback path
     yield c
     c.close()
+
+
+def build_cpp_shim_driver():
+    """g++ build of tests/cpp/shim_frame.cpp (the C++ mirror of j3d's scene / canvas driven like view::render_scene)
+    against libj3dg.so + libj3dg_host.so.  Returns the path of the executable."""
+    import subprocess
+    out = ROOT / "build" / "tests"
+    out.mkdir(parents=True, exist_ok=True)
+    exe = out / "shim_frame"
+    pkg = ROOT / "j3d_b200"
+    cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-I", str(pkg / "host"),
+           str(ROOT / "tests" / "cpp" / "shim_frame.cpp"), "-o", str(exe), "-L", str(pkg), "-lj3dg", "-lj3dg_host", f"-Wl,-rpath,{pkg}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe

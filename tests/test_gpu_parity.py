@@ -622,6 +622,51 @@ def test_voxelize_matches_golden(ctx, oracle, name):
     m.destroy(); om.destroy()
 
 
+def test_cpp_shim_renders_like_the_abi(ctx):
+    """The C++ mirror of j3d's scene / canvas (j3dg_host.h), driven like view::load_*_from_file + view::render_scene by a
+    g++-built program, produces byte-identical pixel records, image, picks and voxels to the ctypes path."""
+    import subprocess
+    from conftest import ROOT, build_cpp_shim_driver
+    exe = build_cpp_shim_driver()
+    w, h, max_dim = 333, 201, 40
+    flags = j.DEFAULT_FLAGS | j.SHADOW
+    verts, tris = j.icosphere(14)
+    pos, nrm, clr = j.cloud(30002)
+    pos = (pos * 1.2).astype(np.float32)
+    inp, outp = ROOT / "build" / "tests" / "shim_in.bin", ROOT / "build" / "tests" / "shim_out.bin"
+    with open(inp, "wb") as f:
+        f.write(np.array([w, h, verts.shape[0], tris.shape[0], pos.shape[0], flags, max_dim], np.uint32).tobytes())
+        for a in (verts, tris, pos, nrm, clr):
+            f.write(np.ascontiguousarray(a).tobytes())
+    res = subprocess.run([str(exe), str(inp), str(outp)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    raw = outp.read_bytes()
+    o = 0
+    got_px = np.frombuffer(raw, j.PIXEL_DTYPE, w * h, o).reshape(h, w); o += w * h * 32
+    got_im = np.frombuffer(raw, np.uint32, w * h, o).reshape(h, w); o += w * h * 4
+    got_picks = np.frombuffer(raw, j.PICK_DTYPE, 3, o); o += 3 * 64
+    dim = np.frombuffer(raw, np.uint32, 3, o); o += 12
+    got_vox = np.frombuffer(raw, np.uint8, int(dim.prod()), o).reshape(dim[2], dim[1], dim[0])
+    # the same calls through ctypes: add_object + prepare_scene + unzoom, then cast -> shade -> splat on host buffers
+    mn, mx = j.compute_bb(np.concatenate([verts, pos]))
+    v = j.make_view(w, h, mn, mx, flags)
+    mc, cav = j.make_matcap(0)
+    m = ctx.mesh_create(verts, tris)
+    cl = ctx.cloud_create(pos, nrm, clr)
+    px = ctx.cast([m], v)
+    pixels = px.copy()
+    im = j.fill_background(w, h)
+    ctx.shade(pixels, v, mc, cav, out=im)
+    ctx.splat([cl], v, pixels, px, im)
+    assert got_px.tobytes() == px.tobytes()
+    assert (got_im == im).all()
+    want_picks = ctx.pick([m], [cl], v, np.array([[w // 2, h // 2], [w // 3, h // 3], [-5, 2]], np.int32))
+    assert got_picks.tobytes() == want_picks.tobytes()
+    assert (got_picks["db_id"][:2] != 0).all() and got_picks["db_id"][2] == 0
+    assert (got_vox == m.voxelize(max_dim)).all() and int((got_vox != 0).sum()) > 1000
+    m.destroy(); cl.destroy()
+
+
 def test_peer_frames_protocol_single_gpu(ctx):
     """The NVLink peer-memory frame exchange (csrc/peer.cu, dist.PeerFrames) with one rank: the shade kernel renders
     into the exchange buffer, arrival / release flags order the steps, and the exchanged frame equals a direct render."""

@@ -79,3 +79,17 @@ def test_background_and_matcap_shapes(native):
     assert bg[0, 0] == 0xFF000000 and (bg >> 24 == 0xFF).all() and bg[-1, 0] != bg[0, 0]
     mc, cav = j.make_matcap(0)
     assert mc.shape == (512, 512) and cav == 0xFF7D7DFF
+
+
+def test_cpp_shim_compiles_and_links(native):
+    """The header-only C++ mirror of scene / canvas (j3d_b200/host/j3dg_host.h) builds warning-free against the C ABI and
+    fails loudly without a GPU (no CPU path)."""
+    import torch
+    from conftest import build_cpp_shim_driver
+    exe = build_cpp_shim_driver()
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: tests/test_gpu_parity.py runs the driver for real")
+    inp = ROOT / "build" / "tests" / "empty.bin"
+    inp.write_bytes(np.array([16, 16, 0, 0, 0, 0, 4], np.uint32).tobytes())
+    res = subprocess.run([str(exe), str(inp), str(inp.with_suffix(".out"))], capture_output=True, text=True)
+    assert res.returncode == 1 and "j3dg_ctx_create" in res.stderr
