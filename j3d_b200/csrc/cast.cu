@@ -3,26 +3,26 @@
 // (jtk/qbvh.h:3303-3387) -> qbvh::find_closest_triangle (1701-1852) with the Woop test
 // (4793-4869), hit -> pixel record (788-834) and the shadow ray (836-857).
 //
-// Two traversal kernels share one BVH (8-wide, 128-byte child-major nodes, leaves of <= 8 triangles):
+// One BVH (8-wide, 128-byte child-major nodes, leaves of <= 8 triangles), two ways to walk it:
 //
-//  lane_kernel  — one ray per LANE, one warp per 8x4-pixel tile, persistent warps pulling tiles from
-//                 a global counter, while-while traversal (all lanes descend nodes, then all test
-//                 leaves), nearest child in registers, short stack in shared memory.  This is the
-//                 throughput path: fewest instructions per ray.  Measured on the 28 M-triangle mesh it
-//                 finishes 98.7 % of the tiles in the first half of its run time and then waits for a
-//                 few silhouette tiles whose 32 grazing rays visit 100-250 nodes each in lockstep
-//                 (profiles/README.md).  So every ray gets a BUDGET of node visits; a ray that exceeds
-//                 it is evicted to a "hard ray" list together with its best hit so far.
-//  group_kernel — one ray per 8 LANES: lane c tests child c of the current node (or triangle c of the
-//                 current leaf), the group votes, picks the nearest child with three shuffle-min steps
-//                 and pushes the other hit children on ONE stack per ray in shared memory.  A traversal
-//                 step is ~8x shorter than in the lane kernel, rays are handed to groups one by one, so
-//                 there is no lockstep tail.  This is the latency path: it finishes the hard rays
-//                 (restarted from the root, pruned by the best hit the lane kernel already found) and
-//                 serves the generic find_closest query.
+//  lane mode  — one ray per LANE, one warp per 8x4-pixel tile, persistent warps pulling tiles from a global counter;
+//               per step the warp votes between a node step (8 quantised child boxes, nearest child in a register,
+//               the others pushed on a short shared-memory stack) and a triangle step (one 48-byte record).  Fewest
+//               instructions per ray — the throughput path.  Left alone it finishes 98.7 % of the tiles in the first
+//               half of its run time and then waits for a few silhouette tiles whose grazing rays visit 100-250
+//               nodes each (profiles/README.md), so every ray gets a BUDGET of node visits; a ray that exceeds it is
+//               evicted, with its best hit so far, into a "hard ray" queue.
+//  group mode — one ray per 8 LANES: lane c tests child c of the node (or triangle c of the leaf), the group votes,
+//               picks the nearest child with three shuffle-min steps and pushes the rest on one stack per ray.  A step
+//               is ~8x shorter and rays are claimed one by one, so there is no lockstep tail — the latency path for
+//               the hard rays (restarted from the root, pruned by the hit the lane warp already found; carrying the
+//               lane's stack along instead was measured and buys nothing) and for the generic find_closest query.
 //
-// Pipeline of one j3dg_cast: lane<PRIMARY> -> group<PRIMARY, hard list> (raw hit: t, u, v, record slot)
-// -> resolve_kernel (hit -> pixel record; appends shadow rays) -> lane<SHADOW> -> group<SHADOW, hard list>.
+// cast_kernel is ONE cooperative launch per ray type: every warp first traces tiles in lane mode (producing the
+// queue), then — warp by warp, on its own slice of the block's shared-memory stacks, no block barrier — turns into
+// four 8-lane groups that drain the queue.  Pipeline of one j3dg_cast:
+//   cast_kernel<PRIMARY> (raw hit: t, u, v, record slot) -> resolve_kernel (hit -> pixel record, hit bounding
+//   rectangle, shadow ray list) -> cast_kernel<SHADOW> (any hit).
 //
 // Parity rules: the ray, the Woop edge functions, t/u/v, the triangle normal and
 // its two transforms are evaluated with separately rounded mul/add/sub (no FMA), in the
@@ -438,12 +438,6 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const st
       const uint32_t nm8 = (__ballot_sync(0xffffffffu, hit && key == nearest) >> gshift) & 0xFFu;
       const int near_lane = __ffs(nm8) - 1;  // -1 when nothing was hit
       const uint32_t next = __shfl_sync(0xffffffffu, ref, gshift + (near_lane & 7));
-#ifdef J3DG_NEXT_PREFETCH
-      if (at_node && hm != 0u) {  // lane c pulls in line c % 4 of the next node's / leaf's 384 bytes (a node is one line)
-        const char* a = (next & J3DG_LEAF_BIT) ? reinterpret_cast<const char*>(tris + (next & J3DG_LEAF_FIRST_MASK)) + 128 * (c & 3) : reinterpret_cast<const char*>(nodes + next);
-        asm volatile("prefetch.global.L1 [%0];" :: "l"(a));
-      }
-#endif
       if (at_node) {
         if (hm == 0u) {
           cur = pop();
@@ -453,12 +447,6 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const st
             const int pos = sp + __popc(others & below);
             if (pos < STACK_SIZE) stk[pos * GSTRIDE] = make_uint2(ref, __float_as_uint(tmin));
             else *overflow_flag = 1u;
-#ifdef J3DG_GROUP_PUSH_PREFETCH
-            {  // pull the postponed child towards L2 while the nearer one is traversed
-              const char* a = (ref & J3DG_LEAF_BIT) ? reinterpret_cast<const char*>(tris + (ref & J3DG_LEAF_FIRST_MASK)) : reinterpret_cast<const char*>(nodes + ref);
-              asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
-            }
-#endif
           }
           sp = min(sp + __popc(others), STACK_SIZE);
           cur = next;
@@ -803,11 +791,7 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* const stk
         }
       } else if (at_node) {
         // ---------------- node step: 8 quantised child boxes ----------------
-#ifdef J3DG_TAIL_BUDGET_DIV
-        if (visits >= (exhausted ? p.budget / J3DG_TAIL_BUDGET_DIV : p.budget)) {  // no rays left to hide a long one behind
-#else
         if (visits >= p.budget) {
-#endif
           evict = true;
         } else {
           ++visits;
@@ -844,23 +828,11 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* const stk
           near_ref = ni == 4u ? c1.x : near_ref; near_ref = ni == 5u ? c1.y : near_ref; near_ref = ni == 6u ? c1.z : near_ref;
           near_ref = ni == 7u ? c1.w : near_ref;
           if ((uint32_t)nearest >= MISS_KEY) near_ref = J3DG_EMPTY_CHILD;
-#ifdef J3DG_NEXT_PREFETCH
-          if (near_ref != J3DG_EMPTY_CHILD) {  // start fetching the next node / first record while the other children are pushed
-            const char* a = (near_ref & J3DG_LEAF_BIT) ? reinterpret_cast<const char*>(tris + (near_ref & J3DG_LEAF_FIRST_MASK)) : reinterpret_cast<const char*>(nodes + near_ref);
-            asm volatile("prefetch.global.L1 [%0];" :: "l"(a));
-          }
-#endif
           // branch-free pushes of the other hit children (row LANE_STACK is scratch; the low key bits are cleared at pop)
           int wanted = sp;
           auto push = [&](uint32_t key, uint32_t ref) {
             stk[sp * LANE_STRIDE] = make_uint2(ref, key);
             const int go = (key < MISS_KEY && (int)key != nearest) ? 1 : 0;
-#ifdef J3DG_PUSH_PREFETCH
-            if (go) {  // pull the postponed child towards L2 while the nearer one is traversed
-              const char* a = (ref & J3DG_LEAF_BIT) ? reinterpret_cast<const char*>(tris + (ref & J3DG_LEAF_FIRST_MASK)) : reinterpret_cast<const char*>(nodes + ref);
-              asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
-            }
-#endif
             wanted += go;
             sp = min(sp + go, LANE_STACK);
           };
