@@ -975,19 +975,28 @@ __global__ void __launch_bounds__(256) resolve_kernel(const MeshDev* __restrict_
     }
   }
   // bounding rectangle of the hit pixels of this frame (stats slots 20, 21 = min x, min y, max x, max y): everything
-  // outside it is a miss record / background, which lets the host copy skip it (j3dg_ctx_set_dirty_rect)
-  if (__any_sync(0xffffffffu, is_hit)) {
-    uint32_t mnx = is_hit ? (uint32_t)x : 0xFFFFFFFFu, mny = is_hit ? (uint32_t)y : 0xFFFFFFFFu;
-    uint32_t mxx = is_hit ? (uint32_t)x : 0u, mxy = is_hit ? (uint32_t)y : 0u;
-    mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
-    mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
-    if (lane == 0) {  // plain reads first: after the first few warps almost nobody still widens the rectangle
+  // outside it is a miss record / background, which lets the host copy skip it (j3dg_ctx_set_dirty_rect).
+  // Reduced per warp, then per block in shared memory; one thread per block touches the global words, and only
+  // if it still widens the rectangle.
+  {
+    __shared__ uint32_t s_bb[4];
+    if (threadIdx.x == 0) { s_bb[0] = 0xFFFFFFFFu; s_bb[1] = 0xFFFFFFFFu; s_bb[2] = 0u; s_bb[3] = 0u; }
+    __syncthreads();
+    if (__any_sync(0xffffffffu, is_hit)) {
+      const uint32_t mnx = __reduce_min_sync(0xffffffffu, is_hit ? (uint32_t)x : 0xFFFFFFFFu);
+      const uint32_t mny = __reduce_min_sync(0xffffffffu, is_hit ? (uint32_t)y : 0xFFFFFFFFu);
+      const uint32_t mxx = __reduce_max_sync(0xffffffffu, is_hit ? (uint32_t)x : 0u);
+      const uint32_t mxy = __reduce_max_sync(0xffffffffu, is_hit ? (uint32_t)y : 0u);
+      if (lane == 0) { atomicMin(&s_bb[0], mnx); atomicMin(&s_bb[1], mny); atomicMax(&s_bb[2], mxx); atomicMax(&s_bb[3], mxy); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_bb[0] <= s_bb[2]) {
       uint32_t* bb = reinterpret_cast<uint32_t*>(stats + 20);
       const uint4 now = __ldcg(reinterpret_cast<const uint4*>(bb));
-      if (mnx < now.x) atomicMin(bb + 0, mnx);
-      if (mny < now.y) atomicMin(bb + 1, mny);
-      if (mxx > now.z) atomicMax(bb + 2, mxx);
-      if (mxy > now.w) atomicMax(bb + 3, mxy);
+      if (s_bb[0] < now.x) atomicMin(bb + 0, s_bb[0]);
+      if (s_bb[1] < now.y) atomicMin(bb + 1, s_bb[1]);
+      if (s_bb[2] > now.z) atomicMax(bb + 2, s_bb[2]);
+      if (s_bb[3] > now.w) atomicMax(bb + 3, s_bb[3]);
     }
   }
   if (vw.flags & J3DG_SHADOW) {  // warp-uniform
