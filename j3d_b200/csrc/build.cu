@@ -124,13 +124,14 @@ __global__ void __launch_bounds__(256) morton_kernel(const float* __restrict__ v
 // ---- 4. binary radix tree (Karras 2012) ----------------------------------------------------
 // Node numbering: inner nodes 0..n-2 (root 0), leaf k = n-1+k.
 struct BinTree {
-  int2* children;    // [n-1]
-  uint2* range;      // [n-1] first,last sorted leaf
+  uint4* topo;       // [n-1] {left child, right child, first sorted leaf, last sorted leaf}: one 16-byte load per node
   uint32_t* parent;  // [2n-1]
   uint32_t* flags;   // [n-1]
-  float4* bmin;      // [2n-1]
-  float4* bmax;      // [2n-1]
+  float4* box;       // [2 (2n-1)] box[2 i] = min, box[2 i + 1] = max: both in one 32-byte sector
 };
+
+__device__ __forceinline__ int2 node_children(const BinTree& t, uint32_t i) { const uint4 v = t.topo[i]; return make_int2((int)v.x, (int)v.y); }
+__device__ __forceinline__ uint2 node_range(const BinTree& t, uint32_t i) { const uint4 v = t.topo[i]; return make_uint2(v.z, v.w); }
 
 // `mask` selects the key bits that were sorted; keys that agree on them are told apart by their position
 __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, uint64_t mask, int n, int i, int j) {
@@ -165,8 +166,7 @@ __global__ void __launch_bounds__(256) radix_tree_kernel(const uint64_t* __restr
   const int lo = min(i, j), hi = max(i, j);
   const int left = (lo == gamma) ? (n - 1 + gamma) : gamma;
   const int right = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
-  t.children[i] = make_int2(left, right);
-  t.range[i] = make_uint2((uint32_t)lo, (uint32_t)hi);
+  t.topo[i] = make_uint4((uint32_t)left, (uint32_t)right, (uint32_t)lo, (uint32_t)hi);
   t.parent[left] = (uint32_t)i;
   t.parent[right] = (uint32_t)i;
   t.flags[i] = 0;
@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __res
     const float4 mx = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.f);
     s_lmn[0][tid] = mn.x; s_lmn[1][tid] = mn.y; s_lmn[2][tid] = mn.z;
     s_lmx[0][tid] = mx.x; s_lmx[1][tid] = mx.y; s_lmx[2][tid] = mx.z;
-    t.bmin[first_leaf + k] = mn;
-    t.bmax[first_leaf + k] = mx;
+    t.box[2 * (size_t)(first_leaf + k)] = mn;
+    t.box[2 * (size_t)(first_leaf + k) + 1] = mx;
   }
   s_ready[tid] = 0;
   if (n == 1) return;
@@ -215,9 +215,9 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __res
   bool mine = false, done = false;
   int2 ch = make_int2(0, 0);
   if (k < e && k < n - 1) {
-    const uint2 r = t.range[k];
-    mine = (int)r.x >= s && (int)r.y < e;
-    if (mine) ch = t.children[k];
+    const uint4 tp = t.topo[k];
+    mine = (int)tp.z >= s && (int)tp.w < e;
+    ch = make_int2((int)tp.x, (int)tp.y);
   }
   __syncthreads();
   for (;;) {
@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __res
       for (int j = 0; j < 3; ++j) { s_imn[j][tid] = mn[j]; s_imx[j][tid] = mx[j]; }
       s_ready[tid] = 1;
       done = true;
-      t.bmin[k] = make_float4(mn[0], mn[1], mn[2], 0.f);
-      t.bmax[k] = make_float4(mx[0], mx[1], mx[2], 0.f);
+      t.box[2 * (size_t)(k)] = make_float4(mn[0], mn[1], mn[2], 0.f);
+      t.box[2 * (size_t)(k) + 1] = make_float4(mx[0], mx[1], mx[2], 0.f);
     }
     if (!__syncthreads_or(fit)) break;
   }
@@ -266,20 +266,20 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __res
     uint32_t p = t.parent[cur];
     if (p == 0xFFFFFFFFu) continue;
     {
-      const uint2 pr = t.range[p];
+      const uint2 pr = node_range(t, p);
       if ((int)pr.x >= s && (int)pr.y < e) continue;  // the parent was fitted in shared memory above
     }
     __threadfence();  // my box (written above) before my arrival
     while (p != 0xFFFFFFFFu) {
       if (atomicAdd(&t.flags[p], 1u) == 0u) break;  // first arrival: the sibling subtree finishes this node
-      const int2 pc = t.children[p];
+      const int2 pc = node_children(t, p);
       const uint32_t other = ((uint32_t)pc.x == cur) ? (uint32_t)pc.y : (uint32_t)pc.x;
-      const float4 omn = __ldcg(&t.bmin[other]);
-      const float4 omx = __ldcg(&t.bmax[other]);
+      const float4 omn = __ldcg(&t.box[2 * (size_t)(other)]);
+      const float4 omx = __ldcg(&t.box[2 * (size_t)(other) + 1]);
       mn = make_float4(fminf(mn.x, omn.x), fminf(mn.y, omn.y), fminf(mn.z, omn.z), 0.f);
       mx = make_float4(fmaxf(mx.x, omx.x), fmaxf(mx.y, omx.y), fmaxf(mx.z, omx.z), 0.f);
-      t.bmin[p] = mn;
-      t.bmax[p] = mx;
+      t.box[2 * (size_t)(p)] = mn;
+      t.box[2 * (size_t)(p) + 1] = mx;
       __threadfence();
       cur = p;
       p = t.parent[p];
@@ -331,12 +331,12 @@ __global__ void __launch_bounds__(128) collapse_kernel(BinTree t, int n, const W
     int nc = 2;
     auto open_area = [&](uint32_t c) -> float {
       if (c >= first_leaf) return -1.f;
-      const uint2 r = t.range[c];
+      const uint2 r = node_range(t, c);
       if (r.y - r.x + 1 <= (uint32_t)J3DG_LEAF_KEEP) return -1.f;
-      return fmaxf(half_area(t.bmin[c], t.bmax[c]), 0.f);
+      return fmaxf(half_area(t.box[2 * (size_t)(c)], t.box[2 * (size_t)(c) + 1]), 0.f);
     };
     {
-      const int2 ch = t.children[item.bin];
+      const int2 ch = node_children(t, item.bin);
       cand[0] = (uint32_t)ch.x;
       cand[1] = (uint32_t)ch.y;
       area[0] = open_area(cand[0]);
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(128) collapse_kernel(BinTree t, int n, const W
       for (int i = 0; i < nc; ++i)
         if (area[i] > ba) { ba = area[i]; best = i; }
       if (best < 0) break;
-      const int2 ch = t.children[cand[best]];
+      const int2 ch = node_children(t, cand[best]);
       cand[best] = (uint32_t)ch.x;
       cand[nc] = (uint32_t)ch.y;
       area[best] = open_area((uint32_t)ch.x);
@@ -356,14 +356,14 @@ __global__ void __launch_bounds__(128) collapse_kernel(BinTree t, int n, const W
       ++nc;
     }
     // node box = box of the binary node
-    const float4 nmn = t.bmin[item.bin], nmx = t.bmax[item.bin];
+    const float4 nmn = t.box[2 * (size_t)(item.bin)], nmx = t.box[2 * (size_t)(item.bin) + 1];
     WideNode node;
     node.ox = nmn.x; node.oy = nmn.y; node.oz = nmn.z;
     node.pad0 = 0u;
     uint32_t e[3] = {pick_exponent(nmx.x - nmn.x), pick_exponent(nmx.y - nmn.y), pick_exponent(nmx.z - nmn.z)};
     const float org[3] = {nmn.x, nmn.y, nmn.z};
     float4 cmn[8], cmx[8];
-    for (int i = 0; i < nc; ++i) { cmn[i] = t.bmin[cand[i]]; cmx[i] = t.bmax[cand[i]]; }
+    for (int i = 0; i < nc; ++i) { cmn[i] = t.box[2 * (size_t)cand[i]]; cmx[i] = t.box[2 * (size_t)cand[i] + 1]; }
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) {
       for (;;) {
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(128) collapse_kernel(BinTree t, int n, const W
         node.child[i] = J3DG_LEAF_BIT | (c - first_leaf);
         mark_leaf_end(recs, c - first_leaf);
       } else {
-        const uint2 r = t.range[c];
+        const uint2 r = node_range(t, c);
         const uint32_t cnt = r.y - r.x + 1;
         if (cnt <= J3DG_MAX_LEAF) {
           node.child[i] = J3DG_LEAF_BIT | r.x;
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(128) collapse_kernel(BinTree t, int n, const W
 
 // n == 1: a root with a single leaf child
 __global__ void single_triangle_root_kernel(BinTree t, WideNode* nodes, TriRec* recs) {
-  const float4 mn = t.bmin[0], mx = t.bmax[0];
+  const float4 mn = t.box[2 * (size_t)(0)], mx = t.box[2 * (size_t)(0) + 1];
   WideNode node;
   node.ox = mn.x; node.oy = mn.y; node.oz = mn.z;
   node.pad0 = 0u;
@@ -496,12 +496,10 @@ int j3dg_build_bvh(j3dg_mesh* m) {
   uint32_t* vals_b = ar.take<uint32_t>(nn);
   uint32_t* sort_scratch = ar.take<uint32_t>(rsort::scratch_bytes(n) / 4);
   BinTree bt;
-  bt.children = ar.take<int2>(nn);
-  bt.range = ar.take<uint2>(nn);
+  bt.topo = ar.take<uint4>(nn);
   bt.parent = ar.take<uint32_t>(2 * nn);
   bt.flags = ar.take<uint32_t>(nn);
-  bt.bmin = ar.take<float4>(2 * nn);
-  bt.bmax = ar.take<float4>(2 * nn);
+  bt.box = ar.take<float4>(4 * nn);
   WorkItem* q0 = ar.take<WorkItem>(nn);
   WorkItem* q1 = ar.take<WorkItem>(nn);
 
