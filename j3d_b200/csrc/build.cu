@@ -133,34 +133,36 @@ struct BinTree {
 __device__ __forceinline__ int2 node_children(const BinTree& t, uint32_t i) { const uint4 v = t.topo[i]; return make_int2((int)v.x, (int)v.y); }
 __device__ __forceinline__ uint2 node_range(const BinTree& t, uint32_t i) { const uint4 v = t.topo[i]; return make_uint2(v.z, v.w); }
 
-// `mask` selects the key bits that were sorted; keys that agree on them are told apart by their position
-__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, uint64_t mask, int n, int i, int j) {
+// `mask` selects the key bits that were sorted; keys that agree on them are told apart by their position.
+// ki = keys[i] & mask, kept in a register by the caller.
+__device__ __forceinline__ int delta(uint64_t ki, const uint64_t* __restrict__ keys, uint64_t mask, int n, int i, int j) {
   if (j < 0 || j >= n) return -1;
-  const uint64_t a = keys[i] & mask, b = keys[j] & mask;
-  if (a != b) return __clzll((long long)(a ^ b));
+  const uint64_t b = __ldg(keys + j) & mask;
+  if (ki != b) return __clzll((long long)(ki ^ b));
   return 64 + __clz(i ^ j);
 }
 
 __global__ void __launch_bounds__(256) radix_tree_kernel(const uint64_t* __restrict__ keys, uint64_t mask, int n, BinTree t) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
-  const int d = (delta(keys, mask, n, i, i + 1) - delta(keys, mask, n, i, i - 1)) >= 0 ? 1 : -1;
-  const int dmin = delta(keys, mask, n, i, i - d);
+  const uint64_t ki = __ldg(keys + i) & mask;
+  const int d = (delta(ki, keys, mask, n, i, i + 1) - delta(ki, keys, mask, n, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = delta(ki, keys, mask, n, i, i - d);
   int lmax = 2;
-  while (delta(keys, mask, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  while (delta(ki, keys, mask, n, i, i + lmax * d) > dmin) lmax <<= 1;
   int l = 0;
   for (int s = lmax >> 1; s >= 1; s >>= 1)
-    if (delta(keys, mask, n, i, i + (l + s) * d) > dmin) l += s;
+    if (delta(ki, keys, mask, n, i, i + (l + s) * d) > dmin) l += s;
   const int j = i + l * d;
-  const int dnode = delta(keys, mask, n, i, j);
+  const int dnode = delta(ki, keys, mask, n, i, j);
   int s = 0;
-  int div = 2;
-  int tstep = (l + div - 1) / div;
+  int sh = 1;  // the step halves (rounded up): ceil(l / 2^sh), divisions by a power of two are shifts
+  int tstep = (l + 1) >> 1;
   while (true) {
-    if (delta(keys, mask, n, i, i + (s + tstep) * d) > dnode) s += tstep;
+    if (delta(ki, keys, mask, n, i, i + (s + tstep) * d) > dnode) s += tstep;
     if (tstep == 1) break;
-    div <<= 1;
-    tstep = (l + div - 1) / div;
+    ++sh;
+    tstep = (l + (1 << sh) - 1) >> sh;
   }
   const int gamma = i + s * d + min(d, 0);
   const int lo = min(i, j), hi = max(i, j);
