@@ -194,7 +194,13 @@ def run_b200(args, f, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on the C-level stdout at the first collective; the contract is ONE JSON line
+        # on stdout, so fd 1 points at stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     ctx = j.Context(local_rank)
     # every kernel of the library, the NCCL collectives and the timing events share ONE stream
@@ -265,7 +271,14 @@ def run_b200(args, f, rank, world, local_rank):
     pf = None
     if world > 1 and args.exchange == "peer":
         from j3d_b200.dist import PeerFrames
-        pf = PeerFrames(ctx, H, W, dev, dst=0)
+        try:
+            pf = PeerFrames(ctx, H, W, dev, dst=0)
+        except RuntimeError as e:  # every rank raises together: CUDA IPC is not available here, gather with NCCL instead
+            if rank == 0:
+                print(f"bench.py: {e}; using --exchange nccl", file=sys.stderr)
+            args.exchange = "nccl"
+            comm = torch.cuda.Stream(device=dev)
+            gather_lists = [[torch.empty_like(rgba) for _ in range(world)] for _ in range(2)] if rank == 0 else [None, None]
 
     total = args.warmup + args.steps
     views = frame_views(j, v0, rank, total, world)  # rank r renders frames r, r+N, r+2N ...
@@ -485,7 +498,11 @@ def run_b200(args, f, rank, world, local_rank):
         line["exchange"] = {"kind": args.exchange, "verified": exchange_ok, "bytes_per_step_into_rank0": (world - 1) * W * H * 4}
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -175,13 +175,35 @@ class PeerFrames:
         self.frame_bytes = height * width * 4
         self.flags_off = peer_flags_offset(self.world, self.frame_bytes)
         self.nbytes = self.flags_off + 256
+        # set-up is collective and must not leave a rank behind: every rank reports whether its step worked, the group
+        # agrees (MIN), and on any failure everybody raises the same error (callers may then fall back to an NCCL gather)
         handle = [None]
+        ok, err = 1, ""
+        self.base = 0
         if self.rank == dst:
-            self.base, h = ctx.peer_alloc(self.nbytes)
-            handle[0] = h
+            try:
+                self.base, h = ctx.peer_alloc(self.nbytes)
+                handle[0] = h
+            except Exception as e:  # noqa: BLE001
+                ok, err = 0, str(e)
         dist.broadcast_object_list(handle, src=dst)
-        if self.rank != dst:
-            self.base = ctx.peer_open(handle[0])
+        if self.rank != dst and handle[0] is not None:
+            try:
+                self.base = ctx.peer_open(handle[0])
+            except Exception as e:  # noqa: BLE001
+                ok, err = 0, str(e)
+        elif handle[0] is None:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if self.base:
+                try:
+                    (ctx.peer_free if self.rank == dst else ctx.peer_close)(self.base)
+                except Exception:  # noqa: BLE001
+                    pass
+                self.base = 0
+            raise RuntimeError("peer-memory frame exchange unavailable on at least one rank" + (f": {err}" if err else ""))
         self.k = 0
         dist.barrier()
 
