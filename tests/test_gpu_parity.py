@@ -845,3 +845,56 @@ def test_full_size_triangle_order_invariance(ctx, config_b):
     assert same.mean() > 0.9999
     assert np.abs(a["depth"][both] - b["depth"][both]).max() <= 1e-5 * a["depth"][both].max()
     m2.destroy()
+
+
+@pytest.mark.timeout(900)
+def test_full_size_all_hits_pick_and_voxel_properties(ctx, config_b):
+    """The query clients on the 28 M-triangle mesh, through size-independent properties: a ray through a closed surface
+    enters as often as it leaves; the nearest of all hits is the closest-hit answer; every voxel the export fills is
+    touched by the surface and the filled shell is closed along the three ray directions; picks reproduce the records."""
+    verts, tris, m, v = config_b
+    rng = np.random.default_rng(3)
+    n = 4096
+    a = rng.normal(size=(n, 3)); a = 3.0 * a / np.linalg.norm(a, axis=1, keepdims=True)
+    b = rng.normal(size=(n, 3)); b = 0.8 * b / np.linalg.norm(b, axis=1, keepdims=True) * rng.random((n, 1)) ** (1 / 3)
+    rays = np.concatenate([a, b - a, np.zeros((n, 1)), np.full((n, 1), FMAX)], axis=1).astype(np.float32)
+    off, hits, ids = m.find_all(rays)
+    counts = np.diff(off.astype(np.int64))
+    assert (counts >= 2).all() and (counts % 2 == 0).mean() > 0.999
+    assert (ids < tris.shape[0]).all() and (hits[:, 2] > 0).all()
+    ch, cid = m.find_closest(rays)
+    assert (ch[:, 3] == 1).all()
+    first = np.array([np.argmin(hits[off[k]:off[k + 1], 2]) + off[k] for k in range(n)])
+    agree = ids[first] == cid
+    assert agree.mean() > 0.999 and np.abs(hits[first, 2][agree] - ch[agree, 2]).max() <= 1e-6
+    # every reported hit lies on its triangle: the barycentric point is on the ray at the reported distance
+    sel = rng.choice(hits.shape[0], 3000, replace=False)
+    ray_of = np.searchsorted(off, sel, side="right") - 1
+    t = tris[ids[sel]]
+    u, w = hits[sel, 0].astype(np.float64), hits[sel, 1].astype(np.float64)
+    p = verts[t[:, 0]] * (1 - u - w)[:, None] + verts[t[:, 1]] * u[:, None] + verts[t[:, 2]] * w[:, None]
+    q = rays[ray_of, :3].astype(np.float64) + rays[ray_of, 3:6].astype(np.float64) * hits[sel, 2][:, None].astype(np.float64)
+    assert np.abs(p - q).max() < 2e-5
+    # voxel export: a closed shell — along x every grid column that meets the solid sees filled voxels at both ends
+    grid = m.voxelize(96)
+    dz, dy, dx = grid.shape
+    assert max(dx, dy, dz) == 96 and (grid[grid != 0] == 255).all()
+    filled = grid != 0
+    centre = np.zeros_like(filled); centre[dz // 4: 3 * dz // 4, dy // 4: 3 * dy // 4, :] = True
+    cols = filled.any(axis=2)
+    assert cols[dz // 4: 3 * dz // 4, dy // 4: 3 * dy // 4].all()             # every central column crosses the surface
+    firsts = filled.argmax(axis=2); lasts = dx - 1 - filled[:, :, ::-1].argmax(axis=2)
+    assert (lasts[cols] > firsts[cols]).mean() > 0.95                          # ... twice (front and back of the shell)
+    assert 0.02 < filled.mean() < 0.2                                           # a shell, not a solid
+    # picking on the resident canvas of a full-size frame
+    mc, cav = j.make_matcap(0)
+    px = np.zeros((1080, 1920), j.PIXEL_DTYPE)
+    ctx.render_frame([m], [], v, mc, cav, pixels_out=px)
+    xy = np.stack([rng.integers(0, 1920, 500), rng.integers(0, 1080, 500)], 1).astype(np.int32)
+    got = ctx.pick([m], [], v, xy)
+    assert got["pixel"].tobytes() == px[xy[:, 1], xy[:, 0]].tobytes()
+    hit = got["db_id"] != 0
+    assert hit.sum() > 100 and (got["closest_vertex"][hit] < verts.shape[0]).all()
+    tri_of = tris[got["pixel"]["object_id"][hit]]
+    assert (got["closest_vertex"][hit][:, None] == tri_of).any(axis=1).all()   # the closest vertex is a corner of the hit triangle
+    assert np.isnan(got["world_pos"][~hit]).all() and np.isfinite(got["world_pos"][hit]).all()
