@@ -150,6 +150,7 @@ J3DG_API int j3dg_ctx_create(int device, j3dg_ctx** out) {
   }
   cudaMemset(ctx->d_stats, 0, 24 * sizeof(unsigned long long));
   if (const char* e = getenv("J3DG_LANE_BUDGET")) ctx->lane_budget = (uint32_t)std::max(1, atoi(e));  // developer tuning knobs
+  if (const char* e = getenv("J3DG_SHADOW_BUDGET")) ctx->shadow_budget = (uint32_t)std::max(1, atoi(e));
   if (const char* e = getenv("J3DG_CONSUMER_BLOCKS")) ctx->consumer_blocks = (uint32_t)std::max(0, atoi(e));
   if (const char* e = getenv("J3DG_CAST_ALGO")) ctx->cast_algo = strcmp(e, "group") == 0 ? 1 : 0;
   *out = ctx;

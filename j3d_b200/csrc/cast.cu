@@ -1185,6 +1185,7 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   if (shadows) {
     const long long pools = ((long long)npx + 31) / 32;
     tp.pool_ctr = ctr(8); tp.hard_count = ctr(9); tp.hard_taken = ctr(10); tp.done_blocks = ctr(12);
+    tp.budget = ctx->shadow_budget;  // any-hit rays that start on the surface: their long ones are long from the start
     if (ctx->cast_algo == 1) {
       if ((rc = persistent_grid(ctx, group_kernel<SHADOW>, pools, &grid)) != J3DG_OK) return rc;
       group_kernel<SHADOW><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
