@@ -237,7 +237,11 @@ J3DG_API int j3dg_mesh_find_all(j3dg_mesh* mesh, const float* rays, uint32_t n, 
   if (n >= 0x7FFFFFFFu) { j3dg_set_error(ctx, "j3dg_mesh_find_all: too many rays"); return J3DG_EINVAL; }
   cudaSetDevice(ctx->device);
   if (total) *total = 0;
-  if (!n) { offsets[0] = 0; return J3DG_OK; }
+  if (!n) {  // offsets may be a device pointer
+    const uint32_t zero = 0;
+    CU_CHECK(ctx, cudaMemcpy(offsets, &zero, sizeof(zero), cudaMemcpyDefault));
+    return J3DG_OK;
+  }
   const bool rays_dev = j3dg_is_device_ptr(rays), out_dev = j3dg_is_device_ptr(offsets);
   if (hits && (j3dg_is_device_ptr(hits) != out_dev || j3dg_is_device_ptr(triangle_ids) != out_dev)) {
     j3dg_set_error(ctx, "j3dg_mesh_find_all: outputs must be all host or all device");

@@ -595,7 +595,7 @@ int copy_dirty(j3dg_ctx* ctx, void* host, const void* dev, uint32_t w, uint32_t 
   for (auto& d : ctx->dirty_bufs)
     if (d.ptr == host) { e = &d; break; }
   Rect todo;
-  if (e && e->w == w && e->h == h && e->key0 == key0 && e->key1 == key1) {
+  if (e && e->w == w && e->h == h && e->elem == (uint32_t)elem && e->key0 == key0 && e->key1 == key1) {
     todo = rect_union(Rect{e->x0, e->y0, e->x1, e->y1}, cur);
   } else {
     todo = Rect{0, 0, (int)w - 1, (int)h - 1};
@@ -605,7 +605,7 @@ int copy_dirty(j3dg_ctx* ctx, void* host, const void* dev, uint32_t w, uint32_t 
       e = &ctx->dirty_bufs.back();
     }
   }
-  *e = j3dg_ctx::DirtyBuf{host, w, h, key0, key1, cur.x0, cur.y0, cur.x1, cur.y1};
+  *e = j3dg_ctx::DirtyBuf{host, w, h, (uint32_t)elem, key0, key1, cur.x0, cur.y0, cur.x1, cur.y1};
   if (todo.empty()) return J3DG_OK;
   ctx->readback_bytes += (uint64_t)(todo.x1 - todo.x0 + 1) * (todo.y1 - todo.y0 + 1) * elem;
   const size_t pitch = (size_t)w * elem, off = ((size_t)todo.y0 * w + todo.x0) * elem;

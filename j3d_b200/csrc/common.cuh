@@ -148,7 +148,7 @@ struct j3dg_ctx {
   } slot[2];
   uint64_t readback_bytes = 0;                       // device->host bytes of frame outputs since the last reset (j3dg_ctx_readback_bytes)
   bool dirty_rect = false;                           // j3dg_ctx_set_dirty_rect
-  struct DirtyBuf { void* ptr; uint32_t w, h, key0, key1; int x0, y0, x1, y1; };  // what a host buffer holds outside-of-miss
+  struct DirtyBuf { void* ptr; uint32_t w, h, elem, key0, key1; int x0, y0, x1, y1; };  // what a host buffer holds outside-of-miss
   std::vector<DirtyBuf> dirty_bufs;
   cudaStream_t copy_stream = nullptr;
   uint64_t frames_submitted = 0, frames_waited = 0;
