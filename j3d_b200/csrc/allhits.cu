@@ -16,7 +16,8 @@
 namespace {
 
 constexpr int AH_THREADS = 64;
-constexpr int AH_STACK = 96;  // entries per ray; 96 * 4 B * 64 lanes = 24 KB shared memory per block
+constexpr int AH_STACK = 64;  // entries per ray; 64 * 4 B * 64 lanes = 16 KB shared memory per block (96: 4.06 ms, 64: 3.56 ms, 48: 3.48 ms
+                              // for the 512-scale voxel grid of the 28 M-triangle mesh); an overflow is reported, never silent
 
 enum AllMode { COUNT = 0, FILL = 1, VOXEL = 2 };
 
