@@ -195,3 +195,70 @@ def test_empty_and_ragged_inputs(oracle):
     om = oracle.mesh(verts, np.zeros((0, 3), np.uint32))
     px = oracle.cast([om], v)
     assert (px["object_id"] == MISS).all()
+
+
+def _rigid(rng, scale=0.3):
+    """Random rotation + translation as a column-major float[16] (jtk::float4x4)."""
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    w, x, y, z = q
+    r = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    m = np.eye(4)
+    m[:3, :3] = r
+    m[:3, 3] = rng.normal(size=3) * scale
+    return np.ascontiguousarray(m.T.reshape(-1), np.float32)  # column-major
+
+
+def test_oracle_equals_reference_random_scenes(oracle):
+    """Randomised pinning against the reference running here: two meshes and a cloud with NON-identity object
+    matrices (the two-level traversal, the normal transform order object_cs * (CS^-1 * n), the shadow ray origin and the
+    cloud's projection chain all depend on them), random settings, random orbit angles, odd canvas heights — pixel
+    records, image, splat and picks bit for bit.  Widths are multiples of 4: for other widths the reference's splat
+    indexes its padded image<uint32_t> / z-buffer rows as if they were tightly packed (canvas.cpp:976, "todo: check
+    stride an alignment") and skews the points; that defect is not reproduced."""
+    from oracle.bindings import Ref, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    rng = np.random.default_rng(2024)
+    flag_sets = [j.DEFAULT_FLAGS, j.DEFAULT_FLAGS | j.SHADOW, j.EDGES | j.VERTEXCOLORS | j.SHADOW, j.DEFAULT_FLAGS | j.WIREFRAME,
+                 j.DEFAULT_FLAGS | j.ONE_BIT, j.SHADING | j.VERTEXCOLORS]
+    for trial in range(6):
+        w, h = 4 * int(rng.integers(15, 50)), int(rng.integers(40, 120))
+        va, ta = j.icosphere(int(rng.integers(3, 12)))
+        vb, tb = j.icosphere(int(rng.integers(2, 8)))
+        vb = (vb * 0.5).astype(np.float32)
+        ca, cb, cc = _rigid(rng, 0.2), _rigid(rng, 0.8), _rigid(rng, 0.3)
+        vca = j.vertex_colors(va) if trial % 2 == 0 else None
+        pos, nrm, clr = j.cloud(int(rng.integers(1000, 9000)) | 1)
+        pos = (pos * 1.1).astype(np.float32)
+        ref = Ref(w, h)
+        ref.add_mesh(va, ta, vcolors=vca, cs=ca)
+        ref.add_mesh(vb, tb, cs=cb)
+        ref.add_cloud(pos, nrm, clr, cs=cc)
+        ref.unzoom()
+        v = ref.view()
+        v.flags = flag_sets[trial % len(flag_sets)]
+        v = j.orbit_view(v, float(rng.uniform(0, 360)))
+        ref.set_view(v)
+        ref.render(7)
+        oa = oracle.mesh(va, ta, vcolors=vca, cs=ca, db_id=0x20000000)
+        ob = oracle.mesh(vb, tb, cs=cb, db_id=0x20000001)
+        px = oracle.cast([oa, ob], v)
+        want = ref.pixels(0)
+        hit = want["object_id"] != MISS
+        assert hit.sum() > 50, trial
+        assert (px["object_id"] == want["object_id"]).all(), trial
+        for f in ("u", "v", "depth", "barycentric_u", "barycentric_v", "mark", "r", "g", "b", "db_id"):
+            assert (px[f][hit] == want[f][hit]).all(), (trial, f)
+        rgba = oracle.shade(px, v, *oracle.make_matcap(0), oracle.fill_background(w, h))
+        after = px.copy()
+        oracle.splat([(pos, nrm, clr, cc, 0x40000000)], v, px, after, rgba)
+        assert (rgba == ref.image()).all(), trial
+        want1 = ref.pixels(1)
+        for f in ("object_id", "depth", "db_id"):
+            assert (after[f] == want1[f]).all(), (trial, f)
+        xy = np.stack([rng.integers(-3, w + 3, 300), rng.integers(-3, h + 3, 300)], 1).astype(np.int32)
+        got = oracle.pick(after, v, [oa, ob], [(pos, cc, 0x40000000)], xy)
+        assert got.tobytes() == ref.pick(xy).tobytes(), trial
+        ref.close(); oa.destroy(); ob.destroy()
