@@ -667,6 +667,56 @@ def test_cpp_shim_renders_like_the_abi(ctx):
     m.destroy(); cl.destroy()
 
 
+def test_random_transformed_scenes_match_oracle(ctx, oracle):
+    """Two meshes and a cloud with random rigid object matrices, random settings / poses / canvas sizes, whole frame in one
+    call: pixel records within the parity bars, splat winners exact, image within 1 LSB, picks exact on the GPU's own
+    records (the oracle side of this test is pinned on the reference by tests/test_oracle.py::
+    test_oracle_equals_reference_random_scenes)."""
+    from test_oracle import _rigid
+    rng = np.random.default_rng(77)
+    flag_sets = [j.DEFAULT_FLAGS, j.DEFAULT_FLAGS | j.SHADOW, j.EDGES | j.VERTEXCOLORS | j.SHADOW, j.DEFAULT_FLAGS | j.WIREFRAME,
+                 j.DEFAULT_FLAGS | j.ONE_BIT, j.SHADING | j.VERTEXCOLORS]
+    mc, cav = j.make_matcap(0)
+    for trial in range(6):
+        w, h = 4 * int(rng.integers(30, 90)), int(rng.integers(60, 200))
+        va, ta = j.icosphere(int(rng.integers(4, 20)))
+        vb, tb = j.icosphere(int(rng.integers(3, 10)))
+        vb = (vb * 0.5).astype(np.float32)
+        ca, cb, cc = _rigid(rng, 0.2), _rigid(rng, 0.8), _rigid(rng, 0.3)
+        vca = j.vertex_colors(va) if trial % 2 == 0 else None
+        pos, nrm, clr = j.cloud(int(rng.integers(2000, 20000)) | 1)
+        pos = (pos * 1.1).astype(np.float32)
+        ma = ctx.mesh_create(va, ta, vcolors=vca, cs=ca, db_id=0x20000000)
+        mb = ctx.mesh_create(vb, tb, cs=cb, db_id=0x20000001)
+        cl = ctx.cloud_create(pos, nrm, clr, cs=cc)
+        oa = oracle.mesh(va, ta, vcolors=vca, cs=ca, db_id=0x20000000)
+        ob = oracle.mesh(vb, tb, cs=cb, db_id=0x20000001)
+        # scene bbox of the transformed objects, like prepare_scene
+        def world(vs, cs):
+            m = np.asarray(cs, np.float32).reshape(4, 4).T
+            return vs @ m[:3, :3].T + m[:3, 3]
+        allp = np.concatenate([world(va, ca), world(vb, cb), world(pos, cc)]).astype(np.float32)
+        v = j.orbit_view(j.make_view(w, h, allp.min(0), allp.max(0), flag_sets[trial % len(flag_sets)]), float(rng.uniform(0, 360)))
+        want = oracle.cast([oa, ob], v)
+        want_rgba = oracle.shade(want, v, mc, cav, oracle.fill_background(w, h))
+        want2 = want.copy()
+        oracle.splat([(pos, nrm, clr, cc, 0x40000000)], v, want, want2, want_rgba)
+        px = np.zeros((h, w), j.PIXEL_DTYPE)
+        rgba = np.zeros((h, w), np.uint32)
+        ctx.render_frame([ma, mb], [cl], v, mc, cav, pixels_out=px, rgba_out=rgba)
+        mesh_px = (want2["db_id"] != 0x40000000) & (px["db_id"] != 0x40000000)
+        compare_pixels(np.where(mesh_px, px, want2), want2, tag=f"random scene {trial}")
+        pts = want2["db_id"] == 0x40000000
+        assert pts.sum() > 20 and (px["db_id"][pts] == 0x40000000).mean() > 0.999
+        both = pts & (px["db_id"] == 0x40000000)
+        assert (px["object_id"][both] == want2["object_id"][both]).mean() > 0.999
+        compare_rgba(rgba, want_rgba, tag=f"random scene {trial}")
+        xy = np.stack([rng.integers(-3, w + 3, 200), rng.integers(-3, h + 3, 200)], 1).astype(np.int32)
+        got = ctx.pick([ma, mb], [cl], v, xy)
+        assert got.tobytes() == oracle.pick(px, v, [oa, ob], [(pos, cc, 0x40000000)], xy).tobytes()
+        ma.destroy(); mb.destroy(); cl.destroy(); oa.destroy(); ob.destroy()
+
+
 def test_peer_frames_protocol_single_gpu(ctx):
     """The NVLink peer-memory frame exchange (csrc/peer.cu, dist.PeerFrames) with one rank: the shade kernel renders
     into the exchange buffer, arrival / release flags order the steps, and the exchanged frame equals a direct render."""
