@@ -91,3 +91,25 @@ def test_peer_exchange_layout():
         assert offs == [i * fb for i in range(2 * world)]
         fo = peer_flags_offset(world, fb)
         assert fo >= 2 * world * fb and fo % 256 == 0
+
+
+def test_reference_arm_under_torchrun():
+    """bench.py --impl reference launched like the driver launches it for N > 1: rank 0 alone runs the reference's CPU
+    renderer and prints ONE JSON line, the other rank exits 0 without work (config A here so that it takes seconds)."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    import pytest
+    root = Path(__file__).resolve().parents[1]
+    if not (root / "oracle" / "_ref" / "libj3d_ref.so").exists():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29546",
+           str(root / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--workload", "A"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(root))
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
