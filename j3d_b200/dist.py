@@ -6,7 +6,6 @@ ray cast itself.
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

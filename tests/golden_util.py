@@ -1,6 +1,5 @@
 """Loads the committed golden fixtures (tests/golden, produced from the unmodified reference by
 tests/golden/make_golden.py) and regenerates their procedural inputs."""
-import ctypes as C
 import json
 import sys
 from pathlib import Path
