@@ -127,7 +127,7 @@ J3DG_API int j3dg_ctx_create(int device, j3dg_ctx** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); j3dg_set_error(nullptr, "cudaGetDeviceProperties failed"); return J3DG_ENODEV; }
   if (prop.major != 10) {
-    char buf[256];
+    char buf[512];
     snprintf(buf, sizeof(buf), "device %d (%s) is sm_%d%d; libj3dg is built for sm_100a only and has no fallback", device, prop.name, prop.major, prop.minor);
     j3dg_set_error(nullptr, buf);
     return J3DG_ENODEV;
