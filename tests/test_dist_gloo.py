@@ -113,3 +113,94 @@ def test_reference_arm_under_torchrun():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+class _RecordingCtx:
+    """Stands in for j3d_b200.Context: records the stream-ordered flag operations PeerFrames enqueues (no GPU)."""
+
+    def __init__(self, rank, fail_open=False):
+        self.rank, self.fail_open, self.ops = rank, fail_open, []
+
+    def peer_alloc(self, nbytes):
+        self.nbytes = nbytes
+        return 0x10000000, b"H" * 64
+
+    def peer_open(self, handle):
+        assert handle == b"H" * 64
+        if self.fail_open:
+            raise RuntimeError("cudaIpcOpenMemHandle failed")
+        return 0x20000000
+
+    def peer_close(self, ptr):
+        self.ops.append(("close", ptr))
+
+    def peer_free(self, ptr):
+        self.ops.append(("free", ptr))
+
+    def stream_signal(self, ptr, value):
+        self.ops.append(("signal", ptr, value))
+
+    def stream_wait_geq(self, ptr, n, value):
+        self.ops.append(("wait", ptr, n, value))
+
+    def synchronize(self):
+        pass
+
+
+def _peer_worker(rank, world, port, out, fail):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        h, w = 8, 16
+        fb = h * w * 4
+        ctx = _RecordingCtx(rank, fail_open=fail and rank == 1)
+        if fail:
+            with pytest.raises(RuntimeError):  # every rank raises together: nobody is left waiting in a collective
+                jd.PeerFrames(ctx, h, w, torch.device("cpu"), dst=0)
+            out[rank] = [op[0] for op in ctx.ops]
+            return
+        pf = jd.PeerFrames(ctx, h, w, torch.device("cpu"), dst=0)
+        base = 0x10000000 if rank == 0 else 0x20000000
+        flags = base + jd.peer_flags_offset(world, fb)
+        targets = []
+        for step in range(4):
+            k = pf.begin()
+            targets.append(pf.target(k) - base)
+            pf.end(k)
+        assert targets == [jd.peer_slot_offset(k & 1, rank, world, fb) for k in range(4)]
+        want = []
+        for k in range(4):
+            if k >= 2:
+                want.append(("wait", flags + 4 * world, 1, k - 1))          # slot k & 1 released by rank 0 (frame k - 2 consumed)
+            want.append(("signal", flags + 4 * rank, k + 1))               # my frame k has arrived
+            if rank == 0:
+                want.append(("wait", flags, world, k + 1))                  # rank 0: every rank's frame k
+                want.append(("signal", flags + 4 * world, k + 1))          # ... consumed: release
+        assert ctx.ops == want, (ctx.ops, want)
+        shared = jd.PeerFrames(_RecordingCtx(rank), h, w, torch.device("cpu"), dst=0, shared_frame=True)
+        assert shared.target(0) - base == 0 and shared.target(1) - base == jd.peer_slot_offset(1, 0, world, fb)  # one frame per slot
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("fail", [False, True])
+def test_peer_frames_protocol_world2_gloo(fail):
+    """The hand-over protocol of the NVLink peer-memory frame exchange (dist.PeerFrames) with two ranks and a recording
+    context: slots, arrival / release flag values and their order; and a failing CUDA-IPC open on one rank makes BOTH
+    ranks raise (so the caller can fall back to an NCCL gather) after cleaning up."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, out, fail)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(100)
+        assert p.exitcode == 0
+    assert sorted(out.keys()) == [0, 1]
+    if fail:
+        assert out[0] == ["free"] and out[1] == []   # rank 0 releases its buffer, rank 1 never mapped it
