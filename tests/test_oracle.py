@@ -262,3 +262,31 @@ def test_oracle_equals_reference_random_scenes(oracle):
         got = oracle.pick(after, v, [oa, ob], [(pos, cc, 0x40000000)], xy)
         assert got.tobytes() == ref.pick(xy).tobytes(), trial
         ref.close(); oa.destroy(); ob.destroy()
+
+
+def test_host_camera_and_pose_equal_reference_random_sizes(oracle):
+    """camera.cpp / scene.cpp numbers (projection, its inverse, near plane, unzoom pose, pivot, diagonal) of the product's
+    host library and of the oracle against the reference running here, for random canvas sizes and random scene boxes."""
+    from oracle.bindings import Ref, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    rng = np.random.default_rng(9)
+    for _ in range(12):
+        w, h = int(rng.integers(16, 4000)), int(rng.integers(16, 2200))
+        verts, tris = j.icosphere(2)
+        verts = (verts * rng.uniform(0.1, 30.0, size=3).astype(np.float32) + rng.normal(size=3).astype(np.float32) * 5).astype(np.float32)
+        ref = Ref(w, h)
+        ref.add_mesh(verts, tris)
+        ref.unzoom()
+        want = ref.view()
+        mn, mx = j.compute_bb(verts)
+        for v in (j.make_view(w, h, mn, mx), oracle.make_view(w, h, mn, mx, j.DEFAULT_FLAGS)):
+            for f in ("projection", "projection_inv", "cs", "cs_inv", "pivot"):
+                assert np.array(list(getattr(v, f)), np.float32).tobytes() == np.array(list(getattr(want, f)), np.float32).tobytes(), (w, h, f)
+            assert v.near_plane == want.near_plane and v.diagonal == want.diagonal
+        # the orbit pose composes like canvas::do_mouse: rigid, about the pivot (checked against the oracle's own matrices)
+        a = j.orbit_view(want, 33.0)
+        cs = np.array(list(a.cs), np.float64).reshape(4, 4).T
+        ci = np.array(list(a.cs_inv), np.float64).reshape(4, 4).T
+        assert np.allclose(cs @ ci, np.eye(4), atol=1e-4 * max(1.0, float(np.abs(cs).max())))
+        ref.close()
