@@ -232,9 +232,13 @@ def test_oracle_equals_reference_random_scenes(oracle):
         vca = j.vertex_colors(va) if trial % 2 == 0 else None
         pos, nrm, clr = j.cloud(int(rng.integers(1000, 9000)) | 1)
         pos = (pos * 1.1).astype(np.float32)
+        uvb = texb = None
+        if trial % 2 == 1:  # the second mesh textured (canvas.cpp:803-820): random per-corner uv, random texels
+            uvb = rng.random((tb.shape[0], 6)).astype(np.float32)
+            texb = (rng.integers(0, 1 << 24, size=(19, 23), dtype=np.uint32) | np.uint32(0xFF000000)).astype(np.uint32)
         ref = Ref(w, h)
         ref.add_mesh(va, ta, vcolors=vca, cs=ca)
-        ref.add_mesh(vb, tb, cs=cb)
+        ref.add_mesh(vb, tb, uv=uvb, texture=texb, cs=cb)
         ref.add_cloud(pos, nrm, clr, cs=cc)
         ref.unzoom()
         v = ref.view()
@@ -243,7 +247,7 @@ def test_oracle_equals_reference_random_scenes(oracle):
         ref.set_view(v)
         ref.render(7)
         oa = oracle.mesh(va, ta, vcolors=vca, cs=ca, db_id=0x20000000)
-        ob = oracle.mesh(vb, tb, cs=cb, db_id=0x20000001)
+        ob = oracle.mesh(vb, tb, uv=uvb, texture=texb, cs=cb, db_id=0x20000001)
         px = oracle.cast([oa, ob], v)
         want = ref.pixels(0)
         hit = want["object_id"] != MISS
