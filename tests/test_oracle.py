@@ -294,3 +294,32 @@ def test_host_camera_and_pose_equal_reference_random_sizes(oracle):
         ci = np.array(list(a.cs_inv), np.float64).reshape(4, 4).T
         assert np.allclose(cs @ ci, np.eye(4), atol=1e-4 * max(1.0, float(np.abs(cs).max())))
         ref.close()
+
+
+def test_find_closest_random_rays_equal_reference(oracle):
+    """qbvh::find_closest_triangle on random rays with one-sided, two-sided and bounded intervals: the restatement returns
+    the reference's triangle, distance and barycentrics (the reference's own tree decides ties between equal |t| by visit
+    order, so a handful of exact ties may name the neighbouring triangle)."""
+    from oracle.bindings import Ref, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    verts, tris = j.icosphere(14)
+    rng = np.random.default_rng(12)
+    n = 6000
+    org = (rng.normal(size=(n, 3)) * 1.5).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    rays = np.concatenate([org, d, np.zeros((n, 1), np.float32), np.full((n, 1), FMAX, np.float32)], axis=1).astype(np.float32)
+    rays[: n // 3, 6] = -FMAX                       # both directions: smallest |t| wins
+    rays[n // 3: n // 2, 7] = 0.7                   # bounded far side
+    ref = Ref(16, 16)
+    want_h, want_i = ref.find_closest(verts, tris, rays)
+    om = oracle.mesh(verts, tris)
+    got_h, got_i = om.find_closest(rays)
+    assert (got_h[:, 3] == want_h[:, 3]).all() and want_h[:, 3].sum() > 500
+    hit = want_h[:, 3] == 1
+    same = hit & (got_i == want_i)
+    assert same.sum() >= hit.sum() - 3
+    assert got_h[same].tobytes() == want_h[same].tobytes()
+    ties = hit & ~same
+    assert np.allclose(np.abs(got_h[ties, 2]), np.abs(want_h[ties, 2]), rtol=1e-6)
+    ref.close(); om.destroy()
