@@ -104,7 +104,7 @@ def test_reference_arm_under_torchrun():
     root = Path(__file__).resolve().parents[1]
     if not (root / "oracle" / "_ref" / "libj3d_ref.so").exists():
         pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29546",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            str(root / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--workload", "A"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(root))
     assert res.returncode == 0, res.stderr[-2000:]

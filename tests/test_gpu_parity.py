@@ -725,7 +725,9 @@ def test_peer_frames_protocol_single_gpu(ctx):
     from j3d_b200.dist import PeerFrames
     created = False
     if not dist.is_initialized():
-        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29577", rank=0, world_size=1)
+        import socket
+        sock = socket.socket(); sock.bind(("127.0.0.1", 0)); port = sock.getsockname()[1]; sock.close()
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
         created = True
     try:
         w, h = 256, 160
