@@ -1,27 +1,36 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the j3d hot path on B200 (contract: see DESIGN.md §Measurement).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload B|A] [--f F]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload B|A|C|P]
 
-Workload (BASELINE.json configs[1]): synthetic 28 037 120-triangle noised geodesic icosphere
-("Lucy scale", f = 1184), 1920x1080, default settings (edges + matcap shading), default camera +
-unzoom pose.  A *step* is one frame of the hot path: ray cast (one primary ray per pixel, misses
-included) + fused shading, the camera orbiting 1 degree per step so successive frames touch
-different parts of the 1.6 GB BVH (inputs larger than the 126 MB L2; nothing is cached between
-steps).  metric = primary Mrays/s = W*H*steps / time.  The BVH build is timed separately
-(`bvh_build_ms`, CUDA events around the build kernels, median of 3 rebuilds from resident data).
+Workload B (default; BASELINE.json configs[1] + configs[4]): synthetic 28 037 120-triangle noised geodesic
+icosphere ("Lucy scale", f = 1184), 1920x1080, default settings (edges + matcap shading), default camera +
+unzoom pose.  A *step* is one frame of the hot path per rank: ray cast (one primary ray per pixel, misses
+included) + fused shading, the camera orbiting so successive frames touch different parts of the 1.6 GB BVH
+(inputs larger than the 126 MB L2; nothing is cached between steps).  metric = primary Mrays/s.
 
-N > 1 (torchrun, one rank per GPU): the 360-frame orbit sweep is sharded frame-wise (BASELINE
-configs[4]) — rank r renders frames r, r+N, ...; the BVH is built once on rank 0 and broadcast
-with NCCL; every step ends with an NCCL gather of the RGBA frame on rank 0.  Weak scaling: each
-rank renders `steps` frames.
+N > 1 (torchrun, one rank per GPU): the mesh is replicated, the BVH is built once on rank 0 and broadcast over
+NCCL, frames are sharded round-robin, every frame's RGBA ends up in rank 0's HBM (stores over NVLink peer memory).
+  * `value` (weak scaling, `steps` frames per rank): the N ranks render an N-times FINER sweep of the SAME arc
+    (frame i at i / N degrees, rank i mod N), so every N sees the same poses' cost — round 1 strode the orbit by N
+    degrees and measured view cost instead of communication.
+  * `sweep360` (strong scaling, BASELINE configs[4]): the fixed 360-frame orbit, frame k on rank k mod N, identical
+    poses for every N; device-resident and end-to-end figures.
+  * `e2e`: the same frames through the pipelined C-ABI calls with pinned HOST buffers, in the interactive-host mode
+    the device-side picking enables (RGBA crosses PCIe, pixel records stay in HBM, j3dg_pick on demand);
+    `e2e_full_records` is the mode that also downloads the 32-byte records every frame.
 
---impl reference: the reference's own std::thread CPU renderer (oracle/_ref, compiled from the
-unmodified j3d sources) on the same mesh / camera path, on this box's host cores.
+Workload A: the same on the 69 620-triangle mesh (configs[0]).  Workload C (configs[2]): ONE 3840x2160 frame with
+shadow rays of the 300 M-triangle mesh, screen bands sharded over the N ranks into ONE frame in rank 0's HBM.
+Workload P (configs[3]): 100 M-point depth splat at 1080p.
+
+--impl reference: the reference's own std::thread CPU renderer (oracle/_ref, compiled from the unmodified j3d
+sources) on the same workload, on this box's host cores, bounded to a few frames.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -34,9 +43,16 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
 
-W, H = 1920, 1080
-WORKLOADS = {"B": 1184, "A": 59}
+SHADOW_FLAG = 1 << 1
+WORKLOADS = {
+    "A": dict(f=59, w=1920, h=1080, shadow=False),
+    "B": dict(f=1184, w=1920, h=1080, shadow=False),
+    "C": dict(f=3873, w=3840, h=2160, shadow=True),
+    "P": dict(points=100_000_000, w=1920, h=1080),
+}
+SPLAT_BYTES_PER_POINT = 12  # the position read; normals / colours only for the <= W*H winners
 
 
 def peaks():
@@ -100,54 +116,114 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_mesh(f):
-    import j3d_b200 as j
-    return j.icosphere(f)
+def pin_to_gpu_numa(gpu_index: int):
+    """Run this process (and allocate its pinned host buffers) on the CPUs next to its GPU: with 8 ranks the
+    device->host streams otherwise land on whichever NUMA node the scheduler picked.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
-def frame_views(j, v0, first, count, stride):
-    return [j.orbit_view(v0, float((first + k * stride) % 360)) for k in range(count)]
+def workload_name(wl, f, nt, w, h):
+    if wl == "C":
+        return f"noised geodesic icosphere f={f} ({nt} triangles), {w}x{h}, 1 primary ray/pixel + 1 shadow ray/hit pixel + fused shading, one frame band-sharded over the ranks"
+    return f"noised geodesic icosphere f={f} ({nt} triangles), {w}x{h}, 1 primary ray/pixel + fused shading, orbit 1 deg/step"
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm: the unmodified reference renderer on the host cores
+# the reference on the host cores (cpu_baseline leg and --impl reference)
 # ----------------------------------------------------------------------------------------------
-def run_reference(args, f, rank, world):
+def reference_frames(j, verts, tris, w, h, views, warm=1, keep_last=False):
+    """add_object once, then the given frames (cast + canvas_to_image).  Returns a dict of timings (+ the last frame)."""
+    from oracle.bindings import Ref
+    ref = Ref(w, h)
+    ref.add_mesh(verts, tris)
+    build_s = ref.times()["build"]
+    ref.unzoom()
+    cast, shade = [], []
+    for k, v in enumerate(views):
+        ref.set_view(v)
+        ref.render(3)
+        t = ref.times()
+        if k >= warm:
+            cast.append(t["cast"]); shade.append(t["shade"])
+    out = {"cores": ref.cores(), "build_s": build_s, "cast_s": cast, "shade_s": shade}
+    if keep_last:
+        out["pixels"], out["image"] = ref.pixels(0), ref.image()
+    ref.close()
+    return out
+
+
+def shadow_rays_of(px):
+    return int((px["object_id"] != 0xFFFFFFFF).sum())
+
+
+def run_reference(args, wl, rank, world):
     if rank != 0:
         return 0
     import j3d_b200 as j
     from oracle.bindings import Ref, ref_available
-    kind = "reference"
     if not ref_available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libj3d_ref.so was not built (reference sources absent at build time)"}))
         return 0
-    verts, tris = make_mesh(f)
-    ref = Ref(W, H)
-    cores = ref.cores()
-    ref.add_mesh(verts, tris)
-    build_s = ref.times()["build"]
-    ref.unzoom()
-    v0 = ref.view()
-    views = frame_views(j, v0, 0, args.warmup + args.steps, 1)
-    cast, shade = [], []
-    for k, v in enumerate(views):
-        ref.set_view(v)
-        ref.render(3)  # cast + shade (no point clouds in this workload)
-        t = ref.times()
-        if k >= args.warmup:
-            cast.append(t["cast"]); shade.append(t["shade"])
-    step_s = [c + s for c, s in zip(cast, shade)]
+    cfg = WORKLOADS[wl]
+    w, h = cfg["w"], cfg["h"]
+    if wl == "P":
+        n = min(args.points or cfg["points"], 10_000_000)  # bounded sample: the reference's splat loop is serial
+        pos, nrm, clr = j.cloud(n)
+        ref = Ref(w, h)
+        ref.add_cloud(pos, nrm, clr)
+        ref.unzoom()
+        v0 = ref.view()
+        ts = []
+        for k in range(1 + min(args.steps, 5)):
+            ref.set_view(j.orbit_view(v0, float(k)))
+            ref.render(7)
+            if k >= 1:
+                ts.append(ref.times()["splat"])
+        value = n * len(ts) / sum(ts) / 1e6
+        sample = f"{n}-point sample of the vertex-coloured cloud, {len(ts)} frames {w}x{h} (render_pointclouds_on_image), 1 warm-up frame"
+        line = {"impl": "reference", "metric": "Mpoints/s splatted @1080p", "value": value, "unit": "Mpoints/s", "n_gpus": args.gpus, "steps": len(ts),
+                "warmup": 1, "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": f"{args.points or cfg['points']}-point vertex-coloured cloud (normals + colours), {w}x{h}, empty mesh scene, orbit 1 deg/frame", "l2": "inputs_larger_than_l2"},
+                "cpu_baseline": {"value": value, "unit": "Mpoints/s", "cores": ref.cores(), "kind": "reference", "sample": sample},
+                "e2e": {"value": value, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+    f = args.f or cfg["f"]
+    verts, tris = j.icosphere(f)
+    mn, mx = j.compute_bb(verts)
+    flags = j.DEFAULT_FLAGS | (j.SHADOW if cfg["shadow"] else 0)
+    v0 = j.make_view(w, h, mn, mx, flags)
+    steps = min(args.steps, 3 if wl == "C" else 12)  # bounded sample: a CPU frame of the 28M mesh takes ~0.1-1 s
+    step_deg = 25.0 if wl == "C" else 1.0
+    views = [j.orbit_view(v0, step_deg * k) for k in range(args.warmup + steps)]
+    r = reference_frames(j, verts, tris, w, h, views, warm=args.warmup, keep_last=cfg["shadow"])
+    step_s = [c + s for c, s in zip(r["cast_s"], r["shade_s"])]
     total = sum(step_s)
-    value = W * H * len(step_s) / total / 1e6
-    sample = f"{tris.shape[0]}-triangle mesh: add_object (normals+bbox+QBVH) once, then {args.steps} frames {W}x{H} (cast + canvas_to_image), {args.warmup} warm-up frames discarded"
+    rays = w * h + (shadow_rays_of(r["pixels"]) if cfg["shadow"] else 0)
+    value = rays * len(step_s) / total / 1e6
+    metric = "primary+shadow Mrays/s @4K (ray cast + shading per frame)" if wl == "C" else "primary Mrays/s @1080p (ray cast + shading per frame)"
+    sample = f"{tris.shape[0]}-triangle mesh: add_object (normals+bbox+QBVH) once, then {steps} frames {w}x{h} (cast + canvas_to_image), {args.warmup} warm-up frames discarded"
     line = {
-        "impl": "reference", "metric": "primary Mrays/s @1080p (ray cast + shading per frame)", "value": value, "unit": "Mrays/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(step_s),
+        "impl": "reference", "metric": metric, "value": value, "unit": "Mrays/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(step_s),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(f, tris.shape[0]), "l2": "inputs_larger_than_l2"},
-        "bvh_build_ms": 1e3 * build_s, "cast_ms": 1e3 * statistics.median(cast), "shade_ms": 1e3 * statistics.median(shade),
-        "cast_only_mrays_s": W * H / statistics.median(cast) / 1e6,
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
+        "config": {"workload": workload_name(wl, f, tris.shape[0], w, h), "l2": "inputs_larger_than_l2"},
+        "bvh_build_ms": 1e3 * r["build_s"], "cast_ms": 1e3 * statistics.median(r["cast_s"]), "shade_ms": 1e3 * statistics.median(r["shade_s"]),
+        "cast_only_mrays_s": rays / statistics.median(r["cast_s"]) / 1e6,
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": r["cores"], "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -155,120 +231,135 @@ def run_reference(args, f, rank, world):
     return 0
 
 
-def workload_name(f, nt):
-    return f"noised geodesic icosphere f={f} ({nt} triangles), {W}x{H}, 1 primary ray/pixel + fused shading, orbit 1 deg/step"
+# ----------------------------------------------------------------------------------------------
+# B200 arm — common set-up
+# ----------------------------------------------------------------------------------------------
+class Rig:
+    """torch stream + NCCL group + library context of one rank."""
+
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        import j3d_b200 as j
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+        self.torch, self.dist, self.j = torch, dist, j
+        self.args, self.rank, self.world, self.local_rank = args, rank, world, local_rank
+        self.numa_cpus = pin_to_gpu_numa(local_rank) if world > 1 else None
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.saved_stdout = None
+        if world > 1:
+            # NCCL prints its version banner on the C-level stdout at the first collective; the contract is ONE JSON
+            # line on stdout, so fd 1 points at stderr until the line is printed
+            sys.stdout.flush()
+            self.saved_stdout = os.dup(1)
+            os.dup2(2, 1)
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.ctx = j.Context(local_rank)
+        # every kernel of the library, the NCCL collectives and the timing events share ONE stream
+        self.stream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.stream)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        mc, cav = j.make_matcap(0)
+        self.ctx.set_matcap(mc, cav)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, *vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def sum_over_ranks(self, *vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+    def build_and_broadcast(self, verts, tris, nv, nt, rebuilds=3):
+        """BVH built once on rank 0; the other ranks receive nodes + triangle records over NCCL.
+        Returns (mesh, info, build_ms (rank 0), mesh_create wall ms (rank 0), broadcast ms)."""
+        torch, dist, ctx = self.torch, self.dist, self.ctx
+        t0 = time.perf_counter()
+        create_ms = bcast_ms = build_ms = None
+        mesh = None
+        if self.rank == 0:
+            mesh = ctx.mesh_create(verts, tris)
+            ctx.synchronize()
+            create_ms = 1e3 * (time.perf_counter() - t0)  # host arrays -> usable BVH (H2D + build)
+            b = [mesh.info().build_ms]
+            for _ in range(rebuilds):
+                mesh.rebuild()
+                b.append(mesh.info().build_ms)
+            build_ms = statistics.median(b[1:]) if rebuilds else b[0]
+        if self.world > 1:
+            from j3d_b200.dist import broadcast_bvh
+            meta = torch.zeros(4, dtype=torch.int64, device=self.dev)
+            if self.rank == 0:
+                meta[0] = mesh.info().nr_of_nodes
+            dist.broadcast(meta, 0)
+            if self.rank != 0:
+                mesh = ctx.mesh_create_empty(nv, nt, int(meta[0].item()))
+            self.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            broadcast_bvh(mesh, src=0, device=self.dev)
+            e1.record()
+            torch.cuda.synchronize()
+            bcast_ms = e0.elapsed_time(e1)
+        return mesh, mesh.info(), build_ms, create_ms, bcast_ms
+
+    def finish(self, line):
+        if self.rank == 0:
+            if self.saved_stdout is not None:
+                sys.stdout.flush()
+                os.dup2(self.saved_stdout, 1)
+                os.close(self.saved_stdout)
+            print(json.dumps(line), flush=True)
+        if self.world > 1:
+            self.dist.destroy_process_group()
 
 
-def cpu_baseline(j, f, verts, tris, v0, budget_frames=3):
-    """Bounded CPU sample of the same workload through the real reference (rank 0, N=1)."""
-    from oracle.bindings import Ref, ref_available
-    if not ref_available():
-        return {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
-    ref = Ref(W, H)
-    ref.add_mesh(verts, tris)
-    build_s = ref.times()["build"]
-    ref.unzoom()
-    t_all = []
-    for k, v in enumerate(frame_views(j, v0, 0, 1 + budget_frames, 1)):
-        ref.set_view(v)
-        ref.render(3)
-        t = ref.times()
-        if k >= 1:
-            t_all.append(t["cast"] + t["shade"])
-    cores = ref.cores()
-    ref.close()
-    return {"value": W * H * len(t_all) / sum(t_all) / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference",
-            "bvh_build_ms": 1e3 * build_s, "ms_per_frame": 1e3 * sum(t_all) / len(t_all),
-            "sample": f"same mesh ({tris.shape[0]} triangles): add_object once + {budget_frames} frames {W}x{H} after 1 warm-up frame"}
+def traffic_citation():
+    """DRAM bytes per cast launch from the committed ncu capture (a citation of profiles/, not a per-run measurement)."""
+    tp = ROOT / "profiles" / "traffic.json"
+    try:
+        d = json.loads(tp.read_text())
+        return d.get("cast_kernel_dram_bytes_per_launch"), d.get("source", "profiles/traffic.json")
+    except Exception:
+        return None, None
 
 
 # ----------------------------------------------------------------------------------------------
-# B200 arm
+# workloads A / B: orbit sweep, frames sharded over the ranks
 # ----------------------------------------------------------------------------------------------
-def run_b200(args, f, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
-    import j3d_b200 as j
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    saved_stdout = None
-    if world > 1:
-        # NCCL prints its version banner on the C-level stdout at the first collective; the contract is ONE JSON line
-        # on stdout, so fd 1 points at stderr until the line is printed
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        dist.init_process_group("nccl", device_id=dev)
-    ctx = j.Context(local_rank)
-    # every kernel of the library, the NCCL collectives and the timing events share ONE stream
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
-
-    verts, tris = make_mesh(f)  # mesh replicated: every rank holds the full geometry in HBM
-    nt = tris.shape[0]
+def run_orbit(args, wl, rank, world, local_rank):
+    rig = Rig(args, rank, world, local_rank)
+    torch, dist, j, ctx, dev, stream = rig.torch, rig.dist, rig.j, rig.ctx, rig.dev, rig.stream
+    cfg = WORKLOADS[wl]
+    W, H = cfg["w"], cfg["h"]
+    f = args.f or cfg["f"]
+    verts, tris = j.icosphere(f)  # mesh replicated: every rank can generate it; only rank 0 uploads and builds
+    nt, nv = tris.shape[0], verts.shape[0]
     mn, mx = j.compute_bb(verts)
     v0 = j.make_view(W, H, mn, mx)
-    mc, cav = j.make_matcap(0)
-    ctx.set_matcap(mc, cav)
+    mesh, info, build_ms, create_ms, bcast_ms = rig.build_and_broadcast(verts, tris, nv, nt)
 
-    # ---- BVH: built once on rank 0; other ranks receive nodes + triangle records over NCCL ----
-    t0 = time.perf_counter()
-    e2e_build_ms = None
-    bcast_ms = None
-    if world == 1 or rank == 0:
-        mesh = ctx.mesh_create(verts, tris)
-        ctx.synchronize()
-        e2e_build_ms = 1e3 * (time.perf_counter() - t0)  # host arrays -> usable BVH (H2D + build)
-    if world > 1:
-        from j3d_b200.dist import broadcast_bvh
-        meta = torch.zeros(4, dtype=torch.int64, device=dev)
-        if rank == 0:
-            meta[0] = mesh.info().nr_of_nodes
-        dist.broadcast(meta, 0)
-        if rank != 0:
-            mesh = ctx.mesh_create_empty(verts.shape[0], nt, int(meta[0].item()))
-        torch.cuda.synchronize()
-        dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        broadcast_bvh(mesh, src=0, device=dev)
-        e1.record()
-        torch.cuda.synchronize()
-        bcast_ms = e0.elapsed_time(e1)
-    info = mesh.info()
-    build_ms = None
-    if rank == 0:
-        b = []
-        for _ in range(3):
-            mesh.rebuild()
-            b.append(mesh.info().build_ms)
-        build_ms = statistics.median(b)
-        if world > 1:  # keep every rank on the same tree
-            dist.barrier()
-    elif world > 1:
-        dist.barrier()
-    if world > 1:
-        from j3d_b200.dist import broadcast_bvh
-        broadcast_bvh(mesh, src=0, device=dev)
-
-    # ---- device-resident frame buffers ----
     px = torch.empty((H, W, 32), dtype=torch.uint8, device=dev)
     rgba2 = [torch.empty((H, W), dtype=torch.int32, device=dev) for _ in range(2)]
-    rgba = rgba2[0]
     # N > 1: every rank's frame must end up on rank 0 each step.
     #   --exchange peer (default): the shade kernel of every rank stores its RGBA straight into rank 0's HBM over
     #       NVLink peer memory (CUDA-IPC mapping, stream-ordered arrival / release flags; j3d_b200/dist.py::PeerFrames)
-    #       — no collective kernel has to find room beside the cooperative cast kernel, which owns every SM.
-    #   --exchange nccl: dist.gather on a second stream, double-buffered RGBA.
-    comm = torch.cuda.Stream(device=dev) if (world > 1 and args.exchange == "nccl") else None
-    gather_lists = [[torch.empty_like(rgba) for _ in range(world)] for _ in range(2)] if (comm is not None and rank == 0) else [None, None]
-    ev_render = [torch.cuda.Event() for _ in range(2)]
-    ev_gather = [torch.cuda.Event() for _ in range(2)]
+    #   --exchange nccl: dist.gather on a second stream, double-buffered RGBA (kept for comparison).
     pf = None
+    comm = None
     if world > 1 and args.exchange == "peer":
         from j3d_b200.dist import PeerFrames
         try:
@@ -277,18 +368,21 @@ def run_b200(args, f, rank, world, local_rank):
             if rank == 0:
                 print(f"bench.py: {e}; using --exchange nccl", file=sys.stderr)
             args.exchange = "nccl"
-            comm = torch.cuda.Stream(device=dev)
-            gather_lists = [[torch.empty_like(rgba) for _ in range(world)] for _ in range(2)] if rank == 0 else [None, None]
-
-    total = args.warmup + args.steps
-    views = frame_views(j, v0, rank, total, world)  # rank r renders frames r, r+N, r+2N ...
-    state = {"k": 0}
+    if world > 1 and args.exchange == "nccl":
+        comm = torch.cuda.Stream(device=dev)
+    gather_lists = [[torch.empty_like(rgba2[0]) for _ in range(world)] for _ in range(2)] if (comm is not None and rank == 0) else [None, None]
+    ev_render = [torch.cuda.Event() for _ in range(2)]
+    ev_gather = [torch.cuda.Event() for _ in range(2)]
+    state = {"k": 0, "checksum": torch.zeros((), dtype=torch.int64, device=dev)}
 
     def step(v):
         if pf is not None:
             k = pf.begin()
             ctx.render_frame([mesh], [], v, pixels_out=px, rgba_out=pf.target(k))
-            pf.end(k)
+            pf.arrive(k)
+            # rank 0 consumes between arrival and release (PeerFrames protocol): nothing in the timed loop — the frames
+            # are what the sweep produces; `verify_exchange` below consumes every frame of a short run instead
+            pf.release(k)
             return
         k = state["k"]
         state["k"] = k + 1
@@ -307,125 +401,130 @@ def run_b200(args, f, rank, world, local_rank):
         if comm is not None:
             stream.wait_stream(comm)
 
-    for v in views[: args.warmup]:
+    def timed(views, warm):
+        """Device-resident loop: `warm` untimed frames, then the rest between barriers; ms = max over ranks."""
+        for v in views[:warm]:
+            step(v)
+        drain()
+        rig.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for v in views[warm:]:
+            step(v)
+        drain()
+        e1.record()
+        rig.barrier()
+        return rig.max_over_ranks(e0.elapsed_time(e1))[0]
+
+    # ---- (1) weak arm: `steps` frames per rank, the N ranks together render an N-times finer sweep of the same arc ----
+    total = args.warmup + args.steps
+    arc = [j.orbit_view(v0, ((k * world + rank) / world) % 360.0) for k in range(total)]
+    for v in arc[: args.warmup]:  # first-touch allocations outside everything
         step(v)
     drain()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    rig.barrier()
     ctx.timings(reset=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for v in views[args.warmup:]:
-        step(v)
-    drain()
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    exchange_ok = True
-    if pf is not None:
-        # the exchanged frame of the last step equals what this rank rendered (rank 0 checks its own slot and the
-        # arrival of everybody else's), and no flag wait ran into its time-out
-        exchange_ok = not ctx.stream_wait_timed_out()
-        if rank == 0:
-            last = pf.frames(pf.k - 1)
-            ctx.render_frame([mesh], [], views[-1], pixels_out=px, rgba_out=rgba2[0])
-            torch.cuda.synchronize()
-            exchange_ok = exchange_ok and bool(torch.equal(last[0], rgba2[0])) and all(int(last[r].abs().sum().item()) != 0 for r in range(world))
-    if pf is not None:
-        pf.close()
+    ms = timed(arc, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     tm = ctx.timings(reset=True)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     rays_total = W * H * args.steps * world
     value = rays_total / (ms * 1e-3) / 1e6
+    cast_ms = tm.cast_ms / max(1, tm.cast_count)
+    shade_ms = tm.shade_ms / max(1, tm.shade_count)
+    launches = int(tm.kernel_launches * args.steps / max(1, tm.cast_count))  # launches of the timed frames of this rank
 
-    # ---- end to end through the C ABI with HOST buffers (pinned), D2H inside the timed region ----
-    # The sweep call a user makes: j3dg_frame_submit / j3dg_frame_wait (pipelined j3dg_render_frame): the
-    # device->host copy of frame k (pixel records + RGBA, 74.6 MB) overlaps the kernels of frame k+1.  Every
-    # frame's host buffers are complete (frame_wait returned) inside the timed region.
+    # ---- exchange check: every frame of a short run, consumed between arrival and release, equals a local render ----
+    exchange_ok = None
+    if pf is not None:
+        nchk = 6
+        chk = [j.orbit_view(v0, 3.0 * (k * world + r)) for k in range(nchk) for r in range(world)]
+        snaps = []
+        for k in range(nchk):
+            kk = pf.begin()
+            ctx.render_frame([mesh], [], chk[k * world + rank], pixels_out=px, rgba_out=pf.target(kk))
+            pf.arrive(kk)
+            if rank == 0:
+                snaps.append(pf.frames(kk).clone())  # the consumer, on the same stream
+            pf.release(kk)
+        torch.cuda.synchronize()
+        exchange_ok = ctx.status() == 0
+        if rank == 0:
+            for k in range(nchk):
+                for r in range(world):
+                    ctx.render_frame([mesh], [], chk[k * world + r], pixels_out=px, rgba_out=rgba2[0])
+                    torch.cuda.synchronize()
+                    exchange_ok = exchange_ok and bool(torch.equal(snaps[k][r], rgba2[0]))
+        rig.barrier()
+
+    # ---- (2) strong arm (BASELINE configs[4]): the fixed 360-frame orbit, frame k on rank k mod N ----
+    n360 = 360
+    per = (n360 + world - 1) // world
+    mine360 = [j.orbit_view(v0, float((k * world + rank) % 360)) for k in range(per)]
+    sweep_ms = timed(mine360[:3] + mine360, 3)
+    sweep360 = {"frames": n360, "scaling": "strong", "device": {"ms": sweep_ms, "frames_per_s": 1e3 * n360 / sweep_ms, "mrays_s": n360 * W * H / sweep_ms / 1e3}}
+
+    # ---- (3) end to end through the C ABI with HOST buffers (pinned), D2H inside the timed region ----
+    # The sweep call a user makes: j3dg_frame_submit / j3dg_frame_wait (pipelined j3dg_render_frame): the device->host
+    # copy of frame k overlaps the kernels of frame k+1.  Every frame's host buffers are complete (frame_wait
+    # returned) inside the timed region.  Each rank owns its frames' host buffers (frames sharded over the ranks).
     hpx = [torch.empty((H, W, 32), dtype=torch.uint8).pin_memory() for _ in range(2)]
     hrgba = [torch.empty((H, W), dtype=torch.int32).pin_memory() for _ in range(2)]
+    centre = np.array([[W // 2, H // 2]], np.int32)
 
-    def sweep(vs):
+    def sweep(vs, records):
         for k, v in enumerate(vs):
-            ctx.frame_submit([mesh], [], v, pixels_out=hpx[k & 1], rgba_out=hrgba[k & 1])
+            ctx.frame_submit([mesh], [], v, pixels_out=hpx[k & 1] if records else None, rgba_out=hrgba[k & 1])
             if k >= 1:
                 ctx.frame_wait()
         if vs:
             ctx.frame_wait()
+            if not records:  # the records stayed in HBM: the host asks for the one under the cursor
+                ctx.pick([mesh], [], vs[-1], centre)
 
-    def timed_sweep():
-        sweep(views[: args.warmup])
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+    def timed_sweep(vs, warm, records):
+        sweep(vs[:warm], records)
+        rig.barrier()
         ctx.readback_bytes(reset=True)
         t0 = time.perf_counter()
-        sweep(views[args.warmup:])
+        sweep(vs[warm:], records)
         dt = time.perf_counter() - t0
-        return dt, ctx.readback_bytes(reset=True) / args.steps
+        nbytes = ctx.readback_bytes(reset=True) / max(1, len(vs) - warm)
+        return rig.max_over_ranks(dt)[0], nbytes
 
-    # (1) every byte of both host buffers copied every frame
-    e2e_full_s, full_bytes = timed_sweep()
-    # (2) dirty-rectangle readback (j3dg_ctx_set_dirty_rect): the host buffers are persistent per-canvas buffers, so only
-    #     the bounding rectangle of the pixels that can differ from what the buffer already holds crosses PCIe; the host
-    #     buffers are byte-identical to (1) (tests/test_gpu_parity.py::test_dirty_rect_readback_is_byte_identical and
-    #     the check below)
-    ref_px, ref_rgba = hpx[(args.steps - 1) & 1].clone(), hrgba[(args.steps - 1) & 1].clone()
     ctx.set_dirty_rect(True)
-    e2e_s, d2h_avg = timed_sweep()
+    e2e_s, e2e_bytes = timed_sweep(arc, args.warmup, records=False)          # headline e2e: RGBA only + pick
+    s360_s, s360_bytes = timed_sweep(mine360[:3] + mine360, 3, records=False)
+    rec_s, rec_bytes = timed_sweep(arc, args.warmup, records=True)            # pixel records + RGBA, dirty rectangle
+    dirty_px, dirty_rgba = hpx[(total - 1) & 1].clone(), hrgba[(total - 1) & 1].clone()
     ctx.set_dirty_rect(False)
-    dirty_identical = bool(torch.equal(ref_px, hpx[(args.steps - 1) & 1]) and torch.equal(ref_rgba, hrgba[(args.steps - 1) & 1]))
+    full_s, full_bytes = timed_sweep(arc, args.warmup, records=True)          # every byte of both buffers, every frame
+    dirty_identical = bool(torch.equal(dirty_px, hpx[(total - 1) & 1]) and torch.equal(dirty_rgba, hrgba[(total - 1) & 1]))
+    sweep360["e2e"] = {"ms": 1e3 * s360_s, "frames_per_s": n360 / s360_s, "mrays_s": n360 * W * H / s360_s / 1e6, "d2h_bytes_per_frame": int(s360_bytes),
+                       "api": "j3dg_frame_submit(pixels_out=NULL)/j3dg_frame_wait, RGBA to pinned host memory on the rendering rank"}
     # the same frames one by one through the synchronous j3dg_render_frame (kernels, then copy)
-    for v in views[:3]:  # untimed: the first call allocates the context's own canvas
+    for v in arc[:3]:  # untimed: the first call allocates the context's own canvas
         ctx.render_frame([mesh], [], v, pixels_out=hpx[0], rgba_out=hrgba[0])
+    nsync = min(args.steps, 20)
     t0 = time.perf_counter()
-    for v in views[args.warmup: args.warmup + min(args.steps, 20)]:
+    for v in arc[args.warmup: args.warmup + nsync]:
         ctx.render_frame([mesh], [], v, pixels_out=hpx[0], rgba_out=hrgba[0])
-    e2e_sync_ms = 1e3 * (time.perf_counter() - t0) / min(args.steps, 20)
-    if world > 1:
-        t = torch.tensor([e2e_s, e2e_full_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s, e2e_full_s = float(t[0].item()), float(t[1].item())
-    e2e_value = rays_total / e2e_s / 1e6
-    import ctypes
+    sync_ms = 1e3 * (time.perf_counter() - t0) / nsync
+    t0 = time.perf_counter()
+    for v in arc[args.warmup: args.warmup + nsync]:
+        ctx.render_frame([mesh], [], v, pixels_out=None, rgba_out=hrgba[0])
+    sync_rgba_ms = 1e3 * (time.perf_counter() - t0) / nsync
     h2d_bytes = ctypes.sizeof(j.View) + 256  # the view (kernel parameters) + the per-mesh table
-    d2h_bytes = int(d2h_avg)
 
-    # ---- interactive-host mode: RGBA-only readback, the pixel records stay in HBM and the host
-    # asks for the record under the cursor with j3dg_pick (64 bytes per query) ----
-    e2e_rgba = None
     extras = None
     if world == 1:
-        def sweep_rgba(vs):
-            for k, v in enumerate(vs):
-                ctx.frame_submit([mesh], [], v, pixels_out=None, rgba_out=hrgba[k & 1])
-                if k >= 1:
-                    ctx.frame_wait()
-            if vs:
-                ctx.frame_wait()
-                ctx.pick([mesh], [], vs[-1], np.array([[W // 2, H // 2]], np.int32))
-        sweep_rgba(views[: args.warmup])
-        t0 = time.perf_counter()
-        sweep_rgba(views[args.warmup:])
-        dt = time.perf_counter() - t0
-        e2e_rgba = {"value": rays_total / dt / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * dt / args.steps, "d2h_bytes_per_step": W * H * 4,
-                    "api": "j3dg_frame_submit(pixels_out=NULL)/j3dg_frame_wait + j3dg_pick: pixel records stay resident, RGBA only crosses PCIe"}
         # ---- the other query clients of the same BVH (SURVEY §8f ranks 2-3), timed through the C ABI ----
         qxy = np.stack(np.meshgrid(np.arange(0, W, 8), np.arange(0, H, 8)), -1).reshape(-1, 2).astype(np.int32)
-        ctx.pick([mesh], [], views[-1], qxy)
+        ctx.pick([mesh], [], arc[-1], qxy)
         t0 = time.perf_counter()
-        picks = ctx.pick([mesh], [], views[-1], qxy)
+        picks = ctx.pick([mesh], [], arc[-1], qxy)
         pick_ms = 1e3 * (time.perf_counter() - t0)
         vox_dim = 512
         grid = torch.empty((vox_dim ** 3 + 64,), dtype=torch.uint8, device=dev)
@@ -441,56 +540,79 @@ def run_b200(args, f, rank, world, local_rank):
                                "mrays_s": 3 * vox_dim * vox_dim / vox_ms / 1e3,
                                "note": "j3dg_mesh_voxelize into a device grid: memset + 3 all-hits ray grids (vox.cpp:300-379)"}}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
     # ---- roofline of the dominant kernel (cast): algorithmic bytes / live event time ----
-    nodes_per_ray, tris_per_ray = ctx.cast_stats([mesh], views[args.warmup])
+    nodes_per_ray, tris_per_ray = ctx.cast_stats([mesh], arc[args.warmup])
     bytes_per_ray = nodes_per_ray * info.node_bytes + tris_per_ray * info.triangle_bytes + 32
-    cast_ms = tm.cast_ms / max(1, tm.cast_count)
     peak, peak_src = peaks()
     achieved = (W * H * bytes_per_ray) / (cast_ms * 1e-3) / 1e9
-    traffic = None
-    tp = ROOT / "profiles" / "traffic.json"
-    if tp.exists():
-        try:
-            traffic = json.loads(tp.read_text()).get("cast_kernel_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "cast stage = cast_kernel (one cooperative launch: lane warps + 8-lane hard-ray groups) + resolve_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
-                "tris_per_ray": tris_per_ray, "kernel_ms": cast_ms, "kernel_mrays_s": W * H / cast_ms / 1e3}
-    cpu = cpu_baseline(j, f, verts, tris, v0) if (world == 1 and not args.no_cpu_baseline) else None
-    # the other stages against the same HBM roofline (algorithmic bytes per unit)
-    nv = verts.shape[0]
+    traffic, traffic_src = traffic_citation() if world == 1 else (None, None)
+    roofline = {"bound": "hbm", "kernel": "cast stage (cast_kernel: one cooperative launch per ray type)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_ray": bytes_per_ray,
+                "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray, "kernel_ms": cast_ms, "kernel_mrays_s": W * H / cast_ms / 1e3,
+                "note": "achieved = ALGORITHMIC bytes (SURVEY §8d) over the live CUDA-event stage time; L1/L2 absorb re-use, so this is not a DRAM-bandwidth share (traffic = DRAM bytes per launch from the cited ncu capture)"}
+
+    if rank != 0:
+        if pf is not None:
+            pf.close()
+        rig.finish(None)
+        return 0
+
+    # ---- CPU baseline (the real reference on this box's host cores) + parity of the same frame, N = 1 only ----
+    cpu = parity = None
     bvh_bytes = int(info.nr_of_nodes) * info.node_bytes + nt * info.triangle_bytes
-    shade_ms = tm.shade_ms / max(1, tm.shade_count)
     stages = {"build": {"ms": build_ms, "algorithmic_bytes": 12 * nt + 12 * nv + bvh_bytes, "mtris_s": nt / build_ms / 1e3 if build_ms else None,
                         "roofline_frac": (12 * nt + 12 * nv + bvh_bytes) / (build_ms * 1e-3) / 1e9 / peak if build_ms else None},
               "shade": {"ms": shade_ms, "algorithmic_bytes": 40 * W * H, "roofline_frac": 40 * W * H / (shade_ms * 1e-3) / 1e9 / peak if shade_ms else None}}
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle.bindings import ref_available
+        if ref_available():
+            from parity import parity_stats
+            nref = 3
+            r = reference_frames(j, verts, tris, W, H, arc[args.warmup - 1: args.warmup + nref], warm=1, keep_last=True)
+            t_all = [c + s for c, s in zip(r["cast_s"], r["shade_s"])]
+            cpu = {"value": W * H * len(t_all) / sum(t_all) / 1e6, "unit": "Mrays/s", "cores": r["cores"], "kind": "reference",
+                   "bvh_build_ms": 1e3 * r["build_s"], "ms_per_frame": 1e3 * sum(t_all) / len(t_all),
+                   "sample": f"same mesh ({nt} triangles): add_object once + {nref} frames {W}x{H} of the timed sweep after 1 warm-up frame"}
+            # parity on the same run: the reference's last frame against the GPU's frame of the same view
+            got_px = np.zeros((H, W), j.PIXEL_DTYPE)
+            got_rgba = np.zeros((H, W), np.uint32)
+            ctx.render_frame([mesh], [], arc[args.warmup + nref - 1], pixels_out=got_px, rgba_out=got_rgba)
+            parity = parity_stats(got_px, r["pixels"], got_rgba, r["image"])
+            parity["frame"] = f"step {nref - 1} of the timed sweep, reference pixel buffer + image of the cpu_baseline leg"
+            parity["pass"] = bool(parity["id_agree_frac"] >= 0.9999 and parity["unclassified"] == 0 and parity.get("max_rel_depth", 0.0) <= 1e-5
+                                  and parity.get("max_abs_bary", 0.0) <= 1e-5 and parity["rgba_within_1lsb_frac"] >= 0.999)
+        else:
+            cpu = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+        # ---- splat stage (BASELINE configs[3]) on the same box ----
+        if not args.no_splat:
+            stages["splat"] = splat_stage(rig, args.points or WORKLOADS["P"]["points"], peak, with_cpu=True)
+    del verts, tris
 
     line = {
         "metric": "primary Mrays/s @1080p (ray cast + shading per frame)", "value": value, "unit": "Mrays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(f, nt), "l2": "inputs_larger_than_l2",
+        "config": {"workload": workload_name(wl, f, nt, W, H), "l2": "inputs_larger_than_l2"},  # the same two keys as the reference arm's line
+        "layout": {"poses": f"frame i at i/{world} degrees on rank i mod {world}: every N renders the same arc, {world}x finer" if world > 1 else "frame i at i degrees",
                    "sharding": "replicas only" if world == 1 else f"orbit frames round-robin over {world} ranks, BVH NCCL-broadcast from rank 0, " + ("every rank's shade kernel stores its RGBA into rank 0's HBM over NVLink peer memory (CUDA IPC), stream-ordered arrival/release flags" if args.exchange == "peer" else "RGBA NCCL-gathered on rank 0 every step (second stream, overlapping the kernels of frame k+1)"),
-                   "bvh_bytes": int(info.nr_of_nodes) * info.node_bytes + nt * info.triangle_bytes},
+                   "bvh_bytes": bvh_bytes},
         "bvh_build_ms": build_ms, "bvh_nodes": int(info.nr_of_nodes), "frames_per_s": 1e3 * args.steps * world / ms,
-        "cast_ms": cast_ms, "shade_ms": tm.shade_ms / max(1, tm.shade_count),
-        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+        "cast_ms": cast_ms, "shade_ms": shade_ms,
+        "e2e": {"value": rays_total / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(e2e_bytes),
                 "ms_per_step": 1e3 * e2e_s / args.steps,
-                "api": "j3dg_frame_submit/j3dg_frame_wait (pipelined, pinned persistent host buffers, dirty-rectangle readback: pixel records + RGBA byte-identical to a full copy)",
-                "host_buffers_identical_to_full_copy": dirty_identical,
-                "full_copy": {"value": rays_total / e2e_full_s / 1e6, "ms_per_step": 1e3 * e2e_full_s / args.steps, "d2h_bytes_per_step": int(full_bytes)},
-                "sync_render_frame_ms_per_step": e2e_sync_ms, "mesh_create_ms": e2e_build_ms},
-        "gpu_launches": int(tm.kernel_launches),
+                "api": "j3dg_frame_submit(pixels_out=NULL)/j3dg_frame_wait (pipelined, pinned persistent host buffer, dirty-rectangle readback) + j3dg_pick: RGBA crosses PCIe every frame, the pixel records stay in HBM and are queried on demand",
+                "sync_render_frame_rgba_ms_per_step": sync_rgba_ms, "mesh_create_ms": create_ms},
+        "e2e_full_records": {"value": rays_total / rec_s / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * rec_s / args.steps, "d2h_bytes_per_step": int(rec_bytes),
+                             "api": "j3dg_frame_submit/j3dg_frame_wait with pixels_out AND rgba_out (36 B/pixel to the host, dirty rectangle)",
+                             "host_buffers_identical_to_full_copy": dirty_identical,
+                             "full_copy": {"value": rays_total / full_s / 1e6, "ms_per_step": 1e3 * full_s / args.steps, "d2h_bytes_per_step": int(full_bytes)},
+                             "sync_render_frame_ms_per_step": sync_ms},
+        "sweep360": sweep360,
+        "gpu_launches": launches,
         "clocks": clocks, "roofline": roofline, "stages": stages,
     }
-    if e2e_rgba is not None:
-        line["e2e_rgba_only"] = e2e_rgba
+    if rig.numa_cpus is not None:
+        line["layout"]["host_affinity"] = f"each rank pinned to the {rig.numa_cpus} CPUs next to its GPU (NVML affinity) before allocating pinned buffers"
     if extras is not None:
         line["queries"] = extras
     if bcast_ms is not None:
@@ -498,41 +620,220 @@ def run_b200(args, f, rank, world, local_rank):
         line["exchange"] = {"kind": args.exchange, "verified": exchange_ok, "bytes_per_step_into_rank0": (world - 1) * W * H * 4}
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    if saved_stdout is not None:
-        sys.stdout.flush()
-        os.dup2(saved_stdout, 1)
-        os.close(saved_stdout)
-    print(json.dumps(line), flush=True)
+    if parity is not None:
+        line["parity"] = parity
+    if pf is not None:
+        pf.close()
+    rig.finish(line)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# splat (configs[3]) — stage of the default line at N = 1, and workload P
+# ----------------------------------------------------------------------------------------------
+def splat_stage(rig, n_points, peak, with_cpu, reps=5):
+    torch, j, ctx, dev = rig.torch, rig.j, rig.ctx, rig.dev
+    W, H = WORKLOADS["P"]["w"], WORKLOADS["P"]["h"]
+    pos, nrm, clr = j.cloud(n_points)
+    mn, mx = j.compute_bb(pos)
+    v0 = j.make_view(W, H, mn, mx)
+    t0 = time.perf_counter()
+    cl = ctx.cloud_create(pos, nrm, clr)
+    ctx.synchronize()
+    upload_ms = 1e3 * (time.perf_counter() - t0)
+    px = torch.empty((H, W, 32), dtype=torch.uint8, device=dev)
+    rgba = torch.empty((H, W), dtype=torch.int32, device=dev)
+    for k in range(2):
+        ctx.render_frame([], [cl], j.orbit_view(v0, float(k)), pixels_out=px, rgba_out=rgba)
+    ctx.timings(reset=True)
+    for k in range(reps):
+        ctx.render_frame([], [cl], j.orbit_view(v0, float(2 + k)), pixels_out=px, rgba_out=rgba)
+    tm = ctx.timings(reset=True)
+    ms = tm.splat_ms / max(1, tm.splat_count)
+    covered = int((px.view(torch.int32)[..., 7] != 0).sum().item())
+    out = {"points": n_points, "ms": ms, "mpoints_s": n_points / ms / 1e3, "algorithmic_bytes": SPLAT_BYTES_PER_POINT * n_points + 44 * W * H,
+           "roofline_frac": (SPLAT_BYTES_PER_POINT * n_points + 44 * W * H) / (ms * 1e-3) / 1e9 / peak, "pixels_covered": covered, "upload_ms": upload_ms,
+           "workload": f"{n_points}-point vertex-coloured cloud (normals + colours), {W}x{H}, empty mesh scene, orbit 1 deg/frame"}
+    cl.destroy()
+    if with_cpu:
+        from oracle.bindings import Ref, ref_available
+        if ref_available():
+            ns = min(n_points, 10_000_000)
+            ref = Ref(W, H)
+            ref.add_cloud(pos[:ns].copy(), nrm[:ns].copy(), clr[:ns].copy())
+            ref.set_view(v0)
+            ts = []
+            for k in range(3):
+                ref.set_view(j.orbit_view(v0, float(k)))
+                ref.render(7)
+                if k:
+                    ts.append(ref.times()["splat"])
+            out["cpu_reference"] = {"points": ns, "ms": 1e3 * sum(ts) / len(ts), "mpoints_s": ns * len(ts) / sum(ts) / 1e6, "cores": ref.cores(),
+                                    "sample": f"first {ns} points of the same cloud, render_pointclouds_on_image, 2 frames after 1 warm-up"}
+            ref.close()
+    return out
+
+
+def run_splat(args, rank, world, local_rank):
+    """Workload P: replicas only (every rank splats the same cloud for its own frames)."""
+    rig = Rig(args, rank, world, local_rank)
+    peak, peak_src = peaks()
+    n = args.points or WORKLOADS["P"]["points"]
+    st = splat_stage(rig, n, peak, with_cpu=(rank == 0 and not args.no_cpu_baseline), reps=max(args.steps, 3))
+    ms = rig.max_over_ranks(st["ms"])[0]
+    W, H = WORKLOADS["P"]["w"], WORKLOADS["P"]["h"]
+    line = None
+    if rank == 0:
+        line = {"metric": "Mpoints/s splatted @1080p", "value": world * n / ms / 1e3, "unit": "Mpoints/s", "n_gpus": world, "steps": max(args.steps, 3), "warmup": 2,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": st["workload"], "l2": "inputs_larger_than_l2"}, "layout": {"sharding": "replicas only"},
+                "roofline": {"bound": "hbm", "kernel": "splat stage (seed + project/atomicMax + resolve)", "achieved": st["algorithmic_bytes"] / (ms * 1e-3) / 1e9, "peak": peak,
+                             "unit": "GB/s", "frac": st["algorithmic_bytes"] / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src},
+                "stages": {"splat": st}, "gpu_launches": 5 * max(args.steps, 3),
+                "e2e": {"value": None, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "stage bench: the frame's e2e is workload B's"}}
+        if "cpu_reference" in st:
+            c = st["cpu_reference"]
+            line["cpu_baseline"] = {"value": c["mpoints_s"], "unit": "Mpoints/s", "cores": c["cores"], "kind": "reference", "sample": c["sample"]}
+    rig.finish(line)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# workload C (configs[2]): ONE huge frame, screen bands sharded over the ranks into ONE frame in rank 0's HBM
+# ----------------------------------------------------------------------------------------------
+def run_sharded_frame(args, rank, world, local_rank):
+    rig = Rig(args, rank, world, local_rank)
+    torch, dist, j, ctx, dev = rig.torch, rig.dist, rig.j, rig.ctx, rig.dev
+    cfg = WORKLOADS["C"]
+    W, H = cfg["w"], cfg["h"]
+    f = args.f or cfg["f"]
+    nt, nv = 20 * f * f, 10 * f * f + 2
+    bb = torch.zeros(6, dtype=torch.float32, device=dev)
+    verts = tris = None
+    gen_s = None
+    if rank == 0:  # only rank 0 needs the indexed mesh: the others receive the finished BVH (triangle records hold the vertices)
+        t0 = time.perf_counter()
+        verts, tris = j.icosphere(f)
+        gen_s = time.perf_counter() - t0
+        mn, mx = j.compute_bb(verts)
+        bb = torch.tensor(np.concatenate([mn, mx]), dtype=torch.float32, device=dev)
+    mesh, info, build_ms, create_ms, bcast_ms = rig.build_and_broadcast(verts, tris, nv, nt, rebuilds=1)
+    del verts, tris
     if world > 1:
-        dist.destroy_process_group()
+        dist.broadcast(bb, 0)
+    bbh = bb.cpu().numpy()
+    v0 = j.make_view(W, H, bbh[:3], bbh[3:], j.DEFAULT_FLAGS | j.SHADOW)
+    total = args.warmup + args.steps
+    views = [j.orbit_view(v0, 25.0 * k) for k in range(total)]
+    px = torch.zeros((H, W, 32), dtype=torch.uint8, device=dev)
+    rgba = torch.zeros((H, W), dtype=torch.int32, device=dev)
+    pf = None
+    if world > 1:
+        from j3d_b200.dist import PeerFrames
+        pf = PeerFrames(ctx, H, W, dev, dst=0, shared_frame=True)
+    ctx.set_screen_shard(rank, world)
+    last = {}
+
+    def frame(v):
+        if pf is None:
+            ctx.render_frame([mesh], [], v, pixels_out=px, rgba_out=rgba)
+            return
+        k = pf.begin()
+        ctx.render_frame([mesh], [], v, pixels_out=px, rgba_out=pf.target(k))
+        pf.arrive(k)
+        last["k"] = k
+        pf.release(k)
+
+    for v in views[: args.warmup]:
+        frame(v)
+    rig.barrier()
+    ctx.timings(reset=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for v in views[args.warmup:]:
+        frame(v)
+    e1.record()
+    rig.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = rig.max_over_ranks(e0.elapsed_time(e1))[0]
+    tm = ctx.timings(reset=True)
+    rays = rig.sum_over_ranks(float(tm.rays))[0]
+    cast_ms, shade_ms = rig.max_over_ranks(tm.cast_ms / max(1, tm.cast_count), tm.shade_ms / max(1, tm.shade_count))
+    launches = int(tm.kernel_launches)
+    # parity of the sharded path at full size: rank 0 renders the last frame alone, unsharded, and compares
+    identical = None
+    hit = shadowed = None
+    if rank == 0:
+        got = (pf.frames(last["k"])[0] if pf is not None else rgba).clone()
+        ctx.set_screen_shard(0, 1)
+        ctx.render_frame([mesh], [], views[-1], pixels_out=px, rgba_out=rgba)
+        torch.cuda.synchronize()
+        identical = bool(torch.equal(got, rgba))
+        p = px.cpu().numpy().view(j.PIXEL_DTYPE).reshape(H, W)
+        hm = p["object_id"] != 0xFFFFFFFF
+        hit, shadowed = int(hm.sum()), int((p["mark"][hm] & 1).sum())
+    rig.barrier()
+    line = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        bvh_bytes = int(info.nr_of_nodes) * info.node_bytes + nt * info.triangle_bytes
+        value = rays / ms / 1e3
+        line = {"metric": "primary+shadow Mrays/s @4K (ray cast + shading per frame)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": workload_name("C", f, nt, W, H), "l2": "inputs_larger_than_l2"},
+                "layout": {"sharding": "replicas only" if world == 1 else f"32-row screen bands round-robin over {world} ranks inside the cast / shade kernels, BVH NCCL-broadcast, every rank's shade kernel stores its bands into ONE frame in rank 0's HBM over NVLink peer memory",
+                           "bvh_bytes": bvh_bytes},
+                "frames_per_s": 1e3 * args.steps / ms, "rays_per_frame": rays / args.steps, "cast_ms_max_rank": cast_ms, "shade_ms_max_rank": shade_ms,
+                "bvh_build_ms": build_ms, "bvh_nodes": int(info.nr_of_nodes), "mesh_create_ms": create_ms, "bvh_broadcast_ms": bcast_ms, "mesh_generate_s": gen_s,
+                "sharded_frame_equals_unsharded": identical, "hit_pixels": hit, "shadowed_pixels": shadowed,
+                "stages": {"build": {"ms": build_ms, "algorithmic_bytes": 12 * nt + 12 * nv + bvh_bytes,
+                                     "roofline_frac": (12 * nt + 12 * nv + bvh_bytes) / (build_ms * 1e-3) / 1e9 / peak if build_ms else None}},
+                "gpu_launches": launches, "clocks": clocks, "exchange_status": ctx.status(),
+                "e2e": {"value": None, "unit": "Mrays/s", "h2d_bytes_per_step": ctypes.sizeof(j.View) + 256, "d2h_bytes_per_step": 0,
+                        "note": "the frame stays in rank 0's HBM; host readback is measured on workload B"}}
+    if pf is not None:
+        pf.close()
+    rig.finish(line)
     return 0
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=360)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=0)
+    ap.add_argument("--warmup", type=int, default=0)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
     ap.add_argument("--f", type=int, default=0, help="override the icosphere frequency (T = 20 f^2)")
+    ap.add_argument("--points", type=int, default=0, help="override the number of points of the splat stage / workload P")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-splat", action="store_true", help="skip the splat stage of the default line")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: how every rank's RGBA frame reaches rank 0")
     args = ap.parse_args()
+    wl = args.workload
+    if not args.steps:
+        args.steps = {"A": 360, "B": 360, "C": 8, "P": 5}[wl]
+    if not args.warmup:
+        args.warmup = {"A": 10, "B": 10, "C": 3, "P": 3}[wl]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
-    f = args.f or WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     if args.impl == "reference":
-        if args.steps > 12:  # bounded sample: a CPU frame of the 28M mesh takes ~0.1-1 s
-            args.steps = 12
-        return run_reference(args, f, rank, world)
+        return run_reference(args, wl, rank, world)
     from j3d_b200 import build
     if not (ROOT / "j3d_b200" / "libj3dg.so").exists():
         build.build_all()
-    return run_b200(args, f, rank, world, local_rank)
+    if wl == "P":
+        return run_splat(args, rank, world, local_rank)
+    if wl == "C":
+        return run_sharded_frame(args, rank, world, local_rank)
+    return run_orbit(args, wl, rank, world, local_rank)
 
 
 if __name__ == "__main__":

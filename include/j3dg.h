@@ -30,6 +30,7 @@ extern "C" {
 #define J3DG_ECUDA (-2)    /* CUDA runtime error (see j3dg_last_error) */
 #define J3DG_ENOMEM (-3)   /* device allocation failed */
 #define J3DG_ENODEV (-4)   /* no CUDA device / wrong architecture: there is NO CPU fallback */
+#define J3DG_ETIMEOUT (-5) /* a stream-ordered flag wait (peer exchange) gave up: a peer is gone; sticky, see j3dg_ctx_status */
 
 /* canvas::canvas_settings (j3d/canvas.h:16-25), one bit per bool, same order. */
 #define J3DG_ONE_BIT      (1u << 0)
@@ -107,6 +108,14 @@ const char* j3dg_last_error(const j3dg_ctx* ctx); /* ctx may be NULL: global str
 int j3dg_ctx_set_stream(j3dg_ctx* ctx, void* cuda_stream);
 int j3dg_ctx_synchronize(j3dg_ctx* ctx);
 int j3dg_ctx_timings(j3dg_ctx* ctx, j3dg_timings* out, int reset);
+/* Sticky error conditions raised by kernels that ran AFTER the call that enqueued them returned (calls with device
+ * outputs are not synchronised): a traversal stack overflow (pixels of that frame are wrong) or a timed-out flag
+ * wait of the peer exchange.  Once set, j3dg_ctx_synchronize, j3dg_render_frame, j3dg_frame_submit / j3dg_frame_wait,
+ * j3dg_cast and the j3dg_stream_* / j3dg_frames_* calls fail (J3DG_ECUDA / J3DG_ETIMEOUT) until the status is
+ * read with reset != 0.  The host reads the words from mapped memory: no synchronisation is needed to poll. */
+#define J3DG_STATUS_WAIT_TIMEOUT   (1u << 0)
+#define J3DG_STATUS_STACK_OVERFLOW (1u << 1)
+int j3dg_ctx_status(j3dg_ctx* ctx, uint32_t* flags_out, int reset);
 /* Per-stage CUDA-event timing on/off (default on; off removes the event records). */
 int j3dg_ctx_set_profiling(j3dg_ctx* ctx, int enabled);
 
@@ -120,9 +129,9 @@ int j3dg_ctx_set_tuning(j3dg_ctx* ctx, uint32_t lane_budget, int cast_algo);
  * j3dg_render_frame trace only this rank's bands plus the single pixel row above each of them (the edge
  * shader's up neighbour, canvas.cpp:625-640 — recomputed instead of exchanged), and j3dg_shade writes only
  * this rank's rows; everything else in the output buffers is left untouched.  The result in the owned rows
- * is identical to the unsharded frame.  Gathering the bands (NCCL) happens above this ABI
- * (j3d_b200/dist.py::gather_bands).  world = 1 (default) switches sharding off.  Point-cloud splats are not
- * sharded.  Bands are counted from the first row of the cast rectangle (row 0 for whole frames). */
+ * is identical to the unsharded frame.  world = 1 (default) switches sharding off.  Point-cloud splats are not
+ * sharded.  Bands are counted from row 0 of the canvas; while world > 1, j3dg_cast accepts whole-canvas
+ * rectangles only (J3DG_EINVAL otherwise: cast and shade must agree on which rows a rank owns). */
 #define J3DG_SHARD_BAND_ROWS 32
 int j3dg_ctx_set_screen_shard(j3dg_ctx* ctx, uint32_t rank, uint32_t world);
 

@@ -16,6 +16,7 @@ import numpy as np
 PKG = Path(__file__).resolve().parent
 
 ONE_BIT, SHADOW, EDGES, WIREFRAME, SHADING, TEXTURED, VERTEXCOLORS = (1 << i for i in range(7))
+STATUS_WAIT_TIMEOUT, STATUS_STACK_OVERFLOW = 1, 2
 DEFAULT_FLAGS = EDGES | SHADING | TEXTURED | VERTEXCOLORS
 
 PIXEL_DTYPE = np.dtype(
@@ -98,6 +99,7 @@ def lib() -> C.CDLL:
         L.j3dg_ctx_synchronize.argtypes = [_vp]
         L.j3dg_ctx_timings.argtypes = [_vp, C.POINTER(Timings), C.c_int]
         L.j3dg_ctx_set_profiling.argtypes = [_vp, C.c_int]
+        L.j3dg_ctx_status.argtypes = [_vp, C.POINTER(_u32), C.c_int]
         L.j3dg_mesh_create.argtypes = [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _u32, C.POINTER(_vp)]
         L.j3dg_mesh_destroy.argtypes = [_vp]
         L.j3dg_mesh_destroy.restype = None
@@ -283,6 +285,12 @@ class Context:
 
     def synchronize(self):
         self._check(self._L.j3dg_ctx_synchronize(self._h), "j3dg_ctx_synchronize")
+
+    def status(self, reset: bool = False) -> int:
+        """Sticky status bits (STATUS_WAIT_TIMEOUT | STATUS_STACK_OVERFLOW), polled from mapped memory without a sync."""
+        f = _u32()
+        self._check(self._L.j3dg_ctx_status(self._h, C.byref(f), int(reset)), "j3dg_ctx_status")
+        return f.value
 
     def set_profiling(self, on: bool):
         self._check(self._L.j3dg_ctx_set_profiling(self._h, int(on)), "j3dg_ctx_set_profiling")

@@ -99,6 +99,17 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) {
   return ms;
 }
 
+}  // namespace
+
+int j3dg_check_sticky(j3dg_ctx* ctx) {
+  if (!ctx->h_status) return J3DG_OK;
+  if (ctx->h_status[0]) { j3dg_set_error(ctx, "a stream-ordered flag wait timed out (peer exchange): a peer did not arrive / release in time"); return J3DG_ETIMEOUT; }
+  if (ctx->h_status[1]) { j3dg_set_error(ctx, "traversal stack overflow in an earlier frame (BVH deeper than the kernel's stack)"); return J3DG_ECUDA; }
+  return J3DG_OK;
+}
+
+namespace {
+
 int check_overflow(j3dg_ctx* ctx) {
   unsigned long long st[4];
   CU_CHECK(ctx, cudaMemcpyAsync(st, ctx->d_stats, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
@@ -149,6 +160,18 @@ J3DG_API int j3dg_ctx_create(int device, j3dg_ctx** out) {
     return J3DG_ENOMEM;
   }
   cudaMemset(ctx->d_stats, 0, 24 * sizeof(unsigned long long));
+  {
+    uint32_t* hs = nullptr;
+    if (cudaHostAlloc((void**)&hs, 4 * sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&ctx->d_status, hs, 0) != cudaSuccess) {
+      cudaGetLastError();
+      j3dg_set_error(nullptr, "cannot allocate the mapped status words");
+      j3dg_ctx_destroy(ctx);
+      return J3DG_ENOMEM;
+    }
+    memset(hs, 0, 4 * sizeof(uint32_t));
+    ctx->h_status = hs;
+  }
   if (const char* e = getenv("J3DG_LANE_BUDGET")) ctx->lane_budget = (uint32_t)std::max(1, atoi(e));  // developer tuning knobs
   if (const char* e = getenv("J3DG_SHADOW_BUDGET")) ctx->shadow_budget = (uint32_t)std::max(1, atoi(e));
   if (const char* e = getenv("J3DG_CONSUMER_BLOCKS")) ctx->consumer_blocks = (uint32_t)std::max(0, atoi(e));
@@ -170,6 +193,7 @@ J3DG_API void j3dg_ctx_destroy(j3dg_ctx* ctx) {
   }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->h_overflow) cudaFreeHost(ctx->h_overflow);
+  if (ctx->h_status) cudaFreeHost((void*)ctx->h_status);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   for (auto& r : ctx->ring) { for (auto e : r.a) cudaEventDestroy(e); for (auto e : r.b) cudaEventDestroy(e); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -194,6 +218,16 @@ J3DG_API int j3dg_ctx_set_stream(j3dg_ctx* ctx, void* cuda_stream) {
 J3DG_API int j3dg_ctx_synchronize(j3dg_ctx* ctx) {
   if (!ctx) return J3DG_EINVAL;
   CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return j3dg_check_sticky(ctx);
+}
+
+J3DG_API int j3dg_ctx_status(j3dg_ctx* ctx, uint32_t* flags_out, int reset) {
+  if (!ctx || !flags_out) return J3DG_EINVAL;
+  *flags_out = (ctx->h_status[0] ? J3DG_STATUS_WAIT_TIMEOUT : 0u) | (ctx->h_status[1] ? J3DG_STATUS_STACK_OVERFLOW : 0u);
+  if (reset && *flags_out) {
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // no kernel that could still raise a word is in flight
+    ctx->h_status[0] = 0u; ctx->h_status[1] = 0u;
+  }
   return J3DG_OK;
 }
 
@@ -367,19 +401,24 @@ J3DG_API int j3dg_mesh_find_closest(j3dg_mesh* m, const float* rays, uint32_t n,
   if (!m || (n && (!rays || !hits || !triangle_ids))) return J3DG_EINVAL;
   j3dg_ctx* ctx = m->ctx;
   if (!n) return J3DG_OK;
-  float *d_rays = nullptr, *d_hits = nullptr;
-  uint32_t* d_ids = nullptr;
-  CU_CHECK(ctx, cudaMalloc((void**)&d_rays, (size_t)n * 32));
-  CU_CHECK(ctx, cudaMalloc((void**)&d_hits, (size_t)n * 16));
-  CU_CHECK(ctx, cudaMalloc((void**)&d_ids, (size_t)n * 4));
-  CU_CHECK(ctx, cudaMemcpyAsync(d_rays, rays, (size_t)n * 32, cudaMemcpyDefault, ctx->stream));
-  int rc = j3dg_launch_find_closest(m, d_rays, n, d_hits, d_ids);
-  if (rc == J3DG_OK) {
+  // one allocation for the three staging arrays, released on every path
+  const size_t off_hits = ((size_t)n * 32 + 255) & ~(size_t)255, off_ids = (off_hits + (size_t)n * 16 + 255) & ~(size_t)255;
+  char* d_buf = nullptr;
+  CU_CHECK(ctx, cudaMalloc((void**)&d_buf, off_ids + (size_t)n * 4));
+  auto body = [&]() -> int {
+    float* d_rays = (float*)d_buf;
+    float* d_hits = (float*)(d_buf + off_hits);
+    uint32_t* d_ids = (uint32_t*)(d_buf + off_ids);
+    CU_CHECK(ctx, cudaMemcpyAsync(d_rays, rays, (size_t)n * 32, cudaMemcpyDefault, ctx->stream));
+    int rc = j3dg_launch_find_closest(m, d_rays, n, d_hits, d_ids);
+    if (rc != J3DG_OK) return rc;
     CU_CHECK(ctx, cudaMemcpyAsync(hits, d_hits, (size_t)n * 16, cudaMemcpyDefault, ctx->stream));
     CU_CHECK(ctx, cudaMemcpyAsync(triangle_ids, d_ids, (size_t)n * 4, cudaMemcpyDefault, ctx->stream));
-    rc = check_overflow(ctx);
-  }
-  cudaFree(d_rays); cudaFree(d_hits); cudaFree(d_ids);
+    return check_overflow(ctx);
+  };
+  const int rc = body();
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_buf);
   return rc;
 }
 
@@ -465,9 +504,14 @@ J3DG_API int j3dg_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, con
                        j3dg_pixel* pixels_out, uint32_t stride) {
   if (!ctx || !view || !pixels_out || (nm && !meshes)) { j3dg_set_error(ctx, "j3dg_cast: bad argument"); return J3DG_EINVAL; }
   cudaSetDevice(ctx->device);
+  { const int st = j3dg_check_sticky(ctx); if (st != J3DG_OK) return st; }
   const uint32_t w = view->width, h = view->height;
   if (!w || !h) return J3DG_OK;
   if (!stride) stride = w;
+  if (ctx->shard_world > 1 && !(x0 <= 0 && y0 <= 0 && x1 >= (int)w - 1 && y1 >= (int)h - 1)) {
+    j3dg_set_error(ctx, "j3dg_cast: with screen sharding on (j3dg_ctx_set_screen_shard) only whole-canvas rectangles are accepted");
+    return J3DG_EINVAL;
+  }
   if (j3dg_is_device_ptr(pixels_out)) return j3dg_launch_cast(ctx, meshes, nm, view, x0, y0, x1, y1, pixels_out, stride, false);
   // host destination: render into the context's device canvas, copy the updated rectangle back
   int rc = j3dg_reserve(ctx, &ctx->d_pixels, &ctx->pixels_cap, (size_t)w * h * sizeof(j3dg_pixel));
@@ -654,6 +698,7 @@ J3DG_API int j3dg_render_frame(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t
                                uint32_t bg_top, uint32_t bg_bottom, j3dg_pixel* pixels_out, uint32_t* rgba_out) {
   if (!ctx || !view || (nm && !meshes) || (nc && !clouds)) { j3dg_set_error(ctx, "j3dg_render_frame: bad argument"); return J3DG_EINVAL; }
   cudaSetDevice(ctx->device);
+  { const int st = j3dg_check_sticky(ctx); if (st != J3DG_OK) return st; }
   const uint32_t w = view->width, h = view->height;
   if (!w || !h) return J3DG_OK;
   const uint32_t* d_mc; uint32_t dmw, dmh, dms, dcav;
@@ -711,6 +756,7 @@ J3DG_API int j3dg_frame_submit(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t
   if (j3dg_is_device_ptr(pixels_out) || j3dg_is_device_ptr(rgba_out)) { j3dg_set_error(ctx, "j3dg_frame_submit: outputs must be host buffers"); return J3DG_EINVAL; }
   if (ctx->frames_submitted - ctx->frames_waited >= 2) { j3dg_set_error(ctx, "j3dg_frame_submit: two frames already in flight, call j3dg_frame_wait"); return J3DG_EINVAL; }
   cudaSetDevice(ctx->device);
+  { const int st = j3dg_check_sticky(ctx); if (st != J3DG_OK) return st; }
   const uint32_t w = view->width, h = view->height;
   if (!w || !h) { j3dg_set_error(ctx, "j3dg_frame_submit: empty canvas"); return J3DG_EINVAL; }
   if (!ctx->copy_stream) {

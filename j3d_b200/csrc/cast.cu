@@ -107,6 +107,7 @@ struct TraceParams {
   TileGrid grid;                 // PRIMARY: the pools of this launch
   j3dg_pixel* out;               // PRIMARY: raw hits are written here; SHADOW: mark bit 0 is set here
   uint32_t stride;
+  uint32_t* sticky;              // mapped host status words (common.cuh, j3dg_ctx::d_status): [1] = a traversal stack overflowed
   unsigned long long* stats;     // [0] node rounds [1] triangle tests [2] overflow flag [3] pool counter [4] shadow rays (accumulating) [5] shadow list length
   const float4* shadow_pos;      // SHADOW: ray origins (xyzw as the reference computes them)
   const uint32_t* shadow_pix;    // SHADOW: pixel offset (y * stride + x) of each ray
@@ -446,7 +447,7 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const st
           if (hit && c != near_lane) {
             const int pos = sp + __popc(others & below);
             if (pos < STACK_SIZE) stk[pos * GSTRIDE] = make_uint2(ref, __float_as_uint(tmin));
-            else *overflow_flag = 1u;
+            else { *overflow_flag = 1u; p.sticky[1] = 1u; }
           }
           sp = min(sp + __popc(others), STACK_SIZE);
           cur = next;
@@ -1135,6 +1136,7 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   tp.out = d_pixels;
   tp.stride = stride;
   tp.stats = ctx->d_stats;
+  tp.sticky = ctx->d_status;
   tp.shadow_pos = (const float4*)ctx->d_shadow;
   tp.shadow_pix = (const uint32_t*)((const char*)ctx->d_shadow + shadow_pix_off);
   tp.hard_best = (float4*)ctx->d_hard;
@@ -1234,6 +1236,7 @@ int j3dg_launch_find_closest(j3dg_mesh* m, const float* d_rays, uint32_t n, floa
   tp.meshes = ctx->d_meshes;
   tp.nm = (d.nodes && d.nt) ? 1u : 0u;
   tp.stats = ctx->d_stats;
+  tp.sticky = ctx->d_status;
   tp.rays = d_rays; tp.hits = d_hits; tp.ids = d_ids; tp.nrays = n;
   tp.pool_ctr = reinterpret_cast<unsigned int*>(ctx->d_stats + 3);
   int grid = 1;

@@ -162,7 +162,14 @@ struct j3dg_ctx {
   int cast_algo = 0;                                 // 0 hybrid (lane + group), 1 group kernel only (J3DG_CAST_ALGO=group)
   void* last_canvas = nullptr; uint32_t last_w = 0, last_h = 0;  // device canvas of the most recent frame (j3dg_pick reads it)
   uint32_t shard_rank = 0, shard_world = 1;          // screen sharding (j3dg_ctx_set_screen_shard): band b of 32 rows belongs to rank b mod world
+  // Sticky status words in mapped pinned host memory (kernels store into d_status, the host reads h_status without a
+  // synchronisation): [0] a stream-ordered flag wait timed out (peer.cu), [1] a traversal stack overflowed (cast.cu).
+  // Never cleared by a render call: j3dg_ctx_status(reset) clears them; j3dg_ctx_synchronize and the frame entry points
+  // fail once one is set, so device-output calls (which return before the kernels ran) cannot lose the condition.
+  volatile uint32_t* h_status = nullptr;
+  uint32_t* d_status = nullptr;
 };
+int j3dg_check_sticky(j3dg_ctx* ctx);  // J3DG_OK, or the error of the first sticky status word that is set
 
 void j3dg_set_error(j3dg_ctx* ctx, const std::string& msg);
 int j3dg_stage_begin(j3dg_ctx* ctx, int stage);  // records the begin event of the next pair (no-op if !profiling)

@@ -84,6 +84,7 @@ J3DG_API int j3dg_peer_close(j3dg_ctx* ctx, void* dev_ptr) {
 J3DG_API int j3dg_stream_signal(j3dg_ctx* ctx, uint32_t* flag, uint32_t value) {
   if (!ctx || !flag) return J3DG_EINVAL;
   cudaSetDevice(ctx->device);
+  { const int st = j3dg_check_sticky(ctx); if (st != J3DG_OK) return st; }
   signal_kernel<<<1, 1, 0, ctx->stream>>>(flag, value);
   KERNEL_CHECK(ctx);
   return J3DG_OK;
@@ -92,7 +93,8 @@ J3DG_API int j3dg_stream_signal(j3dg_ctx* ctx, uint32_t* flag, uint32_t value) {
 J3DG_API int j3dg_stream_wait_geq(j3dg_ctx* ctx, const uint32_t* flags, uint32_t n, uint32_t value) {
   if (!ctx || !flags || !n || n > 32) { j3dg_set_error(ctx, "j3dg_stream_wait_geq: 1..32 flags"); return J3DG_EINVAL; }
   cudaSetDevice(ctx->device);
-  wait_geq_kernel<<<1, 32, 0, ctx->stream>>>(flags, n, value, reinterpret_cast<uint32_t*>(ctx->d_stats + 19));
+  { const int st = j3dg_check_sticky(ctx); if (st != J3DG_OK) return st; }
+  wait_geq_kernel<<<1, 32, 0, ctx->stream>>>(flags, n, value, ctx->d_status);
   KERNEL_CHECK(ctx);
   return J3DG_OK;
 }
@@ -100,10 +102,7 @@ J3DG_API int j3dg_stream_wait_geq(j3dg_ctx* ctx, const uint32_t* flags, uint32_t
 J3DG_API int j3dg_stream_wait_status(j3dg_ctx* ctx, int* timed_out) {
   if (!ctx || !timed_out) return J3DG_EINVAL;
   cudaSetDevice(ctx->device);
-  uint32_t v = 0;
-  CU_CHECK(ctx, cudaMemcpyAsync(&v, ctx->d_stats + 19, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  *timed_out = (int)v;
-  if (v) CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats + 19, 0, sizeof(unsigned long long), ctx->stream));
+  *timed_out = (int)ctx->h_status[0];  // sticky: cleared by j3dg_ctx_status(reset) only
   return J3DG_OK;
 }

@@ -225,11 +225,8 @@ static inline size_t scratch_bytes(uint32_t n) {
 // iota_values: vals_a need not be initialised, the first pass generates 0..n-1.
 static inline int sort_pairs(j3dg_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t n,
                              int key_bits, uint32_t* scratch, bool* result_in_b, bool iota_values = true, int first_bit = 0) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU_CHECK(ctx, cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM));
-    attr_set = true;
-  }
+  // per device, not per process: a second context on another GPU needs it as well (a few microseconds per sort)
+  CU_CHECK(ctx, cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM));
   const uint32_t ntiles = (n + TILE - 1) / TILE;
   const size_t table_n = (size_t)ntiles * RADIX;
   const uint32_t nchunks = (uint32_t)((table_n + SCAN_CHUNK - 1) / SCAN_CHUNK);

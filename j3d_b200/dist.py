@@ -155,14 +155,16 @@ def peer_flags_offset(world: int, frame_bytes: int) -> int:
 
 class PeerFrames:
     """Every rank renders its frame STRAIGHT INTO rank `dst`'s HBM (the shade kernel's stores travel over NVLink);
-    no gather kernel competes with the cooperative cast kernel for SMs.  Double-buffered:
+    no gather kernel competes with the cooperative cast kernel for SMs.  Double-buffered, all stream-ordered:
 
-        k = pf.begin()                 # stream waits until slot k & 1 has been released by dst
+        k = pf.begin()                 # stream waits until dst has RELEASED the frame that lived in slot k & 1
         ctx.render_frame(..., rgba_out=pf.target(k))
-        pf.end(k)                      # signal arrival; dst's stream waits for all ranks, then releases the slot
+        pf.arrive(k)                   # signal arrival; on dst the stream then waits for every rank's frame k
+        ... dst enqueues its consumer of pf.frames(k) on the same stream (copy to host, encode, compare) ...
+        pf.release(k)                  # dst: everything enqueued so far has read the slot; peers may overwrite it
 
-    On `dst`, pf.frames(k) are the world frames of step k ([world, H, W] int32 view of the buffer), valid between
-    end(k) and end(k + 1)... of the same slot parity, i.e. until end(k + 2) is enqueued."""
+    On `dst`, pf.frames(k) ([world, H, W] int32 view of the buffer) is valid for work enqueued between arrive(k) and
+    release(k).  pf.end(k) = arrive(k) + release(k) for callers that do not consume on the stream."""
 
     def __init__(self, ctx, height: int, width: int, device, dst: int = 0, shared_frame: bool = False):
         """shared_frame = False: one frame per rank and slot (orbit sweep: every rank renders its own frame).
@@ -221,12 +223,20 @@ class PeerFrames:
     def target(self, k: int) -> int:
         return self.base + peer_slot_offset(k & 1, 0 if self.shared else self.rank, self.world, self.frame_bytes)
 
-    def end(self, k: int):
+    def arrive(self, k: int):
         self.ctx.stream_signal(self._arrived(self.rank), k + 1)
         if self.rank == self.dst:
             self.ctx.stream_wait_geq(self._arrived(0), self.world, k + 1)
-            self.ctx.stream_signal(self._released(), k + 1)
         self.k = k + 1
+
+    def release(self, k: int):
+        """dst only (a no-op elsewhere): the consumer work of frame k is enqueued; the slot may be overwritten."""
+        if self.rank == self.dst:
+            self.ctx.stream_signal(self._released(), k + 1)
+
+    def end(self, k: int):
+        self.arrive(k)
+        self.release(k)
 
     def frames(self, k: int) -> torch.Tensor:
         assert self.rank == self.dst

@@ -253,8 +253,11 @@ class canvas {
     render_scene(_canvas, s);
   }
   // canvas::canvas_to_image (canvas.cpp:582-670)
-  void canvas_to_image(const std::vector<pixel>& cnv, const matcap& mc, const scene& s) {
-    j3dg_view v = make_view(s);
+  // The shader reads the canvas size, the inverse projection, the near plane and the settings only — all members of
+  // the canvas, as in the reference — so the signature is the reference's (canvas.h:61).
+  void canvas_to_image(const std::vector<pixel>& cnv, const matcap& mc) {
+    scene none;
+    j3dg_view v = make_view(none);
     _ctx.check(j3dg_shade(_ctx.get(), cnv.data(), _w, &v, mc.im.data(), mc.w, mc.h, mc.w, mc.cavity_clr, nullptr, im.data(), _stride),
                "j3dg_shade");
   }

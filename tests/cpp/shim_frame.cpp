@@ -54,7 +54,7 @@ int main(int argc, char** argv) {
     cnv.update_settings(st);
     cnv.render_scene(&s);
     std::vector<j3dg::pixel> pixels = cnv.get_pixels();  // _pixels = _canvas.get_pixels()
-    cnv.canvas_to_image(pixels, mc, s);
+    cnv.canvas_to_image(pixels, mc);
     cnv.render_pointclouds_on_image(&s, pixels);
 
     FILE* o = fopen(argv[2], "wb");

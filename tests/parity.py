@@ -11,7 +11,18 @@ import numpy as np
 MISS = 0xFFFFFFFF
 
 
-def _on_edge(px, tol=2e-4):
+# Mismatch classes.  Both sides evaluate the Woop edge functions U, V, W bit-identically (same
+# operation order, no FMA), so the inside / outside decisions agree; the only arithmetic that differs is 1/det
+# (rcpps + one Newton step in the reference, ~2e-7 relative, against a correctly rounded division here).  An id can
+# therefore differ only where two accepted hits lie within a few 1e-7 of each other in depth: shared-edge ties and
+# surfaces that cross inside one pixel.  TIE_REL is the north_star's 1e-5; EDGE_TOL classifies the remaining
+# silhouette grazes (a hit exactly on a triangle edge) and is kept for comparisons between differently rounded CPU
+# builds (the FMA build).  The counts are returned so a drift becomes visible in the bench line.
+TIE_REL = 1e-5
+EDGE_TOL = 2e-5
+
+
+def _on_edge(px, tol=EDGE_TOL):
     u, v = px["barycentric_u"], px["barycentric_v"]
     return (np.abs(u) < tol) | (np.abs(v) < tol) | (np.abs(1.0 - u - v) < tol)
 
@@ -29,7 +40,7 @@ def compare_pixels(got, want, id_frac=0.9999, rel=1e-5, check_colors=True, tag="
     if mism.any():
         g, w = got[mism], want[mism]
         both = (g["object_id"] != MISS) & (w["object_id"] != MISS)
-        tie = both & (np.abs(g["depth"] - w["depth"]) <= 1e-4 * np.abs(w["depth"]))
+        tie = both & (np.abs(g["depth"] - w["depth"]) <= TIE_REL * np.abs(w["depth"]))
         graze = (_on_edge(g) & (g["object_id"] != MISS)) | (_on_edge(w) & (w["object_id"] != MISS))
         bad = ~(tie | graze)
         stats["tie"] = int(tie.sum())
@@ -76,3 +87,38 @@ def compare_rgba(got, want, frac=0.999, tag=""):
     stats = {"pixels": int(got.size), "exact": int((d == 0).sum()), "gt1": bad, "max": int(d.max())}
     assert bad <= (1.0 - frac) * got.size, f"{tag}: {bad} of {got.size} pixels differ by more than 1 LSB"
     return stats
+
+
+def parity_stats(got_px, want_px, got_rgba=None, want_rgba=None):
+    """The same comparison without assertions: the numbers `bench.py` prints in its `parity` block (GPU frame against
+    the reference's frame of the same run).  Keys: id_mismatch, tie, graze, unclassified, max_rel_depth,
+    max_abs_bary, mark_mismatch, rgba_gt1, rgba_exact_frac."""
+    n = got_px.size
+    w_hit = want_px["object_id"] != MISS
+    same = (got_px["object_id"] == want_px["object_id"]) & (got_px["db_id"] == want_px["db_id"])
+    mism = ~same
+    out = {"pixels": int(n), "hits": int(w_hit.sum()), "id_mismatch": int(mism.sum()), "tie": 0, "graze": 0, "unclassified": 0}
+    if mism.any():
+        g, w = got_px[mism], want_px[mism]
+        both = (g["object_id"] != MISS) & (w["object_id"] != MISS)
+        tie = both & (np.abs(g["depth"] - w["depth"]) <= TIE_REL * np.abs(w["depth"]))
+        graze = ((_on_edge(g) & (g["object_id"] != MISS)) | (_on_edge(w) & (w["object_id"] != MISS))) & ~tie
+        out["tie"], out["graze"] = int(tie.sum()), int(graze.sum())
+        out["unclassified"] = int((~(tie | graze)).sum())
+    m = same & w_hit
+    if m.any():
+        d = np.abs(got_px["depth"][m].astype(np.float64) - want_px["depth"][m]) / np.abs(want_px["depth"][m].astype(np.float64))
+        out["max_rel_depth"] = float(d.max())
+        b = np.maximum(np.abs(got_px["barycentric_u"][m].astype(np.float64) - want_px["barycentric_u"][m]),
+                       np.abs(got_px["barycentric_v"][m].astype(np.float64) - want_px["barycentric_v"][m]))
+        out["max_abs_bary"] = float(b.max())
+        out["mark_mismatch"] = int((got_px["mark"][m] != want_px["mark"][m]).sum())
+    out["id_agree_frac"] = 1.0 - out["id_mismatch"] / max(n, 1)
+    if got_rgba is not None and want_rgba is not None:
+        g = got_rgba.view(np.uint8).reshape(got_rgba.shape + (4,)).astype(np.int32)
+        w = want_rgba.view(np.uint8).reshape(want_rgba.shape + (4,)).astype(np.int32)
+        d = np.abs(g - w).max(axis=-1)
+        out["rgba_gt1"] = int((d > 1).sum())
+        out["rgba_exact_frac"] = float((d == 0).mean())
+        out["rgba_within_1lsb_frac"] = float((d <= 1).mean())
+    return out
