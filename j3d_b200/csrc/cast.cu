@@ -857,17 +857,460 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* const stk
   }
 }
 
+// =====================================================================================================
+// pool mode: the lane kernel with the rays decoupled from the lanes
+// =====================================================================================================
+// The lane kernel above keeps one ray per lane, so a warp step (node or triangle) only uses the lanes whose ray is in
+// the matching state: measured 11.5 of 32 lanes on config B (profiles/README.md, round 2).  Here every warp owns
+// PSLOTS = 64 ray SLOTS in shared memory — the whole traversal state of a ray (reciprocal direction, shear constants,
+// best hit, current node, short stack) lives in its slot, not in a lane.  Every iteration the warp classifies its slots
+// (free / at a node / at a triangle) with two loads and six ballots, picks the kind of step that fills more lanes,
+// compacts up to 32 slots of that kind onto the lanes through a small list, and runs the step: ~30 of 32 lanes do
+// useful work, and a ray that needs 200 node visits no longer idles 31 lanes — it just keeps its slot.  Free slots are
+// refilled from a parked tile of 32 set-up rays, so the slots stay full until the tiles run out.  Rays that exceed the
+// node budget or the short stack are still evicted to the hard-ray queue (the 8-lane groups bound the tail of the
+// frame).  Same arithmetic, same result as lane_loop; only the scheduling differs.
+#ifndef J3DG_POOL_MODE
+#define J3DG_POOL_MODE 1
+#endif
+#ifndef J3DG_POOL_STACK
+#define J3DG_POOL_STACK 8                                 // stack entries per slot (8 B each); overflow = eviction to the 96-entry group stack
+#endif
+#ifndef J3DG_POOL_REFILL_MIN
+#define J3DG_POOL_REFILL_MIN 8                            // free slots that trigger a refill from the parked tile
+#endif
+#ifndef J3DG_POOL_TRI_WEIGHT
+#define J3DG_POOL_TRI_WEIGHT 2                            // a triangle step is ~3x shorter than a node step: it may run with fewer lanes
+#endif
+#ifndef J3DG_POOL_TRI_MIN_LANES
+#define J3DG_POOL_TRI_MIN_LANES 12                        // a triangle step walks on through the leaves while this many lanes stay in theirs
+#endif
+#ifndef J3DG_POOL_PREFETCH
+#define J3DG_POOL_PREFETCH 1                              // 1: prefetch.global.L1 of the next node / record when a step ends (0 off, 2: L2)
+#endif
+#ifndef J3DG_POOL_MIN_BLOCKS
+#define J3DG_POOL_MIN_BLOCKS 6
+#endif
+constexpr int PSLOTS = 64;
+
+template <int MODE, bool STATS>
+struct PoolLayout {
+  static constexpr bool ORG = MODE == SHADOW;               // per-ray origin (primary rays share the camera origin)
+  static constexpr int PSTACK = STATS ? 24 : J3DG_POOL_STACK;  // the counting pass must not lose rays to the (uncounted) group kernel
+  // static words of a slot, copied from the park
+  static constexpr int W_IDX = 0, W_IDY = 1, W_IDZ = 2, W_SX = 3, W_SY = 4, W_SZ = 5;
+  static constexpr int W_K = 6;                              // kx | ky << 2 | kz << 4 | mesh of the best hit << 16
+  static constexpr int W_ID = 7;                             // ray id
+  // dynamic words
+  static constexpr int W_TFAR = 8, W_U = 9, W_V = 10, W_BEST = 11;  // best hit so far (t_far == best t)
+  static constexpr int W_CUR = 12;                           // current node / record; J3DG_EMPTY_CHILD = free slot
+  static constexpr int W_SPV = 13;                           // stack height | node visits << 8 | current mesh << 16
+  static constexpr int W_OX = 14;                            // + oy, oz (ORG only)
+  static constexpr int W_CNT = ORG ? 17 : 14;                // STATS: node visits, triangle tests
+  static constexpr int WORDS = W_CNT + (STATS ? 2 : 0);
+  static constexpr int PARKW = 8 + (ORG ? 3 : 0);
+  static constexpr int STACK_WORDS = 2 * PSTACK * PSLOTS;
+  static constexpr int WARP_WORDS = STACK_WORDS + WORDS * PSLOTS + PARKW * 32 + 64;
+  static_assert((size_t)WARP_WORDS * 4 >= (size_t)STACK_SIZE * 4 * sizeof(uint2), "a warp's region must hold four group stacks");
+  static_assert(WARP_WORDS % 4 == 0, "16-byte aligned warp regions");
+};
+
+template <int MODE, bool STATS>
+__device__ __forceinline__ void pool_loop(const TraceParams& p, uint32_t* const wsm) {
+  using L = PoolLayout<MODE, STATS>;
+  constexpr bool ANY_HIT = MODE == SHADOW;
+  constexpr int PSTACK = L::PSTACK;
+  constexpr uint32_t FREE = J3DG_EMPTY_CHILD, NONE = 0xFFFFFFFFu;
+  uint2* const stk = reinterpret_cast<uint2*>(wsm);           // entry i of slot s at stk[i * PSLOTS + s]
+  uint32_t* const st = wsm + L::STACK_WORDS;                  // word w of slot s at st[w * PSLOTS + s]
+  uint32_t* const park = st + L::WORDS * PSLOTS;              // word w of parked ray r at park[w * 32 + r]
+  uint32_t* const list = park + L::PARKW * 32;                // slots of this step / free slots of a refill
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const float t_near = MODE == PRIMARY ? fdiv(p.vw.diagonal, 100.f) : 1e-3f;  // canvas.cpp:781 / 853
+  uint32_t total_pools, list_n = 0;
+  if (MODE == PRIMARY) {
+    total_pools = p.grid.total_pools;
+  } else {
+    list_n = (uint32_t)p.stats[5];
+    total_pools = (list_n + 31u) / 32u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.stats + 4, (unsigned long long)list_n);  // shadow rays traced
+  }
+  const bool multi = p.nm > 1u;
+  const WideNode* __restrict__ nodes0 = nullptr;
+  const TriRec* __restrict__ tris0 = nullptr;
+  float o0x = 0.f, o0y = 0.f, o0z = 0.f;                      // PRIMARY: the camera origin in the space of mesh 0
+  if (p.nm) {
+    const MeshDev& m0 = p.meshes[0];
+    nodes0 = m0.nodes; tris0 = m0.tris;
+    if (MODE == PRIMARY) {
+      const float4 o = mat_vec(m0.cs_inv, make_float4(p.vw.origin[0], p.vw.origin[1], p.vw.origin[2], p.vw.origin[3]));
+      o0x = o.x; o0y = o.y; o0z = o.z;
+    }
+  }
+  st[L::W_CUR * PSLOTS + lane] = FREE;
+  st[L::W_CUR * PSLOTS + 32 + lane] = FREE;
+  __syncwarp();
+
+  uint32_t park_next = 0, park_count = 0;
+  bool exhausted = false;
+  uint32_t sum_nodes = 0, sum_tris = 0;
+
+  // the ray of slot s is done with its current mesh: next object (qbvh.h:3340-3385), or write the result and free the slot
+  auto finish = [&](uint32_t s, uint32_t spv) {
+    const uint32_t best = st[L::W_BEST * PSLOTS + s];
+    const bool found = best != NONE;
+    const uint32_t mesh_k = spv >> 16;
+    const uint32_t ray_id = st[L::W_ID * PSLOTS + s];
+    if (multi && mesh_k + 1u < p.nm && !(ANY_HIT && found)) {
+      const MeshDev& m = p.meshes[mesh_k + 1u];
+      const LaneRay lr = lane_ray_setup(m, world_ray<MODE>(p, ray_id));
+      st[L::W_IDX * PSLOTS + s] = __float_as_uint(lr.idx); st[L::W_IDY * PSLOTS + s] = __float_as_uint(lr.idy); st[L::W_IDZ * PSLOTS + s] = __float_as_uint(lr.idz);
+      st[L::W_SX * PSLOTS + s] = __float_as_uint(lr.Sx); st[L::W_SY * PSLOTS + s] = __float_as_uint(lr.Sy); st[L::W_SZ * PSLOTS + s] = __float_as_uint(lr.Sz);
+      st[L::W_K * PSLOTS + s] = (st[L::W_K * PSLOTS + s] & 0xFFFF0000u) | lr.kpack;
+      if (L::ORG) { st[(L::W_OX + 0) * PSLOTS + s] = __float_as_uint(lr.ox); st[(L::W_OX + 1) * PSLOTS + s] = __float_as_uint(lr.oy); st[(L::W_OX + 2) * PSLOTS + s] = __float_as_uint(lr.oz); }
+      st[L::W_SPV * PSLOTS + s] = (spv & 0xFF00u) | ((mesh_k + 1u) << 16);  // empty stack, visits kept
+      st[L::W_CUR * PSLOTS + s] = 0u;                                        // root of the next mesh
+      return;
+    }
+    if (MODE == PRIMARY) {
+      const int x = (int)(ray_id & 0xffffu), y = (int)(ray_id >> 16);
+      uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)y * p.stride + x);
+      uint4 lo = make_uint4(0u, 0u, 0u, found ? st[L::W_TFAR * PSLOTS + s] : __float_as_uint(FLT_MAX));  // misses already carry the final record (canvas.cpp:859-866)
+      if (STATS) { lo.y = st[L::W_CNT * PSLOTS + s]; lo.z = st[(L::W_CNT + 1) * PSLOTS + s]; }  // the counting pass returns per-pixel costs in the u / v slots
+      dst[0] = lo;
+      // raw hit: record slot, barycentrics, mesh index (resolve_kernel finishes it)
+      dst[1] = found ? make_uint4(best, st[L::W_U * PSLOTS + s], st[L::W_V * PSLOTS + s], st[L::W_K * PSLOTS + s] >> 16) : make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+    } else if (found) {
+      uint8_t* mark = reinterpret_cast<uint8_t*>(p.out + __ldg(p.shadow_pix + ray_id));
+      *mark = *mark | 1u;  // canvas.cpp:856
+    }
+    if (STATS) { sum_nodes += st[L::W_CNT * PSLOTS + s]; sum_tris += st[(L::W_CNT + 1) * PSLOTS + s]; }
+    st[L::W_CUR * PSLOTS + s] = FREE;
+  };
+  // a group of 8 lanes finishes the ray of slot s, starting from the best hit so far
+  auto evict = [&](uint32_t s) {
+    const uint32_t i = atomicAdd(p.hard_count, 1u);
+    __stcg(p.hard_best + i, make_float4(__uint_as_float(st[L::W_TFAR * PSLOTS + s]), __uint_as_float(st[L::W_U * PSLOTS + s]),
+                                        __uint_as_float(st[L::W_V * PSLOTS + s]), __uint_as_float(st[L::W_BEST * PSLOTS + s])));
+    __threadfence();  // the consumer reads the seed after it has seen the id
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" :: "l"(p.hard_id + i), "r"(st[L::W_ID * PSLOTS + s]), "r"(st[L::W_K * PSLOTS + s] >> 16) : "memory");
+    st[L::W_CUR * PSLOTS + s] = FREE;
+  };
+  auto prefetch = [&](const WideNode* nodes, const TriRec* tris, uint32_t cur) {
+    if (J3DG_POOL_PREFETCH == 0) return;
+    const void* a = (cur & J3DG_LEAF_BIT) ? (const void*)(tris + (cur & J3DG_LEAF_FIRST_MASK)) : (const void*)(nodes + cur);
+    if (J3DG_POOL_PREFETCH == 1) asm volatile("prefetch.global.L1 [%0];" :: "l"(a));
+    else asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
+  };
+
+  for (uint32_t iter = 0;; ++iter) {
+    // =========================== classify the 64 slots ===========================
+    const uint32_t c0 = st[L::W_CUR * PSLOTS + lane], c1 = st[L::W_CUR * PSLOTS + 32 + lane];
+    const uint32_t fLo = __ballot_sync(0xffffffffu, c0 == FREE), fHi = __ballot_sync(0xffffffffu, c1 == FREE);
+    const uint32_t nLo = __ballot_sync(0xffffffffu, !(c0 >> 31)), nHi = __ballot_sync(0xffffffffu, !(c1 >> 31));
+    const uint32_t tLo = ~(fLo | nLo), tHi = ~(fHi | nHi);
+    const int nfree = __popc(fLo) + __popc(fHi), nnode = __popc(nLo) + __popc(nHi), ntri = PSLOTS - nfree - nnode;
+
+    // =========================== refill free slots from the parked tile ===========================
+    if (nfree >= J3DG_POOL_REFILL_MIN && !(exhausted && park_next >= park_count)) {
+      if (park_next >= park_count) {  // fetch the next pool; its 32 rays are set up by the 32 lanes in parallel
+        uint32_t pool = 0;
+        if (lane == 0) pool = atomicAdd(p.pool_ctr, 1u);
+        pool = __shfl_sync(0xffffffffu, pool, 0);
+        if (pool >= total_pools) { exhausted = true; continue; }
+        uint32_t id;
+        bool ok;
+        if (MODE == PRIMARY) {
+          uint32_t tx, ty;
+          bool halo;
+          const bool tile_ok = tile_of_pool(p.grid, pool, tx, ty, halo);
+          const int x = p.x0 + (int)tx * TILE_W + (lane & (TILE_W - 1));
+          const int y = p.y0 + (int)ty * TILE_H + (lane / TILE_W);
+          ok = tile_ok && x <= p.x1 && y <= p.y1 && (!halo || lane / TILE_W == TILE_H - 1);
+          id = ((uint32_t)y << 16) | (uint32_t)x;
+        } else {
+          id = pool * 32u + (uint32_t)lane;
+          ok = id < list_n;
+        }
+        if (ok && p.nm == 0u) {  // empty scene: every ray misses
+          if (MODE == PRIMARY) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)(id >> 16) * p.stride + (id & 0xffffu));
+            dst[0] = make_uint4(0u, 0u, 0u, __float_as_uint(FLT_MAX));
+            dst[1] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+          }
+          ok = false;
+        }
+        const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+          const LaneRay lr = lane_ray_setup(p.meshes[0], world_ray<MODE>(p, id));
+          const uint32_t r = __popc(okmask & lt_mask);  // dense
+          park[0 * 32 + r] = __float_as_uint(lr.idx); park[1 * 32 + r] = __float_as_uint(lr.idy); park[2 * 32 + r] = __float_as_uint(lr.idz);
+          park[3 * 32 + r] = __float_as_uint(lr.Sx); park[4 * 32 + r] = __float_as_uint(lr.Sy); park[5 * 32 + r] = __float_as_uint(lr.Sz);
+          park[6 * 32 + r] = lr.kpack; park[7 * 32 + r] = id;
+          if (L::ORG) { park[8 * 32 + r] = __float_as_uint(lr.ox); park[9 * 32 + r] = __float_as_uint(lr.oy); park[10 * 32 + r] = __float_as_uint(lr.oz); }
+        }
+        __syncwarp();
+        park_next = 0;
+        park_count = __popc(okmask);
+        continue;
+      }
+      // the r-th free slot takes the r-th parked ray
+      if (c0 == FREE) list[__popc(fLo & lt_mask)] = (uint32_t)lane;
+      if (c1 == FREE) list[__popc(fLo) + __popc(fHi & lt_mask)] = 32u + (uint32_t)lane;
+      __syncwarp();
+      const uint32_t take = min((uint32_t)nfree, park_count - park_next);
+      if ((uint32_t)lane < take) {
+        const uint32_t s = list[lane], r = park_next + (uint32_t)lane;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) st[w * PSLOTS + s] = park[w * 32 + r];
+        if (L::ORG) {
+#pragma unroll
+          for (int w = 0; w < 3; ++w) st[(L::W_OX + w) * PSLOTS + s] = park[(8 + w) * 32 + r];
+        }
+        st[L::W_TFAR * PSLOTS + s] = __float_as_uint(FLT_MAX);
+        st[L::W_U * PSLOTS + s] = 0u; st[L::W_V * PSLOTS + s] = 0u;
+        st[L::W_BEST * PSLOTS + s] = NONE;
+        st[L::W_SPV * PSLOTS + s] = 0u;
+        if (STATS) { st[L::W_CNT * PSLOTS + s] = 0u; st[(L::W_CNT + 1) * PSLOTS + s] = 0u; }
+        st[L::W_CUR * PSLOTS + s] = 0u;  // the root (meshes without triangles never reach the kernel)
+      }
+      __syncwarp();
+      park_next += take;
+      continue;
+    }
+    if (nnode + ntri == 0) break;  // nothing in flight and nothing left to refill with
+
+    // =========================== pick the step and compact its slots onto the lanes ===========================
+    const int score_n = min(nnode, 32), score_t = min(ntri, 32) * J3DG_POOL_TRI_WEIGHT;
+    const bool do_tri = nnode == 0 || score_t > score_n || (score_t == score_n && ntri > nnode);
+    const uint32_t mLo = do_tri ? tLo : nLo, mHi = do_tri ? tHi : nHi;
+    uint32_t r0, r1;  // alternate which half is served first: no slot starves
+    if (iter & 1u) { r1 = __popc(mHi & lt_mask); r0 = __popc(mHi) + __popc(mLo & lt_mask); }
+    else { r0 = __popc(mLo & lt_mask); r1 = __popc(mLo) + __popc(mHi & lt_mask); }
+    if (((mLo >> lane) & 1u) && r0 < 32u) list[r0] = (uint32_t)lane;
+    if (((mHi >> lane) & 1u) && r1 < 32u) list[r1] = 32u + (uint32_t)lane;
+    __syncwarp();
+    const bool active = lane < min(32, __popc(mLo) + __popc(mHi));
+    const uint32_t s = active ? list[lane] : 0u;
+
+    if (!do_tri) {
+      // ---------------- node step: 8 quantised child boxes ----------------
+      if (active) {
+        const uint32_t spv = st[L::W_SPV * PSLOTS + s];
+        int sp = (int)(spv & 0xFFu);
+        uint32_t visits = (spv >> 8) & 0xFFu;
+        const uint32_t mesh_k = spv >> 16;
+        if (!STATS && visits >= p.budget) {
+          evict(s);
+        } else {
+          if (STATS) st[L::W_CNT * PSLOTS + s] += 1u; else ++visits;
+          const float idx = __uint_as_float(st[L::W_IDX * PSLOTS + s]), idy = __uint_as_float(st[L::W_IDY * PSLOTS + s]), idz = __uint_as_float(st[L::W_IDZ * PSLOTS + s]);
+          const float t_far = __uint_as_float(st[L::W_TFAR * PSLOTS + s]);
+          const uint32_t cur0 = st[L::W_CUR * PSLOTS + s];
+          float ox = o0x, oy = o0y, oz = o0z;
+          const WideNode* __restrict__ nodes = nodes0;
+          const TriRec* __restrict__ tris = tris0;
+          if (L::ORG) { ox = __uint_as_float(st[(L::W_OX + 0) * PSLOTS + s]); oy = __uint_as_float(st[(L::W_OX + 1) * PSLOTS + s]); oz = __uint_as_float(st[(L::W_OX + 2) * PSLOTS + s]); }
+          if (multi) {
+            const MeshDev& m = p.meshes[mesh_k];
+            nodes = m.nodes; tris = m.tris;
+            if (!L::ORG) {
+              const float4 o = mat_vec(m.cs_inv, make_float4(p.vw.origin[0], p.vw.origin[1], p.vw.origin[2], p.vw.origin[3]));
+              ox = o.x; oy = o.y; oz = o.z;
+            }
+          }
+          const uint32_t sel_nx = plane_sel(idx < 0.f ? 3u : 0u), sel_fx = plane_sel(idx < 0.f ? 0u : 3u);
+          const uint32_t sel_ny = plane_sel(idy < 0.f ? 4u : 1u), sel_fy = plane_sel(idy < 0.f ? 1u : 4u);
+          const uint32_t sel_nz = plane_sel(idz < 0.f ? 5u : 2u), sel_fz = plane_sel(idz < 0.f ? 2u : 5u);
+          const char* np = reinterpret_cast<const char*>(nodes + cur0);
+          const U32x8 q0 = ldg256(np), q1 = ldg256(np + 32), q2 = ldg256(np + 64), q3 = ldg256(np + 96);
+          const Slab X = slab(__uint_as_float(q0.v[4]), __uint_as_float(q0.v[0]), ox, idx);
+          const Slab Y = slab(__uint_as_float(q0.v[5]), __uint_as_float(q0.v[1]), oy, idy);
+          const Slab Z = slab(__uint_as_float(q0.v[6]), __uint_as_float(q0.v[2]), oz, idz);
+          // Entry distance of child i, low 3 bits replaced by i (distances are positive, so their bit patterns
+          // order like integers); missed children get +inf.  Empty slots have inverted boxes and never pass.
+          constexpr uint32_t MISS_KEY = 0x7F800000u;
+          auto child_key = [&](uint32_t lo, uint32_t hi, uint32_t i) -> uint32_t {
+            float tmin = fmaxf(fmaxf(fmaf(plane(lo, hi, sel_nx), X.S, X.Bn), fmaf(plane(lo, hi, sel_ny), Y.S, Y.Bn)), fmaxf(fmaf(plane(lo, hi, sel_nz), Z.S, Z.Bn), t_near));
+            float tmax = fminf(fminf(fmaf(plane(lo, hi, sel_fx), X.S, X.Bf), fmaf(plane(lo, hi, sel_fy), Y.S, Y.Bf)), fminf(fmaf(plane(lo, hi, sel_fz), Z.S, Z.Bf), t_far));
+            // conservative padding against rounding of the slab arithmetic
+            tmin = fmaf(-fabsf(tmin), 2e-6f, tmin);
+            tmax = fmaf(fabsf(tmax), 2e-6f, tmax);
+            return tmin <= tmax ? ((__float_as_uint(tmin) & ~7u) | i) : (MISS_KEY | i);
+          };
+          const uint32_t k0 = child_key(q1.v[0], q1.v[1], 0u), k1 = child_key(q1.v[2], q1.v[3], 1u), k2 = child_key(q1.v[4], q1.v[5], 2u), k3 = child_key(q1.v[6], q1.v[7], 3u);
+          const uint32_t k4 = child_key(q2.v[0], q2.v[1], 4u), k5 = child_key(q2.v[2], q2.v[3], 5u), k6 = child_key(q2.v[4], q2.v[5], 6u), k7 = child_key(q2.v[6], q2.v[7], 7u);
+          const int nearest = min(min(min((int)k0, (int)k1), min((int)k2, (int)k3)), min(min((int)k4, (int)k5), min((int)k6, (int)k7)));
+          const uint32_t ni = (uint32_t)nearest & 7u;
+          uint32_t near_ref = q3.v[0];
+          near_ref = ni == 1u ? q3.v[1] : near_ref; near_ref = ni == 2u ? q3.v[2] : near_ref; near_ref = ni == 3u ? q3.v[3] : near_ref;
+          near_ref = ni == 4u ? q3.v[4] : near_ref; near_ref = ni == 5u ? q3.v[5] : near_ref; near_ref = ni == 6u ? q3.v[6] : near_ref;
+          near_ref = ni == 7u ? q3.v[7] : near_ref;
+          if ((uint32_t)nearest >= MISS_KEY) near_ref = J3DG_EMPTY_CHILD;
+          // pushes of the other hit children (a full stack drops them: the ray is evicted below)
+          int wanted = sp;
+          auto push = [&](uint32_t key, uint32_t ref) {
+            const bool go = key < MISS_KEY && (int)key != nearest;
+            if (go && sp < PSTACK) stk[sp * PSLOTS + s] = make_uint2(ref, key);
+            wanted += go ? 1 : 0;
+            sp = min(sp + (go ? 1 : 0), PSTACK);
+          };
+          push(k0, q3.v[0]); push(k1, q3.v[1]); push(k2, q3.v[2]); push(k3, q3.v[3]);
+          push(k4, q3.v[4]); push(k5, q3.v[5]); push(k6, q3.v[6]); push(k7, q3.v[7]);
+          if (wanted > PSTACK) {  // stack full: the group kernel (96 entries) takes the ray
+            evict(s);
+          } else {
+            uint32_t cur = near_ref;
+            if (cur == J3DG_EMPTY_CHILD) {
+              while (sp > 0) {
+                --sp;
+                const uint2 e = stk[sp * PSLOTS + s];
+                if (__uint_as_float(e.y & ~7u) <= t_far) { cur = e.x; break; }  // entries beyond the shrunk interval are skipped
+              }
+            }
+            const uint32_t nspv = (uint32_t)sp | (visits << 8) | (mesh_k << 16);
+            if (cur == J3DG_EMPTY_CHILD) finish(s, nspv);
+            else {
+              st[L::W_CUR * PSLOTS + s] = cur;
+              st[L::W_SPV * PSLOTS + s] = nspv;
+              prefetch(nodes, tris, cur);
+            }
+          }
+        }
+      }
+    } else {
+      // ---------------- triangle step: one record per lane and round; lanes walk on through their leaf ----------------
+      bool live = active;
+      uint32_t cur = 0, spv = 0, kw = 0;
+      float ox = o0x, oy = o0y, oz = o0z, Sx = 0.f, Sy = 0.f, Sz = 0.f, t_far = 0.f;
+      const WideNode* __restrict__ nodes = nodes0;
+      const TriRec* __restrict__ tris = tris0;
+      bool ended = false;  // the ray has left its leaf (cur = next node / record or EMPTY)
+      if (active) {
+        cur = st[L::W_CUR * PSLOTS + s];
+        spv = st[L::W_SPV * PSLOTS + s];
+        kw = st[L::W_K * PSLOTS + s];
+        Sx = __uint_as_float(st[L::W_SX * PSLOTS + s]); Sy = __uint_as_float(st[L::W_SY * PSLOTS + s]); Sz = __uint_as_float(st[L::W_SZ * PSLOTS + s]);
+        t_far = __uint_as_float(st[L::W_TFAR * PSLOTS + s]);
+        if (L::ORG) { ox = __uint_as_float(st[(L::W_OX + 0) * PSLOTS + s]); oy = __uint_as_float(st[(L::W_OX + 1) * PSLOTS + s]); oz = __uint_as_float(st[(L::W_OX + 2) * PSLOTS + s]); }
+        if (multi) {
+          const MeshDev& m = p.meshes[spv >> 16];
+          nodes = m.nodes; tris = m.tris;
+          if (!L::ORG) {
+            const float4 o = mat_vec(m.cs_inv, make_float4(p.vw.origin[0], p.vw.origin[1], p.vw.origin[2], p.vw.origin[3]));
+            ox = o.x; oy = o.y; oz = o.z;
+          }
+        }
+      }
+      const int kx = (int)(kw & 3u), ky = (int)((kw >> 2) & 3u), kz = (int)((kw >> 4) & 3u);
+      int sp = (int)(spv & 0xFFu);
+      do {
+        if (live) {
+          const uint32_t slot = cur & J3DG_LEAF_FIRST_MASK;
+          const float4* tp = reinterpret_cast<const float4*>(tris + slot);
+          const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+          if (STATS) st[(L::W_CNT + 1) * PSLOTS + s] += 1u;
+          // one lane of intersect_woop (qbvh.h:4825-4869); 1/det is correctly rounded instead of rcpps + NR
+          const float Ax_ = fsub(v0.x, ox), Ay_ = fsub(v0.y, oy), Az_ = fsub(v0.z, oz);
+          const float Bx_ = fsub(v1.x, ox), By_ = fsub(v1.y, oy), Bz_ = fsub(v1.z, oz);
+          const float Cx_ = fsub(v2.x, ox), Cy_ = fsub(v2.y, oy), Cz_ = fsub(v2.z, oz);
+          const float Akz = pick(Ax_, Ay_, Az_, kz), Bkz = pick(Bx_, By_, Bz_, kz), Ckz = pick(Cx_, Cy_, Cz_, kz);
+          const float Ax = fsub(pick(Ax_, Ay_, Az_, kx), fmul(Sx, Akz));
+          const float Ay = fsub(pick(Ax_, Ay_, Az_, ky), fmul(Sy, Akz));
+          const float Bx = fsub(pick(Bx_, By_, Bz_, kx), fmul(Sx, Bkz));
+          const float By = fsub(pick(Bx_, By_, Bz_, ky), fmul(Sy, Bkz));
+          const float Cx = fsub(pick(Cx_, Cy_, Cz_, kx), fmul(Sx, Ckz));
+          const float Cy = fsub(pick(Cx_, Cy_, Cz_, ky), fmul(Sy, Ckz));
+          const float U = fsub(fmul(Cx, By), fmul(Cy, Bx));
+          const float V = fsub(fmul(Ax, Cy), fmul(Ay, Cx));
+          const float W = fsub(fmul(Bx, Ay), fmul(By, Ax));
+          const bool inside = ((U <= 0.f) && (V <= 0.f) && (W <= 0.f)) || ((U >= 0.f) && (V >= 0.f) && (W >= 0.f));
+          const float det = fadd(fadd(U, V), W);
+          bool hit = false;
+          if (inside && det != 0.f) {
+            const float inv_det = fdiv(1.f, det);
+            const float Az = fmul(Sz, Akz), Bz = fmul(Sz, Bkz), Cz = fmul(Sz, Ckz);
+            const float T = fadd(fadd(fmul(U, Az), fmul(V, Bz)), fmul(W, Cz));
+            const float t = fmul(T, inv_det);
+            if ((t_far > t) && (t > t_near)) {  // t_far is the best t so far: strictly closer
+              hit = true;
+              t_far = t;
+              st[L::W_TFAR * PSLOTS + s] = __float_as_uint(t);
+              st[L::W_U * PSLOTS + s] = __float_as_uint(fmul(V, inv_det));
+              st[L::W_V * PSLOTS + s] = __float_as_uint(fmul(W, inv_det));
+              st[L::W_BEST * PSLOTS + s] = slot;
+              kw = (kw & 0xFFFFu) | ((spv >> 16) << 16);
+              st[L::W_K * PSLOTS + s] = kw;
+            }
+          }
+          if (ANY_HIT && hit) { cur = J3DG_EMPTY_CHILD; sp = 0; ended = true; live = false; }
+          else if (__float_as_uint(v1.w) != 0u) {  // end of leaf
+            cur = J3DG_EMPTY_CHILD;
+            while (sp > 0) {
+              --sp;
+              const uint2 e = stk[sp * PSLOTS + s];
+              if (__uint_as_float(e.y & ~7u) <= t_far) { cur = e.x; break; }
+            }
+            ended = true; live = false;
+          } else cur = cur + 1u;
+        }
+      } while (__popc(__ballot_sync(0xffffffffu, live)) >= J3DG_POOL_TRI_MIN_LANES);
+      if (active) {
+        const uint32_t nspv = (uint32_t)sp | (spv & 0xFFFFFF00u);
+        if (ended && cur == J3DG_EMPTY_CHILD) finish(s, nspv);
+        else {
+          st[L::W_CUR * PSLOTS + s] = cur;
+          if (ended) { st[L::W_SPV * PSLOTS + s] = nspv; prefetch(nodes, tris, cur); }
+        }
+      }
+    }
+    __syncwarp();  // the slots' new states are visible to the next classification
+  }
+  if (STATS) {
+    for (int o = 16; o; o >>= 1) {
+      sum_nodes += __shfl_xor_sync(0xffffffffu, sum_nodes, o);
+      sum_tris += __shfl_xor_sync(0xffffffffu, sum_tris, o);
+    }
+    if (lane == 0) {
+      atomicAdd(p.stats + 0, (unsigned long long)sum_nodes);
+      atomicAdd(p.stats + 1, (unsigned long long)sum_tris);
+    }
+  }
+}
+
+template <int MODE, bool STATS>
+constexpr size_t cast_smem_bytes() {
+#if J3DG_POOL_MODE
+  return (size_t)(BLOCK_THREADS / 32) * PoolLayout<MODE, STATS>::WARP_WORDS * sizeof(uint32_t);
+#else
+  return CAST_SMEM;
+#endif
+}
+
 // The cast kernel proper: one launch, two kinds of warps.  Blocks [0, consumer_blocks) consume the hard-ray
 // queue from the start; all other blocks first trace tiles (one ray per lane, evicting long rays into the
 // queue), sign off, and then help to drain the queue.  The launch is cooperative, so every block is resident
 // and the consumers may wait for the producers.
 template <int MODE, bool STATS>
-__global__ void __launch_bounds__(BLOCK_THREADS, J3DG_LANE_MIN_BLOCKS) cast_kernel(const TraceParams p) {
-  __shared__ __align__(16) unsigned char smem[CAST_SMEM];
+__global__ void __launch_bounds__(BLOCK_THREADS, J3DG_POOL_MODE ? J3DG_POOL_MIN_BLOCKS : J3DG_LANE_MIN_BLOCKS) cast_kernel(const TraceParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];  // cast_smem_bytes<MODE, STATS>()
 #ifdef J3DG_TIMELINE
   unsigned long long tl0, tl1, tl2;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl0));
 #endif
+#if J3DG_POOL_MODE
+  uint32_t* const wsm = reinterpret_cast<uint32_t*>(smem) + (threadIdx.x >> 5) * PoolLayout<MODE, STATS>::WARP_WORDS;
+  uint2* const warp_stack = reinterpret_cast<uint2*>(wsm);  // the group stacks reuse the warp's region once its slots are empty
+  if (blockIdx.x >= p.consumer_blocks) {
+    pool_loop<MODE, STATS>(p, wsm);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+      __threadfence();
+      atomicAdd(p.done_blocks, 1u);
+    }
+  }
+#else
   static_assert((LANE_STACK + 1) * 32 / 4 >= STACK_SIZE, "a warp's stack slice must hold four group stacks");
   uint2* const warp_stack = reinterpret_cast<uint2*>(smem) + (threadIdx.x >> 5) * ((LANE_STACK + 1) * 32);
   if (blockIdx.x >= p.consumer_blocks) {
@@ -878,6 +1321,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_LANE_MIN_BLOCKS) cast_kern
       atomicAdd(p.done_blocks, 1u);
     }
   }
+#endif
 #ifdef J3DG_TIMELINE
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl1));
 #endif
@@ -1142,15 +1586,17 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   tp.hard_best = (float4*)ctx->d_hard;
   tp.hard_id = (uint2*)((char*)ctx->d_hard + ctx->hard_id_off);
   tp.hard_capacity = (uint32_t)std::min<size_t>((ctx->hard_cap - ctx->hard_id_off) / sizeof(uint2), ctx->hard_id_off / sizeof(float4));
-  tp.budget = stats ? 0xFFFFFFFFu : ctx->lane_budget;
+  tp.budget = stats ? 0xFFFFFFFFu : std::min<uint32_t>(ctx->lane_budget, 255u);  // pool mode counts visits in 8 bits
   auto ctr = [&](int slot) { return reinterpret_cast<unsigned int*>(ctx->d_stats + slot); };
   const bool sharded = ctx->shard_world > 1 && !stats;
   tp.grid = make_tile_grid(x0, y0, x1, y1, sharded ? ctx->shard_rank : 0u, sharded ? ctx->shard_world : 1u);
   const long long ntiles = tp.grid.total_pools;
   // One cooperative launch of the hybrid kernel: the grid fills the machine once, every block is resident.
-  auto launch_hybrid = [&](auto kernel, long long pools) -> int {
+  auto launch_hybrid = [&](auto kernel, size_t smem, long long pools) -> int {
     int nb = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, BLOCK_THREADS, 0);
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, BLOCK_THREADS, smem);
     if (e != cudaSuccess) return j3dg_cuda_fail(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor", __FILE__, __LINE__);
     const int full = ctx->sm_count * std::max(nb, 1);
     // dedicated consumer blocks only when the machine is full anyway; small jobs just run producers that convert
@@ -1158,7 +1604,7 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
     const long long producers = std::max<long long>(1, std::min<long long>((long long)full - tp.consumer_blocks, (pools + 3) / 4));
     const int grid = (int)(producers + tp.consumer_blocks);
     void* args[] = {(void*)&tp};
-    e = cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(BLOCK_THREADS), args, 0, ctx->stream);
+    e = cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(BLOCK_THREADS), args, smem, ctx->stream);
     if (e != cudaSuccess) return j3dg_cuda_fail(ctx, e, "cudaLaunchCooperativeKernel", __FILE__, __LINE__);
     ctx->launches++;
     return J3DG_OK;
@@ -1169,13 +1615,13 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   // ---- primary rays ----
   tp.pool_ctr = ctr(3); tp.hard_count = ctr(6); tp.hard_taken = ctr(7); tp.done_blocks = ctr(11);
   if (stats) {
-    if ((rc = launch_hybrid(cast_kernel<PRIMARY, true>, ntiles)) != J3DG_OK) return rc;
+    if ((rc = launch_hybrid(cast_kernel<PRIMARY, true>, cast_smem_bytes<PRIMARY, true>(), ntiles)) != J3DG_OK) return rc;
   } else if (ctx->cast_algo == 1) {  // 8-lanes-per-ray kernel only (A/B testing)
     if ((rc = persistent_grid(ctx, group_kernel<PRIMARY>, ntiles, &grid)) != J3DG_OK) return rc;
     group_kernel<PRIMARY><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
     KERNEL_CHECK(ctx);
   } else {
-    if ((rc = launch_hybrid(cast_kernel<PRIMARY, false>, ntiles)) != J3DG_OK) return rc;
+    if ((rc = launch_hybrid(cast_kernel<PRIMARY, false>, cast_smem_bytes<PRIMARY, false>(), ntiles)) != J3DG_OK) return rc;
   }
   if (used && !stats) {
     const uint32_t warps = 256 / 32;
@@ -1187,13 +1633,13 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   if (shadows) {
     const long long pools = ((long long)npx + 31) / 32;
     tp.pool_ctr = ctr(8); tp.hard_count = ctr(9); tp.hard_taken = ctr(10); tp.done_blocks = ctr(12);
-    tp.budget = ctx->shadow_budget;  // any-hit rays that start on the surface: their long ones are long from the start
+    tp.budget = std::min<uint32_t>(ctx->shadow_budget, 255u);  // any-hit rays that start on the surface: their long ones are long from the start
     if (ctx->cast_algo == 1) {
       if ((rc = persistent_grid(ctx, group_kernel<SHADOW>, pools, &grid)) != J3DG_OK) return rc;
       group_kernel<SHADOW><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
       KERNEL_CHECK(ctx);
     } else {
-      if ((rc = launch_hybrid(cast_kernel<SHADOW, false>, pools)) != J3DG_OK) return rc;
+      if ((rc = launch_hybrid(cast_kernel<SHADOW, false>, cast_smem_bytes<SHADOW, false>(), pools)) != J3DG_OK) return rc;
     }
   }
   rc = j3dg_stage_end(ctx, 0);

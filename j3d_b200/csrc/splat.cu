@@ -2,27 +2,32 @@
 // (j3d/canvas.cpp:952-1030) = jtk::bind / _draw / present (jtk/render.h:254-288, 307-512, 514-865).
 //
 // The reference projects all points in parallel and then z-tests them in ONE serial loop, four
-// points per SSE packet.  For a pixel that is touched by at most one lane of any packet the
-// outcome is order-free: the point with the largest 1/w wins, the lowest index wins ties, and
-// it must be strictly in front of the mesh depth.  That case is handled with one 64-bit
-// atomicMax per point on a packed word (float bits of 1/w) << 32 | (0xFFFFFFFE - index)
-// (1/w > 0 so the bit pattern is monotone), seeded from the pixel buffer with low word
-// 0xFFFFFFFF; a resolve pass then shades only the winners (colour / normal are fetched for
-// ~W*H points instead of all N) and patches the pixel records.
-//
-// When two lanes of the SAME packet land on one pixel the reference is order-dependent
-// (render.h:783-807: all four lanes test against the pre-packet depth, then write in lane
-// order; a lane that fails writes the old value back; masked lanes are clamped onto some pixel
-// and write it back too).  Those pixels are detected during projection ("dirty"), every point
-// that touches a dirty pixel is collected, radix-sorted by (pixel, index) and replayed
-// sequentially per pixel with the reference's exact packet semantics — bit-identical results,
-// at a cost proportional to the number of dirty pixels (a few hundred for a random 100 M-point
-// cloud at 1080p; the whole cloud in the worst case of scan-ordered input).
+// points per SSE packet: all four lanes test against the PRE-packet depth, then write in lane order; a lane
+// that fails writes the old depth / colour back; masked lanes are clamped onto some pixel and write it back
+// too (render.h:783-807).  Stated per pixel q, with z the pixel's depth before a packet and d_1..d_j the
+// depths of the packet's lanes that land on q (lane order, masked lanes = never pass):
+//     depth, colour :  z' = max(z, d_j) — only the LAST lane on q counts; an earlier lane's write is always
+//                      overwritten by it (with its own values if it passes, with the old ones if not)
+//     pixel record  :  the canvas callback fires for EVERY passing lane (z < d_i); the last one sticks
+// Folding that over all packets in order gives an order-free statement:
+//     M  = max(z0, depths of last-on-q lanes)                      -> final depth
+//     W  = the lowest-index last-on-q lane with depth M (if M > z0) -> final colour
+//     id = the highest-index NOT-last-on-q lane after W with depth > M, else W
+// (after W's packet z equals M for good, so a later lane passes iff its depth exceeds M, which only a lane
+// that is not the last one on q can do).  So ONE pass suffices: last-on-q lanes do a 64-bit atomicMax on
+// (float bits of 1/w) << 32 | (0xFFFFFFFE - index) (1/w > 0, so the bit pattern is monotone; seeded from the
+// pixel buffer with low word 0xFFFFFFFF, i.e. "strictly in front of the mesh", lowest index wins ties);
+// the rare lanes that share a pixel with a LATER lane of their own packet go to a small list that is
+// checked against the final M in a second, tiny kernel (atomicMax of index + 1 per pixel).  A resolve pass
+// then shades only the winners (colour / normal are fetched for <= W*H points instead of all N) and patches
+// the pixel records.  Bit-identical to the reference's serial loop, without a sort, a second projection pass
+// or a host round trip (round 1 replayed the collisions sequentially: 1.3 of its 2.2 ms on 100 M points).
 //
 // Projection, rounding (round-to-nearest-even; truncation + clip test for the last N mod 4
 // points) and the Lambert term follow the reference's operation order with unfused arithmetic.
 #include "common.cuh"
-#include "sort.cuh"
+
+#include <algorithm>
 
 namespace {
 
@@ -36,7 +41,7 @@ struct SplatParams {
 };
 
 __global__ void __launch_bounds__(256) seed_kernel(const j3dg_pixel* __restrict__ px, uint32_t pstride, int w, int h,
-                                                    unsigned long long* __restrict__ packed, float* __restrict__ zprev) {
+                                                    unsigned long long* __restrict__ packed, uint32_t* __restrict__ idcand) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= w || y >= h) return;
   const j3dg_pixel* p = px + (size_t)y * pstride + x;
@@ -44,14 +49,12 @@ __global__ void __launch_bounds__(256) seed_kernel(const j3dg_pixel* __restrict_
   const float depth = __ldg(reinterpret_cast<const float*>(p) + 3);
   const float z = db != 0u ? fdiv(1.f, depth) : 0.f;  // canvas.cpp:968
   packed[(size_t)y * w + x] = ((unsigned long long)__float_as_uint(z) << 32) | 0xFFFFFFFFull;
-  zprev[(size_t)y * w + x] = z;
+  idcand[(size_t)y * w + x] = 0u;
 }
 
 // _mm_cvtps_epi32 / cvttss2si semantics: NaN and out-of-range give INT_MIN
 __device__ __forceinline__ int cvt_rne(float x) { return (fabsf(x) < 2147483648.f) ? __float2int_rn(x) : (int)0x80000000; }
 __device__ __forceinline__ int cvt_trunc(float x) { return (fabsf(x) < 2147483648.f) ? __float2int_rz(x) : (int)0x80000000; }
-
-constexpr uint32_t REPLAY_MASKED = 0xFFFFFFFFu;  // a NaN pattern: like a masked lane, a NaN depth never passes the test
 
 struct Lane {
   int idx;       // clamped pixel index (render.h:779-781)
@@ -108,62 +111,77 @@ __device__ __forceinline__ void load_packet(const float* __restrict__ pos, uint3
   c[8] = d.x; c[9] = d.y; c[10] = d.z; c[11] = d.w;
 }
 
+// A lane that shares its pixel with a later lane of its own packet (see the header).
+struct Anomaly { uint32_t pixel, index, depth_bits; };
+
+__device__ __forceinline__ void splat_max(unsigned long long* __restrict__ packed, int idx, float depth, uint32_t index) {
+  const unsigned long long word = ((unsigned long long)__float_as_uint(depth) << 32) | (unsigned long long)(0xFFFFFFFEu - index);
+  unsigned long long* cell = packed + idx;
+  if (word > *((volatile unsigned long long*)cell)) atomicMax(cell, word);  // the plain read filters the ~98 % of the points that lose
+}
+
 // Thread t < npackets: one SIMD packet (4 points); the remaining threads: one tail point each.
-// COLLECT = false: atomicMax splat + dirty-pixel detection.
-// COLLECT = true : append every (pixel, point) pair that touches a dirty pixel to `list`.
-template <bool COLLECT>
 __global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ pos, SplatParams s, unsigned long long* __restrict__ packed,
-                                                       uint8_t* __restrict__ dirty, uint32_t* __restrict__ counters,
-                                                       unsigned long long* __restrict__ list, uint32_t* __restrict__ list_depth) {
+                                                       uint32_t* __restrict__ anomaly_count, Anomaly* __restrict__ anomalies) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t npackets = s.tail_start >> 2;
+  uint32_t nanom = 0;     // lanes of this packet that go to the anomaly list (bit k)
+  Lane l[4];
   if (t < npackets) {
     float c[12];
     load_packet(pos, t, c);
-    Lane l[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) l[k] = project_simd(s, c[3 * k], c[3 * k + 1], c[3 * k + 2]);
-    if (l[0].masked && l[1].masked && l[2].masked && l[3].masked) return;  // render.h:734-735
-    if (!COLLECT) {
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = a + 1; b < 4; ++b)
-          if (l[a].idx == l[b].idx && !(l[a].masked && l[b].masked)) {
-            dirty[l[a].idx] = 1;
-            counters[0] = 1u;
-          }
+    if (!(l[0].masked && l[1].masked && l[2].masked && l[3].masked)) {  // render.h:734-735
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (l[k].masked || !(l[k].depth > 0.f)) continue;  // the z-buffer is never negative
-        const unsigned long long word = ((unsigned long long)__float_as_uint(l[k].depth) << 32) | (unsigned long long)(0xFFFFFFFEu - (4u * t + k));
-        unsigned long long* cell = packed + l[k].idx;
-        if (word > *((volatile unsigned long long*)cell)) atomicMax(cell, word);
-      }
-    } else {
+        if (l[k].masked || !(l[k].depth > 0.f)) continue;  // the z-buffer is never negative: such a lane never passes
+        bool last = true;                                   // no later lane (masked or not) lands on the same pixel
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (dirty[l[k].idx]) {  // the replay needs the lane's depth, or that it is masked (then it only writes the old value back)
-          const uint32_t e = atomicAdd(&counters[1], 1u);
-          list[e] = ((unsigned long long)(uint32_t)l[k].idx << 32) | (unsigned long long)(4u * t + k);
-          list_depth[e] = l[k].masked ? REPLAY_MASKED : __float_as_uint(l[k].depth);
-        }
+        for (int j = k + 1; j < 4; ++j) last = last && (l[j].idx != l[k].idx);
+        if (last) splat_max(packed, l[k].idx, l[k].depth, 4u * t + k);
+        else nanom |= 1u << k;
+      }
     }
   } else {
     const uint32_t i = s.tail_start + (t - npackets);
-    if (i >= s.n) return;
-    const Lane l = project_tail(s, __ldg(pos + 3 * (size_t)i), __ldg(pos + 3 * (size_t)i + 1), __ldg(pos + 3 * (size_t)i + 2));
-    if (l.masked) return;
-    if (!COLLECT) {
-      if (!(l.depth > 0.f)) return;
-      const unsigned long long word = ((unsigned long long)__float_as_uint(l.depth) << 32) | (unsigned long long)(0xFFFFFFFEu - i);
-      unsigned long long* cell = packed + l.idx;
-      if (word > *((volatile unsigned long long*)cell)) atomicMax(cell, word);
-    } else if (dirty[l.idx]) {
-      const uint32_t e = atomicAdd(&counters[1], 1u);
-      list[e] = ((unsigned long long)(uint32_t)l.idx << 32) | (unsigned long long)i;
-      list_depth[e] = __float_as_uint(l.depth);
+    if (i < s.n) {
+      const Lane tl = project_tail(s, __ldg(pos + 3 * (size_t)i), __ldg(pos + 3 * (size_t)i + 1), __ldg(pos + 3 * (size_t)i + 2));
+      if (!tl.masked && tl.depth > 0.f) splat_max(packed, tl.idx, tl.depth, i);  // render.h:847-862: plain d > z
     }
+  }
+  // append the anomalies: one atomic per warp
+  if (__any_sync(0xffffffffu, nanom != 0u)) {
+    const uint32_t mine = __popc(nanom);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)(threadIdx.x & 31) >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(anomaly_count, total);
+    base = __shfl_sync(0xffffffffu, base, 0) + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (nanom & (1u << k)) anomalies[base++] = Anomaly{(uint32_t)l[k].idx, 4u * t + k, __float_as_uint(l[k].depth)};
+  }
+}
+
+// The lanes on the list fire the canvas callback iff their depth beats the pixel's FINAL depth and they come after
+// the winner W in index order; the highest such index names the pixel record (header).  Runs after project_kernel.
+__global__ void __launch_bounds__(256) anomaly_kernel(const uint32_t* __restrict__ anomaly_count, const Anomaly* __restrict__ anomalies,
+                                                       const unsigned long long* __restrict__ packed, uint32_t* __restrict__ idcand) {
+  const uint32_t count = *anomaly_count;
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+    const Anomaly a = anomalies[e];
+    const unsigned long long word = packed[a.pixel];
+    const uint32_t low = (uint32_t)word;
+    const float m = __uint_as_float((uint32_t)(word >> 32));
+    if (!(m < __uint_as_float(a.depth_bits))) continue;                      // render.h:791-792 against the final depth
+    if (low != 0xFFFFFFFFu && a.index < 0xFFFFFFFEu - low) continue;         // before the winner: overwritten by it
+    atomicMax(idcand + a.pixel, a.index + 1u);
   }
 }
 
@@ -191,88 +209,32 @@ __device__ __forceinline__ uint32_t shade_point(const SplatParams& s, const floa
   return color;
 }
 
-// Sequential replay of every dirty pixel with the reference's packet semantics.  `list` is sorted by
-// (pixel, point index) and carries each entry's projected depth (REPLAY_MASKED for lanes outside the canvas),
-// so the fold over a pixel's entries touches no point data; the thread at the first entry of a pixel walks
-// that pixel's entries and shades the surviving point once at the end.
-__global__ void __launch_bounds__(128) replay_kernel(SplatParams s, const float* __restrict__ nrm, const uint32_t* __restrict__ clr,
-                                                      const unsigned long long* __restrict__ list, const uint32_t* __restrict__ list_depth, uint32_t count,
-                                                      unsigned long long* __restrict__ packed, float* __restrict__ zprev,
-                                                      j3dg_pixel* __restrict__ px, uint32_t pstride, uint32_t* __restrict__ rgba, uint32_t rstride) {
-  const uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k0 >= count) return;
-  const uint32_t q = (uint32_t)(list[k0] >> 32);
-  if (k0 > 0 && (uint32_t)(list[k0 - 1] >> 32) == q) return;  // not the first entry of its pixel
-  float z = zprev[q];
-  constexpr uint32_t NONE = 0xFFFFFFFFu;
-  uint32_t color_point = NONE;  // the point whose colour the pixel ends up with
-  uint32_t id_point = NONE;     // the point the pixel record ends up naming, and the z-buffer value at that moment
-  float id_z = 0.f;
-  uint32_t k = k0;
-  while (k < count) {
-    unsigned long long e = list[k];
-    if ((uint32_t)(e >> 32) != q) break;
-    const uint32_t i = (uint32_t)e;
-    if (i >= s.tail_start) {  // scalar tail point, render.h:847-862 (clipped ones were never collected)
-      const float d = __uint_as_float(list_depth[k]);
-      if (d > z) { z = d; color_point = i; id_point = i; id_z = z; }
-      ++k;
-      continue;
-    }
-    // all lanes of this packet that touch the pixel: every test sees the pre-packet depth
-    const uint32_t packet = i >> 2;
-    const float z_old = z;
-    uint32_t last_pass_point = NONE;
-    bool last_lane_pass = false;
-    uint32_t last_lane_point = i;
-    float last_lane_depth = 0.f;
-    while (k < count) {
-      e = list[k];
-      const uint32_t pi = (uint32_t)e;
-      if ((uint32_t)(e >> 32) != q || (pi >> 2) != packet || pi >= s.tail_start) break;
-      const uint32_t bits = list_depth[k];
-      const float d = __uint_as_float(bits);
-      const bool pass = bits != REPLAY_MASKED && (z_old < d);  // render.h:791-792
-      if (pass) last_pass_point = pi;                           // the last passing lane's callback wins (canvas.cpp:999-1026)
-      last_lane_pass = pass; last_lane_point = pi; last_lane_depth = d;
-      ++k;
-    }
-    if (last_lane_pass) {  // the highest lane's write is the one that sticks (render.h:797-805)
-      z = last_lane_depth;
-      color_point = last_lane_point;
-    }  // else: it wrote the pre-packet depth and colour back
-    if (last_pass_point != NONE) { id_point = last_pass_point; id_z = z; }  // 1 / zbuffer after the packet's writes
-  }
-  const int qx = (int)(q % (uint32_t)s.w), qy = (int)(q / (uint32_t)s.w);
-  if (color_point != NONE) rgba[(size_t)qy * rstride + qx] = shade_point(s, nrm, clr, color_point);
-  if (id_point != NONE) {
-    j3dg_pixel* out_px = px + (size_t)qy * pstride + qx;
-    out_px->object_id = id_point;
-    out_px->depth = fdiv(1.f, id_z);
-    out_px->db_id = s.db_id;
-  }
-  zprev[q] = z;
-  packed[q] = ((unsigned long long)__float_as_uint(z) << 32) | 0xFFFFFFFFull;  // resolved: resolve_kernel skips it
-}
-
 __global__ void __launch_bounds__(256) resolve_kernel(SplatParams s, const float* __restrict__ nrm, const uint32_t* __restrict__ clr,
-                                                       unsigned long long* __restrict__ packed, float* __restrict__ zprev,
+                                                       unsigned long long* __restrict__ packed, uint32_t* __restrict__ idcand,
                                                        j3dg_pixel* __restrict__ px, uint32_t pstride, uint32_t* __restrict__ rgba, uint32_t rstride) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= s.w || y >= s.h) return;
-  unsigned long long* cell = packed + (size_t)y * s.w + x;
-  const unsigned long long word = *cell;
+  const size_t q = (size_t)y * s.w + x;
+  const unsigned long long word = packed[q];
   const uint32_t low = (uint32_t)word;
-  if (low == 0xFFFFFFFFu) return;  // no point in front of what was there (or already replayed)
-  const uint32_t i = 0xFFFFFFFEu - low;
+  const uint32_t cand = idcand[q];
+  if (low == 0xFFFFFFFFu && cand == 0u) return;  // no point in front of what was there
   const float zb = __uint_as_float((uint32_t)(word >> 32));
-  rgba[(size_t)y * rstride + x] = shade_point(s, nrm, clr, i);
+  uint32_t id_point;
+  if (low != 0xFFFFFFFFu) {  // a winner: depth and colour change
+    const uint32_t i = 0xFFFFFFFEu - low;
+    rgba[(size_t)y * rstride + x] = shade_point(s, nrm, clr, i);
+    id_point = i;
+    packed[q] = (word & 0xFFFFFFFF00000000ull) | 0xFFFFFFFFull;  // becomes the depth the next cloud has to beat
+  }
+  if (cand) {                // a later lane of a colliding packet fired the callback last
+    id_point = cand - 1u;
+    idcand[q] = 0u;
+  }
   j3dg_pixel* p = px + (size_t)y * pstride + x;  // canvas.cpp:997-1027
-  p->object_id = i;
+  p->object_id = id_point;
   p->depth = fdiv(1.f, zb);
   p->db_id = s.db_id;
-  *cell = (word & 0xFFFFFFFF00000000ull) | 0xFFFFFFFFull;  // becomes the depth the next cloud has to beat
-  zprev[(size_t)y * s.w + x] = zb;
 }
 
 // render.h helpers, host side, each operation rounded separately
@@ -307,12 +269,6 @@ void r_invert_orthonormal(float* out, const float* in) {  // render.h:133-154
   }
 }
 
-int bits_for(uint64_t v) {
-  int b = 0;
-  while (b < 64 && (v >> b)) ++b;
-  return b;
-}
-
 }  // namespace
 
 int j3dg_launch_splat(j3dg_ctx* ctx, j3dg_cloud* const* clouds, uint32_t nc, const j3dg_view* view,
@@ -321,27 +277,36 @@ int j3dg_launch_splat(j3dg_ctx* ctx, j3dg_cloud* const* clouds, uint32_t nc, con
   const int w = (int)view->width, h = (int)view->height;
   if (w <= 0 || h <= 0) return J3DG_OK;
   const size_t npx = (size_t)w * h;
-  // packed words | previous depth | dirty flags | counters
-  const size_t off_z = npx * sizeof(unsigned long long);
-  const size_t off_dirty = off_z + npx * sizeof(float);
-  const size_t off_cnt = (off_dirty + npx + 255) & ~(size_t)255;
+  // packed words | id candidates | anomaly counter
+  const size_t off_cand = npx * sizeof(unsigned long long);
+  const size_t off_cnt = (off_cand + npx * sizeof(uint32_t) + 255) & ~(size_t)255;
   {
     void* p = ctx->d_packed;
     int rc = j3dg_reserve(ctx, &p, &ctx->packed_cap, off_cnt + 256);
     ctx->d_packed = (unsigned long long*)p;
     if (rc != J3DG_OK) return rc;
   }
+  // anomaly list: at most three lanes of every packet (a lane is listed only if a LATER lane shares its pixel)
+  uint32_t max_n = 0;
+  for (uint32_t c = 0; c < nc; ++c) {
+    if (!clouds[c]) { j3dg_set_error(ctx, "j3dg_splat: null cloud"); return J3DG_EINVAL; }
+    max_n = std::max(max_n, clouds[c]->n);
+  }
+  {
+    const size_t need = ((size_t)(max_n >> 2) * 3 + 4) * sizeof(Anomaly);
+    int rc = j3dg_reserve(ctx, &ctx->d_misc, &ctx->misc_cap, need);
+    if (rc != J3DG_OK) return rc;
+  }
   unsigned long long* packed = ctx->d_packed;
-  float* zprev = (float*)((char*)ctx->d_packed + off_z);
-  uint8_t* dirty = (uint8_t*)ctx->d_packed + off_dirty;
-  uint32_t* counters = (uint32_t*)((char*)ctx->d_packed + off_cnt);
+  uint32_t* idcand = (uint32_t*)((char*)ctx->d_packed + off_cand);
+  uint32_t* counter = (uint32_t*)((char*)ctx->d_packed + off_cnt);
+  Anomaly* anomalies = (Anomaly*)ctx->d_misc;
   dim3 pgrid((w + 31) / 32, (h + 7) / 8);
   { int rc = j3dg_stage_begin(ctx, 2); if (rc != J3DG_OK) return rc; }
-  seed_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_px_in, pstride, w, h, packed, zprev);
+  seed_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_px_in, pstride, w, h, packed, idcand);
   KERNEL_CHECK(ctx);
   for (uint32_t c = 0; c < nc; ++c) {
     const j3dg_cloud* cl = clouds[c];
-    if (!cl) { j3dg_set_error(ctx, "j3dg_splat: null cloud"); return J3DG_EINVAL; }
     SplatParams s;
     float temp[16];
     r_matmul(temp, view->cs_inv, cl->cs);
@@ -354,47 +319,14 @@ int j3dg_launch_splat(j3dg_ctx* ctx, j3dg_cloud* const* clouds, uint32_t nc, con
     s.w = w; s.h = h; s.n = cl->n; s.tail_start = cl->n - (cl->n & 3u); s.db_id = cl->db_id;
     s.use_normals = ((view->flags & J3DG_SHADING) && cl->d_nrm) ? 1u : 0u;   // canvas.cpp:994
     s.use_colors = (!(view->flags & J3DG_ONE_BIT) && cl->d_clr) ? 1u : 0u;    // canvas.cpp:995
-    if (cl->n) {
-      const uint32_t threads = (s.tail_start >> 2) + (cl->n - s.tail_start);
-      const uint32_t blocks = (threads + 255) / 256;
-      CU_CHECK(ctx, cudaMemsetAsync(dirty, 0, npx, ctx->stream));
-      CU_CHECK(ctx, cudaMemsetAsync(counters, 0, 16, ctx->stream));
-      project_kernel<false><<<blocks, 256, 0, ctx->stream>>>(cl->d_pos, s, packed, dirty, counters, nullptr, nullptr);
-      KERNEL_CHECK(ctx);
-      uint32_t h_cnt[2] = {0, 0};
-      CU_CHECK(ctx, cudaMemcpyAsync(h_cnt, counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
-      CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-      if (h_cnt[0]) {  // some packet hit one pixel with two lanes: exact sequential replay of those pixels
-        const size_t nn = cl->n;
-        const size_t need = 4 * 256 + 2 * nn * sizeof(uint64_t) + 2 * nn * sizeof(uint32_t) + rsort::scratch_bytes(cl->n) + 256;
-        int rc = j3dg_reserve(ctx, &ctx->d_misc, &ctx->misc_cap, need);
-        if (rc != J3DG_OK) return rc;
-        char* base = (char*)ctx->d_misc;
-        size_t off = 0;
-        auto take = [&](size_t bytes) { char* p = base + off; off = (off + bytes + 255) & ~(size_t)255; return p; };
-        uint64_t* keys_a = (uint64_t*)take(nn * 8);
-        uint64_t* keys_b = (uint64_t*)take(nn * 8);
-        uint32_t* vals_a = (uint32_t*)take(nn * 4);
-        uint32_t* vals_b = (uint32_t*)take(nn * 4);
-        uint32_t* scratch = (uint32_t*)take(rsort::scratch_bytes(cl->n));
-        project_kernel<true><<<blocks, 256, 0, ctx->stream>>>(cl->d_pos, s, packed, dirty, counters, (unsigned long long*)keys_a, vals_a);
-        KERNEL_CHECK(ctx);
-        CU_CHECK(ctx, cudaMemcpyAsync(h_cnt, counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
-        CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-        const uint32_t count = h_cnt[1];
-        if (count) {
-          bool in_b = false;
-          const int key_bits = 32 + bits_for(npx - 1);
-          rc = rsort::sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, count, key_bits, scratch, &in_b, false);
-          if (rc != J3DG_OK) return rc;
-          const unsigned long long* sorted = (const unsigned long long*)(in_b ? keys_b : keys_a);
-          replay_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(s, cl->d_nrm, cl->d_clr, sorted, in_b ? vals_b : vals_a, count, packed, zprev,
-                                                                       d_px_inout, pstride, d_rgba, rstride);
-          KERNEL_CHECK(ctx);
-        }
-      }
-    }
-    resolve_kernel<<<pgrid, 256, 0, ctx->stream>>>(s, cl->d_nrm, cl->d_clr, packed, zprev, d_px_inout, pstride, d_rgba, rstride);
+    if (!cl->n) continue;
+    const uint32_t threads = (s.tail_start >> 2) + (cl->n - s.tail_start);
+    CU_CHECK(ctx, cudaMemsetAsync(counter, 0, sizeof(uint32_t), ctx->stream));
+    project_kernel<<<(threads + 255) / 256, 256, 0, ctx->stream>>>(cl->d_pos, s, packed, counter, anomalies);
+    KERNEL_CHECK(ctx);
+    anomaly_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(counter, anomalies, packed, idcand);
+    KERNEL_CHECK(ctx);
+    resolve_kernel<<<pgrid, 256, 0, ctx->stream>>>(s, cl->d_nrm, cl->d_clr, packed, idcand, d_px_inout, pstride, d_rgba, rstride);
     KERNEL_CHECK(ctx);
   }
   return j3dg_stage_end(ctx, 2);
