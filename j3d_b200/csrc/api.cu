@@ -185,7 +185,7 @@ J3DG_API void j3dg_ctx_destroy(j3dg_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->d_pixels); cudaFree(ctx->d_pixels_in); cudaFree(ctx->d_rgba); cudaFree(ctx->d_bg); cudaFree(ctx->d_packed);
-  cudaFree(ctx->d_matcap); cudaFree(ctx->d_meshes); cudaFree(ctx->d_stats); cudaFree(ctx->d_misc); cudaFree(ctx->d_shadow); cudaFree(ctx->d_hard);
+  cudaFree(ctx->d_matcap); cudaFree(ctx->d_meshes); cudaFree(ctx->d_stats); cudaFree(ctx->d_misc); cudaFree(ctx->d_shadow); cudaFree(ctx->d_hard); cudaFree(ctx->d_spill);
   for (auto& sl : ctx->slot) {
     cudaFree(sl.d_px); cudaFree(sl.d_rgba);
     if (sl.kernels_done) cudaEventDestroy(sl.kernels_done);

@@ -107,6 +107,7 @@ struct TraceParams {
   TileGrid grid;                 // PRIMARY: the pools of this launch
   j3dg_pixel* out;               // PRIMARY: raw hits are written here; SHADOW: mark bit 0 is set here
   uint32_t stride;
+  uint2* spill;                  // pool mode: global continuation of the per-slot stacks, [warp][POOL_SPILL][PSLOTS]
   uint32_t* sticky;              // mapped host status words (common.cuh, j3dg_ctx::d_status): [1] = a traversal stack overflowed
   unsigned long long* stats;     // [0] node rounds [1] triangle tests [2] overflow flag [3] pool counter [4] shadow rays (accumulating) [5] shadow list length
   const float4* shadow_pos;      // SHADOW: ray origins (xyzw as the reference computes them)
@@ -191,6 +192,9 @@ __device__ __forceinline__ WorldRay world_ray(const TraceParams& p, uint32_t id)
 //            claimed index lies past the final length after every producer block has signed off.
 enum Source { POOLS = 0, QUEUE = 1 };
 constexpr uint32_t QUEUE_EMPTY = 0xFFFFFFFFu;
+#ifndef J3DG_IDLE_BACKOFF_MAX_NS
+#define J3DG_IDLE_BACKOFF_MAX_NS 8000u                    // longest wait of a warp that found nothing to claim
+#endif
 
 // `stk` = entry 0 of this group's stack, entry i at stk[i * GSTRIDE] (GSTRIDE groups are interleaved).
 template <int MODE, int SRC, int GSTRIDE>
@@ -237,6 +241,8 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const st
   uint32_t claimed = QUEUE_EMPTY;   // QUEUE: entry this group has claimed and waits for
   bool retired = false;             // QUEUE: nothing left for this group
   uint32_t backoff = 250u;          // QUEUE: nanoseconds an idle warp sleeps before it polls again (doubles up to 4 us)
+  uint32_t round_no = 0;            // QUEUE: while other groups of the warp traverse, an idle group polls only every 4th round
+  bool warp_busy = false;
   const uint32_t producer_warps = (gridDim.x - p.consumer_blocks) * (BLOCK_THREADS / 32);  // producers sign off warp by warp
 
   auto pop = [&]() -> uint32_t {
@@ -315,7 +321,8 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const st
     if (SRC == QUEUE) {
       // groups without a ray claim the next queue entry and poll it (once per round: never a spin inside a warp
       // whose other groups are traversing)
-      if (!have_ray && !retired) {
+      ++round_no;
+      if (!have_ray && !retired && (!warp_busy || (round_no & 3u) == 0u)) {
         if (claimed == QUEUE_EMPTY) {
           uint32_t i = 0;
           if (c == 0) i = atomicAdd(p.hard_taken, 1u);
@@ -344,10 +351,19 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const st
         }
       }
       const uint32_t busy = __ballot_sync(0xffffffffu, have_ray);
+      warp_busy = busy != 0u;
       if (!busy) {
         if (__all_sync(0xffffffffu, retired)) break;
-        __nanosleep(backoff);  // nothing to do yet: do not hammer the queue (nor the issue slots of the lane warps)
-        backoff = min(backoff * 2u, 4000u);
+        // nothing to do yet: do not hammer the queue, nor the issue slots of the working warps.  __nanosleep may return
+        // long before its argument has passed (measured: 0.7 us per round with a 4 us request, which made the polling
+        // 20 % of all instructions of the kernel), so the wait is held against the global timer.
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+          __nanosleep(backoff);
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        } while (t1 - t0 < (unsigned long long)backoff);
+        backoff = min(backoff * 2u, J3DG_IDLE_BACKOFF_MAX_NS);
         continue;
       }
       backoff = 250u;
@@ -870,8 +886,14 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* const stk
 // refilled from a parked tile of 32 set-up rays, so the slots stay full until the tiles run out.  Rays that exceed the
 // node budget or the short stack are still evicted to the hard-ray queue (the 8-lane groups bound the tail of the
 // frame).  Same arithmetic, same result as lane_loop; only the scheduling differs.
+//
+// MEASURED (round 2, config B, profiles/README.md "pool mode"): node steps run with 27.5 instead of 18.9 lanes, but the
+// slot bookkeeping (classification, compaction, state in shared memory, 24 instead of 32 warps per SM) costs what the
+// fuller steps save: the main phase takes 540 us against 495 us, the frame 1.00 ms against 0.90 ms.  Both designs end
+// with the same ~250 us drain of the longest grazing rays (up to 400 dependent steps), which is what bounds the frame.
+// The lane kernel therefore stays the default; -DJ3DG_POOL_MODE=1 builds this variant (all parity tests pass on it).
 #ifndef J3DG_POOL_MODE
-#define J3DG_POOL_MODE 1
+#define J3DG_POOL_MODE 0
 #endif
 #ifndef J3DG_POOL_STACK
 #define J3DG_POOL_STACK 8                                 // stack entries per slot (8 B each); overflow = eviction to the 96-entry group stack
@@ -879,11 +901,8 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* const stk
 #ifndef J3DG_POOL_REFILL_MIN
 #define J3DG_POOL_REFILL_MIN 8                            // free slots that trigger a refill from the parked tile
 #endif
-#ifndef J3DG_POOL_TRI_WEIGHT
-#define J3DG_POOL_TRI_WEIGHT 2                            // a triangle step is ~3x shorter than a node step: it may run with fewer lanes
-#endif
-#ifndef J3DG_POOL_TRI_MIN_LANES
-#define J3DG_POOL_TRI_MIN_LANES 12                        // a triangle step walks on through the leaves while this many lanes stay in theirs
+#ifndef J3DG_POOL_NODE_FULL
+#define J3DG_POOL_NODE_FULL 32                            // a node step runs whenever this many slots wait at a node; below it the fuller kind of step wins
 #endif
 #ifndef J3DG_POOL_PREFETCH
 #define J3DG_POOL_PREFETCH 1                              // 1: prefetch.global.L1 of the next node / record when a step ends (0 off, 2: L2)
@@ -891,12 +910,16 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* const stk
 #ifndef J3DG_POOL_MIN_BLOCKS
 #define J3DG_POOL_MIN_BLOCKS 6
 #endif
+#ifndef J3DG_POOL_SPILL
+#define J3DG_POOL_SPILL 56                                // stack entries per slot that continue in global memory above the shared-memory rows
+#endif
 constexpr int PSLOTS = 64;
+constexpr int POOL_SPILL = J3DG_POOL_SPILL;
 
 template <int MODE, bool STATS>
 struct PoolLayout {
   static constexpr bool ORG = MODE == SHADOW;               // per-ray origin (primary rays share the camera origin)
-  static constexpr int PSTACK = STATS ? 24 : J3DG_POOL_STACK;  // the counting pass must not lose rays to the (uncounted) group kernel
+  static constexpr int PSTACK = STATS ? 24 : J3DG_POOL_STACK - 1;  // usable entries (+ one scratch row for the branch-free pushes); the counting pass must not lose rays to the (uncounted) group kernel
   // static words of a slot, copied from the park
   static constexpr int W_IDX = 0, W_IDY = 1, W_IDZ = 2, W_SX = 3, W_SY = 4, W_SZ = 5;
   static constexpr int W_K = 6;                              // kx | ky << 2 | kz << 4 | mesh of the best hit << 16
@@ -909,7 +932,7 @@ struct PoolLayout {
   static constexpr int W_CNT = ORG ? 17 : 14;                // STATS: node visits, triangle tests
   static constexpr int WORDS = W_CNT + (STATS ? 2 : 0);
   static constexpr int PARKW = 8 + (ORG ? 3 : 0);
-  static constexpr int STACK_WORDS = 2 * PSTACK * PSLOTS;
+  static constexpr int STACK_WORDS = 2 * (PSTACK + 1) * PSLOTS;
   static constexpr int WARP_WORDS = STACK_WORDS + WORDS * PSLOTS + PARKW * 32 + 64;
   static_assert((size_t)WARP_WORDS * 4 >= (size_t)STACK_SIZE * 4 * sizeof(uint2), "a warp's region must hold four group stacks");
   static_assert(WARP_WORDS % 4 == 0, "16-byte aligned warp regions");
@@ -925,6 +948,10 @@ __device__ __forceinline__ void pool_loop(const TraceParams& p, uint32_t* const 
   uint32_t* const st = wsm + L::STACK_WORDS;                  // word w of slot s at st[w * PSLOTS + s]
   uint32_t* const park = st + L::WORDS * PSLOTS;              // word w of parked ray r at park[w * 32 + r]
   uint32_t* const list = park + L::PARKW * 32;                // slots of this step / free slots of a refill
+  // Stack entry i of slot s: rows 0 .. PSTACK-1 in shared memory; the few rays that go deeper (grazing rays hit many of
+  // the 8 children of every node they meet) continue in this warp's slice of a global buffer instead of being evicted.
+  uint2* const gstk = p.spill + (size_t)(blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5)) * ((size_t)POOL_SPILL * PSLOTS);
+  auto stack_at = [&](int i, uint32_t s) -> uint2 { return i < PSTACK ? stk[i * PSLOTS + s] : gstk[(i - PSTACK) * PSLOTS + s]; };
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const float t_near = MODE == PRIMARY ? fdiv(p.vw.diagonal, 100.f) : 1e-3f;  // canvas.cpp:781 / 853
@@ -1082,21 +1109,23 @@ __device__ __forceinline__ void pool_loop(const TraceParams& p, uint32_t* const 
     if (nnode + ntri == 0) break;  // nothing in flight and nothing left to refill with
 
     // =========================== pick the step and compact its slots onto the lanes ===========================
-    const int score_n = min(nnode, 32), score_t = min(ntri, 32) * J3DG_POOL_TRI_WEIGHT;
-    const bool do_tri = nnode == 0 || score_t > score_n || (score_t == score_n && ntri > nnode);
+    // a node step serves 32 rays (one per lane), a leaf step 8 (four lanes per ray): run node steps while they are full,
+    // otherwise whichever kind fills more of the warp
+    const bool do_tri = nnode == 0 || (nnode < J3DG_POOL_NODE_FULL && min(ntri, 8) * 4 >= nnode);
+    const uint32_t cap = do_tri ? 8u : 32u;
     const uint32_t mLo = do_tri ? tLo : nLo, mHi = do_tri ? tHi : nHi;
     uint32_t r0, r1;  // alternate which half is served first: no slot starves
     if (iter & 1u) { r1 = __popc(mHi & lt_mask); r0 = __popc(mHi) + __popc(mLo & lt_mask); }
     else { r0 = __popc(mLo & lt_mask); r1 = __popc(mLo) + __popc(mHi & lt_mask); }
-    if (((mLo >> lane) & 1u) && r0 < 32u) list[r0] = (uint32_t)lane;
-    if (((mHi >> lane) & 1u) && r1 < 32u) list[r1] = 32u + (uint32_t)lane;
+    if (((mLo >> lane) & 1u) && r0 < cap) list[r0] = (uint32_t)lane;
+    if (((mHi >> lane) & 1u) && r1 < cap) list[r1] = 32u + (uint32_t)lane;
     __syncwarp();
-    const bool active = lane < min(32, __popc(mLo) + __popc(mHi));
-    const uint32_t s = active ? list[lane] : 0u;
+    const uint32_t ready = (uint32_t)(__popc(mLo) + __popc(mHi));
 
     if (!do_tri) {
-      // ---------------- node step: 8 quantised child boxes ----------------
-      if (active) {
+      // ---------------- node step: one ray per lane, 8 quantised child boxes ----------------
+      if ((uint32_t)lane < min(ready, 32u)) {
+        const uint32_t s = list[lane];
         const uint32_t spv = st[L::W_SPV * PSLOTS + s];
         int sp = (int)(spv & 0xFFu);
         uint32_t visits = (spv >> 8) & 0xFFu;
@@ -1148,24 +1177,37 @@ __device__ __forceinline__ void pool_loop(const TraceParams& p, uint32_t* const 
           near_ref = ni == 4u ? q3.v[4] : near_ref; near_ref = ni == 5u ? q3.v[5] : near_ref; near_ref = ni == 6u ? q3.v[6] : near_ref;
           near_ref = ni == 7u ? q3.v[7] : near_ref;
           if ((uint32_t)nearest >= MISS_KEY) near_ref = J3DG_EMPTY_CHILD;
-          // pushes of the other hit children (a full stack drops them: the ray is evicted below)
-          int wanted = sp;
-          auto push = [&](uint32_t key, uint32_t ref) {
-            const bool go = key < MISS_KEY && (int)key != nearest;
-            if (go && sp < PSTACK) stk[sp * PSLOTS + s] = make_uint2(ref, key);
-            wanted += go ? 1 : 0;
-            sp = min(sp + (go ? 1 : 0), PSTACK);
-          };
-          push(k0, q3.v[0]); push(k1, q3.v[1]); push(k2, q3.v[2]); push(k3, q3.v[3]);
-          push(k4, q3.v[4]); push(k5, q3.v[5]); push(k6, q3.v[6]); push(k7, q3.v[7]);
-          if (wanted > PSTACK) {  // stack full: the group kernel (96 entries) takes the ray
+          const int nh = (k0 < MISS_KEY) + (k1 < MISS_KEY) + (k2 < MISS_KEY) + (k3 < MISS_KEY) + (k4 < MISS_KEY) + (k5 < MISS_KEY) + (k6 < MISS_KEY) + (k7 < MISS_KEY);
+          bool overflow = false;
+          if (sp + max(nh, 1) - 1 <= PSTACK) {
+            // branch-free pushes of the other hit children (row PSTACK is scratch; the low key bits are cleared at pop)
+            auto push = [&](uint32_t key, uint32_t ref) {
+              stk[sp * PSLOTS + s] = make_uint2(ref, key);
+              sp += (key < MISS_KEY && (int)key != nearest) ? 1 : 0;
+            };
+            push(k0, q3.v[0]); push(k1, q3.v[1]); push(k2, q3.v[2]); push(k3, q3.v[3]);
+            push(k4, q3.v[4]); push(k5, q3.v[5]); push(k6, q3.v[6]); push(k7, q3.v[7]);
+          } else {
+            // the stack leaves shared memory: entries PSTACK .. PSTACK + POOL_SPILL - 1 live in the global slice
+            auto push = [&](uint32_t key, uint32_t ref) {
+              if (key < MISS_KEY && (int)key != nearest) {
+                if (sp < PSTACK) stk[sp * PSLOTS + s] = make_uint2(ref, key);
+                else if (sp < PSTACK + POOL_SPILL) gstk[(sp - PSTACK) * PSLOTS + s] = make_uint2(ref, key);
+                else overflow = true;
+                sp = min(sp + 1, PSTACK + POOL_SPILL);
+              }
+            };
+            push(k0, q3.v[0]); push(k1, q3.v[1]); push(k2, q3.v[2]); push(k3, q3.v[3]);
+            push(k4, q3.v[4]); push(k5, q3.v[5]); push(k6, q3.v[6]); push(k7, q3.v[7]);
+          }
+          if (overflow) {  // deeper than shared + global rows: the group kernel restarts the ray
             evict(s);
           } else {
             uint32_t cur = near_ref;
             if (cur == J3DG_EMPTY_CHILD) {
               while (sp > 0) {
                 --sp;
-                const uint2 e = stk[sp * PSLOTS + s];
+                const uint2 e = stack_at(sp, s);
                 if (__uint_as_float(e.y & ~7u) <= t_far) { cur = e.x; break; }  // entries beyond the shrunk interval are skipped
               }
             }
@@ -1180,15 +1222,17 @@ __device__ __forceinline__ void pool_loop(const TraceParams& p, uint32_t* const 
         }
       }
     } else {
-      // ---------------- triangle step: one record per lane and round; lanes walk on through their leaf ----------------
-      bool live = active;
-      uint32_t cur = 0, spv = 0, kw = 0;
+      // ---------------- leaf step: FOUR lanes per ray, 8 rays per step; lane c tests records c and c + 4 of the leaf ----------------
+      // (a leaf holds 1..8 consecutive records, the last one flagged: one round for leaves of <= 4, two otherwise)
+      const int g = lane >> 2, c = lane & 3, gshift = lane & 28;
+      const bool active = (uint32_t)g < min(ready, 8u);
+      const uint32_t s = active ? list[g] : 0u;
+      uint32_t first = 0, spv = 0, kw = 0;
       float ox = o0x, oy = o0y, oz = o0z, Sx = 0.f, Sy = 0.f, Sz = 0.f, t_far = 0.f;
       const WideNode* __restrict__ nodes = nodes0;
       const TriRec* __restrict__ tris = tris0;
-      bool ended = false;  // the ray has left its leaf (cur = next node / record or EMPTY)
       if (active) {
-        cur = st[L::W_CUR * PSLOTS + s];
+        first = st[L::W_CUR * PSLOTS + s] & J3DG_LEAF_FIRST_MASK;
         spv = st[L::W_SPV * PSLOTS + s];
         kw = st[L::W_K * PSLOTS + s];
         Sx = __uint_as_float(st[L::W_SX * PSLOTS + s]); Sy = __uint_as_float(st[L::W_SY * PSLOTS + s]); Sz = __uint_as_float(st[L::W_SZ * PSLOTS + s]);
@@ -1204,14 +1248,25 @@ __device__ __forceinline__ void pool_loop(const TraceParams& p, uint32_t* const 
         }
       }
       const int kx = (int)(kw & 3u), ky = (int)((kw >> 2) & 3u), kz = (int)((kw >> 4) & 3u);
-      int sp = (int)(spv & 0xFFu);
-      do {
-        if (live) {
-          const uint32_t slot = cur & J3DG_LEAF_FIRST_MASK;
+      bool more = active;           // the leaf continues past the records tested so far
+      bool any_found = false;       // ANY_HIT: some record of the leaf was hit
+      uint32_t win_slot = 0xFFFFFFFFu;
+      float win_u = 0.f, win_v = 0.f;
+#pragma unroll 1
+      for (int round = 0; round < 2; ++round) {
+        if (!__any_sync(0xffffffffu, more)) break;
+        const uint32_t slot = first + 4u * round + (uint32_t)c;
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
+        if (more) {
           const float4* tp = reinterpret_cast<const float4*>(tris + slot);
-          const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
-          if (STATS) st[(L::W_CNT + 1) * PSLOTS + s] += 1u;
-          // one lane of intersect_woop (qbvh.h:4825-4869); 1/det is correctly rounded instead of rcpps + NR
+          v0 = __ldg(tp); v1 = __ldg(tp + 1); v2 = __ldg(tp + 2);
+        }
+        const uint32_t lm = (__ballot_sync(0xffffffffu, more && __float_as_uint(v1.w) != 0u) >> gshift) & 0xFu;  // end-of-leaf flags of my ray's 4 records
+        const int last = lm ? __ffs(lm) - 1 : 3;
+        bool hit = more && c <= last;
+        if (STATS && hit) atomicAdd(&st[(L::W_CNT + 1) * PSLOTS + s], 1u);
+        float t = 0.f, u = 0.f, v = 0.f;
+        if (hit) {  // one lane of intersect_woop (qbvh.h:4825-4869); 1/det is correctly rounded instead of rcpps + NR
           const float Ax_ = fsub(v0.x, ox), Ay_ = fsub(v0.y, oy), Az_ = fsub(v0.z, oz);
           const float Bx_ = fsub(v1.x, ox), By_ = fsub(v1.y, oy), Bz_ = fsub(v1.z, oz);
           const float Cx_ = fsub(v2.x, ox), Cy_ = fsub(v2.y, oy), Cz_ = fsub(v2.z, oz);
@@ -1225,43 +1280,56 @@ __device__ __forceinline__ void pool_loop(const TraceParams& p, uint32_t* const 
           const float U = fsub(fmul(Cx, By), fmul(Cy, Bx));
           const float V = fsub(fmul(Ax, Cy), fmul(Ay, Cx));
           const float W = fsub(fmul(Bx, Ay), fmul(By, Ax));
-          const bool inside = ((U <= 0.f) && (V <= 0.f) && (W <= 0.f)) || ((U >= 0.f) && (V >= 0.f) && (W >= 0.f));
+          hit = ((U <= 0.f) && (V <= 0.f) && (W <= 0.f)) || ((U >= 0.f) && (V >= 0.f) && (W >= 0.f));
           const float det = fadd(fadd(U, V), W);
-          bool hit = false;
-          if (inside && det != 0.f) {
+          hit = hit && (det != 0.f);
+          if (hit) {
             const float inv_det = fdiv(1.f, det);
             const float Az = fmul(Sz, Akz), Bz = fmul(Sz, Bkz), Cz = fmul(Sz, Ckz);
             const float T = fadd(fadd(fmul(U, Az), fmul(V, Bz)), fmul(W, Cz));
-            const float t = fmul(T, inv_det);
-            if ((t_far > t) && (t > t_near)) {  // t_far is the best t so far: strictly closer
-              hit = true;
-              t_far = t;
-              st[L::W_TFAR * PSLOTS + s] = __float_as_uint(t);
-              st[L::W_U * PSLOTS + s] = __float_as_uint(fmul(V, inv_det));
-              st[L::W_V * PSLOTS + s] = __float_as_uint(fmul(W, inv_det));
-              st[L::W_BEST * PSLOTS + s] = slot;
-              kw = (kw & 0xFFFFu) | ((spv >> 16) << 16);
-              st[L::W_K * PSLOTS + s] = kw;
-            }
+            t = fmul(T, inv_det);
+            hit = (t_far > t) && (t > t_near);  // t_far is the best t so far: strictly closer
+            u = fmul(V, inv_det);
+            v = fmul(W, inv_det);
           }
-          if (ANY_HIT && hit) { cur = J3DG_EMPTY_CHILD; sp = 0; ended = true; live = false; }
-          else if (__float_as_uint(v1.w) != 0u) {  // end of leaf
-            cur = J3DG_EMPTY_CHILD;
-            while (sp > 0) {
-              --sp;
-              const uint2 e = stk[sp * PSLOTS + s];
-              if (__uint_as_float(e.y & ~7u) <= t_far) { cur = e.x; break; }
-            }
-            ended = true; live = false;
-          } else cur = cur + 1u;
         }
-      } while (__popc(__ballot_sync(0xffffffffu, live)) >= J3DG_POOL_TRI_MIN_LANES);
-      if (active) {
+        // the closest of the (up to) four hits; the lowest record wins ties, like the sequential strict-less update
+        float key = hit ? t : FLT_MAX;
+        float nearest = fminf(key, __shfl_xor_sync(0xffffffffu, key, 1));
+        nearest = fminf(nearest, __shfl_xor_sync(0xffffffffu, nearest, 2));
+        const uint32_t wm = (__ballot_sync(0xffffffffu, hit && key == nearest) >> gshift) & 0xFu;
+        const int win = __ffs(wm) - 1;  // -1: no hit
+        const float wt = __shfl_sync(0xffffffffu, t, gshift + (win & 3));
+        const float wu = __shfl_sync(0xffffffffu, u, gshift + (win & 3));
+        const float wv = __shfl_sync(0xffffffffu, v, gshift + (win & 3));
+        if (more && win >= 0) {
+          t_far = wt; win_u = wu; win_v = wv; win_slot = first + 4u * round + (uint32_t)win;
+          any_found = true;
+        }
+        more = more && lm == 0u && !(ANY_HIT && any_found);
+      }
+      if (active && c == 0) {
+        if (win_slot != 0xFFFFFFFFu) {
+          st[L::W_TFAR * PSLOTS + s] = __float_as_uint(t_far);
+          st[L::W_U * PSLOTS + s] = __float_as_uint(win_u);
+          st[L::W_V * PSLOTS + s] = __float_as_uint(win_v);
+          st[L::W_BEST * PSLOTS + s] = win_slot;
+          st[L::W_K * PSLOTS + s] = (kw & 0xFFFFu) | ((spv >> 16) << 16);
+        }
+        int sp = (int)(spv & 0xFFu);
+        uint32_t cur = J3DG_EMPTY_CHILD;
+        if (ANY_HIT && any_found) sp = 0;
+        while (sp > 0) {
+          --sp;
+          const uint2 e = stack_at(sp, s);
+          if (__uint_as_float(e.y & ~7u) <= t_far) { cur = e.x; break; }  // entries beyond the shrunk interval are skipped
+        }
         const uint32_t nspv = (uint32_t)sp | (spv & 0xFFFFFF00u);
-        if (ended && cur == J3DG_EMPTY_CHILD) finish(s, nspv);
+        if (cur == J3DG_EMPTY_CHILD) finish(s, nspv);
         else {
           st[L::W_CUR * PSLOTS + s] = cur;
-          if (ended) { st[L::W_SPV * PSLOTS + s] = nspv; prefetch(nodes, tris, cur); }
+          st[L::W_SPV * PSLOTS + s] = nspv;
+          prefetch(nodes, tris, cur);
         }
       }
     }
@@ -1599,6 +1667,14 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, BLOCK_THREADS, smem);
     if (e != cudaSuccess) return j3dg_cuda_fail(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor", __FILE__, __LINE__);
     const int full = ctx->sm_count * std::max(nb, 1);
+#if J3DG_POOL_MODE
+    {  // global continuation of the pool-mode stacks: one slice per resident warp
+      const size_t need = (size_t)full * (BLOCK_THREADS / 32) * POOL_SPILL * PSLOTS * sizeof(uint2);
+      int rc2 = j3dg_reserve(ctx, &ctx->d_spill, &ctx->spill_cap, need);
+      if (rc2 != J3DG_OK) return rc2;
+      tp.spill = (uint2*)ctx->d_spill;
+    }
+#endif
     // dedicated consumer blocks only when the machine is full anyway; small jobs just run producers that convert
     tp.consumer_blocks = (stats || pools * 32 < (long long)full * BLOCK_THREADS * 4) ? 0u : (uint32_t)std::min<long long>(ctx->consumer_blocks, full / 2);
     const long long producers = std::max<long long>(1, std::min<long long>((long long)full - tp.consumer_blocks, (pools + 3) / 4));

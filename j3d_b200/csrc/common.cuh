@@ -154,6 +154,7 @@ struct j3dg_ctx {
   uint64_t frames_submitted = 0, frames_waited = 0;
   uint32_t* h_overflow = nullptr;                    // pinned, 8 words per in-flight frame: [0] stack-overflow flag, [1..4] hit bbox
   std::vector<MeshDev> meshes_uploaded;              // last mesh table sent to d_meshes (re-uploaded only when it changes)
+  void* d_spill = nullptr; size_t spill_cap = 0;     // pool-mode stacks that left shared memory (cast.cu)
   void* d_hard = nullptr; size_t hard_cap = 0;       // hard-ray list handed from the lane kernel to the group kernel
   size_t hard_id_off = 0;                            // offset of the id array inside d_hard
   uint32_t consumer_blocks = 0;                      // blocks of the cast kernel that consume the hard-ray queue from the start (J3DG_CONSUMER_BLOCKS)
