@@ -263,6 +263,11 @@ class Rig:
         self.ctx.set_stream(self.stream.cuda_stream)
         mc, cav = j.make_matcap(0)
         self.ctx.set_matcap(mc, cav)
+        # the multi-GPU plumbing lives behind the C ABI (j3dg_group_*, csrc/group.cu); torch.distributed only ships the NCCL id
+        self.group = None
+        if world > 1:
+            from j3d_b200.dist import make_group
+            self.group = make_group(self.ctx)
 
     def barrier(self):
         self.torch.cuda.synchronize()
@@ -300,17 +305,18 @@ class Rig:
                 b.append(mesh.info().build_ms)
             build_ms = statistics.median(b[1:]) if rebuilds else b[0]
         if self.world > 1:
-            from j3d_b200.dist import broadcast_bvh
-            meta = torch.zeros(4, dtype=torch.int64, device=self.dev)
+            # NCCL sets its channels up inside the first collective of each kind (hundreds of ms): warm them with a
+            # one-triangle mesh so the timed broadcast measures the transfer
+            tiny = None
             if self.rank == 0:
-                meta[0] = mesh.info().nr_of_nodes
-            dist.broadcast(meta, 0)
-            if self.rank != 0:
-                mesh = ctx.mesh_create_empty(nv, nt, int(meta[0].item()))
+                tiny = ctx.mesh_create(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.uint32))
+            tiny = self.group.broadcast_mesh(tiny, root=0)
+            ctx.synchronize()
+            tiny.destroy()
             self.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            broadcast_bvh(mesh, src=0, device=self.dev)
+            mesh = self.group.broadcast_mesh(mesh if self.rank == 0 else None, root=0)  # BVH + records + indexed geometry, NCCL over NVLink
             e1.record()
             torch.cuda.synchronize()
             bcast_ms = e0.elapsed_time(e1)
@@ -324,6 +330,8 @@ class Rig:
                 os.close(self.saved_stdout)
             print(json.dumps(line), flush=True)
         if self.world > 1:
+            if self.group is not None:
+                self.group.destroy()
             self.dist.destroy_process_group()
 
 
@@ -363,7 +371,7 @@ def run_orbit(args, wl, rank, world, local_rank):
     if world > 1 and args.exchange == "peer":
         from j3d_b200.dist import PeerFrames
         try:
-            pf = PeerFrames(ctx, H, W, dev, dst=0)
+            pf = PeerFrames(ctx, H, W, dev, dst=0, group=rig.group)
         except RuntimeError as e:  # every rank raises together: CUDA IPC is not available here, gather with NCCL instead
             if rank == 0:
                 print(f"bench.py: {e}; using --exchange nccl", file=sys.stderr)
@@ -594,7 +602,7 @@ def run_orbit(args, wl, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(wl, f, nt, W, H), "l2": "inputs_larger_than_l2"},  # the same two keys as the reference arm's line
         "layout": {"poses": f"frame i at i/{world} degrees on rank i mod {world}: every N renders the same arc, {world}x finer" if world > 1 else "frame i at i degrees",
-                   "sharding": "replicas only" if world == 1 else f"orbit frames round-robin over {world} ranks, BVH NCCL-broadcast from rank 0, " + ("every rank's shade kernel stores its RGBA into rank 0's HBM over NVLink peer memory (CUDA IPC), stream-ordered arrival/release flags" if args.exchange == "peer" else "RGBA NCCL-gathered on rank 0 every step (second stream, overlapping the kernels of frame k+1)"),
+                   "sharding": "replicas only" if world == 1 else f"orbit frames round-robin over {world} ranks, mesh + BVH built on rank 0 and replicated by j3dg_group_broadcast_mesh (NCCL), " + ("every rank's shade kernel stores its RGBA into rank 0's HBM over NVLink peer memory (CUDA IPC), stream-ordered arrival/release flags" if args.exchange == "peer" else "RGBA NCCL-gathered on rank 0 every step (second stream, overlapping the kernels of frame k+1)"),
                    "bvh_bytes": bvh_bytes},
         "bvh_build_ms": build_ms, "bvh_nodes": int(info.nr_of_nodes), "frames_per_s": 1e3 * args.steps * world / ms,
         "cast_ms": cast_ms, "shade_ms": shade_ms,
@@ -730,7 +738,7 @@ def run_sharded_frame(args, rank, world, local_rank):
     pf = None
     if world > 1:
         from j3d_b200.dist import PeerFrames
-        pf = PeerFrames(ctx, H, W, dev, dst=0, shared_frame=True)
+        pf = PeerFrames(ctx, H, W, dev, dst=0, shared_frame=True, group=rig.group)
     ctx.set_screen_shard(rank, world)
     last = {}
 

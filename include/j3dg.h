@@ -98,8 +98,8 @@ typedef struct j3dg_timings {
 } j3dg_timings;
 
 /* ---- context ------------------------------------------------------------- */
-/* One context per process per GPU (one process per GPU; multi-GPU plumbing is
- * torch.distributed/NCCL above this ABI).  Fails with J3DG_ENODEV if `device` is
+/* One context per process per GPU (one process per GPU; the multi-GPU plumbing is the
+ * j3dg_group / j3dg_frames section below).  Fails with J3DG_ENODEV if `device` is
  * not a CUDA device of compute capability 10.x.  */
 int j3dg_ctx_create(int device, j3dg_ctx** out);
 void j3dg_ctx_destroy(j3dg_ctx* ctx);
@@ -153,6 +153,55 @@ int j3dg_peer_close(j3dg_ctx* ctx, void* dev_ptr);
 int j3dg_stream_signal(j3dg_ctx* ctx, uint32_t* flag, uint32_t value);
 int j3dg_stream_wait_geq(j3dg_ctx* ctx, const uint32_t* flags, uint32_t n, uint32_t value);
 int j3dg_stream_wait_status(j3dg_ctx* ctx, int* timed_out);
+
+/* ---- multi-GPU: one process per GPU (SURVEY §8b "Context / multi-GPU", §8e).  j3d has no distributed code, so there
+ *      is no reference interface to mirror; a C++ host that wants N GPUs does, in every process:
+ *          j3dg_ctx_create(local_gpu, &ctx);
+ *          j3dg_group_create(ctx, rank, world, id, &group);        // id: j3dg_group_unique_id() of one rank, shipped by any channel
+ *          if (rank == 0) j3dg_mesh_create(ctx, ..., &mesh);        // load + build once ...
+ *          j3dg_group_broadcast_mesh(group, 0, &mesh);              // ... replicate BVH + geometry into every GPU's HBM (NCCL over NVLink)
+ *          j3dg_frames_create(group, w, h, 0, shared, &frames);     // rank 0 will hold everybody's frames
+ *          per frame:  j3dg_frames_begin -> j3dg_render_frame(..., rgba_out = j3dg_frames_target) -> j3dg_frames_arrive
+ *                      -> (rank 0 enqueues its consumer of j3dg_frames_view on the context stream) -> j3dg_frames_release
+ *      The group owns an NCCL communicator (libnccl.so.2 is loaded with dlopen by the first j3dg_group_unique_id /
+ *      j3dg_group_create; single-GPU users do not need it).  All group / frames calls are COLLECTIVE: every rank
+ *      makes the same calls in the same order.  Work is enqueued on the context stream. -------------------------- */
+typedef struct j3dg_group j3dg_group;
+typedef struct j3dg_frames j3dg_frames;
+#define J3DG_GROUP_ID_BYTES 128
+int j3dg_group_unique_id(unsigned char id_out[J3DG_GROUP_ID_BYTES]);
+int j3dg_group_create(j3dg_ctx* ctx, int rank, int world, const unsigned char id[J3DG_GROUP_ID_BYTES], j3dg_group** out);
+void j3dg_group_destroy(j3dg_group* group);
+int j3dg_group_rank(const j3dg_group* group);
+int j3dg_group_world(const j3dg_group* group);
+/* Every rank's context stream has drained up to this point on return (also reports sticky errors, j3dg_ctx_status). */
+int j3dg_group_barrier(j3dg_group* group);
+/* values[0..n) <- the maximum over the ranks (n <= 64): "time on the device as the max over ranks". */
+int j3dg_group_max_float(j3dg_group* group, float* values, uint32_t n);
+/* In-place per-word maximum over the ranks of n DEVICE uint64 words (packed (depth, index) splat words of a
+ * point-range-sharded cloud).  Enqueued on the context stream. */
+int j3dg_group_allreduce_max_u64(j3dg_group* group, unsigned long long* dev_words, size_t n);
+/* Replicates a built mesh: `root` passes its mesh, every other rank passes a pointer to NULL and receives a new
+ * mesh handle holding the same BVH, triangle records, vertices, indices, colours, uv and texture (destroy it with
+ * j3dg_mesh_destroy).  Replaces "every process loads the file and builds its own BVH". */
+int j3dg_group_broadcast_mesh(j3dg_group* group, int root, j3dg_mesh** mesh_inout);
+
+/* Frame exchange: rank `dst` allocates [2 slots][world][height*width] RGBA (shared_frame != 0: [2 slots][1] — ONE frame
+ * per slot that all ranks write disjoint rows of, for j3dg_ctx_set_screen_shard) and the other ranks map it through
+ * CUDA IPC; a rank renders with rgba_out = j3dg_frames_target(k), so its shade kernel's stores travel over NVLink
+ * into dst's HBM — no gather kernel has to find room beside the cooperative ray-cast kernel.  Stream-ordered flags
+ * hand the slots over (csrc/peer.cu): begin(k) makes the stream wait until dst has RELEASED frame k - 2 (same slot),
+ * arrive(k) signals this rank's frame and, on dst, makes the stream wait for every rank's frame k; release(k)
+ * (a no-op off dst) lets the peers overwrite the slot and must be enqueued AFTER the work that reads
+ * j3dg_frames_view(k).  A peer that never arrives times the wait out after 5 s (J3DG_ETIMEOUT, sticky). */
+int j3dg_frames_create(j3dg_group* group, uint32_t width, uint32_t height, int dst, int shared_frame, j3dg_frames** out);
+void j3dg_frames_destroy(j3dg_frames* frames);
+int j3dg_frames_begin(j3dg_frames* frames, uint32_t* k_out);
+int j3dg_frames_target(j3dg_frames* frames, uint32_t k, uint32_t** rgba_out);
+int j3dg_frames_arrive(j3dg_frames* frames, uint32_t k);
+int j3dg_frames_release(j3dg_frames* frames, uint32_t k);
+/* dst only: device pointer to the frames of step k, [world][height*width] ([1][...] for a shared frame). */
+int j3dg_frames_view(j3dg_frames* frames, uint32_t k, const uint32_t** frames_out);
 
 /* ---- BVH build: replaces `new qbvh(triangles, vertices)` + compute_triangle_normals
  *      + compute_bb in add_object (j3d/scene.cpp:8-25; jtk/qbvh.h:1679-1686). -------

@@ -137,6 +137,24 @@ def lib() -> C.CDLL:
         L.j3dg_stream_wait_geq.argtypes = [_vp, _vp, _u32, _u32]
         L.j3dg_stream_wait_status.argtypes = [_vp, C.POINTER(C.c_int)]
         L.j3dg_pick.argtypes = [_vp, C.POINTER(_vp), _u32, C.POINTER(_vp), _u32, C.POINTER(View), _vp, _u32, _vp, _u32, _vp]
+        L.j3dg_group_unique_id.argtypes = [_vp]
+        L.j3dg_group_create.argtypes = [_vp, C.c_int, C.c_int, _vp, C.POINTER(_vp)]
+        L.j3dg_group_destroy.argtypes = [_vp]
+        L.j3dg_group_destroy.restype = None
+        L.j3dg_group_rank.argtypes = [_vp]
+        L.j3dg_group_world.argtypes = [_vp]
+        L.j3dg_group_barrier.argtypes = [_vp]
+        L.j3dg_group_max_float.argtypes = [_vp, _vp, _u32]
+        L.j3dg_group_allreduce_max_u64.argtypes = [_vp, _vp, C.c_size_t]
+        L.j3dg_group_broadcast_mesh.argtypes = [_vp, C.c_int, C.POINTER(_vp)]
+        L.j3dg_frames_create.argtypes = [_vp, _u32, _u32, C.c_int, C.c_int, C.POINTER(_vp)]
+        L.j3dg_frames_destroy.argtypes = [_vp]
+        L.j3dg_frames_destroy.restype = None
+        L.j3dg_frames_begin.argtypes = [_vp, C.POINTER(_u32)]
+        L.j3dg_frames_target.argtypes = [_vp, _u32, C.POINTER(_vp)]
+        L.j3dg_frames_arrive.argtypes = [_vp, _u32]
+        L.j3dg_frames_release.argtypes = [_vp, _u32]
+        L.j3dg_frames_view.argtypes = [_vp, _u32, C.POINTER(_vp)]
         _lib = L
     return _lib
 
@@ -527,3 +545,85 @@ class Cloud:
         if self._h:
             self.ctx._L.j3dg_cloud_destroy(self._h)
             self._h = _vp()
+
+
+# ---------------------------------------------------------------------------------------
+# multi-GPU: one process per GPU (include/j3dg.h "multi-GPU"; csrc/group.cu)
+# ---------------------------------------------------------------------------------------
+def group_unique_id() -> bytes:
+    """The NCCL id one rank creates and ships to the others (any channel) before Group(...)."""
+    buf = (C.c_ubyte * 128)()
+    rc = lib().j3dg_group_unique_id(C.cast(buf, _vp))
+    if rc != 0:
+        raise J3dgError(f"j3dg_group_unique_id = {rc}: {lib().j3dg_last_error(None).decode()}")
+    return bytes(buf)
+
+
+class Group:
+    """j3dg_group: this context's membership in a set of `world` processes, one per GPU.  Every call is collective."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, unique_id: bytes):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self._h = _vp()
+        idb = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        ctx._check(ctx._L.j3dg_group_create(ctx._h, rank, world, C.cast(idb, _vp), C.byref(self._h)), "j3dg_group_create")
+
+    def destroy(self):
+        if self._h:
+            self.ctx._L.j3dg_group_destroy(self._h)
+            self._h = _vp()
+
+    def barrier(self):
+        self.ctx._check(self.ctx._L.j3dg_group_barrier(self._h), "j3dg_group_barrier")
+
+    def max_float(self, *values: float) -> list[float]:
+        arr = (C.c_float * len(values))(*values)
+        self.ctx._check(self.ctx._L.j3dg_group_max_float(self._h, C.cast(arr, _vp), len(values)), "j3dg_group_max_float")
+        return list(arr)
+
+    def allreduce_max_u64(self, dev_ptr: int, n: int):
+        self.ctx._check(self.ctx._L.j3dg_group_allreduce_max_u64(self._h, _vp(dev_ptr), n), "j3dg_group_allreduce_max_u64")
+
+    def broadcast_mesh(self, mesh: "Mesh | None", root: int = 0) -> "Mesh":
+        """root passes its built mesh, the other ranks None; every rank returns a mesh holding the same BVH + geometry."""
+        h = mesh._h if mesh is not None else _vp()
+        self.ctx._check(self.ctx._L.j3dg_group_broadcast_mesh(self._h, root, C.byref(h)), "j3dg_group_broadcast_mesh")
+        return mesh if mesh is not None else Mesh(self.ctx, h)
+
+    def frames(self, width: int, height: int, dst: int = 0, shared_frame: bool = False) -> "Frames":
+        return Frames(self, width, height, dst, shared_frame)
+
+
+class Frames:
+    """j3dg_frames: every rank renders straight into rank dst's HBM (include/j3dg.h has the protocol)."""
+
+    def __init__(self, group: Group, width: int, height: int, dst: int, shared_frame: bool):
+        self.group, self.ctx, self.w, self.h, self.dst, self.shared = group, group.ctx, width, height, dst, shared_frame
+        self._h = _vp()
+        self.ctx._check(self.ctx._L.j3dg_frames_create(group._h, width, height, dst, int(shared_frame), C.byref(self._h)), "j3dg_frames_create")
+
+    def destroy(self):
+        if self._h:
+            self.ctx._L.j3dg_frames_destroy(self._h)
+            self._h = _vp()
+
+    def begin(self) -> int:
+        k = _u32()
+        self.ctx._check(self.ctx._L.j3dg_frames_begin(self._h, C.byref(k)), "j3dg_frames_begin")
+        return k.value
+
+    def target(self, k: int) -> int:
+        p = _vp()
+        self.ctx._check(self.ctx._L.j3dg_frames_target(self._h, k, C.byref(p)), "j3dg_frames_target")
+        return p.value
+
+    def arrive(self, k: int):
+        self.ctx._check(self.ctx._L.j3dg_frames_arrive(self._h, k), "j3dg_frames_arrive")
+
+    def release(self, k: int):
+        self.ctx._check(self.ctx._L.j3dg_frames_release(self._h, k), "j3dg_frames_release")
+
+    def view(self, k: int) -> int:
+        p = _vp()
+        self.ctx._check(self.ctx._L.j3dg_frames_view(self._h, k, C.byref(p)), "j3dg_frames_view")
+        return p.value

@@ -1,13 +1,25 @@
-"""Multi-GPU plumbing above the C ABI: one process per GPU, torch.distributed (NCCL over NVLink on
-the GPU box, gloo in the CPU tests).  The path shards only where it does so naturally
-(SURVEY §8e): the mesh is replicated, the BVH is built once and broadcast, orbit frames or
-screen tiles are partitioned, rank 0 gathers the results.  There is no collective inside the
-ray cast itself.
+"""Python side of the multi-GPU path: one process per GPU.  The plumbing itself — NCCL communicator, mesh / BVH
+broadcast, the peer-memory frame exchange — lives behind the C ABI (include/j3dg.h "multi-GPU", csrc/group.cu, driven
+from plain C++ by tests/cpp/group_ranks.cpp); this module is a thin binding for torchrun-launched Python processes
+(torch.distributed only ships the 128-byte NCCL id and serves the gloo CPU tests) plus the pure partition functions.
+The path shards only where it does so naturally: the mesh is replicated, the BVH is built once and
+broadcast, orbit frames or screen bands are partitioned, rank 0 ends up with the results.  There is no collective
+inside the ray cast itself.
 """
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
+
+from . import capi
+
+
+def make_group(ctx) -> "capi.Group":
+    """j3dg_group for this torchrun-launched process: rank 0 creates the NCCL id, torch.distributed ships it."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [capi.group_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return capi.Group(ctx, rank, world, box[0])
 
 
 # ---- partitioning (pure functions; tested on CPU with gloo, world_size 2) -------------------
@@ -63,7 +75,8 @@ def device_bytes(ptr: int, nbytes: int, device) -> torch.Tensor:
 
 
 def broadcast_bvh(mesh, src: int = 0, device=None, chunk: int = 1 << 30):
-    """Broadcast the built BVH (wide nodes + triangle records) in place from `src`."""
+    """Broadcast the built BVH (wide nodes + triangle records) in place from `src` with torch.distributed — kept for
+    the NCCL-gather comparison arm; the product path is Group.broadcast_mesh (j3dg_group_broadcast_mesh)."""
     for kind in (0, 1):
         ptr, nbytes = mesh.bvh_buffer(kind)
         if not nbytes:
@@ -142,7 +155,64 @@ def gather_bands(img: torch.Tensor, dst: int = 0) -> torch.Tensor | None:
     return g[: img.shape[0]]
 
 
-# ---- frames handed to rank 0 through NVLink peer memory instead of a collective (include/j3dg.h, csrc/peer.cu) ----
+# ---- frames handed to rank 0 through NVLink peer memory instead of a collective (include/j3dg.h, csrc/group.cu, csrc/peer.cu) ----
+class PeerFrames:
+    """Every rank renders its frame STRAIGHT INTO rank `dst`'s HBM (the shade kernel's stores travel over NVLink);
+    no gather kernel competes with the cooperative cast kernel for SMs.  A thin wrapper over j3dg_frames_* (the
+    protocol is in include/j3dg.h).  Double-buffered, all stream-ordered:
+
+        k = pf.begin()                 # stream waits until dst has RELEASED the frame that lived in slot k & 1
+        ctx.render_frame(..., rgba_out=pf.target(k))
+        pf.arrive(k)                   # signal arrival; on dst the stream then waits for every rank's frame k
+        ... dst enqueues its consumer of pf.frames(k) on the same stream (copy to host, encode, compare) ...
+        pf.release(k)                  # dst: everything enqueued so far has read the slot; peers may overwrite it
+
+    shared_frame = True: ONE frame per slot that all ranks write disjoint rows of (j3dg_ctx_set_screen_shard)."""
+
+    def __init__(self, ctx, height: int, width: int, device, dst: int = 0, shared_frame: bool = False, group=None):
+        self.ctx, self.h, self.w, self.device, self.dst, self.shared = ctx, height, width, device, dst, shared_frame
+        self._own_group = group is None
+        self.group = make_group(ctx) if group is None else group
+        self.rank, self.world = self.group.rank, self.group.world
+        self.frame_bytes = height * width * 4
+        try:
+            self.f = self.group.frames(width, height, dst, shared_frame)
+        except capi.J3dgError as e:  # raised on every rank together (the set-up is collective)
+            if self._own_group:
+                self.group.destroy()
+            raise RuntimeError(str(e)) from e
+        self.k = 0
+
+    def begin(self) -> int:
+        return self.f.begin()
+
+    def target(self, k: int) -> int:
+        return self.f.target(k)
+
+    def arrive(self, k: int):
+        self.f.arrive(k)
+        self.k = k + 1
+
+    def release(self, k: int):
+        """dst only (a no-op elsewhere): the consumer work of frame k is enqueued; the slot may be overwritten."""
+        self.f.release(k)
+
+    def end(self, k: int):
+        self.arrive(k)
+        self.release(k)
+
+    def frames(self, k: int) -> torch.Tensor:
+        assert self.rank == self.dst
+        n = 1 if self.shared else self.world
+        t = device_bytes(self.f.view(k), n * self.frame_bytes, self.device)
+        return t.view(torch.int32).view(n, self.h, self.w)
+
+    def close(self):
+        self.f.destroy()
+        if self._own_group:
+            self.group.destroy()
+
+
 def peer_slot_offset(slot: int, rank: int, world: int, frame_bytes: int) -> int:
     """Byte offset of (slot, rank)'s frame inside the exchange buffer: [2 slots][world][frame]."""
     return (slot * world + rank) * frame_bytes
@@ -153,18 +223,11 @@ def peer_flags_offset(world: int, frame_bytes: int) -> int:
     return (2 * world * frame_bytes + 255) & ~255
 
 
-class PeerFrames:
-    """Every rank renders its frame STRAIGHT INTO rank `dst`'s HBM (the shade kernel's stores travel over NVLink);
-    no gather kernel competes with the cooperative cast kernel for SMs.  Double-buffered, all stream-ordered:
-
-        k = pf.begin()                 # stream waits until dst has RELEASED the frame that lived in slot k & 1
-        ctx.render_frame(..., rgba_out=pf.target(k))
-        pf.arrive(k)                   # signal arrival; on dst the stream then waits for every rank's frame k
-        ... dst enqueues its consumer of pf.frames(k) on the same stream (copy to host, encode, compare) ...
-        pf.release(k)                  # dst: everything enqueued so far has read the slot; peers may overwrite it
-
-    On `dst`, pf.frames(k) ([world, H, W] int32 view of the buffer) is valid for work enqueued between arrive(k) and
-    release(k).  pf.end(k) = arrive(k) + release(k) for callers that do not consume on the stream."""
+class PeerFramesPy:
+    """Executable specification of the hand-over protocol that csrc/group.cu implements (j3dg_frames_*), written on
+    the flag primitives of the ABI (j3dg_peer_alloc / j3dg_peer_open / j3dg_stream_signal / j3dg_stream_wait_geq) and
+    torch.distributed.  tests/test_dist_gloo.py runs it with two gloo ranks and a recording context to pin the slots,
+    the flag values and their order without a GPU; the product path is PeerFrames above."""
 
     def __init__(self, ctx, height: int, width: int, device, dst: int = 0, shared_frame: bool = False):
         """shared_frame = False: one frame per rank and slot (orbit sweep: every rank renders its own frame).

@@ -68,3 +68,20 @@ def build_cpp_shim_driver():
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     return exe
+
+
+def build_cpp_group_driver():
+    """g++ build of tests/cpp/group_ranks.cpp: a plain C++ host (no Python, no torch) that forks one process per GPU and
+    drives the multi-GPU part of the C ABI (j3dg_group_*, j3dg_frames_*).  Returns the path of the executable."""
+    import subprocess
+    out = ROOT / "build" / "tests"
+    out.mkdir(parents=True, exist_ok=True)
+    exe = out / "group_ranks"
+    pkg = ROOT / "j3d_b200"
+    cuda = Path("/usr/local/cuda")
+    cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-I", str(pkg / "host"),
+           "-I", str(cuda / "include"), str(ROOT / "tests" / "cpp" / "group_ranks.cpp"), "-o", str(exe), "-L", str(pkg), "-lj3dg", "-lj3dg_host",
+           "-L", str(cuda / "lib64"), "-lcudart", f"-Wl,-rpath,{pkg}", f"-Wl,-rpath,{cuda / 'lib64'}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe

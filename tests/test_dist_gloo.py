@@ -157,17 +157,19 @@ def _peer_worker(rank, world, port, out, fail):
         ctx = _RecordingCtx(rank, fail_open=fail and rank == 1)
         if fail:
             with pytest.raises(RuntimeError):  # every rank raises together: nobody is left waiting in a collective
-                jd.PeerFrames(ctx, h, w, torch.device("cpu"), dst=0)
+                jd.PeerFramesPy(ctx, h, w, torch.device("cpu"), dst=0)
             out[rank] = [op[0] for op in ctx.ops]
             return
-        pf = jd.PeerFrames(ctx, h, w, torch.device("cpu"), dst=0)
+        pf = jd.PeerFramesPy(ctx, h, w, torch.device("cpu"), dst=0)
         base = 0x10000000 if rank == 0 else 0x20000000
         flags = base + jd.peer_flags_offset(world, fb)
         targets = []
         for step in range(4):
             k = pf.begin()
             targets.append(pf.target(k) - base)
-            pf.end(k)
+            pf.arrive(k)
+            ctx.ops.append(("consume", k))   # what rank 0 enqueues between arrival and release (a no-op marker elsewhere)
+            pf.release(k)
         assert targets == [jd.peer_slot_offset(k & 1, rank, world, fb) for k in range(4)]
         want = []
         for k in range(4):
@@ -176,9 +178,11 @@ def _peer_worker(rank, world, port, out, fail):
             want.append(("signal", flags + 4 * rank, k + 1))               # my frame k has arrived
             if rank == 0:
                 want.append(("wait", flags, world, k + 1))                  # rank 0: every rank's frame k
+            want.append(("consume", k))
+            if rank == 0:
                 want.append(("signal", flags + 4 * world, k + 1))          # ... consumed: release
         assert ctx.ops == want, (ctx.ops, want)
-        shared = jd.PeerFrames(_RecordingCtx(rank), h, w, torch.device("cpu"), dst=0, shared_frame=True)
+        shared = jd.PeerFramesPy(_RecordingCtx(rank), h, w, torch.device("cpu"), dst=0, shared_frame=True)
         assert shared.target(0) - base == 0 and shared.target(1) - base == jd.peer_slot_offset(1, 0, world, fb)  # one frame per slot
         out[rank] = 1
     finally:
@@ -188,7 +192,8 @@ def _peer_worker(rank, world, port, out, fail):
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("fail", [False, True])
 def test_peer_frames_protocol_world2_gloo(fail):
-    """The hand-over protocol of the NVLink peer-memory frame exchange (dist.PeerFrames) with two ranks and a recording
+    """The hand-over protocol of the NVLink peer-memory frame exchange (dist.PeerFramesPy, the executable specification of
+    j3dg_frames_* in csrc/group.cu) with two ranks and a recording
     context: slots, arrival / release flag values and their order; and a failing CUDA-IPC open on one rank makes BOTH
     ranks raise (so the caller can fall back to an NCCL gather) after cleaning up."""
     world = 2

@@ -880,6 +880,26 @@ def test_peer_frames_protocol_single_gpu(ctx):
             dist.destroy_process_group()
 
 
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world", [1, 2])
+def test_cpp_host_drives_the_group_abi(ctx, world):
+    """Multi-GPU behind the C ABI (SURVEY §8b "Context / multi-GPU"): a g++-built host without Python or torch forks one
+    process per GPU, creates the NCCL group, broadcasts the mesh rank 0 built, renders an orbit sweep into rank 0's
+    frame buffer over peer memory (every frame consumed between arrival and release and compared with rank 0's own
+    render of that pose) and one band-sharded frame with shadows.  world = 2 needs two GPUs (exit code 77 = skipped)."""
+    import subprocess
+    import torch
+    from conftest import build_cpp_group_driver
+    if world > torch.cuda.device_count():
+        pytest.skip(f"needs {world} GPUs")
+    exe = build_cpp_group_driver()
+    res = subprocess.run([str(exe), str(world), "480", "270", "4"], capture_output=True, text=True, timeout=500)
+    if res.returncode == 77:
+        pytest.skip("fewer GPUs than ranks")
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "OK" in res.stdout
+
+
 # ---- BASELINE.json full size (config B: 28 037 120 triangles, 1080p): size-independent properties ----
 def _numpy_closest(verts, tris, org, d, t_near):
     """Brute-force restatement of the Woop test over ALL triangles for one ray (float32, unfused)."""
