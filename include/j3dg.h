@@ -336,6 +336,50 @@ int j3dg_mesh_find_all(j3dg_mesh* mesh, const float* rays, uint32_t n, uint32_t*
 int j3dg_mesh_voxel_dims(const j3dg_mesh* mesh, uint32_t max_dim, uint32_t dims_out[3]);
 int j3dg_mesh_voxelize(j3dg_mesh* mesh, uint32_t max_dim, uint32_t dims_out[3], uint8_t* data, size_t capacity);
 
+/* ---- ingest: the step before the path — what view::load_mesh_from_file / load_pc_from_file do
+ *      between the file and add_object (j3d/view.cpp:206-270).
+ *
+ *      Binary PLY: jtk::read_ply (jtk/ply.h:577-690, reached through j3d/io.cpp:733).  file_bytes: the whole file in
+ *      HOST memory; the header is parsed on the host, the element data is uploaded once and decoded by two kernels
+ *      into device arrays: vertices nv x 3 float, normals nv x 3 float (if nx, ny, nz exist), colours nv x uint32
+ *      0xAABBGGRR (if a red / r / diffuse_red channel exists; missing channels 0xff), triangles nf x 3 uint32 (the
+ *      first three indices of every face, like the reference), uv nf x 6 float (texcoord list, cut / zero-padded).
+ *      Any scalar type per property, little or big endian.  ASCII files are rejected (J3DG_EINVAL): parsing text
+ *      stays on the host. ------------------------------------------------------------------------------------- */
+typedef struct j3dg_ply j3dg_ply;
+typedef struct j3dg_ply_info {
+  uint32_t nr_of_vertices, nr_of_faces;
+  uint32_t has_normals, has_colors, has_uv;
+  uint32_t format;              /* 1 binary_little_endian, 2 binary_big_endian */
+  uint64_t header_bytes, file_bytes;
+  float upload_ms, decode_ms;   /* device times (CUDA events) of the byte upload and of the decode kernels */
+} j3dg_ply_info;
+int j3dg_ply_decode(j3dg_ctx* ctx, const void* file_bytes, size_t nr_of_bytes, j3dg_ply** out);
+void j3dg_ply_destroy(j3dg_ply* ply);
+int j3dg_ply_info_get(const j3dg_ply* ply, j3dg_ply_info* out);
+/* Device pointers of the decoded arrays (NULL for what the file does not have); owned by the handle. */
+int j3dg_ply_arrays(const j3dg_ply* ply, const float** vertices, const float** normals, const uint32_t** colors,
+                    const uint32_t** triangles, const float** uv);
+/* Copies one decoded array to the host: which = 0 vertices, 1 normals, 2 colours, 3 triangles, 4 uv. */
+int j3dg_ply_copy(const j3dg_ply* ply, int which, void* host_out, size_t capacity_bytes);
+/* read_from_file(mesh&, "x.ply") + add_object (j3d/mesh.cpp:104-116, 179-183; j3d/scene.cpp:8-25): colours become the
+ * float triples of convert_vertex_colors, texture coordinates without a texture get make_dummy_texture's checkerboard. */
+int j3dg_mesh_create_from_ply(j3dg_ctx* ctx, const j3dg_ply* ply, const float* cs, uint32_t db_id, j3dg_mesh** out);
+/* read_from_file(pc&, "x.ply") + add_object (j3d/pc.cpp:51-60). */
+int j3dg_cloud_create_from_ply(j3dg_ctx* ctx, const j3dg_ply* ply, const float* cs, uint32_t db_id, j3dg_cloud** out);
+
+/* Point-cloud normal estimation: estimate_normals (j3d/pc.cpp:256-334).  For every point the k nearest points (the
+ * point itself included, jtk::point_tree::find_k_nearest) are found on the device through a uniform grid, a plane is
+ * fitted to them (jtk::fit_plane: the eigenvector of the smallest eigenvalue of the 3 x 3 scatter matrix) — both
+ * data parallel — and the normals are then oriented consistently by the reference's propagation over the neighbour
+ * graph (a priority queue on |n_i . n_j|, serial by nature: it runs on the host on the downloaded k-NN lists).
+ * The cloud's normals are replaced (the splat shades with them); normals_out: nullable, n x 3 floats, host or device.
+ * The sign of a whole connected component is arbitrary in the reference too (it follows its SVD). 1 <= k <= 64. */
+int j3dg_cloud_estimate_normals(j3dg_cloud* cloud, uint32_t k, float* normals_out);
+/* The same without the orientation pass, plus the neighbour lists: knn_out nullable, n x k uint32 in ascending
+ * distance order (host or device). */
+int j3dg_cloud_knn_normals(j3dg_cloud* cloud, uint32_t k, float* normals_out, uint32_t* knn_out);
+
 /* Traversal statistics of the device BVH for the given view (a counting pass, not the
  * timed kernel): mean wide-node visits and triangle tests per primary ray.  SURVEY §8d. */
 int j3dg_cast_stats(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nr_of_meshes, const j3dg_view* view,

@@ -5,7 +5,7 @@ include/j3dg.h.  See DESIGN.md.  There is no CPU fallback: the CUDA library must
 """
 from .capi import (  # noqa: F401
     DEFAULT_FLAGS, EDGES, ONE_BIT, PICK_DTYPE, PIXEL_DTYPE, SHADING, SHADOW, TEXTURED, VERTEXCOLORS, WIREFRAME,
-    Cloud, Context, Frames, Group, J3dgError, Mesh, MeshInfo, Timings, View, group_unique_id,
+    Cloud, Context, Frames, Group, J3dgError, Mesh, MeshInfo, Ply, PlyInfo, Timings, View, group_unique_id,
     cloud, compute_bb, fill_background, icosphere, make_matcap, make_view, orbit_view, vertex_colors,
 )
 

@@ -51,6 +51,12 @@ class MeshInfo(C.Structure):
     ]
 
 
+class PlyInfo(C.Structure):
+    _fields_ = [("nr_of_vertices", C.c_uint32), ("nr_of_faces", C.c_uint32), ("has_normals", C.c_uint32), ("has_colors", C.c_uint32),
+                ("has_uv", C.c_uint32), ("format", C.c_uint32), ("header_bytes", C.c_uint64), ("file_bytes", C.c_uint64),
+                ("upload_ms", C.c_float), ("decode_ms", C.c_float)]
+
+
 class Timings(C.Structure):
     _fields_ = [("cast_ms", C.c_float), ("shade_ms", C.c_float), ("splat_ms", C.c_float), ("copy_ms", C.c_float),
                 ("cast_count", C.c_uint32), ("shade_count", C.c_uint32), ("splat_count", C.c_uint32),
@@ -155,6 +161,16 @@ def lib() -> C.CDLL:
         L.j3dg_frames_arrive.argtypes = [_vp, _u32]
         L.j3dg_frames_release.argtypes = [_vp, _u32]
         L.j3dg_frames_view.argtypes = [_vp, _u32, C.POINTER(_vp)]
+        L.j3dg_ply_decode.argtypes = [_vp, _vp, C.c_size_t, C.POINTER(_vp)]
+        L.j3dg_ply_destroy.argtypes = [_vp]
+        L.j3dg_ply_destroy.restype = None
+        L.j3dg_ply_info_get.argtypes = [_vp, C.POINTER(PlyInfo)]
+        L.j3dg_ply_arrays.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]
+        L.j3dg_ply_copy.argtypes = [_vp, C.c_int, _vp, C.c_size_t]
+        L.j3dg_mesh_create_from_ply.argtypes = [_vp, _vp, _vp, _u32, C.POINTER(_vp)]
+        L.j3dg_cloud_create_from_ply.argtypes = [_vp, _vp, _vp, _u32, C.POINTER(_vp)]
+        L.j3dg_cloud_estimate_normals.argtypes = [_vp, _u32, _vp]
+        L.j3dg_cloud_knn_normals.argtypes = [_vp, _u32, _vp, _vp]
         _lib = L
     return _lib
 
@@ -347,7 +363,14 @@ class Context:
         h = _vp()
         csb = None if cs is None else np.ascontiguousarray(cs, np.float32)
         self._check(self._L.j3dg_cloud_create(self._h, _ptr(pos), _ptr(nrm), _ptr(clr), n, _ptr(csb), db_id, C.byref(h)), "j3dg_cloud_create")
-        return Cloud(self, h)
+        return Cloud(self, h, i_n=n)
+
+    def ply_decode(self, data) -> "Ply":
+        """jtk::read_ply for binary files: `data` = the whole file (bytes / uint8 array); decoded on the device."""
+        buf = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+        h = _vp()
+        self._check(self._L.j3dg_ply_decode(self._h, _ptr(buf), buf.size, C.byref(h)), "j3dg_ply_decode")
+        return Ply(self, h)
 
     # -- frame stages -----------------------------------------------------------------
     @staticmethod
@@ -537,9 +560,63 @@ class Mesh:
         return out
 
 
-class Cloud:
+class Ply:
+    """j3dg_ply: the arrays of one decoded binary PLY file, resident on the device."""
+    _KINDS = {"vertices": (0, np.float32, 3), "normals": (1, np.float32, 3), "colors": (2, np.uint32, 0),
+              "triangles": (3, np.uint32, 3), "uv": (4, np.float32, 6)}
+
     def __init__(self, ctx: Context, h):
         self.ctx, self._h = ctx, h
+
+    def destroy(self):
+        if self._h:
+            self.ctx._L.j3dg_ply_destroy(self._h)
+            self._h = _vp()
+
+    def info(self) -> PlyInfo:
+        i = PlyInfo()
+        self.ctx._check(self.ctx._L.j3dg_ply_info_get(self._h, C.byref(i)), "j3dg_ply_info_get")
+        return i
+
+    def array(self, kind: str) -> np.ndarray:
+        which, dt, cols = self._KINDS[kind]
+        i = self.info()
+        rows = i.nr_of_faces if which >= 3 else i.nr_of_vertices
+        if (which == 1 and not i.has_normals) or (which == 2 and not i.has_colors) or (which == 4 and not i.has_uv):
+            rows = 0
+        out = np.zeros((rows, cols) if cols else (rows,), dt)
+        self.ctx._check(self.ctx._L.j3dg_ply_copy(self._h, which, _ptr(out), out.nbytes), "j3dg_ply_copy")
+        return out
+
+    def to_mesh(self, cs=None, db_id: int = 0x20000000) -> "Mesh":
+        h = _vp()
+        csb = None if cs is None else np.ascontiguousarray(cs, np.float32)
+        self.ctx._check(self.ctx._L.j3dg_mesh_create_from_ply(self.ctx._h, self._h, _ptr(csb), db_id, C.byref(h)), "j3dg_mesh_create_from_ply")
+        return Mesh(self.ctx, h)
+
+    def to_cloud(self, cs=None, db_id: int = 0x40000000) -> "Cloud":
+        h = _vp()
+        csb = None if cs is None else np.ascontiguousarray(cs, np.float32)
+        self.ctx._check(self.ctx._L.j3dg_cloud_create_from_ply(self.ctx._h, self._h, _ptr(csb), db_id, C.byref(h)), "j3dg_cloud_create_from_ply")
+        return Cloud(self.ctx, h, i_n=self.info().nr_of_vertices)
+
+
+class Cloud:
+    def __init__(self, ctx: Context, h, i_n: int = 0):
+        self.ctx, self._h, self.n = ctx, h, i_n
+
+    def estimate_normals(self, k: int) -> np.ndarray:
+        """estimate_normals (j3d/pc.cpp:256): k-NN + plane fit on the device, orientation propagation; replaces the cloud's normals."""
+        out = np.zeros((self.n, 3), np.float32)
+        self.ctx._check(self.ctx._L.j3dg_cloud_estimate_normals(self._h, k, _ptr(out)), "j3dg_cloud_estimate_normals")
+        return out
+
+    def knn_normals(self, k: int):
+        """Unoriented normals + the neighbour lists (ascending distance)."""
+        nrm = np.zeros((self.n, 3), np.float32)
+        knn = np.zeros((self.n, min(k, self.n)), np.uint32)
+        self.ctx._check(self.ctx._L.j3dg_cloud_knn_normals(self._h, k, _ptr(nrm), _ptr(knn)), "j3dg_cloud_knn_normals")
+        return nrm, knn
 
     def destroy(self):
         if self._h:

@@ -198,7 +198,7 @@ constexpr uint32_t QUEUE_EMPTY = 0xFFFFFFFFu;
 
 // `stk` = entry 0 of this group's stack, entry i at stk[i * GSTRIDE] (GSTRIDE groups are interleaved).
 template <int MODE, int SRC, int GSTRIDE>
-__device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const stk) {
+__device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const stk, const bool helper = false) {
   constexpr bool ANY_HIT = MODE == SHADOW;
   constexpr bool GENERAL = MODE == RAYLIST;
   const int lane = threadIdx.x & 31;
@@ -324,9 +324,17 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const st
       ++round_no;
       if (!have_ray && !retired && (!warp_busy || (round_no & 3u) == 0u)) {
         if (claimed == QUEUE_EMPTY) {
-          uint32_t i = 0;
-          if (c == 0) i = atomicAdd(p.hard_taken, 1u);
+          // A warp that has traced its tiles only HELPS with the queue: once nothing is waiting it leaves, so its block's
+          // slot goes to the next frame's kernel (frames in flight on two streams) instead of idling through the drain of
+          // this frame's longest rays; the dedicated consumer blocks take what is appended later.
+          uint32_t i = QUEUE_EMPTY;
+          if (c == 0) {
+            bool take = true;
+            if (helper) take = *reinterpret_cast<volatile unsigned int*>(p.hard_taken) < *reinterpret_cast<volatile unsigned int*>(p.hard_count);
+            if (take) i = atomicAdd(p.hard_taken, 1u);
+          }
           claimed = __shfl_sync(0xFFu << gshift, i, gshift);
+          if (claimed == QUEUE_EMPTY) retired = true;
         }
         uint2 e = make_uint2(QUEUE_EMPTY, 0u);
         if (claimed < p.hard_capacity)  // claims run past the end of the queue while it drains
@@ -1393,7 +1401,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_POOL_MODE ? J3DG_POOL_MIN_
 #ifdef J3DG_TIMELINE
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl1));
 #endif
-  group_loop<MODE, QUEUE, 4>(p, warp_stack + ((threadIdx.x & 31) >> 3));
+  group_loop<MODE, QUEUE, 4>(p, warp_stack + ((threadIdx.x & 31) >> 3), p.consumer_blocks != 0u && blockIdx.x >= p.consumer_blocks);
 #ifdef J3DG_TIMELINE
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl2));
   if (MODE == PRIMARY && threadIdx.x == 0) {  // [13] first start, [14] last end of the lane phase, [15] last end; + sums for means

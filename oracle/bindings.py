@@ -325,3 +325,35 @@ class Ref:
         ids = np.zeros((n,), np.uint32)
         self.L.ref_find_closest(_p(verts), verts.shape[0], _p(tris), tris.shape[0], leaf_size, _p(rays), n, _p(hits), _p(ids))
         return hits, ids
+
+
+# ---- ingest (oracle/ref_ingest.cpp: the unmodified jtk PLY reader and j3d/pc.cpp estimate_normals) -------------------
+def _ref_lib():
+    path = HERE / "_ref" / "libj3d_ref.so"
+    if not path.exists():
+        raise RuntimeError(f"{path} missing: run `make -C oracle ref` where /root/reference exists")
+    L = C.CDLL(str(path))
+    L.ref_read_ply.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), _vp, _vp, _vp, _vp, _vp]
+    L.ref_estimate_normals.argtypes = [_vp, _u32, _u32, _vp]
+    L.ref_estimate_normals.restype = None
+    return L
+
+
+def ref_read_ply(data: bytes):
+    """jtk::read_ply_from_memory -> dict(vertices, normals, colors, triangles, uv), or None when the reader rejects the file."""
+    L = _ref_lib()
+    counts = (C.c_uint64 * 5)()
+    if not L.ref_read_ply(data, len(data), counts, None, None, None, None, None):
+        return None
+    v = np.zeros((counts[0], 3), np.float32); n = np.zeros((counts[1], 3), np.float32); c = np.zeros((counts[2],), np.uint32)
+    t = np.zeros((counts[3], 3), np.uint32); u = np.zeros((counts[4], 6), np.float32)
+    L.ref_read_ply(data, len(data), counts, _p(v), _p(n), _p(c), _p(t), _p(u))
+    return {"vertices": v, "normals": n, "colors": c, "triangles": t, "uv": u}
+
+
+def ref_estimate_normals(pos: np.ndarray, k: int) -> np.ndarray:
+    """estimate_normals (j3d/pc.cpp:256-334)."""
+    pos = np.ascontiguousarray(pos, np.float32)
+    out = np.zeros_like(pos)
+    _ref_lib().ref_estimate_normals(_p(pos), pos.shape[0], k, _p(out))
+    return out
