@@ -263,6 +263,19 @@ class Rig:
         self.ctx.set_stream(self.stream.cuda_stream)
         mc, cav = j.make_matcap(0)
         self.ctx.set_matcap(mc, cav)
+        # Two frames in flight per GPU: a second context of the same device with its own stream.  Frame k is rendered by
+        # context k & 1; while the longest rays of frame k are still being finished by a few warps, the cast kernel of
+        # frame k + 1 moves into the SM slots that frame k has already left (csrc/cast.cu, plain launch).  Meshes are
+        # shared between the contexts of one device.
+        self.lanes = max(1, min(2, args.lanes))
+        self.ctxs, self.streams = [self.ctx], [self.stream]
+        if self.lanes == 2:
+            c2 = j.Context(local_rank)
+            s2 = torch.cuda.Stream(device=self.dev)
+            c2.set_stream(s2.cuda_stream)
+            c2.set_matcap(mc, cav)
+            self.ctxs.append(c2)
+            self.streams.append(s2)
         # the multi-GPU plumbing lives behind the C ABI (j3dg_group_*, csrc/group.cu); torch.distributed only ships the NCCL id
         self.group = None
         if world > 1:
@@ -360,7 +373,9 @@ def run_orbit(args, wl, rank, world, local_rank):
     v0 = j.make_view(W, H, mn, mx)
     mesh, info, build_ms, create_ms, bcast_ms = rig.build_and_broadcast(verts, tris, nv, nt)
 
-    px = torch.empty((H, W, 32), dtype=torch.uint8, device=dev)
+    ctxs, streams, L = rig.ctxs, rig.streams, rig.lanes
+    pxs = [torch.empty((H, W, 32), dtype=torch.uint8, device=dev) for _ in range(L)]  # one canvas per frame in flight
+    px = pxs[0]
     rgba2 = [torch.empty((H, W), dtype=torch.int32, device=dev) for _ in range(2)]
     # N > 1: every rank's frame must end up on rank 0 each step.
     #   --exchange peer (default): the shade kernel of every rank stores its RGBA straight into rank 0's HBM over
@@ -378,15 +393,20 @@ def run_orbit(args, wl, rank, world, local_rank):
             args.exchange = "nccl"
     if world > 1 and args.exchange == "nccl":
         comm = torch.cuda.Stream(device=dev)
+        L = 1  # the gather path keeps one frame in flight
+    if pf is not None and L == 2:
+        pf.set_lane(1, ctxs[1])  # begin / arrive / release of the odd frames go to the second context's stream
     gather_lists = [[torch.empty_like(rgba2[0]) for _ in range(world)] for _ in range(2)] if (comm is not None and rank == 0) else [None, None]
     ev_render = [torch.cuda.Event() for _ in range(2)]
     ev_gather = [torch.cuda.Event() for _ in range(2)]
     state = {"k": 0, "checksum": torch.zeros((), dtype=torch.int64, device=dev)}
 
-    def step(v):
-        if pf is not None:
+    def step(v, lanes=None, local=False):
+        lanes = L if lanes is None else lanes
+        if pf is not None and not local:
             k = pf.begin()
-            ctx.render_frame([mesh], [], v, pixels_out=px, rgba_out=pf.target(k))
+            ln = k & 1 if L == 2 else 0   # the slot of the exchange buffer IS the lane
+            ctxs[ln].render_frame([mesh], [], v, pixels_out=pxs[ln], rgba_out=pf.target(k))
             pf.arrive(k)
             # rank 0 consumes between arrival and release (PeerFrames protocol): nothing in the timed loop — the frames
             # are what the sweep produces; `verify_exchange` below consumes every frame of a short run instead
@@ -395,9 +415,10 @@ def run_orbit(args, wl, rank, world, local_rank):
         k = state["k"]
         state["k"] = k + 1
         b = k & 1
+        ln = b if lanes == 2 else 0
         if comm is not None and k >= 2:
             stream.wait_event(ev_gather[b])  # the gather of frame k - 2 has left this buffer
-        ctx.render_frame([mesh], [], v, pixels_out=px, rgba_out=rgba2[b])
+        ctxs[ln].render_frame([mesh], [], v, pixels_out=pxs[ln], rgba_out=rgba2[b])
         if comm is not None:
             ev_render[b].record(stream)
             with torch.cuda.stream(comm):
@@ -408,21 +429,31 @@ def run_orbit(args, wl, rank, world, local_rank):
     def drain():
         if comm is not None:
             stream.wait_stream(comm)
+        for s2 in streams[1:]:
+            stream.wait_stream(s2)   # the timing events live on lane 0's stream
 
-    def timed(views, warm):
+    def timed(views, warm, lanes=None, local=False):
         """Device-resident loop: `warm` untimed frames, then the rest between barriers; ms = max over ranks."""
         for v in views[:warm]:
-            step(v)
+            step(v, lanes, local)
         drain()
         rig.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        for s2 in streams[1:]:
+            s2.wait_stream(stream)   # nothing of lane 1 starts before the first event
         for v in views[warm:]:
-            step(v)
+            step(v, lanes, local)
         drain()
         e1.record()
         rig.barrier()
         return rig.max_over_ranks(e0.elapsed_time(e1))[0]
+
+    def timings_reset():
+        tms = [c.timings(reset=True) for c in ctxs]
+        n = max(1, sum(t.cast_count for t in tms))
+        return (sum(t.cast_ms for t in tms) / n, sum(t.shade_ms for t in tms) / max(1, sum(t.shade_count for t in tms)),
+                sum(t.kernel_launches for t in tms), sum(t.cast_count for t in tms))
 
     # ---- (1) weak arm: `steps` frames per rank, the N ranks together render an N-times finer sweep of the same arc ----
     total = args.warmup + args.steps
@@ -431,18 +462,30 @@ def run_orbit(args, wl, rank, world, local_rank):
         step(v)
     drain()
     rig.barrier()
-    ctx.timings(reset=True)
+    # ---- (0) one frame at a time (N = 1): the same frames back to back on ONE stream.  This is the latency of a single
+    #      j3dg_render_frame and the isolated duration of the cast kernel that the roofline block divides by. ----
+    single = None
+    if comm is None:
+        nsingle = min(args.steps, 60)
+        timings_reset()
+        single_ms = timed(arc[: args.warmup + nsingle], args.warmup, lanes=1, local=True)
+        s_cast, s_shade, _, _ = timings_reset()
+        single = {"frames": nsingle, "ms_per_frame": single_ms / nsingle, "mrays_s": W * H * nsingle / single_ms / 1e3, "cast_ms": s_cast, "shade_ms": s_shade,
+                  "note": "one frame in flight: frames back to back on one stream through one context" + (" (every rank its own frames, no exchange)" if world > 1 else "")}
+    timings_reset()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ms = timed(arc, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    tm = ctx.timings(reset=True)
+    cast_ms_inflight, shade_ms_inflight, nlaunch, ncast = timings_reset()
     rays_total = W * H * args.steps * world
     value = rays_total / (ms * 1e-3) / 1e6
-    cast_ms = tm.cast_ms / max(1, tm.cast_count)
-    shade_ms = tm.shade_ms / max(1, tm.shade_count)
-    launches = int(tm.kernel_launches * args.steps / max(1, tm.cast_count))  # launches of the timed frames of this rank
+    # the stage timers of overlapping frames include the time a kernel shares the machine with its neighbour: the
+    # isolated figures come from the one-frame-at-a-time run when there is one
+    cast_ms = single["cast_ms"] if single else cast_ms_inflight
+    shade_ms = single["shade_ms"] if single else shade_ms_inflight
+    launches = int(nlaunch * args.steps / max(1, ncast))  # launches of the timed frames of this rank
 
     # ---- exchange check: every frame of a short run, consumed between arrival and release, equals a local render ----
     exchange_ok = None
@@ -452,13 +495,15 @@ def run_orbit(args, wl, rank, world, local_rank):
         snaps = []
         for k in range(nchk):
             kk = pf.begin()
-            ctx.render_frame([mesh], [], chk[k * world + rank], pixels_out=px, rgba_out=pf.target(kk))
+            ln = kk & 1 if L == 2 else 0
+            ctxs[ln].render_frame([mesh], [], chk[k * world + rank], pixels_out=pxs[ln], rgba_out=pf.target(kk))
             pf.arrive(kk)
             if rank == 0:
-                snaps.append(pf.frames(kk).clone())  # the consumer, on the same stream
+                with torch.cuda.stream(streams[ln]):
+                    snaps.append(pf.frames(kk).clone())  # the consumer, on the stream that handed the frame over
             pf.release(kk)
         torch.cuda.synchronize()
-        exchange_ok = ctx.status() == 0
+        exchange_ok = all(c.status() == 0 for c in ctxs)
         if rank == 0:
             for k in range(nchk):
                 for r in range(world):
@@ -478,51 +523,64 @@ def run_orbit(args, wl, rank, world, local_rank):
     # The sweep call a user makes: j3dg_frame_submit / j3dg_frame_wait (pipelined j3dg_render_frame): the device->host
     # copy of frame k overlaps the kernels of frame k+1.  Every frame's host buffers are complete (frame_wait
     # returned) inside the timed region.  Each rank owns its frames' host buffers (frames sharded over the ranks).
-    hpx = [torch.empty((H, W, 32), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    hrgba = [torch.empty((H, W), dtype=torch.int32).pin_memory() for _ in range(2)]
+    # host buffers: every context pipelines two frames of its own, so [lane][2]
+    hpx = [[torch.empty((H, W, 32), dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(L)]
+    hrgba = [[torch.empty((H, W), dtype=torch.int32).pin_memory() for _ in range(2)] for _ in range(L)]
     centre = np.array([[W // 2, H // 2]], np.int32)
+    last_buf = {"ln": 0, "b": 0}
 
     def sweep(vs, records):
+        # frame k: context k mod L, host buffer (k div L) & 1 of that context; a context waits for its previous frame
+        # right after it has submitted the next one (the copy of frame k - L overlaps the kernels of frames k - L + 1 .. k)
+        n = len(vs)
         for k, v in enumerate(vs):
-            ctx.frame_submit([mesh], [], v, pixels_out=hpx[k & 1] if records else None, rgba_out=hrgba[k & 1])
-            if k >= 1:
-                ctx.frame_wait()
+            ln, b = k % L, (k // L) & 1
+            ctxs[ln].frame_submit([mesh], [], v, pixels_out=hpx[ln][b] if records else None, rgba_out=hrgba[ln][b])
+            if k >= L:
+                ctxs[ln].frame_wait()
+        for k in range(max(0, n - L), n):
+            ctxs[k % L].frame_wait()
         if vs:
-            ctx.frame_wait()
+            last_buf["ln"], last_buf["b"] = (n - 1) % L, ((n - 1) // L) & 1
             if not records:  # the records stayed in HBM: the host asks for the one under the cursor
-                ctx.pick([mesh], [], vs[-1], centre)
+                ctxs[(n - 1) % L].pick([mesh], [], vs[-1], centre)
 
     def timed_sweep(vs, warm, records):
         sweep(vs[:warm], records)
         rig.barrier()
-        ctx.readback_bytes(reset=True)
+        for c in ctxs:
+            c.readback_bytes(reset=True)
         t0 = time.perf_counter()
         sweep(vs[warm:], records)
         dt = time.perf_counter() - t0
-        nbytes = ctx.readback_bytes(reset=True) / max(1, len(vs) - warm)
+        nbytes = sum(c.readback_bytes(reset=True) for c in ctxs) / max(1, len(vs) - warm)
         return rig.max_over_ranks(dt)[0], nbytes
 
-    ctx.set_dirty_rect(True)
+    def set_dirty(on):
+        for c in ctxs:
+            c.set_dirty_rect(on)
+
+    set_dirty(True)
     e2e_s, e2e_bytes = timed_sweep(arc, args.warmup, records=False)          # headline e2e: RGBA only + pick
     s360_s, s360_bytes = timed_sweep(mine360[:3] + mine360, 3, records=False)
     rec_s, rec_bytes = timed_sweep(arc, args.warmup, records=True)            # pixel records + RGBA, dirty rectangle
-    dirty_px, dirty_rgba = hpx[(total - 1) & 1].clone(), hrgba[(total - 1) & 1].clone()
-    ctx.set_dirty_rect(False)
+    dirty_px, dirty_rgba = hpx[last_buf["ln"]][last_buf["b"]].clone(), hrgba[last_buf["ln"]][last_buf["b"]].clone()
+    set_dirty(False)
     full_s, full_bytes = timed_sweep(arc, args.warmup, records=True)          # every byte of both buffers, every frame
-    dirty_identical = bool(torch.equal(dirty_px, hpx[(total - 1) & 1]) and torch.equal(dirty_rgba, hrgba[(total - 1) & 1]))
+    dirty_identical = bool(torch.equal(dirty_px, hpx[last_buf["ln"]][last_buf["b"]]) and torch.equal(dirty_rgba, hrgba[last_buf["ln"]][last_buf["b"]]))
     sweep360["e2e"] = {"ms": 1e3 * s360_s, "frames_per_s": n360 / s360_s, "mrays_s": n360 * W * H / s360_s / 1e6, "d2h_bytes_per_frame": int(s360_bytes),
                        "api": "j3dg_frame_submit(pixels_out=NULL)/j3dg_frame_wait, RGBA to pinned host memory on the rendering rank"}
     # the same frames one by one through the synchronous j3dg_render_frame (kernels, then copy)
     for v in arc[:3]:  # untimed: the first call allocates the context's own canvas
-        ctx.render_frame([mesh], [], v, pixels_out=hpx[0], rgba_out=hrgba[0])
+        ctx.render_frame([mesh], [], v, pixels_out=hpx[0][0], rgba_out=hrgba[0][0])
     nsync = min(args.steps, 20)
     t0 = time.perf_counter()
     for v in arc[args.warmup: args.warmup + nsync]:
-        ctx.render_frame([mesh], [], v, pixels_out=hpx[0], rgba_out=hrgba[0])
+        ctx.render_frame([mesh], [], v, pixels_out=hpx[0][0], rgba_out=hrgba[0][0])
     sync_ms = 1e3 * (time.perf_counter() - t0) / nsync
     t0 = time.perf_counter()
     for v in arc[args.warmup: args.warmup + nsync]:
-        ctx.render_frame([mesh], [], v, pixels_out=None, rgba_out=hrgba[0])
+        ctx.render_frame([mesh], [], v, pixels_out=None, rgba_out=hrgba[0][0])
     sync_rgba_ms = 1e3 * (time.perf_counter() - t0) / nsync
     h2d_bytes = ctypes.sizeof(j.View) + 256  # the view (kernel parameters) + the per-mesh table
 
@@ -554,9 +612,10 @@ def run_orbit(args, wl, rank, world, local_rank):
     peak, peak_src = peaks()
     achieved = (W * H * bytes_per_ray) / (cast_ms * 1e-3) / 1e9
     traffic, traffic_src = traffic_citation() if world == 1 else (None, None)
-    roofline = {"bound": "hbm", "kernel": "cast stage (cast_kernel: one cooperative launch per ray type)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "cast stage (cast_kernel: one persistent launch per ray type), timed alone — one frame in flight", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_ray": bytes_per_ray,
                 "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray, "kernel_ms": cast_ms, "kernel_mrays_s": W * H / cast_ms / 1e3,
+                "achieved_frames_in_flight": (W * H * bytes_per_ray) / (ms / args.steps * 1e-3) / 1e9 if world == 1 else None,
                 "note": "achieved = ALGORITHMIC bytes (SURVEY §8d) over the live CUDA-event stage time; L1/L2 absorb re-use, so this is not a DRAM-bandwidth share (traffic = DRAM bytes per launch from the cited ncu capture)"}
 
     if rank != 0:
@@ -601,6 +660,8 @@ def run_orbit(args, wl, rank, world, local_rank):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(wl, f, nt, W, H), "l2": "inputs_larger_than_l2"},  # the same two keys as the reference arm's line
+        "frames_in_flight": {"per_gpu": L, "how": "frame k is rendered by context k mod 2 of the same device (two streams, meshes shared): the cast kernel of frame k + 1 moves into the SM slots frame k has left while a few warps still finish its longest rays; every frame is complete and in its output buffer inside the timed region" if L == 2 else "one context, frames back to back on one stream",
+                             "one_frame_at_a_time": single},
         "layout": {"poses": f"frame i at i/{world} degrees on rank i mod {world}: every N renders the same arc, {world}x finer" if world > 1 else "frame i at i degrees",
                    "sharding": "replicas only" if world == 1 else f"orbit frames round-robin over {world} ranks, mesh + BVH built on rank 0 and replicated by j3dg_group_broadcast_mesh (NCCL), " + ("every rank's shade kernel stores its RGBA into rank 0's HBM over NVLink peer memory (CUDA IPC), stream-ordered arrival/release flags" if args.exchange == "peer" else "RGBA NCCL-gathered on rank 0 every step (second stream, overlapping the kernels of frame k+1)"),
                    "bvh_bytes": bvh_bytes},
@@ -818,6 +879,7 @@ def main():
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
     ap.add_argument("--f", type=int, default=0, help="override the icosphere frequency (T = 20 f^2)")
     ap.add_argument("--points", type=int, default=0, help="override the number of points of the splat stage / workload P")
+    ap.add_argument("--lanes", type=int, default=2, help="frames in flight per GPU (1 or 2 contexts / streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-splat", action="store_true", help="skip the splat stage of the default line")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: how every rank's RGBA frame reaches rank 0")

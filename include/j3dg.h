@@ -196,6 +196,11 @@ int j3dg_group_broadcast_mesh(j3dg_group* group, int root, j3dg_mesh** mesh_inou
  * j3dg_frames_view(k).  A peer that never arrives times the wait out after 5 s (J3DG_ETIMEOUT, sticky). */
 int j3dg_frames_create(j3dg_group* group, uint32_t width, uint32_t height, int dst, int shared_frame, j3dg_frames** out);
 void j3dg_frames_destroy(j3dg_frames* frames);
+/* Two frames in flight per GPU: the frames of slot 0 / slot 1 (k even / odd) may be rendered by two CONTEXTS of the same
+ * device (two streams; see "frames in flight" at j3dg_render_frame): begin / arrive / release of frame k are enqueued on
+ * the stream of the context registered for slot k & 1 (default: the group's context for both).  The flag words are per
+ * slot, so the two streams never order each other.  Local (not collective). */
+int j3dg_frames_set_lane(j3dg_frames* frames, int slot, j3dg_ctx* ctx);
 int j3dg_frames_begin(j3dg_frames* frames, uint32_t* k_out);
 int j3dg_frames_target(j3dg_frames* frames, uint32_t k, uint32_t** rgba_out);
 int j3dg_frames_arrive(j3dg_frames* frames, uint32_t k);

@@ -156,6 +156,7 @@ def lib() -> C.CDLL:
         L.j3dg_frames_create.argtypes = [_vp, _u32, _u32, C.c_int, C.c_int, C.POINTER(_vp)]
         L.j3dg_frames_destroy.argtypes = [_vp]
         L.j3dg_frames_destroy.restype = None
+        L.j3dg_frames_set_lane.argtypes = [_vp, C.c_int, _vp]
         L.j3dg_frames_begin.argtypes = [_vp, C.POINTER(_u32)]
         L.j3dg_frames_target.argtypes = [_vp, _u32, C.POINTER(_vp)]
         L.j3dg_frames_arrive.argtypes = [_vp, _u32]
@@ -683,6 +684,9 @@ class Frames:
         if self._h:
             self.ctx._L.j3dg_frames_destroy(self._h)
             self._h = _vp()
+
+    def set_lane(self, slot: int, ctx: "Context"):
+        self.ctx._check(self.ctx._L.j3dg_frames_set_lane(self._h, slot, ctx._h), "j3dg_frames_set_lane")
 
     def begin(self) -> int:
         k = _u32()

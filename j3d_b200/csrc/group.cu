@@ -81,6 +81,7 @@ struct j3dg_frames {
   char* base = nullptr;         // the exchange buffer: [2 slots][world or 1][h*w] RGBA, then the flag words
   size_t frame_bytes = 0, flags_off = 0, nbytes = 0;
   uint32_t k = 0;               // next frame number
+  j3dg_ctx* lane[2] = {nullptr, nullptr};  // the context (stream) that renders the frames of slot 0 / 1 (j3dg_frames_set_lane)
 };
 
 namespace {
@@ -275,6 +276,7 @@ J3DG_API int j3dg_frames_create(j3dg_group* g, uint32_t width, uint32_t height, 
   cudaSetDevice(ctx->device);
   j3dg_frames* f = new j3dg_frames();
   f->g = g; f->w = width; f->h = height; f->dst = dst; f->shared = shared_frame != 0;
+  f->lane[0] = f->lane[1] = ctx;
   f->frame_bytes = (size_t)width * height * 4;
   f->flags_off = (2 * (size_t)(f->shared ? 1 : g->world) * f->frame_bytes + 255) & ~(size_t)255;
   f->nbytes = f->flags_off + 256;
@@ -312,6 +314,7 @@ J3DG_API void j3dg_frames_destroy(j3dg_frames* f) {
   j3dg_ctx* ctx = g->ctx;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (j3dg_ctx* l : f->lane) if (l != ctx) cudaStreamSynchronize(l->stream);
   int one = 1;
   all_min(g, &one);  // everybody is done with the buffer
   if (g->rank != f->dst) j3dg_peer_close(ctx, f->base);
@@ -320,16 +323,26 @@ J3DG_API void j3dg_frames_destroy(j3dg_frames* f) {
   delete f;
 }
 
-static uint32_t* frames_arrived(j3dg_frames* f, int r) { return reinterpret_cast<uint32_t*>(f->base + f->flags_off) + r; }
-static uint32_t* frames_released(j3dg_frames* f) { return reinterpret_cast<uint32_t*>(f->base + f->flags_off) + f->g->world; }
+// Flag words behind the frames: arrived[slot][rank] (2 * world words), then released[slot] (2 words).  One set PER SLOT:
+// the two slots may be driven from two streams (two frames in flight), and the frames of one slot follow each other on
+// one stream, so every word only ever grows.
+static uint32_t* frames_arrived(j3dg_frames* f, uint32_t slot, int r) { return reinterpret_cast<uint32_t*>(f->base + f->flags_off) + slot * (uint32_t)f->g->world + r; }
+static uint32_t* frames_released(j3dg_frames* f, uint32_t slot) { return reinterpret_cast<uint32_t*>(f->base + f->flags_off) + 2 * (uint32_t)f->g->world + slot; }
+
+J3DG_API int j3dg_frames_set_lane(j3dg_frames* f, int slot, j3dg_ctx* ctx) {
+  if (!f || slot < 0 || slot > 1 || !ctx) return J3DG_EINVAL;
+  if (ctx->device != f->g->ctx->device) { j3dg_set_error(f->g->ctx, "j3dg_frames_set_lane: the lane context must live on the group's device"); return J3DG_EINVAL; }
+  f->lane[slot] = ctx;
+  return J3DG_OK;
+}
 
 J3DG_API int j3dg_frames_begin(j3dg_frames* f, uint32_t* k_out) {
   if (!f || !k_out) return J3DG_EINVAL;
   const uint32_t k = f->k;
   *k_out = k;
-  if (k >= 2)  // frame k - 2 lived in this slot: dst must have released it (`released` counts consumed frames)
-    return j3dg_stream_wait_geq(f->g->ctx, frames_released(f), 1, k - 1);
-  return j3dg_check_sticky(f->g->ctx);
+  if (k >= 2)  // frame k - 2 lived in this slot: dst must have released it (released[slot] = number of the last consumed frame + 1)
+    return j3dg_stream_wait_geq(f->lane[k & 1u], frames_released(f, k & 1u), 1, k - 1);
+  return j3dg_check_sticky(f->lane[k & 1u]);
 }
 
 J3DG_API int j3dg_frames_target(j3dg_frames* f, uint32_t k, uint32_t** rgba_out) {
@@ -341,10 +354,10 @@ J3DG_API int j3dg_frames_target(j3dg_frames* f, uint32_t k, uint32_t** rgba_out)
 
 J3DG_API int j3dg_frames_arrive(j3dg_frames* f, uint32_t k) {
   if (!f || k != f->k) { j3dg_set_error(f ? f->g->ctx : nullptr, "j3dg_frames_arrive: frames arrive in order (k must be the value j3dg_frames_begin returned)"); return J3DG_EINVAL; }
-  j3dg_ctx* ctx = f->g->ctx;
-  int rc = j3dg_stream_signal(ctx, frames_arrived(f, f->g->rank), k + 1);
+  j3dg_ctx* ctx = f->lane[k & 1u];
+  int rc = j3dg_stream_signal(ctx, frames_arrived(f, k & 1u, f->g->rank), k + 1);
   if (rc != J3DG_OK) return rc;
-  if (f->g->rank == f->dst && (rc = j3dg_stream_wait_geq(ctx, frames_arrived(f, 0), (uint32_t)f->g->world, k + 1)) != J3DG_OK) return rc;
+  if (f->g->rank == f->dst && (rc = j3dg_stream_wait_geq(ctx, frames_arrived(f, k & 1u, 0), (uint32_t)f->g->world, k + 1)) != J3DG_OK) return rc;
   f->k = k + 1;
   return J3DG_OK;
 }
@@ -352,7 +365,7 @@ J3DG_API int j3dg_frames_arrive(j3dg_frames* f, uint32_t k) {
 J3DG_API int j3dg_frames_release(j3dg_frames* f, uint32_t k) {
   if (!f) return J3DG_EINVAL;
   if (f->g->rank != f->dst) return J3DG_OK;
-  return j3dg_stream_signal(f->g->ctx, frames_released(f), k + 1);
+  return j3dg_stream_signal(f->lane[k & 1u], frames_released(f, k & 1u), k + 1);
 }
 
 J3DG_API int j3dg_frames_view(j3dg_frames* f, uint32_t k, const uint32_t** frames_out) {

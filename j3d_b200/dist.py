@@ -183,6 +183,10 @@ class PeerFrames:
             raise RuntimeError(str(e)) from e
         self.k = 0
 
+    def set_lane(self, slot: int, ctx):
+        """Two frames in flight: the frames of slot 0 / 1 (k even / odd) are rendered by this context (j3dg_frames_set_lane)."""
+        self.f.set_lane(slot, ctx)
+
     def begin(self) -> int:
         return self.f.begin()
 
@@ -269,33 +273,41 @@ class PeerFramesPy:
                 self.base = 0
             raise RuntimeError("peer-memory frame exchange unavailable on at least one rank" + (f": {err}" if err else ""))
         self.k = 0
+        self.lane = [ctx, ctx]
         dist.barrier()
 
-    def _arrived(self, r: int) -> int:
-        return self.base + self.flags_off + 4 * r
+    # flag words: arrived[slot][rank] (2 * world words), then released[slot] (2 words) — one set per slot, so that the
+    # two slots can be driven from two streams (two frames in flight) and every word only ever grows
+    def _arrived(self, slot: int, r: int) -> int:
+        return self.base + self.flags_off + 4 * (slot * self.world + r)
 
-    def _released(self) -> int:
-        return self.base + self.flags_off + 4 * self.world
+    def _released(self, slot: int) -> int:
+        return self.base + self.flags_off + 4 * (2 * self.world + slot)
+
+    def set_lane(self, slot: int, ctx):
+        """The frames of slot 0 / 1 (k even / odd) are rendered and handed over on this context's stream."""
+        self.lane[slot] = ctx
 
     def begin(self) -> int:
         k = self.k
-        if k >= 2:  # frame k - 2 lived in this slot: dst must have released it (released counts consumed frames)
-            self.ctx.stream_wait_geq(self._released(), 1, k - 1)
+        if k >= 2:  # frame k - 2 lived in this slot: dst must have released it (released[slot] = last consumed frame + 1)
+            self.lane[k & 1].stream_wait_geq(self._released(k & 1), 1, k - 1)
         return k
 
     def target(self, k: int) -> int:
         return self.base + peer_slot_offset(k & 1, 0 if self.shared else self.rank, self.world, self.frame_bytes)
 
     def arrive(self, k: int):
-        self.ctx.stream_signal(self._arrived(self.rank), k + 1)
+        ctx = self.lane[k & 1]
+        ctx.stream_signal(self._arrived(k & 1, self.rank), k + 1)
         if self.rank == self.dst:
-            self.ctx.stream_wait_geq(self._arrived(0), self.world, k + 1)
+            ctx.stream_wait_geq(self._arrived(k & 1, 0), self.world, k + 1)
         self.k = k + 1
 
     def release(self, k: int):
         """dst only (a no-op elsewhere): the consumer work of frame k is enqueued; the slot may be overwritten."""
         if self.rank == self.dst:
-            self.ctx.stream_signal(self._released(), k + 1)
+            self.lane[k & 1].stream_signal(self._released(k & 1), k + 1)
 
     def end(self, k: int):
         self.arrive(k)

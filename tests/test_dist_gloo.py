@@ -173,15 +173,27 @@ def _peer_worker(rank, world, port, out, fail):
         assert targets == [jd.peer_slot_offset(k & 1, rank, world, fb) for k in range(4)]
         want = []
         for k in range(4):
+            s = k & 1                                                        # flag words per slot: arrived[slot][rank], then released[slot]
             if k >= 2:
-                want.append(("wait", flags + 4 * world, 1, k - 1))          # slot k & 1 released by rank 0 (frame k - 2 consumed)
-            want.append(("signal", flags + 4 * rank, k + 1))               # my frame k has arrived
+                want.append(("wait", flags + 4 * (2 * world + s), 1, k - 1))   # slot k & 1 released by rank 0 (frame k - 2 consumed)
+            want.append(("signal", flags + 4 * (s * world + rank), k + 1))     # my frame k has arrived
             if rank == 0:
-                want.append(("wait", flags, world, k + 1))                  # rank 0: every rank's frame k
+                want.append(("wait", flags + 4 * s * world, world, k + 1))      # rank 0: every rank's frame k
             want.append(("consume", k))
             if rank == 0:
-                want.append(("signal", flags + 4 * world, k + 1))          # ... consumed: release
+                want.append(("signal", flags + 4 * (2 * world + s), k + 1))    # ... consumed: release
         assert ctx.ops == want, (ctx.ops, want)
+        # two frames in flight: the frames of slot 1 are handed over on a second context's stream
+        lane0, lane1 = _RecordingCtx(rank), _RecordingCtx(rank)
+        two = jd.PeerFramesPy(lane0, h, w, torch.device("cpu"), dst=0)
+        two.set_lane(1, lane1)
+        for step in range(4):
+            k = two.begin()
+            two.arrive(k)
+            two.release(k)
+        assert all(op[1] in (flags + 4 * rank, flags, flags + 8 * world) for op in lane0.ops if op[0] in ("signal", "wait"))
+        assert all(op[1] in (flags + 4 * (world + rank), flags + 4 * world, flags + 4 * (2 * world + 1)) for op in lane1.ops if op[0] in ("signal", "wait"))
+        assert len(lane0.ops) == len(lane1.ops) > 0
         shared = jd.PeerFramesPy(_RecordingCtx(rank), h, w, torch.device("cpu"), dst=0, shared_frame=True)
         assert shared.target(0) - base == 0 and shared.target(1) - base == jd.peer_slot_offset(1, 0, world, fb)  # one frame per slot
         out[rank] = 1

@@ -1092,3 +1092,57 @@ def test_full_size_all_hits_pick_and_voxel_properties(ctx, config_b):
     tri_of = tris[got["pixel"]["object_id"][hit]]
     assert (got["closest_vertex"][hit][:, None] == tri_of).any(axis=1).all()   # the closest vertex is a corner of the hit triangle
     assert np.isnan(got["world_pos"][~hit]).all() and np.isfinite(got["world_pos"][hit]).all()
+
+
+def test_two_contexts_share_a_mesh_and_keep_two_frames_in_flight(ctx):
+    """Frames in flight (include/j3dg.h, j3dg_render_frame): a second context of the same device renders the odd frames of
+    a sweep on its own stream, from the SAME mesh handle, while the even frames run on the first — nothing is synchronised
+    in between.  Every frame equals the frame rendered alone; the same through j3dg_frame_submit / j3dg_frame_wait."""
+    import torch
+    verts, tris = j.icosphere(150)
+    mesh = ctx.mesh_create(verts, tris, vcolors=j.vertex_colors(verts))
+    mn, mx = j.compute_bb(verts)
+    w, h = 960, 540
+    v0 = j.make_view(w, h, mn, mx, j.DEFAULT_FLAGS | j.SHADOW | j.VERTEXCOLORS)
+    views = [j.orbit_view(v0, 11.0 * k) for k in range(12)]
+    mc, cav = j.make_matcap(0)
+    ctx.set_matcap(mc, cav)
+    ctx2 = j.Context(0)
+    ctx2.set_matcap(mc, cav)
+    lanes = [ctx, ctx2]
+    dev = torch.device("cuda", 0)
+    want = []
+    for v in views:
+        px = np.zeros((h, w), j.PIXEL_DTYPE); rgba = np.zeros((h, w), np.uint32)
+        ctx.render_frame([mesh], [], v, pixels_out=px, rgba_out=rgba)
+        want.append((px, rgba))
+    d_px = [torch.zeros((h, w, 32), dtype=torch.uint8, device=dev) for _ in views]
+    d_rgba = [torch.zeros((h, w), dtype=torch.int32, device=dev) for _ in views]
+    for rep in range(3):
+        for k, v in enumerate(views):  # device outputs: the calls return before the kernels ran
+            lanes[k & 1].render_frame([mesh], [], v, pixels_out=d_px[k], rgba_out=d_rgba[k])
+    for c in lanes:
+        c.synchronize()
+    for k in range(len(views)):
+        assert d_px[k].cpu().numpy().tobytes() == want[k][0].tobytes(), k
+        assert d_rgba[k].cpu().numpy().view(np.uint32).tobytes() == want[k][1].tobytes(), k
+    # pipelined host frames on both contexts
+    hpx = [[np.zeros((h, w), j.PIXEL_DTYPE) for _ in range(2)] for _ in range(2)]
+    hrgba = [[np.zeros((h, w), np.uint32) for _ in range(2)] for _ in range(2)]
+    done = []
+    for k, v in enumerate(views):
+        ln, b = k & 1, (k >> 1) & 1
+        lanes[ln].frame_submit([mesh], [], v, pixels_out=hpx[ln][b], rgba_out=hrgba[ln][b])
+        if k >= 2:
+            lanes[ln].frame_wait()
+            kk = k - 2
+            done.append((kk, hpx[kk & 1][(kk >> 1) & 1].copy(), hrgba[kk & 1][(kk >> 1) & 1].copy()))
+    for kk in (len(views) - 2, len(views) - 1):
+        lanes[kk & 1].frame_wait()
+        done.append((kk, hpx[kk & 1][(kk >> 1) & 1].copy(), hrgba[kk & 1][(kk >> 1) & 1].copy()))
+    assert sorted(d[0] for d in done) == list(range(len(views)))
+    for kk, px, rgba in done:
+        assert px.tobytes() == want[kk][0].tobytes() and rgba.tobytes() == want[kk][1].tobytes(), kk
+    assert ctx.status() == 0 and ctx2.status() == 0
+    ctx2.close()
+    mesh.destroy()
