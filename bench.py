@@ -263,13 +263,13 @@ class Rig:
         self.ctx.set_stream(self.stream.cuda_stream)
         mc, cav = j.make_matcap(0)
         self.ctx.set_matcap(mc, cav)
-        # Two frames in flight per GPU: a second context of the same device with its own stream.  Frame k is rendered by
-        # context k & 1; while the longest rays of frame k are still being finished by a few warps, the cast kernel of
-        # frame k + 1 moves into the SM slots that frame k has already left (csrc/cast.cu, plain launch).  Meshes are
+        # Frames in flight per GPU: more contexts of the same device, each with its own stream.  Frame k is rendered by
+        # context k mod L; while the longest rays of frame k are still being finished by a few warps, the cast kernels of
+        # the next frames move into the SM slots that frame k has already left (csrc/cast.cu, plain launch).  Meshes are
         # shared between the contexts of one device.
-        self.lanes = max(1, min(2, args.lanes))
+        self.lanes = max(1, min(4, args.lanes))
         self.ctxs, self.streams = [self.ctx], [self.stream]
-        if self.lanes == 2:
+        for _ in range(1, self.lanes):
             c2 = j.Context(local_rank)
             s2 = torch.cuda.Stream(device=self.dev)
             c2.set_stream(s2.cuda_stream)
@@ -376,7 +376,7 @@ def run_orbit(args, wl, rank, world, local_rank):
     ctxs, streams, L = rig.ctxs, rig.streams, rig.lanes
     pxs = [torch.empty((H, W, 32), dtype=torch.uint8, device=dev) for _ in range(L)]  # one canvas per frame in flight
     px = pxs[0]
-    rgba2 = [torch.empty((H, W), dtype=torch.int32, device=dev) for _ in range(2)]
+    rgba2 = [torch.empty((H, W), dtype=torch.int32, device=dev) for _ in range(max(2, L))]
     # N > 1: every rank's frame must end up on rank 0 each step.
     #   --exchange peer (default): the shade kernel of every rank stores its RGBA straight into rank 0's HBM over
     #       NVLink peer memory (CUDA-IPC mapping, stream-ordered arrival / release flags; j3d_b200/dist.py::PeerFrames)
@@ -386,7 +386,7 @@ def run_orbit(args, wl, rank, world, local_rank):
     if world > 1 and args.exchange == "peer":
         from j3d_b200.dist import PeerFrames
         try:
-            pf = PeerFrames(ctx, H, W, dev, dst=0, group=rig.group)
+            pf = PeerFrames(ctx, H, W, dev, dst=0, group=rig.group, nslots=max(2, L))
         except RuntimeError as e:  # every rank raises together: CUDA IPC is not available here, gather with NCCL instead
             if rank == 0:
                 print(f"bench.py: {e}; using --exchange nccl", file=sys.stderr)
@@ -394,8 +394,8 @@ def run_orbit(args, wl, rank, world, local_rank):
     if world > 1 and args.exchange == "nccl":
         comm = torch.cuda.Stream(device=dev)
         L = 1  # the gather path keeps one frame in flight
-    if pf is not None and L == 2:
-        pf.set_lane(1, ctxs[1])  # begin / arrive / release of the odd frames go to the second context's stream
+    for ln in range(1, L if pf is not None else 0):
+        pf.set_lane(ln, ctxs[ln])  # begin / arrive / release of the frames of slot ln go to that context's stream
     gather_lists = [[torch.empty_like(rgba2[0]) for _ in range(world)] for _ in range(2)] if (comm is not None and rank == 0) else [None, None]
     ev_render = [torch.cuda.Event() for _ in range(2)]
     ev_gather = [torch.cuda.Event() for _ in range(2)]
@@ -405,7 +405,7 @@ def run_orbit(args, wl, rank, world, local_rank):
         lanes = L if lanes is None else lanes
         if pf is not None and not local:
             k = pf.begin()
-            ln = k & 1 if L == 2 else 0   # the slot of the exchange buffer IS the lane
+            ln = k % L   # the slot of the exchange buffer IS the lane
             ctxs[ln].render_frame([mesh], [], v, pixels_out=pxs[ln], rgba_out=pf.target(k))
             pf.arrive(k)
             # rank 0 consumes between arrival and release (PeerFrames protocol): nothing in the timed loop — the frames
@@ -415,10 +415,10 @@ def run_orbit(args, wl, rank, world, local_rank):
         k = state["k"]
         state["k"] = k + 1
         b = k & 1
-        ln = b if lanes == 2 else 0
+        ln = k % lanes
         if comm is not None and k >= 2:
             stream.wait_event(ev_gather[b])  # the gather of frame k - 2 has left this buffer
-        ctxs[ln].render_frame([mesh], [], v, pixels_out=pxs[ln], rgba_out=rgba2[b])
+        ctxs[ln].render_frame([mesh], [], v, pixels_out=pxs[ln], rgba_out=rgba2[b if comm is not None else ln])
         if comm is not None:
             ev_render[b].record(stream)
             with torch.cuda.stream(comm):
@@ -495,7 +495,7 @@ def run_orbit(args, wl, rank, world, local_rank):
         snaps = []
         for k in range(nchk):
             kk = pf.begin()
-            ln = kk & 1 if L == 2 else 0
+            ln = kk % L
             ctxs[ln].render_frame([mesh], [], chk[k * world + rank], pixels_out=pxs[ln], rgba_out=pf.target(kk))
             pf.arrive(kk)
             if rank == 0:
@@ -660,7 +660,7 @@ def run_orbit(args, wl, rank, world, local_rank):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(wl, f, nt, W, H), "l2": "inputs_larger_than_l2"},  # the same two keys as the reference arm's line
-        "frames_in_flight": {"per_gpu": L, "how": "frame k is rendered by context k mod 2 of the same device (two streams, meshes shared): the cast kernel of frame k + 1 moves into the SM slots frame k has left while a few warps still finish its longest rays; every frame is complete and in its output buffer inside the timed region" if L == 2 else "one context, frames back to back on one stream",
+        "frames_in_flight": {"per_gpu": L, "how": f"frame k is rendered by context k mod {L} of the same device ({L} streams, meshes shared): the cast kernels of the next frames move into the SM slots frame k has left while a few warps still finish its longest rays; every frame is complete and in its output buffer inside the timed region" if L > 1 else "one context, frames back to back on one stream",
                              "one_frame_at_a_time": single},
         "layout": {"poses": f"frame i at i/{world} degrees on rank i mod {world}: every N renders the same arc, {world}x finer" if world > 1 else "frame i at i degrees",
                    "sharding": "replicas only" if world == 1 else f"orbit frames round-robin over {world} ranks, mesh + BVH built on rank 0 and replicated by j3dg_group_broadcast_mesh (NCCL), " + ("every rank's shade kernel stores its RGBA into rank 0's HBM over NVLink peer memory (CUDA IPC), stream-ordered arrival/release flags" if args.exchange == "peer" else "RGBA NCCL-gathered on rank 0 every step (second stream, overlapping the kernels of frame k+1)"),
@@ -879,7 +879,7 @@ def main():
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
     ap.add_argument("--f", type=int, default=0, help="override the icosphere frequency (T = 20 f^2)")
     ap.add_argument("--points", type=int, default=0, help="override the number of points of the splat stage / workload P")
-    ap.add_argument("--lanes", type=int, default=2, help="frames in flight per GPU (1 or 2 contexts / streams)")
+    ap.add_argument("--lanes", type=int, default=3, help="frames in flight per GPU (1 .. 4 contexts / streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-splat", action="store_true", help="skip the splat stage of the default line")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: how every rank's RGBA frame reaches rank 0")

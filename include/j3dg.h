@@ -136,7 +136,7 @@ int j3dg_ctx_set_tuning(j3dg_ctx* ctx, uint32_t lane_budget, int cast_algo);
 int j3dg_ctx_set_screen_shard(j3dg_ctx* ctx, uint32_t rank, uint32_t world);
 
 /* ---- result exchange over NVLink peer memory (BASELINE configs[2], [4]).  The ray-cast kernel is a
- *      cooperative launch that owns every SM, so a collective kernel cannot run beside it; instead every rank's
+ *      persistent launch that fills every SM, so a collective kernel finds no room beside it; instead every rank's
  *      shade kernel stores its RGBA straight into a buffer that rank 0 owns and the others map through CUDA IPC
  *      (pass the mapped address as rgba_out of j3dg_render_frame / j3dg_shade), and frames are handed over with
  *      stream-ordered flags.  j3dg_peer_alloc: zeroed device buffer + its 64-byte IPC handle (ship the handle to
@@ -189,17 +189,21 @@ int j3dg_group_broadcast_mesh(j3dg_group* group, int root, j3dg_mesh** mesh_inou
 /* Frame exchange: rank `dst` allocates [2 slots][world][height*width] RGBA (shared_frame != 0: [2 slots][1] — ONE frame
  * per slot that all ranks write disjoint rows of, for j3dg_ctx_set_screen_shard) and the other ranks map it through
  * CUDA IPC; a rank renders with rgba_out = j3dg_frames_target(k), so its shade kernel's stores travel over NVLink
- * into dst's HBM — no gather kernel has to find room beside the cooperative ray-cast kernel.  Stream-ordered flags
+ * into dst's HBM — no gather kernel has to find room beside the persistent ray-cast kernel.  Stream-ordered flags
  * hand the slots over (csrc/peer.cu): begin(k) makes the stream wait until dst has RELEASED frame k - 2 (same slot),
  * arrive(k) signals this rank's frame and, on dst, makes the stream wait for every rank's frame k; release(k)
  * (a no-op off dst) lets the peers overwrite the slot and must be enqueued AFTER the work that reads
  * j3dg_frames_view(k).  A peer that never arrives times the wait out after 5 s (J3DG_ETIMEOUT, sticky). */
 int j3dg_frames_create(j3dg_group* group, uint32_t width, uint32_t height, int dst, int shared_frame, j3dg_frames** out);
+/* The same with nslots (2 .. J3DG_FRAMES_MAX_SLOTS) instead of 2 slots: frame k lives in slot k mod nslots, begin(k)
+ * waits for the release of frame k - nslots. */
+#define J3DG_FRAMES_MAX_SLOTS 8
+int j3dg_frames_create_n(j3dg_group* group, uint32_t width, uint32_t height, int dst, int shared_frame, uint32_t nslots, j3dg_frames** out);
 void j3dg_frames_destroy(j3dg_frames* frames);
-/* Two frames in flight per GPU: the frames of slot 0 / slot 1 (k even / odd) may be rendered by two CONTEXTS of the same
- * device (two streams; see "frames in flight" at j3dg_render_frame): begin / arrive / release of frame k are enqueued on
- * the stream of the context registered for slot k & 1 (default: the group's context for both).  The flag words are per
- * slot, so the two streams never order each other.  Local (not collective). */
+/* Several frames in flight per GPU: the frames of every slot may be rendered by their own CONTEXT of the same device
+ * (own stream; see "frames in flight" at j3dg_render_frame): begin / arrive / release of frame k are enqueued on the
+ * stream of the context registered for slot k mod nslots (default: the group's context for all).  The flag words are per
+ * slot, so the streams never order each other.  Local (not collective). */
 int j3dg_frames_set_lane(j3dg_frames* frames, int slot, j3dg_ctx* ctx);
 int j3dg_frames_begin(j3dg_frames* frames, uint32_t* k_out);
 int j3dg_frames_target(j3dg_frames* frames, uint32_t k, uint32_t** rgba_out);

@@ -156,6 +156,7 @@ def lib() -> C.CDLL:
         L.j3dg_frames_create.argtypes = [_vp, _u32, _u32, C.c_int, C.c_int, C.POINTER(_vp)]
         L.j3dg_frames_destroy.argtypes = [_vp]
         L.j3dg_frames_destroy.restype = None
+        L.j3dg_frames_create_n.argtypes = [_vp, _u32, _u32, C.c_int, C.c_int, _u32, C.POINTER(_vp)]
         L.j3dg_frames_set_lane.argtypes = [_vp, C.c_int, _vp]
         L.j3dg_frames_begin.argtypes = [_vp, C.POINTER(_u32)]
         L.j3dg_frames_target.argtypes = [_vp, _u32, C.POINTER(_vp)]
@@ -668,17 +669,17 @@ class Group:
         self.ctx._check(self.ctx._L.j3dg_group_broadcast_mesh(self._h, root, C.byref(h)), "j3dg_group_broadcast_mesh")
         return mesh if mesh is not None else Mesh(self.ctx, h)
 
-    def frames(self, width: int, height: int, dst: int = 0, shared_frame: bool = False) -> "Frames":
-        return Frames(self, width, height, dst, shared_frame)
+    def frames(self, width: int, height: int, dst: int = 0, shared_frame: bool = False, nslots: int = 2) -> "Frames":
+        return Frames(self, width, height, dst, shared_frame, nslots)
 
 
 class Frames:
     """j3dg_frames: every rank renders straight into rank dst's HBM (include/j3dg.h has the protocol)."""
 
-    def __init__(self, group: Group, width: int, height: int, dst: int, shared_frame: bool):
-        self.group, self.ctx, self.w, self.h, self.dst, self.shared = group, group.ctx, width, height, dst, shared_frame
+    def __init__(self, group: Group, width: int, height: int, dst: int, shared_frame: bool, nslots: int = 2):
+        self.group, self.ctx, self.w, self.h, self.dst, self.shared, self.nslots = group, group.ctx, width, height, dst, shared_frame, nslots
         self._h = _vp()
-        self.ctx._check(self.ctx._L.j3dg_frames_create(group._h, width, height, dst, int(shared_frame), C.byref(self._h)), "j3dg_frames_create")
+        self.ctx._check(self.ctx._L.j3dg_frames_create_n(group._h, width, height, dst, int(shared_frame), nslots, C.byref(self._h)), "j3dg_frames_create_n")
 
     def destroy(self):
         if self._h:

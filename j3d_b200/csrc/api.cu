@@ -174,7 +174,6 @@ J3DG_API int j3dg_ctx_create(int device, j3dg_ctx** out) {
   }
   if (const char* e = getenv("J3DG_LANE_BUDGET")) ctx->lane_budget = (uint32_t)std::max(1, atoi(e));  // developer tuning knobs
   if (const char* e = getenv("J3DG_SHADOW_BUDGET")) ctx->shadow_budget = (uint32_t)std::max(1, atoi(e));
-  if (const char* e = getenv("J3DG_CONSUMER_BLOCKS")) ctx->consumer_blocks = (uint32_t)std::max(0, atoi(e));
   if (const char* e = getenv("J3DG_CAST_ALGO")) ctx->cast_algo = strcmp(e, "group") == 0 ? 1 : 0;
   *out = ctx;
   return J3DG_OK;
@@ -239,7 +238,7 @@ J3DG_API int j3dg_ctx_set_profiling(j3dg_ctx* ctx, int enabled) {
 
 J3DG_API int j3dg_ctx_set_tuning(j3dg_ctx* ctx, uint32_t lane_budget, int cast_algo) {
   if (!ctx || cast_algo < 0 || cast_algo > 1) return J3DG_EINVAL;
-  ctx->lane_budget = lane_budget ? lane_budget : 24u;
+  ctx->lane_budget = lane_budget ? lane_budget : 28u;
   ctx->cast_algo = cast_algo;
   return J3DG_OK;
 }

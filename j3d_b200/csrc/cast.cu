@@ -18,7 +18,7 @@
 //               the hard rays (restarted from the root, pruned by the hit the lane warp already found; carrying the
 //               lane's stack along instead was measured and buys nothing) and for the generic find_closest query.
 //
-// cast_kernel is ONE cooperative launch per ray type: every warp first traces tiles in lane mode (producing the
+// cast_kernel is ONE persistent launch per ray type (a plain launch of at most one machine-full of blocks): every warp first traces tiles in lane mode (producing the
 // queue), then — warp by warp, on its own slice of the block's shared-memory stacks, no block barrier — turns into
 // four 8-lane groups that drain the queue.  Pipeline of one j3dg_cast:
 //   cast_kernel<PRIMARY> (raw hit: t, u, v, record slot) -> resolve_kernel (hit -> pixel record, hit bounding
@@ -40,7 +40,11 @@ namespace {
 constexpr int GROUP = 8;                                  // group kernel: lanes per ray = children per node = max triangles per leaf
 constexpr int BLOCK_THREADS = 128;
 #ifndef J3DG_LANE_MIN_BLOCKS
-#define J3DG_LANE_MIN_BLOCKS 8
+// 7 blocks of 4 warps per SM = 72 registers per thread: the node step (32 registers of node data on top of the ray) fits
+// without spills.  At 8 blocks (64 registers) ptxas parks 6 registers in local memory around EVERY node step as soon as
+// anything is added to the kernel (measured on config B: 1.02 instead of 0.97 ms per frame); 6 blocks lose more in
+// occupancy than the registers give (1.05 ms).
+#define J3DG_LANE_MIN_BLOCKS 7
 #endif
 #ifndef J3DG_LANE_REFILL_MIN
 #define J3DG_LANE_REFILL_MIN 4                            // lane kernel: idle lanes that trigger a refill from the pool
@@ -119,8 +123,8 @@ struct TraceParams {
   unsigned int* hard_count;      // producers: append position
   unsigned int* hard_taken;      // consumers: next entry to claim
   unsigned int* done_blocks;     // lane WARPS that have finished producing
+  unsigned int* started;         // lane WARPS that have begun to produce (bumped before a warp's first pool fetch)
   uint32_t hard_capacity;        // entries the queue arrays hold
-  uint32_t consumer_blocks;      // blocks [0, consumer_blocks) consume from the start; the others trace tiles first
   uint2* hard_id;                // {ray id (0xFFFFFFFF = entry not written yet), mesh of the best hit so far}
   float4* hard_best;             // {t, u, v, record slot bits} of the best hit so far (slot 0xFFFFFFFF: none)
   const float* rays;             // RAYLIST: n x 8 floats
@@ -190,6 +194,14 @@ __device__ __forceinline__ WorldRay world_ray(const TraceParams& p, uint32_t id)
 //            is claimed with an atomic, polled until its ray id is written (the producer writes the seed,
 //            fences, then the id; the consumer restores the empty marker), and a group retires when its
 //            claimed index lies past the final length after every producer block has signed off.
+//            "Every producer has signed off" counts the warps that HAVE STARTED, not the warps of the grid: a warp
+//            announces itself (TraceParams::started) before its first pool fetch and signs off after its last ray,
+//            and a warp turns consumer only when the pool counter has run out — so whatever a waiting group still
+//            waits for is being traced by RUNNING warps.  Blocks of the launch that have not started yet (frames
+//            in flight: the machine is shared with the previous frame's kernel) have nothing left to take, announce
+//            and sign off in one go when they finally run, and nobody waits for them.  Producers never wait.
+//            Hence launches cannot deadlock however many of them share the machine, and no block has to be
+//            resident at any particular time.
 enum Source { POOLS = 0, QUEUE = 1 };
 constexpr uint32_t QUEUE_EMPTY = 0xFFFFFFFFu;
 #ifndef J3DG_IDLE_BACKOFF_MAX_NS
@@ -243,7 +255,6 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const st
   uint32_t backoff = 250u;          // QUEUE: nanoseconds an idle warp sleeps before it polls again (doubles up to 4 us)
   uint32_t round_no = 0;            // QUEUE: while other groups of the warp traverse, an idle group polls only every 4th round
   bool warp_busy = false;
-  const uint32_t producer_warps = (gridDim.x - p.consumer_blocks) * (BLOCK_THREADS / 32);  // producers sign off warp by warp
 
   auto pop = [&]() -> uint32_t {
     while (sp > 0) {
@@ -345,9 +356,13 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const st
           mesh_k = 0;
           enter_mesh(wr, 0);
           have_ray = true;
-        } else if (*reinterpret_cast<volatile unsigned int*>(p.done_blocks) >= producer_warps) {
-          // every producer has signed off (after fencing its writes): the queue length is final
-          if (claimed >= *reinterpret_cast<volatile unsigned int*>(p.hard_count)) retired = true;
+        } else {
+          // done | started in one load.  A group only gets here after the pool counter has run out, so no warp can take
+          // a first pool any more: every warp that ever will produce has bumped `started` (it does so before its first
+          // fetch), and once as many have signed off (after fencing their writes) the queue length is final.
+          uint2 ds;
+          asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(ds.x), "=r"(ds.y) : "l"(p.done_blocks));
+          if (ds.x >= ds.y && claimed >= *reinterpret_cast<volatile unsigned int*>(p.hard_count)) retired = true;
         }
       }
       const uint32_t busy = __ballot_sync(0xffffffffu, have_ray);
@@ -637,6 +652,7 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* const stk
   // ---- warp-uniform pool state ----
   uint32_t pool_next = 0, pool_count = 0;
   bool exhausted = false;
+  if (lane == 0) atomicAdd(p.started, 1u);  // before the first pool fetch (group_loop, SRC QUEUE)
 
   auto enter = [&](const LaneRay& lr, uint32_t k) {
     const MeshDev& m = p.meshes[k];
@@ -1356,10 +1372,10 @@ constexpr size_t cast_smem_bytes() {
 #endif
 }
 
-// The cast kernel proper: one launch, two kinds of warps.  Blocks [0, consumer_blocks) consume the hard-ray
-// queue from the start; all other blocks first trace tiles (one ray per lane, evicting long rays into the
-// queue), sign off, and then help to drain the queue.  The launch is cooperative, so every block is resident
-// and the consumers may wait for the producers.
+// The cast kernel proper: one launch, every warp plays two roles.  It first traces tiles (one ray per lane, evicting
+// long rays into the queue), signs off, and then helps to drain the queue as four 8-lane groups (group_loop<QUEUE>).
+// A plain launch of at most one machine-full of blocks: producers never wait, and consumers only wait for warps that
+// are running (group_loop, SRC QUEUE) — no block has to be resident at any particular time.
 template <int MODE, bool STATS>
 __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_POOL_MODE ? J3DG_POOL_MIN_BLOCKS : J3DG_LANE_MIN_BLOCKS) cast_kernel(const TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem[];  // cast_smem_bytes<MODE, STATS>()
@@ -1370,7 +1386,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_POOL_MODE ? J3DG_POOL_MIN_
 #if J3DG_POOL_MODE
   uint32_t* const wsm = reinterpret_cast<uint32_t*>(smem) + (threadIdx.x >> 5) * PoolLayout<MODE, STATS>::WARP_WORDS;
   uint2* const warp_stack = reinterpret_cast<uint2*>(wsm);  // the group stacks reuse the warp's region once its slots are empty
-  if (blockIdx.x >= p.consumer_blocks) {
+  {
     pool_loop<MODE, STATS>(p, wsm);
     __syncwarp();
     if ((threadIdx.x & 31) == 0) {
@@ -1381,7 +1397,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_POOL_MODE ? J3DG_POOL_MIN_
 #else
   static_assert((LANE_STACK + 1) * 32 / 4 >= STACK_SIZE, "a warp's stack slice must hold four group stacks");
   uint2* const warp_stack = reinterpret_cast<uint2*>(smem) + (threadIdx.x >> 5) * ((LANE_STACK + 1) * 32);
-  if (blockIdx.x >= p.consumer_blocks) {
+  {
     lane_loop<MODE, STATS>(p, warp_stack + (threadIdx.x & 31), reinterpret_cast<uint32_t*>(smem + LANE_SMEM_STACK));
     __syncwarp();
     if ((threadIdx.x & 31) == 0) {
@@ -1630,7 +1646,7 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   // stats slots (u64 each): [0] node visits [1] triangle tests [2] stack overflow flag [3] pool counter PRIMARY
   // [4] shadow rays traced (accumulates until the timings are reset) [5] shadow list length [6] queue length PRIMARY
   // [7] queue claims PRIMARY [8] pool counter SHADOW [9] queue length SHADOW [10] queue claims SHADOW
-  // [11] producer blocks done PRIMARY [12] producer blocks done SHADOW
+  // [11] producer warps done (low word) + producer warps started (high word) PRIMARY [12] the same SHADOW
   CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
   CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats + 5, 0, 8 * sizeof(unsigned long long), ctx->stream));
   CU_CHECK(ctx, cudaMemsetAsync(ctx->d_stats + 20, 0xFF, sizeof(unsigned long long), ctx->stream));  // hit bbox: min x, min y
@@ -1659,7 +1675,7 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   const bool sharded = ctx->shard_world > 1 && !stats;
   tp.grid = make_tile_grid(x0, y0, x1, y1, sharded ? ctx->shard_rank : 0u, sharded ? ctx->shard_world : 1u);
   const long long ntiles = tp.grid.total_pools;
-  // One cooperative launch of the hybrid kernel: the grid fills the machine once, every block is resident.
+  // One launch of the hybrid kernel: the grid fills the machine at most once.
   auto launch_hybrid = [&](auto kernel, size_t smem, long long pools) -> int {
     int nb = 0;
     cudaError_t e = cudaSuccess;
@@ -1675,15 +1691,12 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
       tp.spill = (uint2*)ctx->d_spill;
     }
 #endif
-    // dedicated consumer blocks only when the machine is full anyway; small jobs just run producers that convert
-    tp.consumer_blocks = (stats || pools * 32 < (long long)full * BLOCK_THREADS * 4) ? 0u : (uint32_t)std::min<long long>(ctx->consumer_blocks, full / 2);
-    const long long producers = std::max<long long>(1, std::min<long long>((long long)full - tp.consumer_blocks, (pools + 3) / 4));
-    const int grid = (int)(producers + tp.consumer_blocks);
-    // A plain launch of at most one machine-full of blocks.  Producers never wait for anything, consumers only wait
-    // for producers of their own launch, and a launch never needs more slots than the machine has — so the launch
-    // cannot deadlock whatever else is resident, and TWO casts (consecutive frames rendered by two contexts on two
-    // streams) may share the machine: groups retire one by one once the queue has run dry, so the blocks of the next
-    // frame move in while this frame's longest rays are still being finished (measured: 0.96 -> 0.79 ms per frame).
+    const int grid = (int)std::max<long long>(1, std::min<long long>((long long)full, (pools + 3) / 4));
+    // A plain launch of at most one machine-full of blocks.  Producers never wait for anything; consumers wait for
+    // warps that are RUNNING, never for a block that has not started — so the launch cannot deadlock whatever else
+    // is resident, and several casts (consecutive frames rendered by two contexts on two streams) may
+    // share the machine: groups retire one by one once the queue has run dry, so the blocks of the next frame move in
+    // while this frame's longest rays are still being finished (measured: 0.96 -> 0.79 ms per frame).
     kernel<<<grid, BLOCK_THREADS, smem, ctx->stream>>>(tp);
     KERNEL_CHECK(ctx);
     return J3DG_OK;
@@ -1692,7 +1705,7 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   rc = j3dg_stage_begin(ctx, 0);
   if (rc != J3DG_OK) return rc;
   // ---- primary rays ----
-  tp.pool_ctr = ctr(3); tp.hard_count = ctr(6); tp.hard_taken = ctr(7); tp.done_blocks = ctr(11);
+  tp.pool_ctr = ctr(3); tp.hard_count = ctr(6); tp.hard_taken = ctr(7); tp.done_blocks = ctr(11); tp.started = ctr(11) + 1;
   if (stats) {
     if ((rc = launch_hybrid(cast_kernel<PRIMARY, true>, cast_smem_bytes<PRIMARY, true>(), ntiles)) != J3DG_OK) return rc;
   } else if (ctx->cast_algo == 1) {  // 8-lanes-per-ray kernel only (A/B testing)
@@ -1711,7 +1724,7 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   // ---- shadow rays of the hit pixels ----
   if (shadows) {
     const long long pools = ((long long)npx + 31) / 32;
-    tp.pool_ctr = ctr(8); tp.hard_count = ctr(9); tp.hard_taken = ctr(10); tp.done_blocks = ctr(12);
+    tp.pool_ctr = ctr(8); tp.hard_count = ctr(9); tp.hard_taken = ctr(10); tp.done_blocks = ctr(12); tp.started = ctr(12) + 1;
     tp.budget = std::min<uint32_t>(ctx->shadow_budget, 255u);  // any-hit rays that start on the surface: their long ones are long from the start
     if (ctx->cast_algo == 1) {
       if ((rc = persistent_grid(ctx, group_kernel<SHADOW>, pools, &grid)) != J3DG_OK) return rc;

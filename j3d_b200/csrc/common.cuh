@@ -157,9 +157,8 @@ struct j3dg_ctx {
   void* d_spill = nullptr; size_t spill_cap = 0;     // pool-mode stacks that left shared memory (cast.cu)
   void* d_hard = nullptr; size_t hard_cap = 0;       // hard-ray list handed from the lane kernel to the group kernel
   size_t hard_id_off = 0;                            // offset of the id array inside d_hard
-  uint32_t consumer_blocks = 0;                      // blocks of the cast kernel that consume the hard-ray queue from the start (J3DG_CONSUMER_BLOCKS)
   uint32_t shadow_budget = 16;                       // the same for shadow rays (J3DG_SHADOW_BUDGET; 8 / 12 / 16 / 24 / 48: 1.64 / 1.60 / 1.58 / 1.65 / 1.70 ms for 0.73 M rays)
-  uint32_t lane_budget = 24;                         // node visits per ray before the lane kernel evicts it (J3DG_LANE_BUDGET)
+  uint32_t lane_budget = 28;                         // node visits per ray before the lane kernel evicts it (J3DG_LANE_BUDGET)
   int cast_algo = 0;                                 // 0 hybrid (lane + group), 1 group kernel only (J3DG_CAST_ALGO=group)
   void* last_canvas = nullptr; uint32_t last_w = 0, last_h = 0;  // device canvas of the most recent frame (j3dg_pick reads it)
   uint32_t shard_rank = 0, shard_world = 1;          // screen sharding (j3dg_ctx_set_screen_shard): band b of 32 rows belongs to rank b mod world

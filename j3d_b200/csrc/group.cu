@@ -81,7 +81,8 @@ struct j3dg_frames {
   char* base = nullptr;         // the exchange buffer: [2 slots][world or 1][h*w] RGBA, then the flag words
   size_t frame_bytes = 0, flags_off = 0, nbytes = 0;
   uint32_t k = 0;               // next frame number
-  j3dg_ctx* lane[2] = {nullptr, nullptr};  // the context (stream) that renders the frames of slot 0 / 1 (j3dg_frames_set_lane)
+  uint32_t nslots = 2;          // frames that may be in flight (frame k lives in slot k mod nslots)
+  j3dg_ctx* lane[J3DG_FRAMES_MAX_SLOTS] = {};  // the context (stream) that renders the frames of each slot (j3dg_frames_set_lane)
 };
 
 namespace {
@@ -270,16 +271,21 @@ J3DG_API int j3dg_group_broadcast_mesh(j3dg_group* g, int root, j3dg_mesh** mesh
 
 // ---- frames handed to one rank through NVLink peer memory (protocol: csrc/peer.cu header) ----------------------
 J3DG_API int j3dg_frames_create(j3dg_group* g, uint32_t width, uint32_t height, int dst, int shared_frame, j3dg_frames** out) {
-  if (!g || !out || !width || !height || dst < 0 || dst >= g->world) { j3dg_set_error(g ? g->ctx : nullptr, "j3dg_frames_create: bad argument"); return J3DG_EINVAL; }
+  return j3dg_frames_create_n(g, width, height, dst, shared_frame, 2, out);
+}
+
+J3DG_API int j3dg_frames_create_n(j3dg_group* g, uint32_t width, uint32_t height, int dst, int shared_frame, uint32_t nslots, j3dg_frames** out) {
+  if (!g || !out || !width || !height || dst < 0 || dst >= g->world || nslots < 2 || nslots > J3DG_FRAMES_MAX_SLOTS) { j3dg_set_error(g ? g->ctx : nullptr, "j3dg_frames_create: bad argument"); return J3DG_EINVAL; }
   *out = nullptr;
   j3dg_ctx* ctx = g->ctx;
   cudaSetDevice(ctx->device);
   j3dg_frames* f = new j3dg_frames();
   f->g = g; f->w = width; f->h = height; f->dst = dst; f->shared = shared_frame != 0;
-  f->lane[0] = f->lane[1] = ctx;
+  f->nslots = nslots;
+  for (auto& l : f->lane) l = ctx;
   f->frame_bytes = (size_t)width * height * 4;
-  f->flags_off = (2 * (size_t)(f->shared ? 1 : g->world) * f->frame_bytes + 255) & ~(size_t)255;
-  f->nbytes = f->flags_off + 256;
+  f->flags_off = (nslots * (size_t)(f->shared ? 1 : g->world) * f->frame_bytes + 255) & ~(size_t)255;
+  f->nbytes = f->flags_off + 4 * (size_t)nslots * ((size_t)g->world + 1) + 256;
   unsigned char handle[J3DG_IPC_HANDLE_BYTES];
   memset(handle, 0, sizeof(handle));
   int ok = 1;
@@ -323,14 +329,14 @@ J3DG_API void j3dg_frames_destroy(j3dg_frames* f) {
   delete f;
 }
 
-// Flag words behind the frames: arrived[slot][rank] (2 * world words), then released[slot] (2 words).  One set PER SLOT:
-// the two slots may be driven from two streams (two frames in flight), and the frames of one slot follow each other on
-// one stream, so every word only ever grows.
+// Flag words behind the frames: arrived[slot][rank] (nslots * world words), then released[slot] (nslots words).  One set
+// PER SLOT: the slots may be driven from different streams (several frames in flight), and the frames of one slot
+// follow each other on one stream, so every word only ever grows.
 static uint32_t* frames_arrived(j3dg_frames* f, uint32_t slot, int r) { return reinterpret_cast<uint32_t*>(f->base + f->flags_off) + slot * (uint32_t)f->g->world + r; }
-static uint32_t* frames_released(j3dg_frames* f, uint32_t slot) { return reinterpret_cast<uint32_t*>(f->base + f->flags_off) + 2 * (uint32_t)f->g->world + slot; }
+static uint32_t* frames_released(j3dg_frames* f, uint32_t slot) { return reinterpret_cast<uint32_t*>(f->base + f->flags_off) + f->nslots * (uint32_t)f->g->world + slot; }
 
 J3DG_API int j3dg_frames_set_lane(j3dg_frames* f, int slot, j3dg_ctx* ctx) {
-  if (!f || slot < 0 || slot > 1 || !ctx) return J3DG_EINVAL;
+  if (!f || slot < 0 || slot >= (int)f->nslots || !ctx) return J3DG_EINVAL;
   if (ctx->device != f->g->ctx->device) { j3dg_set_error(f->g->ctx, "j3dg_frames_set_lane: the lane context must live on the group's device"); return J3DG_EINVAL; }
   f->lane[slot] = ctx;
   return J3DG_OK;
@@ -340,24 +346,26 @@ J3DG_API int j3dg_frames_begin(j3dg_frames* f, uint32_t* k_out) {
   if (!f || !k_out) return J3DG_EINVAL;
   const uint32_t k = f->k;
   *k_out = k;
-  if (k >= 2)  // frame k - 2 lived in this slot: dst must have released it (released[slot] = number of the last consumed frame + 1)
-    return j3dg_stream_wait_geq(f->lane[k & 1u], frames_released(f, k & 1u), 1, k - 1);
-  return j3dg_check_sticky(f->lane[k & 1u]);
+  const uint32_t s = k % f->nslots;
+  if (k >= f->nslots)  // frame k - nslots lived in this slot: dst must have released it (released[slot] = number of the last consumed frame + 1)
+    return j3dg_stream_wait_geq(f->lane[s], frames_released(f, s), 1, k - f->nslots + 1);
+  return j3dg_check_sticky(f->lane[s]);
 }
 
 J3DG_API int j3dg_frames_target(j3dg_frames* f, uint32_t k, uint32_t** rgba_out) {
   if (!f || !rgba_out) return J3DG_EINVAL;
   const size_t per = f->shared ? 1 : (size_t)f->g->world;
-  *rgba_out = reinterpret_cast<uint32_t*>(f->base + ((k & 1u) * per + (f->shared ? 0 : (size_t)f->g->rank)) * f->frame_bytes);
+  *rgba_out = reinterpret_cast<uint32_t*>(f->base + ((k % f->nslots) * per + (f->shared ? 0 : (size_t)f->g->rank)) * f->frame_bytes);
   return J3DG_OK;
 }
 
 J3DG_API int j3dg_frames_arrive(j3dg_frames* f, uint32_t k) {
   if (!f || k != f->k) { j3dg_set_error(f ? f->g->ctx : nullptr, "j3dg_frames_arrive: frames arrive in order (k must be the value j3dg_frames_begin returned)"); return J3DG_EINVAL; }
-  j3dg_ctx* ctx = f->lane[k & 1u];
-  int rc = j3dg_stream_signal(ctx, frames_arrived(f, k & 1u, f->g->rank), k + 1);
+  const uint32_t s = k % f->nslots;
+  j3dg_ctx* ctx = f->lane[s];
+  int rc = j3dg_stream_signal(ctx, frames_arrived(f, s, f->g->rank), k + 1);
   if (rc != J3DG_OK) return rc;
-  if (f->g->rank == f->dst && (rc = j3dg_stream_wait_geq(ctx, frames_arrived(f, k & 1u, 0), (uint32_t)f->g->world, k + 1)) != J3DG_OK) return rc;
+  if (f->g->rank == f->dst && (rc = j3dg_stream_wait_geq(ctx, frames_arrived(f, s, 0), (uint32_t)f->g->world, k + 1)) != J3DG_OK) return rc;
   f->k = k + 1;
   return J3DG_OK;
 }
@@ -365,13 +373,13 @@ J3DG_API int j3dg_frames_arrive(j3dg_frames* f, uint32_t k) {
 J3DG_API int j3dg_frames_release(j3dg_frames* f, uint32_t k) {
   if (!f) return J3DG_EINVAL;
   if (f->g->rank != f->dst) return J3DG_OK;
-  return j3dg_stream_signal(f->lane[k & 1u], frames_released(f, k & 1u), k + 1);
+  return j3dg_stream_signal(f->lane[k % f->nslots], frames_released(f, k % f->nslots), k + 1);
 }
 
 J3DG_API int j3dg_frames_view(j3dg_frames* f, uint32_t k, const uint32_t** frames_out) {
   if (!f || !frames_out) return J3DG_EINVAL;
   if (f->g->rank != f->dst) { j3dg_set_error(f->g->ctx, "j3dg_frames_view: only the destination rank holds the frames"); return J3DG_EINVAL; }
   const size_t per = f->shared ? 1 : (size_t)f->g->world;
-  *frames_out = reinterpret_cast<const uint32_t*>(f->base + (k & 1u) * per * f->frame_bytes);
+  *frames_out = reinterpret_cast<const uint32_t*>(f->base + (k % f->nslots) * per * f->frame_bytes);
   return J3DG_OK;
 }

@@ -158,7 +158,7 @@ def gather_bands(img: torch.Tensor, dst: int = 0) -> torch.Tensor | None:
 # ---- frames handed to rank 0 through NVLink peer memory instead of a collective (include/j3dg.h, csrc/group.cu, csrc/peer.cu) ----
 class PeerFrames:
     """Every rank renders its frame STRAIGHT INTO rank `dst`'s HBM (the shade kernel's stores travel over NVLink);
-    no gather kernel competes with the cooperative cast kernel for SMs.  A thin wrapper over j3dg_frames_* (the
+    no gather kernel competes with the persistent cast kernel for SMs.  A thin wrapper over j3dg_frames_* (the
     protocol is in include/j3dg.h).  Double-buffered, all stream-ordered:
 
         k = pf.begin()                 # stream waits until dst has RELEASED the frame that lived in slot k & 1
@@ -169,14 +169,14 @@ class PeerFrames:
 
     shared_frame = True: ONE frame per slot that all ranks write disjoint rows of (j3dg_ctx_set_screen_shard)."""
 
-    def __init__(self, ctx, height: int, width: int, device, dst: int = 0, shared_frame: bool = False, group=None):
-        self.ctx, self.h, self.w, self.device, self.dst, self.shared = ctx, height, width, device, dst, shared_frame
+    def __init__(self, ctx, height: int, width: int, device, dst: int = 0, shared_frame: bool = False, group=None, nslots: int = 2):
+        self.ctx, self.h, self.w, self.device, self.dst, self.shared, self.nslots = ctx, height, width, device, dst, shared_frame, nslots
         self._own_group = group is None
         self.group = make_group(ctx) if group is None else group
         self.rank, self.world = self.group.rank, self.group.world
         self.frame_bytes = height * width * 4
         try:
-            self.f = self.group.frames(width, height, dst, shared_frame)
+            self.f = self.group.frames(width, height, dst, shared_frame, nslots)
         except capi.J3dgError as e:  # raised on every rank together (the set-up is collective)
             if self._own_group:
                 self.group.destroy()
@@ -184,7 +184,7 @@ class PeerFrames:
         self.k = 0
 
     def set_lane(self, slot: int, ctx):
-        """Two frames in flight: the frames of slot 0 / 1 (k even / odd) are rendered by this context (j3dg_frames_set_lane)."""
+        """Frames in flight: the frames of this slot (k mod nslots) are rendered by this context (j3dg_frames_set_lane)."""
         self.f.set_lane(slot, ctx)
 
     def begin(self) -> int:
@@ -218,13 +218,13 @@ class PeerFrames:
 
 
 def peer_slot_offset(slot: int, rank: int, world: int, frame_bytes: int) -> int:
-    """Byte offset of (slot, rank)'s frame inside the exchange buffer: [2 slots][world][frame]."""
+    """Byte offset of (slot, rank)'s frame inside the exchange buffer: [nslots][world][frame]."""
     return (slot * world + rank) * frame_bytes
 
 
-def peer_flags_offset(world: int, frame_bytes: int) -> int:
-    """The flag words follow the frames: arrived[0..world) then `released`, 256-byte aligned."""
-    return (2 * world * frame_bytes + 255) & ~255
+def peer_flags_offset(world: int, frame_bytes: int, nslots: int = 2) -> int:
+    """The flag words follow the frames (256-byte aligned): arrived[slot][rank], then released[slot]."""
+    return (nslots * world * frame_bytes + 255) & ~255
 
 
 class PeerFramesPy:
@@ -233,16 +233,18 @@ class PeerFramesPy:
     torch.distributed.  tests/test_dist_gloo.py runs it with two gloo ranks and a recording context to pin the slots,
     the flag values and their order without a GPU; the product path is PeerFrames above."""
 
-    def __init__(self, ctx, height: int, width: int, device, dst: int = 0, shared_frame: bool = False):
-        """shared_frame = False: one frame per rank and slot (orbit sweep: every rank renders its own frame).
+    def __init__(self, ctx, height: int, width: int, device, dst: int = 0, shared_frame: bool = False, nslots: int = 2):
+        """nslots: frames that may be in flight (frame k lives in slot k mod nslots).
+        shared_frame = False: one frame per rank and slot (orbit sweep: every rank renders its own frame).
         shared_frame = True : ONE frame per slot that all ranks write disjoint rows of (screen sharding,
         j3dg_ctx_set_screen_shard: each rank's shade kernel writes only its own bands) — the gather disappears."""
         self.ctx, self.h, self.w, self.device, self.dst = ctx, height, width, device, dst
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.shared = shared_frame
         self.frame_bytes = height * width * 4
-        self.flags_off = peer_flags_offset(self.world, self.frame_bytes)
-        self.nbytes = self.flags_off + 256
+        self.nslots = nslots
+        self.flags_off = peer_flags_offset(self.world, self.frame_bytes, nslots)
+        self.nbytes = self.flags_off + 4 * nslots * (self.world + 1) + 256
         # set-up is collective and must not leave a rank behind: every rank reports whether its step worked, the group
         # agrees (MIN), and on any failure everybody raises the same error (callers may then fall back to an NCCL gather)
         handle = [None]
@@ -273,41 +275,43 @@ class PeerFramesPy:
                 self.base = 0
             raise RuntimeError("peer-memory frame exchange unavailable on at least one rank" + (f": {err}" if err else ""))
         self.k = 0
-        self.lane = [ctx, ctx]
+        self.lane = [ctx] * nslots
         dist.barrier()
 
-    # flag words: arrived[slot][rank] (2 * world words), then released[slot] (2 words) — one set per slot, so that the
-    # two slots can be driven from two streams (two frames in flight) and every word only ever grows
+    # flag words: arrived[slot][rank] (nslots * world words), then released[slot] (nslots words) — one set per slot, so
+    # that the slots can be driven from different streams (frames in flight) and every word only ever grows
     def _arrived(self, slot: int, r: int) -> int:
         return self.base + self.flags_off + 4 * (slot * self.world + r)
 
     def _released(self, slot: int) -> int:
-        return self.base + self.flags_off + 4 * (2 * self.world + slot)
+        return self.base + self.flags_off + 4 * (self.nslots * self.world + slot)
 
     def set_lane(self, slot: int, ctx):
-        """The frames of slot 0 / 1 (k even / odd) are rendered and handed over on this context's stream."""
+        """The frames of this slot (k mod nslots) are rendered and handed over on this context's stream."""
         self.lane[slot] = ctx
 
     def begin(self) -> int:
         k = self.k
-        if k >= 2:  # frame k - 2 lived in this slot: dst must have released it (released[slot] = last consumed frame + 1)
-            self.lane[k & 1].stream_wait_geq(self._released(k & 1), 1, k - 1)
+        s = k % self.nslots
+        if k >= self.nslots:  # frame k - nslots lived in this slot: dst must have released it (released[slot] = last consumed frame + 1)
+            self.lane[s].stream_wait_geq(self._released(s), 1, k - self.nslots + 1)
         return k
 
     def target(self, k: int) -> int:
-        return self.base + peer_slot_offset(k & 1, 0 if self.shared else self.rank, self.world, self.frame_bytes)
+        return self.base + peer_slot_offset(k % self.nslots, 0 if self.shared else self.rank, self.world, self.frame_bytes)
 
     def arrive(self, k: int):
-        ctx = self.lane[k & 1]
-        ctx.stream_signal(self._arrived(k & 1, self.rank), k + 1)
+        s = k % self.nslots
+        ctx = self.lane[s]
+        ctx.stream_signal(self._arrived(s, self.rank), k + 1)
         if self.rank == self.dst:
-            ctx.stream_wait_geq(self._arrived(k & 1, 0), self.world, k + 1)
+            ctx.stream_wait_geq(self._arrived(s, 0), self.world, k + 1)
         self.k = k + 1
 
     def release(self, k: int):
         """dst only (a no-op elsewhere): the consumer work of frame k is enqueued; the slot may be overwritten."""
         if self.rank == self.dst:
-            self.lane[k & 1].stream_signal(self._released(k & 1), k + 1)
+            self.lane[k % self.nslots].stream_signal(self._released(k % self.nslots), k + 1)
 
     def end(self, k: int):
         self.arrive(k)
@@ -315,7 +319,7 @@ class PeerFramesPy:
 
     def frames(self, k: int) -> torch.Tensor:
         assert self.rank == self.dst
-        off = peer_slot_offset(k & 1, 0, self.world, self.frame_bytes)
+        off = peer_slot_offset(k % self.nslots, 0, self.world, self.frame_bytes)
         n = 1 if self.shared else self.world
         t = device_bytes(self.base + off, n * self.frame_bytes, self.device)
         return t.view(torch.int32).view(n, self.h, self.w)

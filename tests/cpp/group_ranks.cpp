@@ -161,30 +161,31 @@ static int run_rank(int rank, int world, uint32_t w, uint32_t h, int frames, con
     }
     j3dg_frames_destroy(fr);
   }
-  // ---- (3) the sweep again with TWO frames in flight: a second context of the same device (own stream, own scratch, the
-  //          SAME mesh) renders the odd frames; the hand-over flags are per slot, so the two streams never order each other ----
+  // ---- (3) the sweep again with THREE frames in flight: two more contexts of the same device (own streams, own scratch,
+  //          the SAME mesh) render the frames of slots 1 and 2; the hand-over flags are per slot, so the streams never
+  //          order each other ----
   {
-    j3dg_ctx* ctx2 = nullptr;
-    CHECK(j3dg_ctx_create(rank, &ctx2));
-    cudaStream_t stream2;
-    cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking);
-    CHECK(j3dg_ctx_set_stream(ctx2, stream2));
-    CHECK(j3dg_ctx_set_matcap(ctx2, mc.im.data(), mc.w, mc.h, mc.w, mc.cavity_clr));
-    j3dg_pixel* d_px2 = nullptr;
-    cudaMalloc((void**)&d_px2, npx * sizeof(j3dg_pixel));
+    constexpr int LANES = 3;
+    j3dg_ctx* lane_ctx[LANES] = {ctx, nullptr, nullptr};
+    cudaStream_t lane_stream[LANES] = {stream, nullptr, nullptr};
+    j3dg_pixel* lane_px[LANES] = {d_px, nullptr, nullptr};
+    for (int l = 1; l < LANES; ++l) {
+      CHECK(j3dg_ctx_create(rank, &lane_ctx[l]));
+      cudaStreamCreateWithFlags(&lane_stream[l], cudaStreamNonBlocking);
+      CHECK(j3dg_ctx_set_stream(lane_ctx[l], lane_stream[l]));
+      CHECK(j3dg_ctx_set_matcap(lane_ctx[l], mc.im.data(), mc.w, mc.h, mc.w, mc.cavity_clr));
+      cudaMalloc((void**)&lane_px[l], npx * sizeof(j3dg_pixel));
+    }
     j3dg_frames* fr = nullptr;
-    CHECK(j3dg_frames_create(group, w, h, 0, 0, &fr));
-    CHECK(j3dg_frames_set_lane(fr, 1, ctx2));
-    j3dg_ctx* lane_ctx[2] = {ctx, ctx2};
-    cudaStream_t lane_stream[2] = {stream, stream2};
-    j3dg_pixel* lane_px[2] = {d_px, d_px2};
-    const int frames2 = 2 * frames;
+    CHECK(j3dg_frames_create_n(group, w, h, 0, 0, LANES, &fr));
+    for (int l = 1; l < LANES; ++l) CHECK(j3dg_frames_set_lane(fr, l, lane_ctx[l]));
+    const int frames2 = 3 * frames;
     std::vector<std::vector<uint32_t>> got(frames2);
     for (int k = 0; k < frames2; ++k) {
       uint32_t kk = 0;
       uint32_t* target = nullptr;
       CHECK(j3dg_frames_begin(fr, &kk));
-      const int ln = (int)(kk & 1u);
+      const int ln = (int)(kk % LANES);
       CHECK(j3dg_frames_target(fr, kk, &target));
       const j3dg_view v = pose(k * world + rank, J3DG_DEFAULT_FLAGS);
       if (j3dg_render_frame(lane_ctx[ln], &mesh, 1, nullptr, 0, &v, nullptr, 0, 0, 0, 0, 0xff000000u, 0xff404040u, lane_px[ln], target) != J3DG_OK) {
@@ -200,24 +201,26 @@ static int run_rank(int rank, int world, uint32_t w, uint32_t h, int frames, con
       }
       CHECK(j3dg_frames_release(fr, kk));
     }
-    CHECK(j3dg_ctx_synchronize(ctx));
-    if (j3dg_ctx_synchronize(ctx2) != J3DG_OK) { fprintf(stderr, "rank %d: lane 1: %s\n", rank, j3dg_last_error(ctx2)); return 1; }
+    for (int l = 0; l < LANES; ++l)
+      if (j3dg_ctx_synchronize(lane_ctx[l]) != J3DG_OK) { fprintf(stderr, "rank %d: lane %d: %s\n", rank, l, j3dg_last_error(lane_ctx[l])); return 1; }
     if (rank == 0) {
       std::vector<uint32_t> want(npx);
       for (int k = 0; k < frames2; ++k)
         for (int r = 0; r < world; ++r) {
           const j3dg_view v = pose(k * world + r, J3DG_DEFAULT_FLAGS);
           CHECK(j3dg_render_frame(ctx, &mesh, 1, nullptr, 0, &v, nullptr, 0, 0, 0, 0, 0xff000000u, 0xff404040u, nullptr, want.data()));
-          if (memcmp(want.data(), got[k].data() + (size_t)r * npx, npx * 4) != 0) { fprintf(stderr, "two lanes: frame %d of rank %d differs\n", k, r); ++bad; }
+          if (memcmp(want.data(), got[k].data() + (size_t)r * npx, npx * 4) != 0) { fprintf(stderr, "three lanes: frame %d of rank %d differs\n", k, r); ++bad; }
         }
     }
     j3dg_frames_destroy(fr);
-    uint32_t st2 = 0;
-    j3dg_ctx_status(ctx2, &st2, 0);
-    if (st2) ++bad;
-    cudaFree(d_px2);
-    j3dg_ctx_destroy(ctx2);
-    cudaStreamDestroy(stream2);
+    for (int l = 1; l < LANES; ++l) {
+      uint32_t st2 = 0;
+      j3dg_ctx_status(lane_ctx[l], &st2, 0);
+      if (st2) ++bad;
+      cudaFree(lane_px[l]);
+      j3dg_ctx_destroy(lane_ctx[l]);
+      cudaStreamDestroy(lane_stream[l]);
+    }
   }
   float worst = (float)bad;
   CHECK(j3dg_group_max_float(group, &worst, 1));
@@ -230,7 +233,7 @@ static int run_rank(int rank, int world, uint32_t w, uint32_t h, int frames, con
   j3dg_ctx_destroy(ctx);
   cudaStreamDestroy(stream);
   if (rank == 0) {
-    printf("group_ranks: world %d, %d frames %ux%u + 1 sharded frame + %d frames with two in flight: %s\n", world, frames * world, w, h, 2 * frames * world, (worst == 0.f && status == 0) ? "OK" : "FAILED");
+    printf("group_ranks: world %d, %d frames %ux%u + 1 sharded frame + %d frames with three in flight: %s\n", world, frames * world, w, h, 3 * frames * world, (worst == 0.f && status == 0) ? "OK" : "FAILED");
     fflush(stdout);  // the ranks leave through _exit
   }
   return (worst == 0.f && status == 0) ? 0 : 1;

@@ -194,6 +194,27 @@ def _peer_worker(rank, world, port, out, fail):
         assert all(op[1] in (flags + 4 * rank, flags, flags + 8 * world) for op in lane0.ops if op[0] in ("signal", "wait"))
         assert all(op[1] in (flags + 4 * (world + rank), flags + 4 * world, flags + 4 * (2 * world + 1)) for op in lane1.ops if op[0] in ("signal", "wait"))
         assert len(lane0.ops) == len(lane1.ops) > 0
+        # three slots, three lanes: frame k on lane k mod 3, begin(k) waits for the release of frame k - 3
+        lanes = [_RecordingCtx(rank) for _ in range(3)]
+        three = jd.PeerFramesPy(lanes[0], h, w, torch.device("cpu"), dst=0, nslots=3)
+        flags3 = base + jd.peer_flags_offset(world, fb, 3)
+        for s in (1, 2):
+            three.set_lane(s, lanes[s])
+        for step in range(7):
+            k = three.begin()
+            assert three.target(k) - base == jd.peer_slot_offset(k % 3, rank, world, fb)
+            three.arrive(k)
+            three.release(k)
+        for s in range(3):
+            want3 = []
+            for k in range(s, 7, 3):
+                if k >= 3:
+                    want3.append(("wait", flags3 + 4 * (3 * world + s), 1, k - 2))
+                want3.append(("signal", flags3 + 4 * (s * world + rank), k + 1))
+                if rank == 0:
+                    want3.append(("wait", flags3 + 4 * s * world, world, k + 1))
+                    want3.append(("signal", flags3 + 4 * (3 * world + s), k + 1))
+            assert lanes[s].ops == want3, (s, lanes[s].ops, want3)
         shared = jd.PeerFramesPy(_RecordingCtx(rank), h, w, torch.device("cpu"), dst=0, shared_frame=True)
         assert shared.target(0) - base == 0 and shared.target(1) - base == jd.peer_slot_offset(1, 0, world, fb)  # one frame per slot
         out[rank] = 1
