@@ -618,6 +618,23 @@ def run_orbit(args, wl, rank, world, local_rank):
                 "achieved_frames_in_flight": (W * H * bytes_per_ray) / (ms / args.steps * 1e-3) / 1e9 if world == 1 else None,
                 "note": "achieved = ALGORITHMIC bytes (SURVEY §8d) over the live CUDA-event stage time; L1/L2 absorb re-use, so this is not a DRAM-bandwidth share (traffic = DRAM bytes per launch from the cited ncu capture)"}
 
+    # ---- BASELINE configs[2] on the same box(es): 300 M triangles, 3840x2160 + shadow rays, ONE frame sharded over the
+    #      N ranks (collective: every rank takes part) ----
+    cstage = None
+    if not args.no_config_c:
+        if pf is not None:
+            pf.close()
+            pf = None
+        cm = sharded_frame_measure(rig, args, steps=6, warmup=2)
+        if rank == 0:
+            cstage = {"workload": workload_name("C", cm["f"], cm["nt"], cm["W"], cm["H"]), "n_gpus": world, "frames": cm["steps"], "ms_per_frame": cm["ms"] / cm["steps"],
+                      "mrays_s": cm["rays"] / cm["ms"] / 1e3, "rays_per_frame": cm["rays"] / cm["steps"], "frames_per_s": 1e3 * cm["steps"] / cm["ms"],
+                      "cast_ms_max_rank": cm["cast_ms"], "shade_ms_max_rank": cm["shade_ms"], "bvh_build_ms": cm["build_ms"], "bvh_bytes": cm["bvh_bytes"],
+                      "bvh_broadcast_ms": cm["bcast_ms"], "mesh_create_ms": cm["create_ms"], "mesh_generate_s": cm["gen_s"],
+                      "build_roofline_frac": (12 * cm["nt"] + 12 * cm["nv"] + cm["bvh_bytes"]) / (cm["build_ms"] * 1e-3) / 1e9 / cm["peak"] if cm["build_ms"] else None,
+                      "sharded_frame_equals_unsharded": cm["identical"], "hit_pixels": cm["hit"], "shadowed_pixels": cm["shadowed"], "exchange_status": cm["status"],
+                      "sharding": "one GPU" if world == 1 else f"32-row screen bands round-robin over {world} ranks inside the cast / shade kernels, BVH NCCL-broadcast, bands stored into ONE frame in rank 0's HBM over NVLink peer memory"}
+
     if rank != 0:
         if pf is not None:
             pf.close()
@@ -682,6 +699,8 @@ def run_orbit(args, wl, rank, world, local_rank):
     }
     if rig.numa_cpus is not None:
         line["layout"]["host_affinity"] = f"each rank pinned to the {rig.numa_cpus} CPUs next to its GPU (NVML affinity) before allocating pinned buffers"
+    if cstage is not None:
+        line["stages"]["config_c"] = cstage
     if extras is not None:
         line["queries"] = extras
     if bcast_ms is not None:
@@ -770,9 +789,12 @@ def run_splat(args, rank, world, local_rank):
 # ----------------------------------------------------------------------------------------------
 # workload C (configs[2]): ONE huge frame, screen bands sharded over the ranks into ONE frame in rank 0's HBM
 # ----------------------------------------------------------------------------------------------
-def run_sharded_frame(args, rank, world, local_rank):
-    rig = Rig(args, rank, world, local_rank)
+def sharded_frame_measure(rig, args, steps, warmup):
+    """BASELINE configs[2]: ONE frame with shadow rays rendered by all ranks together (32-row screen bands round-robin over
+    the ranks inside the cast / shade kernels, the bands stored into one frame in rank 0's HBM over NVLink peer memory).
+    Collective: every rank calls it.  Returns the measurements (a dict; meaningful on rank 0)."""
     torch, dist, j, ctx, dev = rig.torch, rig.dist, rig.j, rig.ctx, rig.dev
+    rank, world, local_rank = rig.rank, rig.world, rig.local_rank
     cfg = WORKLOADS["C"]
     W, H = cfg["w"], cfg["h"]
     f = args.f or cfg["f"]
@@ -792,7 +814,7 @@ def run_sharded_frame(args, rank, world, local_rank):
         dist.broadcast(bb, 0)
     bbh = bb.cpu().numpy()
     v0 = j.make_view(W, H, bbh[:3], bbh[3:], j.DEFAULT_FLAGS | j.SHADOW)
-    total = args.warmup + args.steps
+    total = warmup + steps
     views = [j.orbit_view(v0, 25.0 * k) for k in range(total)]
     px = torch.zeros((H, W, 32), dtype=torch.uint8, device=dev)
     rgba = torch.zeros((H, W), dtype=torch.int32, device=dev)
@@ -813,7 +835,7 @@ def run_sharded_frame(args, rank, world, local_rank):
         last["k"] = k
         pf.release(k)
 
-    for v in views[: args.warmup]:
+    for v in views[:warmup]:
         frame(v)
     rig.barrier()
     ctx.timings(reset=True)
@@ -822,7 +844,7 @@ def run_sharded_frame(args, rank, world, local_rank):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for v in views[args.warmup:]:
+    for v in views[warmup:]:
         frame(v)
     e1.record()
     rig.barrier()
@@ -845,27 +867,38 @@ def run_sharded_frame(args, rank, world, local_rank):
         hm = p["object_id"] != 0xFFFFFFFF
         hit, shadowed = int(hm.sum()), int((p["mark"][hm] & 1).sum())
     rig.barrier()
-    line = None
-    if rank == 0:
-        peak, peak_src = peaks()
-        bvh_bytes = int(info.nr_of_nodes) * info.node_bytes + nt * info.triangle_bytes
-        value = rays / ms / 1e3
-        line = {"metric": "primary+shadow Mrays/s @4K (ray cast + shading per frame)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": workload_name("C", f, nt, W, H), "l2": "inputs_larger_than_l2"},
-                "layout": {"sharding": "replicas only" if world == 1 else f"32-row screen bands round-robin over {world} ranks inside the cast / shade kernels, BVH NCCL-broadcast, every rank's shade kernel stores its bands into ONE frame in rank 0's HBM over NVLink peer memory",
-                           "bvh_bytes": bvh_bytes},
-                "frames_per_s": 1e3 * args.steps / ms, "rays_per_frame": rays / args.steps, "cast_ms_max_rank": cast_ms, "shade_ms_max_rank": shade_ms,
-                "bvh_build_ms": build_ms, "bvh_nodes": int(info.nr_of_nodes), "mesh_create_ms": create_ms, "bvh_broadcast_ms": bcast_ms, "mesh_generate_s": gen_s,
-                "sharded_frame_equals_unsharded": identical, "hit_pixels": hit, "shadowed_pixels": shadowed,
-                "stages": {"build": {"ms": build_ms, "algorithmic_bytes": 12 * nt + 12 * nv + bvh_bytes,
-                                     "roofline_frac": (12 * nt + 12 * nv + bvh_bytes) / (build_ms * 1e-3) / 1e9 / peak if build_ms else None}},
-                "gpu_launches": launches, "clocks": clocks, "exchange_status": ctx.status(),
-                "e2e": {"value": None, "unit": "Mrays/s", "h2d_bytes_per_step": ctypes.sizeof(j.View) + 256, "d2h_bytes_per_step": 0,
-                        "note": "the frame stays in rank 0's HBM; host readback is measured on workload B"}}
+    ctx.set_screen_shard(0, 1)
+    peak, _ = peaks()
+    bvh_bytes = int(info.nr_of_nodes) * info.node_bytes + nt * info.triangle_bytes
+    out = dict(f=f, nt=nt, nv=nv, W=W, H=H, ms=ms, rays=rays, cast_ms=cast_ms, shade_ms=shade_ms, launches=launches, identical=identical, hit=hit,
+               shadowed=shadowed, build_ms=build_ms, create_ms=create_ms, bcast_ms=bcast_ms, gen_s=gen_s, info_nodes=int(info.nr_of_nodes), bvh_bytes=bvh_bytes,
+               clocks=clocks, status=ctx.status(), peak=peak, steps=steps, warmup=warmup)
     if pf is not None:
         pf.close()
+    mesh.destroy()
+    return out
+
+
+def run_sharded_frame(args, rank, world, local_rank):
+    rig = Rig(args, rank, world, local_rank)
+    m = sharded_frame_measure(rig, args, args.steps, args.warmup)
+    line = None
+    if rank == 0:
+        value = m["rays"] / m["ms"] / 1e3
+        line = {"metric": "primary+shadow Mrays/s @4K (ray cast + shading per frame)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": workload_name("C", m["f"], m["nt"], m["W"], m["H"]), "l2": "inputs_larger_than_l2"},
+                "layout": {"sharding": "replicas only" if world == 1 else f"32-row screen bands round-robin over {world} ranks inside the cast / shade kernels, BVH NCCL-broadcast, every rank's shade kernel stores its bands into ONE frame in rank 0's HBM over NVLink peer memory",
+                           "bvh_bytes": m["bvh_bytes"]},
+                "frames_per_s": 1e3 * args.steps / m["ms"], "rays_per_frame": m["rays"] / args.steps, "cast_ms_max_rank": m["cast_ms"], "shade_ms_max_rank": m["shade_ms"],
+                "bvh_build_ms": m["build_ms"], "bvh_nodes": m["info_nodes"], "mesh_create_ms": m["create_ms"], "bvh_broadcast_ms": m["bcast_ms"], "mesh_generate_s": m["gen_s"],
+                "sharded_frame_equals_unsharded": m["identical"], "hit_pixels": m["hit"], "shadowed_pixels": m["shadowed"],
+                "stages": {"build": {"ms": m["build_ms"], "algorithmic_bytes": 12 * m["nt"] + 12 * m["nv"] + m["bvh_bytes"],
+                                     "roofline_frac": (12 * m["nt"] + 12 * m["nv"] + m["bvh_bytes"]) / (m["build_ms"] * 1e-3) / 1e9 / m["peak"] if m["build_ms"] else None}},
+                "gpu_launches": m["launches"], "clocks": m["clocks"], "exchange_status": m["status"],
+                "e2e": {"value": None, "unit": "Mrays/s", "h2d_bytes_per_step": ctypes.sizeof(rig.j.View) + 256, "d2h_bytes_per_step": 0,
+                        "note": "the frame stays in rank 0's HBM; host readback is measured on workload B"}}
     rig.finish(line)
     return 0
 
@@ -882,6 +915,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=3, help="frames in flight per GPU (1 .. 4 contexts / streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-splat", action="store_true", help="skip the splat stage of the default line")
+    ap.add_argument("--no-config-c", action="store_true", help="skip the 300 M-triangle sharded 4K frame (BASELINE configs[2]) of the default line")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: how every rank's RGBA frame reaches rank 0")
     args = ap.parse_args()
     wl = args.workload

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "cpp_host or peer" > gpurun_out/d4_pytest_n2.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/d4_pytest_n2.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 120 --warmup 5 > gpurun_out/d4_bench_n2.json 2> gpurun_out/d4_bench_n2.err; echo "bench n2 rc=$?"; tail -3 gpurun_out/d4_bench_n2.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 120 --warmup 6 > gpurun_out/d4_bench_n2.json 2> gpurun_out/d4_bench_n2.err; echo "bench n2 rc=$?"; tail -3 gpurun_out/d4_bench_n2.err
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/d4_bench_n2.json'))
