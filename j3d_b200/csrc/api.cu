@@ -175,6 +175,7 @@ J3DG_API int j3dg_ctx_create(int device, j3dg_ctx** out) {
   if (const char* e = getenv("J3DG_LANE_BUDGET")) ctx->lane_budget = (uint32_t)std::max(1, atoi(e));  // developer tuning knobs
   if (const char* e = getenv("J3DG_SHADOW_BUDGET")) ctx->shadow_budget = (uint32_t)std::max(1, atoi(e));
   if (const char* e = getenv("J3DG_CAST_ALGO")) ctx->cast_algo = strcmp(e, "group") == 0 ? 1 : 0;
+  if (const char* e = getenv("J3DG_TOP_MIN")) ctx->top_min = (uint32_t)std::max(2, atoi(e));
   *out = ctx;
   return J3DG_OK;
 }
@@ -184,7 +185,7 @@ J3DG_API void j3dg_ctx_destroy(j3dg_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->d_pixels); cudaFree(ctx->d_pixels_in); cudaFree(ctx->d_rgba); cudaFree(ctx->d_bg); cudaFree(ctx->d_packed);
-  cudaFree(ctx->d_matcap); cudaFree(ctx->d_meshes); cudaFree(ctx->d_stats); cudaFree(ctx->d_misc); cudaFree(ctx->d_shadow); cudaFree(ctx->d_hard); cudaFree(ctx->d_spill);
+  cudaFree(ctx->d_matcap); cudaFree(ctx->d_meshes); cudaFree(ctx->d_top); cudaFree(ctx->d_stats); cudaFree(ctx->d_misc); cudaFree(ctx->d_shadow); cudaFree(ctx->d_hard); cudaFree(ctx->d_spill);
   for (auto& sl : ctx->slot) {
     cudaFree(sl.d_px); cudaFree(sl.d_rgba);
     if (sl.kernels_done) cudaEventDestroy(sl.kernels_done);

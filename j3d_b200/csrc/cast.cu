@@ -103,9 +103,23 @@ __device__ __forceinline__ bool tile_of_pool(const TileGrid& g, uint32_t pool, u
   return band != 0u;
 }
 
+// Top-level tree over the objects of a scene (qbvh_two_level_with_transformations, jtk/qbvh.h:3251-3301: a QBVH over the
+// transformed root boxes, rebuilt every frame, canvas.cpp:762).  8-wide, plain float boxes in WORLD space, built on the
+// host whenever the object table changes (build_top_tree below).  child: bit 31 = object leaf (low bits = index into the
+// mesh table), otherwise index of a top node; unused slots hold J3DG_EMPTY_CHILD.  Node 0 is the root.
+struct __align__(16) TopNode {
+  float lo[8][3], hi[8][3];
+  uint32_t child[8];
+  uint32_t pad[8];
+};
+static_assert(sizeof(TopNode) == 256, "TopNode is 256 bytes");
+constexpr int TOP_DEPTH = 8;                 // 8^8 objects
+constexpr uint32_t TOP_NONE = 0xFFFFFFFFu;
+
 struct TraceParams {
   const MeshDev* meshes;
   uint32_t nm;
+  const TopNode* top;            // TOP kernels: the tree over the nm objects
   ViewDev vw;
   int x0, y0, x1, y1;
   TileGrid grid;                 // PRIMARY: the pools of this launch
@@ -185,6 +199,70 @@ __device__ __forceinline__ WorldRay world_ray(const TraceParams& p, uint32_t id)
   return r;
 }
 
+// Walk of the top-level tree, one per ray: a stack of (node << 8 | children still to visit).  top_next returns the next
+// object whose world box the ray meets inside [t_near, t_far] (t_far as of NOW: boxes behind the best hit so far are
+// dropped when they come up), or TOP_NONE.  Only called where a ray changes objects, so it lives in local memory and is
+// written for size, not speed; object order = tree order (ties between objects may fall differently than in a linear
+// loop, as they do in the reference's own top-level traversal).
+struct TopWalk {
+  uint32_t stk[TOP_DEPTH];
+  int sp;
+};
+
+__device__ __forceinline__ uint32_t top_box_mask(const TopNode& n, const float o[3], const float inv[3], float t_near, float t_far) {
+  uint32_t m = 0;
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    if (n.child[c] == J3DG_EMPTY_CHILD) continue;  // unused slot (the min / max slab form would take its inverted box for everything)
+    float tmin = t_near, tmax = t_far;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float t0 = (n.lo[c][a] - o[a]) * inv[a], t1 = (n.hi[c][a] - o[a]) * inv[a];
+      tmin = fmaxf(tmin, fminf(t0, t1));
+      tmax = fminf(tmax, fmaxf(t0, t1));
+    }
+    tmin = fmaf(-fabsf(tmin), 4e-6f, tmin);  // conservative against the rounding of the slab arithmetic
+    tmax = fmaf(fabsf(tmax), 4e-6f, tmax);
+    if (tmin <= tmax) m |= 1u << c;
+  }
+  return m;
+}
+
+__device__ __noinline__ uint32_t top_next(const TopNode* __restrict__ top, TopWalk& w, const WorldRay& wr, float t_far, bool restart) {
+  const float o[3] = {wr.org.x, wr.org.y, wr.org.z};
+  const float inv[3] = {safe_rcp(wr.dir.x), safe_rcp(wr.dir.y), safe_rcp(wr.dir.z)};
+  if (restart) {
+    w.sp = 1;
+    w.stk[0] = top_box_mask(top[0], o, inv, wr.t_near, t_far);  // node 0
+  }
+  while (w.sp > 0) {
+    const uint32_t e = w.stk[w.sp - 1];
+    const uint32_t mask = e & 0xFFu, node = e >> 8;
+    if (!mask) { --w.sp; continue; }
+    const int c = __ffs(mask) - 1;
+    w.stk[w.sp - 1] = (node << 8) | (mask & (mask - 1u));
+    const TopNode& n = top[node];
+    const uint32_t ref = n.child[c];
+    if (ref & J3DG_LEAF_BIT) {
+      // the object's box again, against the interval as it is now
+      float tmin = wr.t_near, tmax = t_far;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float t0 = (n.lo[c][a] - o[a]) * inv[a], t1 = (n.hi[c][a] - o[a]) * inv[a];
+        tmin = fmaxf(tmin, fminf(t0, t1));
+        tmax = fminf(tmax, fmaxf(t0, t1));
+      }
+      tmin = fmaf(-fabsf(tmin), 4e-6f, tmin);
+      tmax = fmaf(fabsf(tmax), 4e-6f, tmax);
+      if (tmin <= tmax) return ref & ~J3DG_LEAF_BIT;
+    } else if (w.sp < TOP_DEPTH) {
+      const uint32_t m = top_box_mask(top[ref], o, inv, wr.t_near, t_far);
+      if (m) w.stk[w.sp++] = (ref << 8) | m;
+    }
+  }
+  return TOP_NONE;
+}
+
 // MODE PRIMARY: closest hit per pixel, raw result into the pixel buffer.
 // MODE SHADOW : any hit (first accepted triangle ends the ray), sets mark bit 0.
 // MODE RAYLIST: qbvh::find_closest_triangle semantics for arbitrary (also negative) t ranges:
@@ -209,10 +287,12 @@ constexpr uint32_t QUEUE_EMPTY = 0xFFFFFFFFu;
 #endif
 
 // `stk` = entry 0 of this group's stack, entry i at stk[i * GSTRIDE] (GSTRIDE groups are interleaved).
-template <int MODE, int SRC, int GSTRIDE>
+template <int MODE, int SRC, int GSTRIDE, bool TOP = false>
 __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const stk) {
   constexpr bool ANY_HIT = MODE == SHADOW;
   constexpr bool GENERAL = MODE == RAYLIST;
+  TopWalk walk;  // TOP only (replicated in the 8 lanes of a group)
+  walk.sp = 0;
   const int lane = threadIdx.x & 31;
   const int c = lane & 7;                               // my child / triangle slot
   const int gshift = lane & 24;                         // first lane of my group
@@ -296,12 +376,23 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const st
   for (;;) {
     // =========================== (A) finish rays, move to the next mesh, refill ===========================
     if (have_ray && cur == J3DG_EMPTY_CHILD) {
-      ++mesh_k;
       const bool found = best_slot != 0xFFFFFFFFu;
-      if (mesh_k < p.nm && !(ANY_HIT && found)) {
-        const WorldRay wr = world_ray<MODE>(p, ray_id);
-        enter_mesh(wr, mesh_k);
+      bool more = false;
+      if (TOP) {  // next object of the top-level walk (qbvh.h:3340-3385)
+        if (!(ANY_HIT && found)) {
+          const WorldRay wr = world_ray<MODE>(p, ray_id);
+          const uint32_t k = top_next(p.top, walk, wr, t_far, false);
+          if (k != TOP_NONE) { mesh_k = k; enter_mesh(wr, k); more = true; }
+        }
       } else {
+        ++mesh_k;
+        if (mesh_k < p.nm && !(ANY_HIT && found)) {
+          const WorldRay wr = world_ray<MODE>(p, ray_id);
+          enter_mesh(wr, mesh_k);
+          more = true;
+        }
+      }
+      if (!more) {
         // ---- write the result ----
         if (MODE == PRIMARY) {
           const int x = (int)(ray_id & 0xffffu), y = (int)(ray_id >> 16);
@@ -354,7 +445,13 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const st
           best_t = seed.x; best_u = seed.y; best_v = seed.z; best_slot = __float_as_uint(seed.w); best_mesh = e.y;
           if (best_slot != 0xFFFFFFFFu) t_far = best_t;  // the lane warp's best hit so far prunes the restart
           mesh_k = 0;
-          enter_mesh(wr, 0);
+          if (TOP) {
+            const uint32_t k = top_next(p.top, walk, wr, t_far, true);
+            if (k != TOP_NONE) { mesh_k = k; enter_mesh(wr, k); }
+            else { cur = J3DG_EMPTY_CHILD; sp = 0; }
+          } else {
+            enter_mesh(wr, 0);
+          }
           have_ray = true;
         } else {
           // done | started in one load.  A group only gets here after the pool counter has run out, so no warp can take
@@ -429,7 +526,13 @@ __device__ __forceinline__ void group_loop(const TraceParams& p, uint2* const st
           t_near = wr.t_near; t_far = wr.t_far;
           best_t = FLT_MAX; best_u = 0.f; best_v = 0.f; best_slot = 0xFFFFFFFFu; best_mesh = 0;
           mesh_k = 0;
-          enter_mesh(wr, 0);
+          if (TOP) {
+            const uint32_t k = top_next(p.top, walk, wr, t_far, true);
+            if (k != TOP_NONE) { mesh_k = k; enter_mesh(wr, k); }
+            else { cur = J3DG_EMPTY_CHILD; sp = 0; }
+          } else {
+            enter_mesh(wr, 0);
+          }
           have_ray = true;
         }
       }
@@ -619,9 +722,11 @@ constexpr size_t LANE_SMEM_RAYS = (size_t)(BLOCK_THREADS / 32) * RAY_WORDS * 32 
 constexpr size_t GROUP_SMEM = (size_t)STACK_SIZE * GROUPS_PER_BLOCK * sizeof(uint2);
 constexpr size_t CAST_SMEM = LANE_SMEM_STACK + LANE_SMEM_RAYS > GROUP_SMEM ? LANE_SMEM_STACK + LANE_SMEM_RAYS : GROUP_SMEM;
 
-template <int MODE, bool STATS>
+template <int MODE, bool STATS, bool TOP = false>
 __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* const stk, uint32_t* s_rays) {  // stk: row i of this lane at stk[i * LANE_STRIDE]
   constexpr bool ANY_HIT = MODE == SHADOW;
+  TopWalk walk;  // TOP only
+  walk.sp = 0;
   uint32_t* const park = s_rays + (threadIdx.x >> 5) * (RAY_WORDS * 32);              // word w of slot s at park[w * 32 + s]
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -678,10 +783,19 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* const stk
     // =========================== (A) rays that are done or evicted ===========================
     if (have && (cur == J3DG_EMPTY_CHILD || evict)) {
       const bool found = best_slot != 0xFFFFFFFFu;
-      if (!evict && mesh_k + 1 < p.nm && !(ANY_HIT && found)) {  // next object (qbvh.h:3340-3385)
-        ++mesh_k;
-        enter(lane_ray_setup(p.meshes[mesh_k], world_ray<MODE>(p, ray_id)), mesh_k);
-      } else {
+      bool more = false;
+      if (!evict && !(ANY_HIT && found)) {  // next object (qbvh.h:3340-3385)
+        if (TOP) {
+          const WorldRay wr = world_ray<MODE>(p, ray_id);
+          const uint32_t k = top_next(p.top, walk, wr, t_far, false);
+          if (k != TOP_NONE) { mesh_k = k; enter(lane_ray_setup(p.meshes[k], wr), k); more = true; }
+        } else if (mesh_k + 1 < p.nm) {
+          ++mesh_k;
+          enter(lane_ray_setup(p.meshes[mesh_k], world_ray<MODE>(p, ray_id)), mesh_k);
+          more = true;
+        }
+      }
+      if (!more) {
         if (evict) {  // a group of 8 lanes finishes this ray, starting from the best hit so far
           const uint32_t i = atomicAdd(p.hard_count, 1u);
           __stcg(p.hard_best + i, make_float4(best_t, best_u, best_v, __uint_as_float(best_slot)));
@@ -761,7 +875,14 @@ __device__ __forceinline__ void lane_loop(const TraceParams& p, uint2* const stk
           ray_id = park[11 * 32 + s];
           best_t = FLT_MAX; best_u = 0.f; best_v = 0.f; best_slot = 0xFFFFFFFFu; best_mesh = 0;
           mesh_k = 0; visits = 0; ntris = 0; evict = false;
-          enter(lr, 0);
+          if (TOP) {  // the parked constants are those of object 0; the walk says which object comes first
+            const WorldRay wr = world_ray<MODE>(p, ray_id);
+            const uint32_t k = top_next(p.top, walk, wr, t_far, true);
+            if (k == TOP_NONE) { sp = 0; cur = J3DG_EMPTY_CHILD; r = lr; }
+            else { mesh_k = k; enter(k == 0u ? lr : lane_ray_setup(p.meshes[k], wr), k); }
+          } else {
+            enter(lr, 0);
+          }
           have = true;
         }
         pool_next += __popc(idle);
@@ -1376,7 +1497,7 @@ constexpr size_t cast_smem_bytes() {
 // long rays into the queue), signs off, and then helps to drain the queue as four 8-lane groups (group_loop<QUEUE>).
 // A plain launch of at most one machine-full of blocks: producers never wait, and consumers only wait for warps that
 // are running (group_loop, SRC QUEUE) — no block has to be resident at any particular time.
-template <int MODE, bool STATS>
+template <int MODE, bool STATS, bool TOP = false>
 __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_POOL_MODE ? J3DG_POOL_MIN_BLOCKS : J3DG_LANE_MIN_BLOCKS) cast_kernel(const TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem[];  // cast_smem_bytes<MODE, STATS>()
 #ifdef J3DG_TIMELINE
@@ -1398,7 +1519,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_POOL_MODE ? J3DG_POOL_MIN_
   static_assert((LANE_STACK + 1) * 32 / 4 >= STACK_SIZE, "a warp's stack slice must hold four group stacks");
   uint2* const warp_stack = reinterpret_cast<uint2*>(smem) + (threadIdx.x >> 5) * ((LANE_STACK + 1) * 32);
   {
-    lane_loop<MODE, STATS>(p, warp_stack + (threadIdx.x & 31), reinterpret_cast<uint32_t*>(smem + LANE_SMEM_STACK));
+    lane_loop<MODE, STATS, TOP>(p, warp_stack + (threadIdx.x & 31), reinterpret_cast<uint32_t*>(smem + LANE_SMEM_STACK));
     __syncwarp();
     if ((threadIdx.x & 31) == 0) {
       __threadfence();
@@ -1409,7 +1530,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, J3DG_POOL_MODE ? J3DG_POOL_MIN_
 #ifdef J3DG_TIMELINE
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl1));
 #endif
-  group_loop<MODE, QUEUE, 4>(p, warp_stack + ((threadIdx.x & 31) >> 3));
+  group_loop<MODE, QUEUE, 4, TOP>(p, warp_stack + ((threadIdx.x & 31) >> 3));
 #ifdef J3DG_TIMELINE
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl2));
   if (MODE == PRIMARY && threadIdx.x == 0) {  // [13] first start, [14] last end of the lane phase, [15] last end; + sums for means
@@ -1582,6 +1703,73 @@ int persistent_grid(j3dg_ctx* ctx, K kernel, long long pools, int* grid) {
   return J3DG_OK;
 }
 
+// ---- top-level tree over the objects (host, whenever the object table changes) -------------------------------------
+// World box of an object = the box of the 8 corners of its root box under cs, padded by 1e-4 of its size (the walk
+// tests it in world space with fused arithmetic, the object is then traversed in object space with the reference's).
+// Objects are ordered along a 30-bit Morton curve of their centres; a node takes a contiguous run and cuts it into
+// (up to) 8 runs of equal length, runs of one object become leaves.  Node 0 is the root (pre-order allocation).
+struct TopItem { float lo[3], hi[3]; uint32_t mesh; uint32_t code; };
+
+uint32_t top_build_rec(std::vector<TopNode>& nodes, const std::vector<TopItem>& items, size_t a, size_t b) {
+  const uint32_t me = (uint32_t)nodes.size();
+  nodes.emplace_back();
+  TopNode n;
+  for (int c = 0; c < 8; ++c) {
+    for (int j = 0; j < 3; ++j) { n.lo[c][j] = INFINITY; n.hi[c][j] = -INFINITY; }
+    n.child[c] = J3DG_EMPTY_CHILD;  // unused slot: skipped by top_box_mask
+    n.pad[c] = 0;
+  }
+  const size_t cnt = b - a, parts = std::min<size_t>(8, cnt);
+  for (size_t c = 0; c < parts; ++c) {
+    const size_t ca = a + cnt * c / parts, cb = a + cnt * (c + 1) / parts;
+    for (size_t i = ca; i < cb; ++i)
+      for (int j = 0; j < 3; ++j) { n.lo[c][j] = std::min(n.lo[c][j], items[i].lo[j]); n.hi[c][j] = std::max(n.hi[c][j], items[i].hi[j]); }
+    n.child[c] = (cb - ca == 1) ? (J3DG_LEAF_BIT | items[ca].mesh) : top_build_rec(nodes, items, ca, cb);
+  }
+  nodes[me] = n;
+  return me;
+}
+
+void build_top_tree(const std::vector<MeshDev>& meshes, std::vector<TopNode>& nodes) {
+  std::vector<TopItem> items(meshes.size());
+  double glo[3] = {1e300, 1e300, 1e300}, ghi[3] = {-1e300, -1e300, -1e300};
+  for (size_t k = 0; k < meshes.size(); ++k) {
+    const MeshDev& m = meshes[k];
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int corner = 0; corner < 8; ++corner) {
+      const double v[3] = {corner & 1 ? m.root_max[0] : m.root_min[0], corner & 2 ? m.root_max[1] : m.root_min[1], corner & 4 ? m.root_max[2] : m.root_min[2]};
+      double w4 = m.cs[3] * v[0] + m.cs[7] * v[1] + m.cs[11] * v[2] + m.cs[15];
+      if (w4 == 0.0) w4 = 1.0;
+      for (int j = 0; j < 3; ++j) {
+        const double x = (m.cs[j] * v[0] + m.cs[4 + j] * v[1] + m.cs[8 + j] * v[2] + m.cs[12 + j]) / w4;
+        lo[j] = std::min(lo[j], x); hi[j] = std::max(hi[j], x);
+      }
+    }
+    for (int j = 0; j < 3; ++j) {
+      const double padj = 1e-4 * (hi[j] - lo[j]) + 1e-6 * (std::fabs(lo[j]) + std::fabs(hi[j])) + 1e-30;
+      items[k].lo[j] = (float)(lo[j] - padj); items[k].hi[j] = (float)(hi[j] + padj);
+      glo[j] = std::min(glo[j], lo[j]); ghi[j] = std::max(ghi[j], hi[j]);
+    }
+    items[k].mesh = (uint32_t)k;
+  }
+  for (TopItem& it : items) {
+    uint32_t code = 0;
+    uint32_t q[3];
+    for (int j = 0; j < 3; ++j) {
+      const double ext = ghi[j] - glo[j];
+      const double f = ext > 0.0 ? (0.5 * ((double)it.lo[j] + it.hi[j]) - glo[j]) / ext : 0.0;
+      q[j] = (uint32_t)std::min(1023.0, std::max(0.0, f * 1024.0));
+    }
+    for (int bit = 9; bit >= 0; --bit)
+      for (int j = 0; j < 3; ++j) code = (code << 1) | ((q[j] >> bit) & 1u);
+    it.code = code;
+  }
+  std::stable_sort(items.begin(), items.end(), [](const TopItem& x, const TopItem& y) { return x.code < y.code; });
+  nodes.clear();
+  nodes.reserve(items.size() / 4 + 2);
+  top_build_rec(nodes, items, 0, items.size());
+}
+
 }  // namespace
 
 void j3dg_make_view_dev(const j3dg_view* v, ViewDev& d) {
@@ -1626,7 +1814,18 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_meshes, host.data(), sizeof(MeshDev) * used, cudaMemcpyHostToDevice, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // pageable source
     ctx->meshes_uploaded = host;
+    ctx->top_nodes = 0;
+    if (used >= ctx->top_min) {  // many objects: a tree over their world boxes instead of a loop over all of them
+      std::vector<TopNode> top;
+      build_top_tree(host, top);
+      int rc = j3dg_reserve(ctx, &ctx->d_top, &ctx->top_cap, top.size() * sizeof(TopNode));
+      if (rc != J3DG_OK) return rc;
+      CU_CHECK(ctx, cudaMemcpyAsync(ctx->d_top, top.data(), top.size() * sizeof(TopNode), cudaMemcpyHostToDevice, ctx->stream));
+      CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+      ctx->top_nodes = (uint32_t)top.size();
+    }
   }
+  const bool use_top = ctx->top_nodes != 0 && used >= ctx->top_min && !stats && ctx->cast_algo == 0;
   const bool shadows = (view->flags & J3DG_SHADOW) && used && !stats;
   const int rw = x1 - x0 + 1, rh = y1 - y0 + 1;
   const size_t npx = (size_t)rw * rh;
@@ -1658,6 +1857,7 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
   TraceParams tp = {};
   tp.meshes = ctx->d_meshes;
   tp.nm = used;
+  tp.top = use_top ? (const TopNode*)ctx->d_top : nullptr;
   j3dg_make_view_dev(view, tp.vw);
   if (!shadows) tp.vw.flags &= ~J3DG_SHADOW;
   tp.x0 = x0; tp.y0 = y0; tp.x1 = x1; tp.y1 = y1;
@@ -1713,7 +1913,9 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
     group_kernel<PRIMARY><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
     KERNEL_CHECK(ctx);
   } else {
-    if ((rc = launch_hybrid(cast_kernel<PRIMARY, false>, cast_smem_bytes<PRIMARY, false>(), ntiles)) != J3DG_OK) return rc;
+    if (use_top) rc = launch_hybrid(cast_kernel<PRIMARY, false, true>, cast_smem_bytes<PRIMARY, false>(), ntiles);
+    else rc = launch_hybrid(cast_kernel<PRIMARY, false>, cast_smem_bytes<PRIMARY, false>(), ntiles);
+    if (rc != J3DG_OK) return rc;
   }
   if (used && !stats) {
     const uint32_t warps = 256 / 32;
@@ -1731,7 +1933,9 @@ int j3dg_launch_cast(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nm, const
       group_kernel<SHADOW><<<grid, BLOCK_THREADS, 0, ctx->stream>>>(tp);
       KERNEL_CHECK(ctx);
     } else {
-      if ((rc = launch_hybrid(cast_kernel<SHADOW, false>, cast_smem_bytes<SHADOW, false>(), pools)) != J3DG_OK) return rc;
+      if (use_top) rc = launch_hybrid(cast_kernel<SHADOW, false, true>, cast_smem_bytes<SHADOW, false>(), pools);
+      else rc = launch_hybrid(cast_kernel<SHADOW, false>, cast_smem_bytes<SHADOW, false>(), pools);
+      if (rc != J3DG_OK) return rc;
     }
   }
   rc = j3dg_stage_end(ctx, 0);

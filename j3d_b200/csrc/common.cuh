@@ -132,6 +132,8 @@ struct j3dg_ctx {
   unsigned long long* d_packed = nullptr; size_t packed_cap = 0;
   uint32_t* d_matcap = nullptr; size_t matcap_cap = 0; uint32_t mw = 0, mh = 0, mstride = 0, cavity = 0;
   MeshDev* d_meshes = nullptr; size_t meshes_cap = 0;
+  void* d_top = nullptr; size_t top_cap = 0; uint32_t top_nodes = 0;  // top-level tree over the objects of the uploaded mesh table (cast.cu)
+  uint32_t top_min = 9;                              // scenes with at least this many objects are cast through the top-level tree (J3DG_TOP_MIN)
   unsigned long long* d_stats = nullptr;
   void* d_misc = nullptr; size_t misc_cap = 0;
   void* d_shadow = nullptr; size_t shadow_cap = 0;   // shadow ray list (origins + pixel offsets)

@@ -1146,3 +1146,58 @@ def test_two_contexts_share_a_mesh_and_keep_two_frames_in_flight(ctx):
     assert ctx.status() == 0 and ctx2.status() == 0
     ctx2.close()
     mesh.destroy()
+
+
+@pytest.mark.timeout(900)
+def test_many_objects_through_the_top_level_tree(ctx, oracle):
+    """a8 (jtk/qbvh.h:3251-3387): scenes with many objects are cast through a per-frame top-level tree over the objects'
+    world boxes instead of a loop over all of them.  1 200 rigidly placed small meshes (some overlapping), primary and
+    shadow rays: the frame equals the oracle's (which loops over the objects) within the parity bars, and equals the
+    frame of the linear loop of the same kernels (a second context with the tree switched off) except at exact ties
+    between objects."""
+    import os
+    from test_oracle import _rigid
+    rng = np.random.default_rng(123)
+    w, h = 480, 272
+    base_v, base_t = j.icosphere(3)
+    n_obj = 1200
+    gm, om, pts = [], [], []
+    for k in range(n_obj):
+        cs = np.asarray(_rigid(rng, 1.0), np.float32).copy()
+        cs[12:15] = rng.uniform(-6.0, 6.0, 3).astype(np.float32)   # column-major translation
+        scale = np.float32(rng.uniform(0.15, 0.6))
+        vk = (base_v * scale).astype(np.float32)
+        gm.append(ctx.mesh_create(vk, base_t, cs=cs, db_id=0x20000000 + k))
+        om.append(oracle.mesh(vk, base_t, cs=cs, db_id=0x20000000 + k))
+        m = cs.reshape(4, 4).T
+        pts.append(vk @ m[:3, :3].T + m[:3, 3])
+    allp = np.concatenate(pts).astype(np.float32)
+    mc, cav = j.make_matcap(0)
+    old = os.environ.get("J3DG_TOP_MIN")
+    os.environ["J3DG_TOP_MIN"] = "1000000"
+    linear = j.Context(0)   # the same kernels, objects looped
+    if old is None:
+        del os.environ["J3DG_TOP_MIN"]
+    else:
+        os.environ["J3DG_TOP_MIN"] = old
+    for angle, flags in ((20.0, j.DEFAULT_FLAGS | j.SHADOW), (200.0, j.DEFAULT_FLAGS)):
+        v = j.orbit_view(j.make_view(w, h, allp.min(0), allp.max(0), flags), angle)
+        want = oracle.cast(om, v)
+        want_rgba = oracle.shade(want, v, mc, cav, oracle.fill_background(w, h))
+        px = np.zeros((h, w), j.PIXEL_DTYPE); rgba = np.zeros((h, w), np.uint32)
+        ctx.render_frame(gm, [], v, mc, cav, pixels_out=px, rgba_out=rgba)
+        st = compare_pixels(px, want, tag=f"1200 objects @{angle}")
+        assert st["hits"] > 0.1 * w * h
+        compare_rgba(rgba, want_rgba, tag=f"1200 objects @{angle}")
+        px2 = np.zeros((h, w), j.PIXEL_DTYPE); rgba2 = np.zeros((h, w), np.uint32)
+        linear.render_frame(gm, [], v, mc, cav, pixels_out=px2, rgba_out=rgba2)
+        same = (px["db_id"] == px2["db_id"]) & (px["object_id"] == px2["object_id"])
+        assert same.mean() > 0.9995, same.mean()
+        assert (px["depth"][same] == px2["depth"][same]).all() and (px["mark"][same] == px2["mark"][same]).mean() > 0.9995
+        t_tree, t_lin = ctx.timings(reset=True).cast_ms, linear.timings(reset=True).cast_ms
+        print(f"1200 objects @{angle}: cast {t_tree:.3f} ms through the tree, {t_lin:.3f} ms looping")
+    linear.close()
+    for m in gm:
+        m.destroy()
+    for m in om:
+        m.destroy()
