@@ -670,6 +670,8 @@ def run_orbit(args, wl, rank, world, local_rank):
         # ---- splat stage (BASELINE configs[3]) on the same box ----
         if not args.no_splat:
             stages["splat"] = splat_stage(rig, args.points or WORKLOADS["P"]["points"], peak, with_cpu=True)
+        if not args.no_ingest:
+            stages["ingest"] = ingest_stage(rig, verts, tris, peak, with_cpu=True)
     del verts, tris
 
     line = {
@@ -759,6 +761,83 @@ def splat_stage(rig, n_points, peak, with_cpu, reps=5):
             out["cpu_reference"] = {"points": ns, "ms": 1e3 * sum(ts) / len(ts), "mpoints_s": ns * len(ts) / sum(ts) / 1e6, "cores": ref.cores(),
                                     "sample": f"first {ns} points of the same cloud, render_pointclouds_on_image, 2 frames after 1 warm-up"}
             ref.close()
+    return out
+
+
+def ply_bytes(verts, tris):
+    """A binary little-endian PLY file of an indexed triangle mesh (float x y z; uchar count + 3 int indices per face)."""
+    head = (f"ply\nformat binary_little_endian 1.0\ncomment bench.py\nelement vertex {verts.shape[0]}\nproperty float x\nproperty float y\n"
+            f"property float z\nelement face {tris.shape[0]}\nproperty list uchar int vertex_indices\nend_header\n").encode("ascii")
+    faces = np.empty(tris.shape[0], dtype=[("n", "u1"), ("i", "<i4", 3)])
+    faces["n"] = 3
+    faces["i"] = tris
+    return head + np.ascontiguousarray(verts, "<f4").tobytes() + faces.tobytes()
+
+
+def ingest_stage(rig, verts, tris, peak, with_cpu):
+    """SURVEY §8f rank 4 on the same box: the config-B mesh as a binary PLY file decoded on the device (j3dg_ply_decode,
+    file bytes in pinned host memory -> vertex / index arrays in HBM -> j3dg_mesh_create_from_ply), and k-NN normal
+    estimation of a point cloud (j3dg_cloud_knn_normals / j3dg_cloud_estimate_normals), each with the reference's CPU code
+    (jtk::read_ply_from_memory, estimate_normals) on a bounded sample."""
+    torch, j, ctx = rig.torch, rig.j, rig.ctx
+    data = ply_bytes(verts, tris)
+    pinned = torch.empty(len(data), dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = np.frombuffer(data, np.uint8)
+    nv, nt = verts.shape[0], tris.shape[0]
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ply = ctx.ply_decode(pinned.numpy())
+        wall = 1e3 * (time.perf_counter() - t0)
+        info = ply.info()
+        if best is None or wall < best[0]:
+            best = (wall, info.upload_ms, info.decode_ms)
+        ok = bool(info.nr_of_vertices == nv and info.nr_of_faces == nt)
+        if _ < 2:
+            ply.destroy()
+    t0 = time.perf_counter()
+    m = ply.to_mesh()
+    ctx.synchronize()
+    to_mesh_ms = 1e3 * (time.perf_counter() - t0)
+    build_ms = m.info().build_ms
+    m.destroy()
+    ply.destroy()
+    alg = len(data) + 12 * nv + 12 * nt
+    out = {"ply": {"file_bytes": len(data), "vertices": nv, "faces": nt, "decode_call_ms": best[0], "upload_ms": best[1], "decode_kernels_ms": best[2],
+                   "decode_gb_s": alg / (best[2] * 1e-3) / 1e9, "roofline_frac": alg / (best[2] * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg,
+                   "mesh_create_from_ply_ms": to_mesh_ms, "bvh_build_ms": build_ms, "counts_ok": ok,
+                   "note": "decode = two kernels over the uploaded element data (file read once, records staged in shared memory); upload = one H2D copy of the file from pinned memory"}}
+    del pinned
+    n_pts, k = 2_000_000, 10
+    pos, _, _ = j.cloud(n_pts)
+    cl = ctx.cloud_create(pos)
+    cl.knn_normals(k)  # warm-up (allocations)
+    t0 = time.perf_counter()
+    cl.knn_normals(k)
+    knn_ms = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    cl.estimate_normals(k)
+    est_ms = 1e3 * (time.perf_counter() - t0)
+    cl.destroy()
+    out["normals"] = {"points": n_pts, "k": k, "knn_fit_ms": knn_ms, "mpoints_s": n_pts / knn_ms / 1e3, "estimate_normals_ms": est_ms,
+                      "note": "knn_fit = grid build + k-NN + plane fit on the device, lists and normals copied to the host; estimate_normals adds the serial orientation walk on the host"}
+    if with_cpu:
+        from oracle.bindings import ref_available, ref_estimate_normals, ref_read_ply
+        if ref_available():
+            fs = min(nt, 2_000_000)
+            sample = ply_bytes(verts, tris[:fs])
+            t0 = time.perf_counter()
+            got = ref_read_ply(sample)
+            dt = time.perf_counter() - t0
+            out["ply"]["cpu_reference"] = {"file_bytes": len(sample), "faces": fs, "ms": 1e3 * dt, "gb_s": (len(sample) + 12 * nv + 12 * fs) / dt / 1e9, "cores": 1,
+                                           "ok": bool(got is not None and got["triangles"].shape[0] == fs),
+                                           "sample": f"the same vertices + the first {fs} faces, jtk::read_ply_from_memory (rply, one thread; includes the binding's copy of the arrays)"}
+            ns = 30_000  # the reference's estimate_normals is far from linear in practice: 200 000 points take 43 s on this box
+            t0 = time.perf_counter()
+            ref_estimate_normals(pos[:ns].copy(), k)
+            dt = time.perf_counter() - t0
+            out["normals"]["cpu_reference"] = {"points": ns, "ms": 1e3 * dt, "mpoints_s": ns / dt / 1e6, "cores": 1,
+                                               "sample": f"first {ns} points, estimate_normals (j3d/pc.cpp:256: k-d tree, one thread)"}
     return out
 
 
@@ -919,6 +998,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=3, help="frames in flight per GPU (1 .. 4 contexts / streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-splat", action="store_true", help="skip the splat stage of the default line")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the PLY decode / normal estimation stage of the default line")
     ap.add_argument("--no-config-c", action="store_true", help="skip the 300 M-triangle sharded 4K frame (BASELINE configs[2]) of the default line")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: how every rank's RGBA frame reaches rank 0")
     args = ap.parse_args()
