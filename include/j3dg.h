@@ -271,7 +271,17 @@ int j3dg_splat(j3dg_ctx* ctx, j3dg_cloud* const* clouds, uint32_t nr_of_clouds, 
 
 /* ---- whole frame: view::render_scene (j3d/view.cpp:421-430) in one call:
  *      cast -> (snapshot) -> shade -> splat, everything resident on the device; only
- *      the requested outputs cross PCIe.  pixels_out / rgba_out nullable. ---------- */
+ *      the requested outputs cross PCIe.  pixels_out / rgba_out nullable.
+ *
+ *      Frames in flight.  One frame leaves most of the machine idle while its longest rays finish (the last fifth of the
+ *      ray-cast kernel's run time on a 28 M-triangle mesh).  A sweep should therefore keep two or three frames in
+ *      flight PER GPU, each through its OWN context of the same device (own stream, own scratch; j3dg_ctx_create
+ *      may be called any number of times per device): the ray-cast kernel is a plain launch that never waits for a
+ *      block that is not running, so the next frame's kernel moves into the SMs as this frame's blocks leave.  Meshes
+ *      and clouds may be rendered from ANY context of the device they live on (they must not be rebuilt, moved or
+ *      destroyed while a frame that uses them is in flight in another context).  Settings are per context
+ *      (j3dg_ctx_set_matcap, _set_tuning, _set_dirty_rect, ...).  j3dg_ctx_synchronize / j3dg_frame_wait of the
+ *      context that rendered a frame completes that frame. ---------- */
 int j3dg_render_frame(j3dg_ctx* ctx, j3dg_mesh* const* meshes, uint32_t nr_of_meshes,
                       j3dg_cloud* const* clouds, uint32_t nr_of_clouds, const j3dg_view* view,
                       const uint32_t* matcap, uint32_t mw, uint32_t mh, uint32_t mstride, uint32_t cavity_clr,
