@@ -386,7 +386,9 @@ def run_orbit(args, wl, rank, world, local_rank):
     if world > 1 and args.exchange == "peer":
         from j3d_b200.dist import PeerFrames
         try:
-            pf = PeerFrames(ctx, H, W, dev, dst=0, group=rig.group, nslots=max(2, L))
+XX
+            # not advance in lockstep with the slowest one of every single frame
+            pf = PeerFrames(ctx, H, W, dev, dst=0, group=rig.group, nslots=args.slots_per_lane * max(2, L) if L > 1 else 2)
         except RuntimeError as e:  # every rank raises together: CUDA IPC is not available here, gather with NCCL instead
             if rank == 0:
                 print(f"bench.py: {e}; using --exchange nccl", file=sys.stderr)
@@ -394,8 +396,8 @@ def run_orbit(args, wl, rank, world, local_rank):
     if world > 1 and args.exchange == "nccl":
         comm = torch.cuda.Stream(device=dev)
         L = 1  # the gather path keeps one frame in flight
-    for ln in range(1, L if pf is not None else 0):
-        pf.set_lane(ln, ctxs[ln])  # begin / arrive / release of the frames of slot ln go to that context's stream
+    for sl in range(pf.nslots if (pf is not None and L > 1) else 0):
+        pf.set_lane(sl, ctxs[sl % L])  # begin / arrive / release of the frames of slot sl go to the stream of the context that renders them
     gather_lists = [[torch.empty_like(rgba2[0]) for _ in range(world)] for _ in range(2)] if (comm is not None and rank == 0) else [None, None]
     ev_render = [torch.cuda.Event() for _ in range(2)]
     ev_gather = [torch.cuda.Event() for _ in range(2)]
@@ -405,7 +407,7 @@ def run_orbit(args, wl, rank, world, local_rank):
         lanes = L if lanes is None else lanes
         if pf is not None and not local:
             k = pf.begin()
-            ln = k % L   # the slot of the exchange buffer IS the lane
+            ln = k % L   # slot k mod nslots, nslots a multiple of L: the frames of a slot always run on the same lane
             ctxs[ln].render_frame([mesh], [], v, pixels_out=pxs[ln], rgba_out=pf.target(k))
             pf.arrive(k)
             # rank 0 consumes between arrival and release (PeerFrames protocol): nothing in the timed loop — the frames
@@ -1003,6 +1005,7 @@ def main():
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
     ap.add_argument("--f", type=int, default=0, help="override the icosphere frequency (T = 20 f^2)")
     ap.add_argument("--points", type=int, default=0, help="override the number of points of the splat stage / workload P")
+    ap.add_argument("--slots-per-lane", type=int, default=1, help="N > 1: slots of the frame exchange per lane")
     ap.add_argument("--lanes", type=int, default=3, help="frames in flight per GPU (1 .. 4 contexts / streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-splat", action="store_true", help="skip the splat stage of the default line")
