@@ -386,8 +386,8 @@ def run_orbit(args, wl, rank, world, local_rank):
     if world > 1 and args.exchange == "peer":
         from j3d_b200.dist import PeerFrames
         try:
-XX
-            # not advance in lockstep with the slowest one of every single frame
+            # --slots-per-lane 2 lets a rank run further ahead of rank 0's consumption; measured on 8 GPUs it buys nothing
+            # (20.9 vs 20.8 Grays/s, profiles/r2_n8_exchange_slots_ab.log): the ranks are not waiting for each other
             pf = PeerFrames(ctx, H, W, dev, dst=0, group=rig.group, nslots=args.slots_per_lane * max(2, L) if L > 1 else 2)
         except RuntimeError as e:  # every rank raises together: CUDA IPC is not available here, gather with NCCL instead
             if rank == 0:
