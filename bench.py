@@ -548,15 +548,22 @@ def run_orbit(args, wl, rank, world, local_rank):
                 ctxs[(n - 1) % L].pick([mesh], [], vs[-1], centre)
 
     def timed_sweep(vs, warm, records):
-        sweep(vs[:warm], records)
-        rig.barrier()
-        for c in ctxs:
-            c.readback_bytes(reset=True)
-        t0 = time.perf_counter()
-        sweep(vs[warm:], records)
-        dt = time.perf_counter() - t0
-        nbytes = sum(c.readback_bytes(reset=True) for c in ctxs) / max(1, len(vs) - warm)
-        return rig.max_over_ranks(dt)[0], nbytes
+        """Host wall clock around K = len(vs) - warm frames, max over ranks.  A short run (the driver's 20 steps last
+        15 ms) is at the mercy of one host hiccup, so it is repeated (up to 5 times, every repetition its own warm-up and
+        exactly K timed frames) and the MEDIAN is reported."""
+        reps = max(1, min(5, 100 // max(1, len(vs) - warm)))
+        times, nbytes = [], 0
+        for _ in range(reps):
+            sweep(vs[:warm], records)
+            rig.barrier()
+            for c in ctxs:
+                c.readback_bytes(reset=True)
+            t0 = time.perf_counter()
+            sweep(vs[warm:], records)
+            dt = time.perf_counter() - t0
+            nbytes = sum(c.readback_bytes(reset=True) for c in ctxs) / max(1, len(vs) - warm)
+            times.append(rig.max_over_ranks(dt)[0])
+        return statistics.median(times), nbytes
 
     def set_dirty(on):
         for c in ctxs:
@@ -697,7 +704,7 @@ def run_orbit(args, wl, rank, world, local_rank):
         "bvh_build_ms": build_ms, "bvh_nodes": int(info.nr_of_nodes), "frames_per_s": 1e3 * args.steps * world / ms,
         "cast_ms": cast_ms, "shade_ms": shade_ms,
         "e2e": {"value": rays_total / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(e2e_bytes),
-                "ms_per_step": 1e3 * e2e_s / args.steps,
+                "ms_per_step": 1e3 * e2e_s / args.steps, "repetitions_median_of": max(1, min(5, 100 // max(1, args.steps))),
                 "api": "j3dg_frame_submit(pixels_out=NULL)/j3dg_frame_wait (pipelined, pinned persistent host buffer, dirty-rectangle readback) + j3dg_pick: RGBA crosses PCIe every frame, the pixel records stay in HBM and are queried on demand",
                 "sync_render_frame_rgba_ms_per_step": sync_rgba_ms, "mesh_create_ms": create_ms},
         "e2e_full_records": {"value": rays_total / rec_s / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * rec_s / args.steps, "d2h_bytes_per_step": int(rec_bytes),

@@ -310,9 +310,10 @@ __device__ __forceinline__ uint32_t pick_exponent(float extent) {
 
 // A candidate child is opened further only while it owns more than J3DG_LEAF_KEEP triangles: the
 // traversal kernel tests all (<= 8) triangles of a leaf in ONE lane-parallel round, so very small
-// leaves only add node levels.
+// leaves only add node levels.  Measured on config B with three frames in flight (profiles/r2_cast_refill_leafkeep_knobs.log):
+// 4 / 2 / 1 -> 0.771 / 0.757 / 0.756 ms per frame.
 #ifndef J3DG_LEAF_KEEP
-#define J3DG_LEAF_KEEP 4
+#define J3DG_LEAF_KEEP 2
 #endif
 
 __device__ __forceinline__ void mark_leaf_end(TriRec* __restrict__ recs, uint32_t last) {
