@@ -303,7 +303,7 @@ J3DG_API int j3dg_ply_decode(j3dg_ctx* ctx, const void* file_bytes, size_t nbyte
   const size_t data_bytes = nbytes - h.bytes;
   if (data_bytes) {
     if (cudaMalloc((void**)&d_file, data_bytes + 64) != cudaSuccess) { cudaGetLastError(); j3dg_set_error(ctx, "out of device memory (PLY bytes)"); return fail(J3DG_ENOMEM); }
-    if (cudaMemcpyAsync(d_file, file + h.bytes, data_bytes, cudaMemcpyDefault, ctx->stream) != cudaSuccess) { cudaGetLastError(); cudaFree(d_file); j3dg_set_error(ctx, "PLY upload failed"); return fail(J3DG_ECUDA); }
+    if (j3dg_copy_to_device(ctx, d_file, file + h.bytes, data_bytes) != J3DG_OK) { cudaGetLastError(); cudaFree(d_file); return fail(J3DG_ECUDA); }
   }
   cudaEventRecord(e1, ctx->stream);
   vbase -= h.bytes; fbase -= h.bytes;
