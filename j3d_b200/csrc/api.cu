@@ -16,6 +16,22 @@
 constexpr size_t STAGE_CHUNK = 16u << 20;
 constexpr int STAGE_THREADS = 8;
 
+static void j3dg_stage_ring_start(j3dg_ctx* ctx) {
+  ctx->stage_init = new std::thread([ctx]() {
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < 4; ++i)
+      if (cudaHostAlloc(&ctx->h_stage[i], STAGE_CHUNK, cudaHostAllocDefault) != cudaSuccess) { ctx->h_stage[i] = nullptr; break; }
+  });
+}
+static void j3dg_stage_ring_join(j3dg_ctx* ctx) {
+  if (!ctx->stage_init) return;
+  std::thread* t = (std::thread*)ctx->stage_init;
+  t->join();
+  delete t;
+  ctx->stage_init = nullptr;
+  cudaGetLastError();
+}
+
 int j3dg_copy_to_device(j3dg_ctx* ctx, void* dst, const void* src, size_t bytes) {
   cudaPointerAttributes a;
   bool pageable = true;
@@ -25,14 +41,13 @@ int j3dg_copy_to_device(j3dg_ctx* ctx, void* dst, const void* src, size_t bytes)
     CU_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
     return J3DG_OK;
   }
+  j3dg_stage_ring_join(ctx);  // page-locking 64 MB takes tens of milliseconds: j3dg_ctx_create started it in the background
   for (int i = 0; i < 4; ++i) {
-    if (!ctx->h_stage[i]) {
-      if (cudaHostAlloc(&ctx->h_stage[i], STAGE_CHUNK, cudaHostAllocDefault) != cudaSuccess) {  // no pinned memory to spare: the plain copy still works
-        cudaGetLastError();
-        ctx->h_stage[i] = nullptr;
-        CU_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
-        return J3DG_OK;
-      }
+    if (!ctx->h_stage[i]) {  // no pinned memory to spare: the plain copy still works
+      CU_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+      return J3DG_OK;
+    }
+    if (!ctx->stage_ev[i]) {
       CU_CHECK(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
       ctx->stage_busy[i] = false;
     }
@@ -227,6 +242,7 @@ J3DG_API int j3dg_ctx_create(int device, j3dg_ctx** out) {
   if (const char* e = getenv("J3DG_SHADOW_BUDGET")) ctx->shadow_budget = (uint32_t)std::max(1, atoi(e));
   if (const char* e = getenv("J3DG_CAST_ALGO")) ctx->cast_algo = strcmp(e, "group") == 0 ? 1 : 0;
   if (const char* e = getenv("J3DG_TOP_MIN")) ctx->top_min = (uint32_t)std::max(2, atoi(e));
+  j3dg_stage_ring_start(ctx);
   *out = ctx;
   return J3DG_OK;
 }
@@ -242,8 +258,10 @@ J3DG_API void j3dg_ctx_destroy(j3dg_ctx* ctx) {
     if (sl.kernels_done) cudaEventDestroy(sl.kernels_done);
     if (sl.copy_done) cudaEventDestroy(sl.copy_done);
   }
+  j3dg_stage_ring_join(ctx);
   for (int i = 0; i < 4; ++i) {
-    if (ctx->h_stage[i]) { cudaFreeHost(ctx->h_stage[i]); cudaEventDestroy(ctx->stage_ev[i]); }
+    if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
+    if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
   }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->h_overflow) cudaFreeHost(ctx->h_overflow);

@@ -132,7 +132,8 @@ struct j3dg_ctx {
   unsigned long long* d_packed = nullptr; size_t packed_cap = 0;
   uint32_t* d_matcap = nullptr; size_t matcap_cap = 0; uint32_t mw = 0, mh = 0, mstride = 0, cavity = 0;
   MeshDev* d_meshes = nullptr; size_t meshes_cap = 0;
-  void* h_stage[4] = {}; cudaEvent_t stage_ev[4] = {}; bool stage_busy[4] = {};  // pinned ring of the pageable-source upload (api.cu, copy_to_device)
+  void* h_stage[4] = {}; cudaEvent_t stage_ev[4] = {}; bool stage_busy[4] = {};  // pinned ring of the pageable-source upload (api.cu, j3dg_copy_to_device)
+  void* stage_init = nullptr;                        // std::thread* that pins the ring in the background from j3dg_ctx_create on (joined at first use)
   void* d_top = nullptr; size_t top_cap = 0; uint32_t top_nodes = 0;  // top-level tree over the objects of the uploaded mesh table (cast.cu)
   uint32_t top_min = 9;                              // scenes with at least this many objects are cast through the top-level tree (J3DG_TOP_MIN)
   unsigned long long* d_stats = nullptr;

@@ -249,3 +249,20 @@ def test_estimate_normals_equals_reference_live_200k(ctx):
     ctx.render_frame([], [c], view, mc, cav, rgba_out=rgba)
     assert len(np.unique(rgba)) > 50
     c.destroy()
+
+
+def test_bench_ply_writer_is_read_by_the_oracle_and_the_reference():
+    """bench.py's in-memory PLY writer (the ingest stage of the default line) produces a file that the oracle — and the
+    unmodified jtk reader where it is available — decode back to the same arrays."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", str(HERE.parent / "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    verts, tris = j.icosphere(7)
+    data = bench.ply_bytes(verts, tris)
+    got = io.read_ply_binary(data)
+    assert _same(got["vertices"], verts) and _same(got["triangles"], tris)
+    if ref_available():
+        from oracle.bindings import ref_read_ply
+        want = ref_read_ply(data)
+        assert _same(want["vertices"], verts) and _same(want["triangles"], tris)
