@@ -12,7 +12,7 @@
 // Host -> device copy of a big PAGEABLE array (the std::vectors of j3d's mesh / pc structs): cudaMemcpy from pageable
 // memory stages through one driver thread at ~10 GB/s.  Here eight host threads copy 16 MB chunks into a ring of four
 // pinned buffers while the DMA engine drains the previous chunks, which keeps PCIe busy (config B, 504 MB of vertices and
-// indices: 51 -> 25 ms with four threads).  Pinned and device sources, and small arrays, take the direct path.
+// indices: 51 -> 17-19 ms).  Pinned and device sources, and small arrays, take the direct path.
 constexpr size_t STAGE_CHUNK = 16u << 20;
 constexpr int STAGE_THREADS = 8;
 
@@ -21,6 +21,10 @@ static void j3dg_stage_ring_start(j3dg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (int i = 0; i < 4; ++i)
       if (cudaHostAlloc(&ctx->h_stage[i], STAGE_CHUNK, cudaHostAllocDefault) != cudaSuccess) { ctx->h_stage[i] = nullptr; break; }
+    __sync_synchronize();
+    ctx->stage_ready = 1;
+    j3dg_preload_build_kernels();  // lazy module loading: have the kernels of the first mesh_create / frame resident by then
+    j3dg_preload_cast_kernels();
   });
 }
 static void j3dg_stage_ring_join(j3dg_ctx* ctx) {
@@ -41,7 +45,8 @@ int j3dg_copy_to_device(j3dg_ctx* ctx, void* dst, const void* src, size_t bytes)
     CU_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
     return J3DG_OK;
   }
-  j3dg_stage_ring_join(ctx);  // page-locking 64 MB takes tens of milliseconds: j3dg_ctx_create started it in the background
+  while (!ctx->stage_ready) std::this_thread::yield();  // page-locking 64 MB takes tens of milliseconds: j3dg_ctx_create started it in the background
+  __sync_synchronize();
   for (int i = 0; i < 4; ++i) {
     if (!ctx->h_stage[i]) {  // no pinned memory to spare: the plain copy still works
       CU_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));

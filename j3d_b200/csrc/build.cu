@@ -465,6 +465,18 @@ struct Arena {
 
 }  // namespace
 
+// CUDA loads kernels lazily, at their first launch (about a millisecond each): the first j3dg_mesh_create of a process
+// paid ~25 ms for that.  j3dg_ctx_create calls this from its background thread instead.
+void j3dg_preload_build_kernels() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, bbox_init_kernel); cudaFuncGetAttributes(&a, bbox_kernel); cudaFuncGetAttributes(&a, morton_kernel);
+  cudaFuncGetAttributes(&a, rsort::histogram_kernel); cudaFuncGetAttributes(&a, rsort::scan_chunk_sums); cudaFuncGetAttributes(&a, rsort::scan_sums_serial);
+  cudaFuncGetAttributes(&a, rsort::scan_apply); cudaFuncGetAttributes(&a, rsort::scatter_kernel);
+  cudaFuncGetAttributes(&a, radix_tree_kernel); cudaFuncGetAttributes(&a, refit_kernel); cudaFuncGetAttributes(&a, collapse_kernel);
+  cudaFuncGetAttributes(&a, init_queue_kernel); cudaFuncGetAttributes(&a, reset_count_kernel);
+  cudaGetLastError();
+}
+
 // Builds m->d_nodes / m->d_tris from m->d_vertices / m->d_indices (device resident).
 int j3dg_build_bvh(j3dg_mesh* m) {
   j3dg_ctx* ctx = m->ctx;

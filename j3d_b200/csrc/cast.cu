@@ -1772,6 +1772,12 @@ void build_top_tree(const std::vector<MeshDev>& meshes, std::vector<TopNode>& no
 
 }  // namespace
 
+void j3dg_preload_cast_kernels() {  // see j3dg_preload_build_kernels
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, cast_kernel<PRIMARY, false>); cudaFuncGetAttributes(&a, cast_kernel<SHADOW, false>); cudaFuncGetAttributes(&a, resolve_kernel);
+  cudaGetLastError();
+}
+
 void j3dg_make_view_dev(const j3dg_view* v, ViewDev& d) {
   d.width = v->width; d.height = v->height;
   d.near_plane = v->near_plane; d.diagonal = v->diagonal;

@@ -133,7 +133,8 @@ struct j3dg_ctx {
   uint32_t* d_matcap = nullptr; size_t matcap_cap = 0; uint32_t mw = 0, mh = 0, mstride = 0, cavity = 0;
   MeshDev* d_meshes = nullptr; size_t meshes_cap = 0;
   void* h_stage[4] = {}; cudaEvent_t stage_ev[4] = {}; bool stage_busy[4] = {};  // pinned ring of the pageable-source upload (api.cu, j3dg_copy_to_device)
-  void* stage_init = nullptr;                        // std::thread* that pins the ring in the background from j3dg_ctx_create on (joined at first use)
+  void* stage_init = nullptr;                        // std::thread* that pins the ring (and preloads the kernels) in the background from j3dg_ctx_create on
+  volatile int stage_ready = 0;                      // 0: still pinning, 1: ring usable (or unavailable: h_stage[i] == nullptr)
   void* d_top = nullptr; size_t top_cap = 0; uint32_t top_nodes = 0;  // top-level tree over the objects of the uploaded mesh table (cast.cu)
   uint32_t top_min = 9;                              // scenes with at least this many objects are cast through the top-level tree (J3DG_TOP_MIN)
   unsigned long long* d_stats = nullptr;
@@ -181,6 +182,8 @@ int j3dg_stage_end(j3dg_ctx* ctx, int stage);
 int j3dg_cuda_fail(j3dg_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
 bool j3dg_is_device_ptr(const void* p);
 int j3dg_reserve(j3dg_ctx* ctx, void** ptr, size_t* cap, size_t bytes);
+void j3dg_preload_build_kernels();
+void j3dg_preload_cast_kernels();
 int j3dg_copy_to_device(j3dg_ctx* ctx, void* dst, const void* src, size_t bytes);  // stream-ordered; pageable sources go through a pinned ring (api.cu)
 
 #define CU_CHECK(ctx, call)                                                         \
