@@ -330,4 +330,69 @@ class canvas {
   canvas_settings _settings;
 };
 
+// A sweep of frames of one scene (turntables, orbit renders; BASELINE configs[4]) with several frames in flight per GPU
+// (include/j3dg.h, "Frames in flight"): `lanes` contexts of one device, each pipelining frames of its own
+// (j3dg_frame_submit / j3dg_frame_wait), all rendering the SAME mesh / cloud handles.  Frames complete in submission
+// order.  Not part of j3d (its view renders one frame per UI event); it is the call a batch renderer built on j3d makes.
+class sweep {
+ public:
+  sweep(int device, const matcap& mc, int lanes = 3) {
+    for (int i = 0; i < (lanes < 1 ? 1 : lanes); ++i) {
+      j3dg_ctx* c = nullptr;
+      if (j3dg_ctx_create(device, &c) != J3DG_OK) { release(); throw std::runtime_error(std::string("j3dg_ctx_create: ") + j3dg_last_error(nullptr)); }
+      _ctx.push_back(c);
+      _pending.push_back(0);
+      if (j3dg_ctx_set_matcap(c, mc.im.data(), mc.w, mc.h, mc.w, mc.cavity_clr) != J3DG_OK || j3dg_ctx_set_dirty_rect(c, 1) != J3DG_OK) {
+        const std::string why = j3dg_last_error(c);
+        release();
+        throw std::runtime_error("sweep: " + why);
+      }
+    }
+  }
+  ~sweep() { release(); }
+  sweep(const sweep&) = delete;
+  sweep& operator=(const sweep&) = delete;
+
+  // Enqueues one frame.  rgba_out (width * height uint32) and pixels_out (nullable, width * height records) are HOST
+  // buffers that stay untouched by the caller until the matching wait(); every lane wants its own persistent buffers
+  // (the dirty-rectangle readback only rewrites what changed since the SAME buffer was last filled).
+  void submit(const scene& s, const j3dg_view& v, uint32_t* rgba_out, pixel* pixels_out = nullptr, uint32_t bg_top = 0xff000000, uint32_t bg_bottom = 0xff404040) {
+    const size_t lane = _next % _ctx.size();
+    while (_pending[lane] >= 2) wait();  // a lane double-buffers: two frames of its own at most
+    std::vector<j3dg_mesh*> meshes;
+    std::vector<j3dg_cloud*> clouds;
+    for (const auto& o : s.objects) if (o.bvh) meshes.push_back(o.bvh);
+    for (const auto& o : s.pointclouds) if (o.cloud) clouds.push_back(o.cloud);
+    if (j3dg_frame_submit(_ctx[lane], meshes.data(), (uint32_t)meshes.size(), clouds.data(), (uint32_t)clouds.size(), &v, nullptr, 0, 0, 0, 0, bg_top, bg_bottom,
+                          pixels_out, rgba_out) != J3DG_OK)
+      throw std::runtime_error(std::string("j3dg_frame_submit: ") + j3dg_last_error(_ctx[lane]));
+    _order.push_back(lane);
+    ++_pending[lane];
+    ++_next;
+  }
+  // Completes the oldest frame in flight (its host buffers are final on return); false: nothing was in flight.
+  bool wait() {
+    if (_head == _order.size()) return false;
+    const size_t lane = _order[_head++];
+    if (j3dg_frame_wait(_ctx[lane]) != J3DG_OK) throw std::runtime_error(std::string("j3dg_frame_wait: ") + j3dg_last_error(_ctx[lane]));
+    --_pending[lane];
+    if (_head == _order.size()) { _order.clear(); _head = 0; }
+    return true;
+  }
+  size_t in_flight() const { return _order.size() - _head; }
+  size_t lanes() const { return _ctx.size(); }
+  // the lane the NEXT submit uses (callers that keep one set of host buffers per lane index them with this)
+  size_t next_lane() const { return _next % _ctx.size(); }
+
+ private:
+  void release() {
+    for (j3dg_ctx* c : _ctx) j3dg_ctx_destroy(c);
+    _ctx.clear();
+  }
+  std::vector<j3dg_ctx*> _ctx;
+  std::vector<int> _pending;
+  std::vector<size_t> _order;
+  size_t _head = 0, _next = 0;
+};
+
 }  // namespace j3dg

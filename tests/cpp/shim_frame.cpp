@@ -5,7 +5,8 @@
 //
 //   shim_frame <in.bin> <out.bin>
 //   in : u32 w, h, nv, nt, np, flags, max_dim | float verts[3nv] | u32 tris[3nt] | float ppos[3np] | float pnrm[3np] | u32 pclr[np]
-//   out: pixel records w*h*32 | u32 image w*h (stride removed) | 3 picks (64 B each) | u32 dim[3] | u8 voxels
+//   out: pixel records w*h*32 | u32 image w*h (stride removed) | 3 picks (64 B each) | u32 dim[3] | u8 voxels |
+//        u32 number of sweep frames (three in flight, j3dg::sweep) that differ from the synchronous frame
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -71,6 +72,32 @@ int main(int argc, char** argv) {
     j3dg::voxelize(ctx, s.objects.front(), max_dim, dim, vox);
     fwrite(dim, 4, 3, o);
     fwrite(vox.data(), 1, vox.size(), o);
+    // ---- a sweep with three frames in flight (j3dg::sweep): 7 orbit poses, every frame equal to the synchronous one ----
+    {
+      const int nframes = 7;
+      j3dg::sweep sw(0, mc, 3);
+      std::vector<std::vector<uint32_t>> host(nframes, std::vector<uint32_t>((size_t)w * h));
+      std::vector<j3dg_view> views;
+      for (int k = 0; k < nframes; ++k) {
+        j3dg_view v = cnv.make_view(s);
+        j3dgh_orbit(s.coordinate_system_inv.f, s.pivot, 13.f * (float)k, v.cs, v.cs_inv);
+        views.push_back(v);
+        sw.submit(s, v, host[k].data());
+      }
+      while (sw.wait()) {}
+      uint32_t bad = 0;
+      std::vector<uint32_t> want((size_t)w * h);
+      for (int k = 0; k < nframes; ++k) {
+        std::vector<j3dg_mesh*> meshes;
+        std::vector<j3dg_cloud*> clouds;
+        for (const auto& ob : s.objects) meshes.push_back(ob.bvh);
+        for (const auto& ob : s.pointclouds) clouds.push_back(ob.cloud);
+        ctx.check(j3dg_render_frame(ctx.get(), meshes.data(), (uint32_t)meshes.size(), clouds.data(), (uint32_t)clouds.size(), &views[k], mc.im.data(), mc.w, mc.h, mc.w,
+                                    mc.cavity_clr, 0xff000000u, 0xff404040u, nullptr, want.data()), "j3dg_render_frame");
+        if (want != host[k]) ++bad;
+      }
+      fwrite(&bad, 4, 1, o);
+    }
     fclose(o);
     j3dg::remove_object(0x20000000u, s);
     if (np) j3dg::remove_object(0x40000000u, s);

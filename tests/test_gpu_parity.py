@@ -754,7 +754,9 @@ def test_cpp_shim_renders_like_the_abi(ctx):
     got_im = np.frombuffer(raw, np.uint32, w * h, o).reshape(h, w); o += w * h * 4
     got_picks = np.frombuffer(raw, j.PICK_DTYPE, 3, o); o += 3 * 64
     dim = np.frombuffer(raw, np.uint32, 3, o); o += 12
-    got_vox = np.frombuffer(raw, np.uint8, int(dim.prod()), o).reshape(dim[2], dim[1], dim[0])
+    got_vox = np.frombuffer(raw, np.uint8, int(dim.prod()), o).reshape(dim[2], dim[1], dim[0]); o += int(dim.prod())
+    sweep_bad = int(np.frombuffer(raw, np.uint32, 1, o)[0])
+    assert sweep_bad == 0, f"{sweep_bad} frames of the three-lane j3dg::sweep differ from the synchronous frames"
     # the same calls through ctypes: add_object + prepare_scene + unzoom, then cast -> shade -> splat on host buffers
     mn, mx = j.compute_bb(np.concatenate([verts, pos]))
     v = j.make_view(w, h, mn, mx, flags)
