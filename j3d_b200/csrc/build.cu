@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(256) radix_tree_kernel(const uint64_t* __restr
 constexpr int REFIT_THREADS = 256;
 
 __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __restrict__ verts, const uint32_t* __restrict__ idx,
-                                                               const uint32_t* __restrict__ sorted_tri, int n, BinTree t, TriRec* __restrict__ recs) {
+                                                               const uint32_t* __restrict__ sorted_tri, const uint64_t* __restrict__ packed, uint32_t idx_mask,
+                                                               int n, BinTree t, TriRec* __restrict__ recs) {
   __shared__ float s_lmn[3][REFIT_THREADS], s_lmx[3][REFIT_THREADS];  // leaf boxes
   __shared__ float s_imn[3][REFIT_THREADS], s_imx[3][REFIT_THREADS];  // boxes of the inner nodes fitted here
   __shared__ uint8_t s_ready[REFIT_THREADS];
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __res
   const uint32_t first_leaf = (uint32_t)(n - 1);
   // ---- leaves: gather, emit the record, leaf box ----
   if (k < e) {
-    const uint32_t tri = sorted_tri[k];
+    const uint32_t tri = packed ? ((uint32_t)packed[k] & idx_mask) : sorted_tri[k];  // packed sort: the triangle rides in the low bits of its key
     const uint32_t i0 = idx[3 * (size_t)tri], i1 = idx[3 * (size_t)tri + 1], i2 = idx[3 * (size_t)tri + 2];
     const float3 a = make_float3(verts[3 * (size_t)i0], verts[3 * (size_t)i0 + 1], verts[3 * (size_t)i0 + 2]);
     const float3 b = make_float3(verts[3 * (size_t)i1], verts[3 * (size_t)i1 + 1], verts[3 * (size_t)i1 + 2]);
@@ -472,6 +473,7 @@ void j3dg_preload_build_kernels() {
   cudaFuncGetAttributes(&a, bbox_init_kernel); cudaFuncGetAttributes(&a, bbox_kernel); cudaFuncGetAttributes(&a, morton_kernel);
   cudaFuncGetAttributes(&a, rsort::histogram_kernel); cudaFuncGetAttributes(&a, rsort::scan_chunk_sums); cudaFuncGetAttributes(&a, rsort::scan_sums_serial);
   cudaFuncGetAttributes(&a, rsort::scan_apply); cudaFuncGetAttributes(&a, rsort::scatter_kernel);
+  cudaFuncGetAttributes(&a, rsort::digit_histograms_kernel); cudaFuncGetAttributes(&a, rsort::onesweep_kernel<true>); cudaFuncGetAttributes(&a, rsort::onesweep_kernel<false>);
   cudaFuncGetAttributes(&a, radix_tree_kernel); cudaFuncGetAttributes(&a, refit_kernel); cudaFuncGetAttributes(&a, collapse_kernel);
   cudaFuncGetAttributes(&a, init_queue_kernel); cudaFuncGetAttributes(&a, reset_count_kernel);
   cudaGetLastError();
@@ -562,18 +564,30 @@ int j3dg_build_bvh(j3dg_mesh* m) {
       int axis_bits = std::min(MORTON_BITS_PER_AXIS, std::max(10, (int)std::ceil(mean_bits) + 1));
       if (const char* e = getenv("J3DG_MORTON_BITS")) axis_bits = std::min(MORTON_BITS_PER_AXIS, std::max(1, atoi(e)));  // developer knob
       const int passes = (3 * axis_bits + 7) / 8;
-      const int first_bit = MORTON_BITS - 8 * passes;  // sort the top 8 * passes bits
-      const uint64_t key_mask = ~0ull << first_bit;
+      int first_bit = MORTON_BITS - 8 * passes;  // sort the top 8 * passes bits
+      uint64_t key_mask = ~0ull << first_bit;
       bool in_b = false;
-      int rc = rsort::sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, n, MORTON_BITS, sort_scratch, &in_b, true, first_bit);
+      // When the sorted code bits and the triangle index fit one 64-bit word together (config B: 36 bits are worth sorting, five
+      // passes would sort 40, 39 + 25 index bits fit: the top digit is then only partly used), the sort moves 8-byte packed keys
+      // instead of 12-byte (key, value) pairs.
+      // Same order (equal codes keep their input order either way), same tree: the radix tree masks the index bits.
+      int idx_bits = 1;
+      while (idx_bits < 32 && (1ull << idx_bits) < (unsigned long long)n) ++idx_bits;
+      int sorted_bits = 8 * passes;
+      if (sorted_bits + idx_bits > 64 && 3 * axis_bits + idx_bits <= 64) sorted_bits = 64 - idx_bits;  // still at least the bits worth sorting
+      const bool packed = rsort::can_sort_packed(n, passes, idx_bits, sorted_bits);
+      if (packed) { first_bit = MORTON_BITS - sorted_bits; key_mask = ~0ull << first_bit; }
+      int rc = packed ? rsort::sort_packed(ctx, keys_a, keys_b, n, first_bit, passes, idx_bits, sort_scratch, &in_b)
+                      : rsort::sort_pairs(ctx, keys_a, vals_a, keys_b, vals_b, n, MORTON_BITS, sort_scratch, &in_b, true, first_bit);
       if (rc != J3DG_OK) return rc;
+      if (packed) key_mask = ~0ull << idx_bits;
       const uint64_t* keys = in_b ? keys_b : keys_a;
-      const uint32_t* vals = in_b ? vals_b : vals_a;
+      const uint32_t* vals = packed ? nullptr : (in_b ? vals_b : vals_a);
       if (n > 1) {
         radix_tree_kernel<<<(n - 1 + 255) / 256, 256, 0, st>>>(keys, key_mask, (int)n, bt);
         KERNEL_CHECK(ctx);
       }
-      refit_kernel<<<tb, 256, 0, st>>>(m->d_vertices, m->d_indices, vals, (int)n, bt, m->d_tris);
+      refit_kernel<<<tb, 256, 0, st>>>(m->d_vertices, m->d_indices, vals, packed ? keys : nullptr, (uint32_t)((1ull << idx_bits) - 1ull), (int)n, bt, m->d_tris);
       KERNEL_CHECK(ctx);
       if (n == 1) {
         single_triangle_root_kernel<<<1, 1, 0, st>>>(bt, m->d_nodes, m->d_tris);
