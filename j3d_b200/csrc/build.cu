@@ -321,103 +321,158 @@ __device__ __forceinline__ void mark_leaf_end(TriRec* __restrict__ recs, uint32_
   reinterpret_cast<uint32_t*>(&recs[last].v1)[3] = 1u;
 }
 
-__global__ void __launch_bounds__(128) collapse_kernel(BinTree t, int n, const WorkItem* __restrict__ in, const uint32_t* __restrict__ in_count,
-                                                        WorkItem* __restrict__ out, uint32_t* __restrict__ out_count,
-                                                        WideNode* __restrict__ nodes, uint32_t* __restrict__ node_count, uint32_t node_cap,
-                                                        uint32_t* __restrict__ overflow, TriRec* __restrict__ recs) {
-  const uint32_t count = *in_count;
+// One thread per wide node.  The kernel is bound by the latency of DEPENDENT loads (ncu, round 2: 3.9 warps per scheduler, 0.08
+// eligible, 85 % of the stall cycles on L1TEX), so the work is arranged to keep the chain short:
+//   * a candidate keeps everything that was loaded with it — children, leaf range, box — in registers (the arrays are only
+//     indexed with unrolled compile-time indices), so opening a candidate needs no load for ITS topology, only one round of
+//     independent loads (topology + box of both children): one latency per opening, ~9 per node instead of ~60;
+//   * the wide-node indices and the queue slots of all children of all 32 nodes of a warp are taken with ONE pair of atomics
+//     (siblings end up adjacent in memory);
+//   * the level counters rotate over three words (read, append, zero for the next level): no reset launches.
+struct Cand {
+  uint32_t id, l, r, lo, hi;  // binary node, its children, its range of sorted triangle records
+  float area;                 // < 0: not opened any further
+  float mn[3], mx[3];
+};
+
+__device__ __forceinline__ void load_pair(const BinTree& t, uint32_t first_leaf, uint32_t a, uint32_t b, Cand& ca, Cand& cb) {
+  const bool la = a >= first_leaf, lb = b >= first_leaf;
+  // every load is issued before the first use
+  const uint4 ta = t.topo[la ? 0u : a], tb = t.topo[lb ? 0u : b];
+  const float4 amn = t.box[2 * (size_t)a], amx = t.box[2 * (size_t)a + 1];
+  const float4 bmn = t.box[2 * (size_t)b], bmx = t.box[2 * (size_t)b + 1];
+  ca.id = a; ca.l = ta.x; ca.r = ta.y;
+  ca.lo = la ? a - first_leaf : ta.z; ca.hi = la ? a - first_leaf : ta.w;
+  ca.mn[0] = amn.x; ca.mn[1] = amn.y; ca.mn[2] = amn.z; ca.mx[0] = amx.x; ca.mx[1] = amx.y; ca.mx[2] = amx.z;
+  ca.area = (la || ca.hi - ca.lo + 1u <= (uint32_t)J3DG_LEAF_KEEP) ? -1.f : fmaxf(half_area(amn, amx), 0.f);
+  cb.id = b; cb.l = tb.x; cb.r = tb.y;
+  cb.lo = lb ? b - first_leaf : tb.z; cb.hi = lb ? b - first_leaf : tb.w;
+  cb.mn[0] = bmn.x; cb.mn[1] = bmn.y; cb.mn[2] = bmn.z; cb.mx[0] = bmx.x; cb.mx[1] = bmx.y; cb.mx[2] = bmx.z;
+  cb.area = (lb || cb.hi - cb.lo + 1u <= (uint32_t)J3DG_LEAF_KEEP) ? -1.f : fmaxf(half_area(bmn, bmx), 0.f);
+}
+
+// counts[0..2]: queue sizes, rotating (level L reads [L % 3], appends to [(L + 1) % 3], zeroes [(L + 2) % 3]); counts[3] node count, counts[4] overflow
+#ifndef J3DG_COLLAPSE_MIN_BLOCKS
+#define J3DG_COLLAPSE_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, J3DG_COLLAPSE_MIN_BLOCKS) collapse_kernel(BinTree t, int n, const WorkItem* __restrict__ in, WorkItem* __restrict__ out, uint32_t* __restrict__ counts, int level,
+                                                        WideNode* __restrict__ nodes, uint32_t node_cap, TriRec* __restrict__ recs) {
+  const uint32_t count = counts[level % 3];
+  uint32_t* out_count = counts + (level + 1) % 3;
+  uint32_t* node_count = counts + 3;
+  if (blockIdx.x == 0 && threadIdx.x == 0) counts[(level + 2) % 3] = 0u;  // the append counter of the NEXT level; nobody reads or writes it during this one
   const uint32_t first_leaf = (uint32_t)(n - 1);
-  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
-    const WorkItem item = in[w];
-    // candidate children: binary node ids (inner < n-1, leaf >= n-1)
-    uint32_t cand[8];
-    float area[8];  // < 0 for entries that are not opened (few triangles)
+  const uint32_t lane = threadIdx.x & 31u;
+  // warp-uniform trip count: all 32 lanes stay in the loop (full-mask shuffles below)
+  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < count; base += gridDim.x * blockDim.x) {
+    const uint32_t w = base + lane;
+    const bool valid = w < count;
+    const WorkItem item = valid ? in[w] : WorkItem{0u, 0u};
+    const int2 root = node_children(t, item.bin);
+    const float4 nmn = t.box[2 * (size_t)(item.bin)], nmx = t.box[2 * (size_t)(item.bin) + 1];
+    Cand c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i].id = 0; c[i].l = c[i].r = c[i].lo = c[i].hi = 0; c[i].area = -1.f; for (int j = 0; j < 3; ++j) { c[i].mn[j] = 0.f; c[i].mx[j] = 0.f; } }
     int nc = 2;
-    auto open_area = [&](uint32_t c) -> float {
-      if (c >= first_leaf) return -1.f;
-      const uint2 r = node_range(t, c);
-      if (r.y - r.x + 1 <= (uint32_t)J3DG_LEAF_KEEP) return -1.f;
-      return fmaxf(half_area(t.box[2 * (size_t)(c)], t.box[2 * (size_t)(c) + 1]), 0.f);
-    };
-    {
-      const int2 ch = node_children(t, item.bin);
-      cand[0] = (uint32_t)ch.x;
-      cand[1] = (uint32_t)ch.y;
-      area[0] = open_area(cand[0]);
-      area[1] = open_area(cand[1]);
-    }
+    load_pair(t, first_leaf, (uint32_t)root.x, (uint32_t)root.y, c[0], c[1]);
     while (nc < 8) {
       int best = -1;
       float ba = -1.f;
-      for (int i = 0; i < nc; ++i)
-        if (area[i] > ba) { ba = area[i]; best = i; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nc && c[i].area > ba) { ba = c[i].area; best = i; }
       if (best < 0) break;
-      const int2 ch = node_children(t, cand[best]);
-      cand[best] = (uint32_t)ch.x;
-      cand[nc] = (uint32_t)ch.y;
-      area[best] = open_area((uint32_t)ch.x);
-      area[nc] = open_area((uint32_t)ch.y);
+      uint32_t a = 0, b = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i == best) { a = c[i].l; b = c[i].r; }
+      Cand ca, cb;
+      load_pair(t, first_leaf, a, b, ca, cb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i == best) c[i] = ca;
+        if (i == nc) c[i] = cb;
+      }
       ++nc;
     }
-    // node box = box of the binary node
-    const float4 nmn = t.box[2 * (size_t)(item.bin)], nmx = t.box[2 * (size_t)(item.bin) + 1];
     WideNode node;
     node.ox = nmn.x; node.oy = nmn.y; node.oz = nmn.z;
     node.pad0 = 0u;
     uint32_t e[3] = {pick_exponent(nmx.x - nmn.x), pick_exponent(nmx.y - nmn.y), pick_exponent(nmx.z - nmn.z)};
     const float org[3] = {nmn.x, nmn.y, nmn.z};
-    float4 cmn[8], cmx[8];
-    for (int i = 0; i < nc; ++i) { cmn[i] = t.box[2 * (size_t)cand[i]]; cmx[i] = t.box[2 * (size_t)cand[i] + 1]; }
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) {
       for (;;) {
         const float scale = __uint_as_float(e[ax] << 23);
         const float inv = 1.f / scale;
         bool ok = true;
-        for (int i = 0; i < nc; ++i) {
-          const float lo = ax == 0 ? cmn[i].x : ax == 1 ? cmn[i].y : cmn[i].z;
-          const float hi = ax == 0 ? cmx[i].x : ax == 1 ? cmx[i].y : cmx[i].z;
-          int ql = (int)floorf((lo - org[ax]) * inv);
-          int qh = (int)ceilf((hi - org[ax]) * inv);
-          ql = max(0, min(ql, 255));
-          qh = max(0, qh);
-          // conservative against the rounding of the decode fl(q*scale + origin)
-          while (ql > 0 && __fmaf_rn((float)ql, scale, org[ax]) > lo) --ql;
-          while (qh <= 255 && __fmaf_rn((float)qh, scale, org[ax]) < hi) ++qh;
-          if (qh > 255) { ok = false; break; }
-          node.box[i][ax] = (uint8_t)ql;
-          node.box[i][3 + ax] = (uint8_t)qh;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < nc && ok) {
+            const float lo = c[i].mn[ax], hi = c[i].mx[ax];
+            int ql = (int)floorf((lo - org[ax]) * inv);
+            int qh = (int)ceilf((hi - org[ax]) * inv);
+            ql = max(0, min(ql, 255));
+            qh = max(0, qh);
+            // conservative against the rounding of the decode fl(q*scale + origin)
+            while (ql > 0 && __fmaf_rn((float)ql, scale, org[ax]) > lo) --ql;
+            while (qh <= 255 && __fmaf_rn((float)qh, scale, org[ax]) < hi) ++qh;
+            if (qh > 255) ok = false;
+            else { node.box[i][ax] = (uint8_t)ql; node.box[i][3 + ax] = (uint8_t)qh; }
+          }
         }
         if (ok) break;
         e[ax] += 1;
       }
-      for (int i = nc; i < 8; ++i) { node.box[i][ax] = 255; node.box[i][3 + ax] = 0; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i >= nc) { node.box[i][ax] = 255; node.box[i][3 + ax] = 0; }
     }
+#pragma unroll
     for (int i = 0; i < 8; ++i) { node.box[i][6] = 0x80; node.box[i][7] = 0x3F; }
     node.sx = __uint_as_float((e[0] + 15u) << 23); node.sy = __uint_as_float((e[1] + 15u) << 23); node.sz = __uint_as_float((e[2] + 15u) << 23);  // step * 2^15
     node.nchild = (uint32_t)nc;
-    for (int i = 0; i < 8; ++i) node.child[i] = J3DG_EMPTY_CHILD;
-    for (int i = 0; i < nc; ++i) {
-      const uint32_t c = cand[i];
-      if (c >= first_leaf) {
-        node.child[i] = J3DG_LEAF_BIT | (c - first_leaf);
-        mark_leaf_end(recs, c - first_leaf);
-      } else {
-        const uint2 r = node_range(t, c);
-        const uint32_t cnt = r.y - r.x + 1;
-        if (cnt <= J3DG_MAX_LEAF) {
-          node.child[i] = J3DG_LEAF_BIT | r.x;
-          mark_leaf_end(recs, r.y);
+    // children: leaves refer to their record range, the others get a wide node and a queue slot
+    uint32_t need = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      node.child[i] = J3DG_EMPTY_CHILD;
+      if (valid && i < nc) {
+        if (c[i].hi - c[i].lo + 1u <= (uint32_t)J3DG_MAX_LEAF) {
+          node.child[i] = J3DG_LEAF_BIT | c[i].lo;
+          mark_leaf_end(recs, c[i].hi);
         } else {
-          const uint32_t wi = atomicAdd(node_count, 1u);
-          if (wi >= node_cap) { *overflow = 1u; node.child[i] = J3DG_EMPTY_CHILD; node.box[i][0] = 255; node.box[i][3] = 0; continue; }
-          node.child[i] = wi;
-          const uint32_t oi = atomicAdd(out_count, 1u);
-          out[oi] = WorkItem{c, wi};
+          need |= 1u << i;
         }
       }
     }
-    nodes[item.wide] = node;
+    const uint32_t k = (uint32_t)__popc(need);
+    uint32_t incl = k;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t wbase = 0, qbase = 0;
+    if (lane == 0 && total) { wbase = atomicAdd(node_count, total); qbase = atomicAdd(out_count, total); }
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    qbase = __shfl_sync(0xffffffffu, qbase, 0);
+    uint32_t wi = wbase + incl - k, qi = qbase + incl - k;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (need & (1u << i)) {
+        if (wi >= node_cap) {  // node array too small: the host retries with the hard bound
+          counts[4] = 1u;
+          node.box[i][0] = 255; node.box[i][3] = 0;
+        } else {
+          node.child[i] = wi;
+          out[qi] = WorkItem{c[i].id, wi};
+        }
+        ++wi; ++qi;
+      }
+    }
+    if (valid) nodes[item.wide] = node;
   }
 }
 
@@ -444,14 +499,14 @@ __global__ void single_triangle_root_kernel(BinTree t, WideNode* nodes, TriRec* 
   nodes[0] = node;
 }
 
-__global__ void init_queue_kernel(WorkItem* q, uint32_t* counts, uint32_t* node_count, uint32_t* overflow) {
+__global__ void init_queue_kernel(WorkItem* q, uint32_t* counts) {
   q[0] = WorkItem{0u, 0u};
-  counts[0] = 1u;
+  counts[0] = 1u;  // queue sizes of levels 0, 1, 2 (rotating)
   counts[1] = 0u;
-  *node_count = 1u;
-  *overflow = 0u;
+  counts[2] = 0u;
+  counts[3] = 1u;  // wide nodes
+  counts[4] = 0u;  // overflow
 }
-__global__ void reset_count_kernel(uint32_t* c) { *c = 0u; }
 
 struct Arena {
   char* base = nullptr;
@@ -475,7 +530,7 @@ void j3dg_preload_build_kernels() {
   cudaFuncGetAttributes(&a, rsort::scan_apply); cudaFuncGetAttributes(&a, rsort::scatter_kernel);
   cudaFuncGetAttributes(&a, rsort::digit_histograms_kernel); cudaFuncGetAttributes(&a, rsort::onesweep_kernel<true>); cudaFuncGetAttributes(&a, rsort::onesweep_kernel<false>);
   cudaFuncGetAttributes(&a, radix_tree_kernel); cudaFuncGetAttributes(&a, refit_kernel); cudaFuncGetAttributes(&a, collapse_kernel);
-  cudaFuncGetAttributes(&a, init_queue_kernel); cudaFuncGetAttributes(&a, reset_count_kernel);
+  cudaFuncGetAttributes(&a, init_queue_kernel);
   cudaGetLastError();
 }
 
@@ -505,7 +560,7 @@ int j3dg_build_bvh(j3dg_mesh* m) {
   ar.base = (char*)ctx->d_misc;
   ar.cap = ctx->misc_cap;
   uint32_t* d_bb = ar.take<uint32_t>(8);
-  uint32_t* d_counts = ar.take<uint32_t>(8);  // [0],[1] queue sizes, [2] node count, [3] overflow
+  uint32_t* d_counts = ar.take<uint32_t>(8);  // [0..2] queue sizes (rotating over the levels), [3] node count, [4] overflow
   unsigned long long* d_size_acc = ar.take<unsigned long long>(2);
   uint64_t* keys_a = ar.take<uint64_t>(nn);
   uint64_t* keys_b = ar.take<uint64_t>(nn);
@@ -548,7 +603,7 @@ int j3dg_build_bvh(j3dg_mesh* m) {
       bbox_kernel<<<blocks, 256, 0, st>>>(m->d_vertices, m->nv, d_bb);
       KERNEL_CHECK(ctx);
     }
-    uint32_t h_counts[8] = {0, 0, 1, 0, 0, 0, 0, 0};
+    uint32_t h_counts[8] = {0, 0, 0, 1, 0, 0, 0, 0};
     if (n) {
       const uint32_t tb = (n + 255) / 256;
       CU_CHECK(ctx, cudaMemsetAsync(d_size_acc, 0, 2 * sizeof(unsigned long long), st));
@@ -593,7 +648,7 @@ int j3dg_build_bvh(j3dg_mesh* m) {
         single_triangle_root_kernel<<<1, 1, 0, st>>>(bt, m->d_nodes, m->d_tris);
         KERNEL_CHECK(ctx);
       } else {
-        init_queue_kernel<<<1, 1, 0, st>>>(q0, d_counts, d_counts + 2, d_counts + 3);
+        init_queue_kernel<<<1, 1, 0, st>>>(q0, d_counts);
         KERNEL_CHECK(ctx);
         // Level-synchronous collapse without host round trips: a fixed-size grid strides over
         // the device-side queue; the loop runs until the host sees an empty level (checked every
@@ -604,30 +659,26 @@ int j3dg_build_bvh(j3dg_mesh* m) {
           for (int k = 0; k < 8; ++k, ++level) {
             WorkItem* qi = (level & 1) ? q1 : q0;
             WorkItem* qo = (level & 1) ? q0 : q1;
-            uint32_t* ci = d_counts + (level & 1);
-            uint32_t* co = d_counts + ((level + 1) & 1);
-            collapse_kernel<<<grid, 128, 0, st>>>(bt, (int)n, qi, ci, qo, co, m->d_nodes, d_counts + 2, m->node_cap, d_counts + 3, m->d_tris);
-            KERNEL_CHECK(ctx);
-            reset_count_kernel<<<1, 1, 0, st>>>(ci);
+            collapse_kernel<<<grid, 128, 0, st>>>(bt, (int)n, qi, qo, d_counts, level, m->d_nodes, m->node_cap, m->d_tris);
             KERNEL_CHECK(ctx);
           }
           CU_CHECK(ctx, cudaMemcpyAsync(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
           CU_CHECK(ctx, cudaStreamSynchronize(st));
-          if (h_counts[level & 1] == 0 || h_counts[3]) break;
+          if (h_counts[level % 3] == 0 || h_counts[4]) break;
           if (level > 4096) { j3dg_set_error(ctx, "BVH collapse did not terminate"); return J3DG_ECUDA; }
         }
       }
     }
     CU_CHECK(ctx, cudaEventRecord(ctx->ev[7], st));
     CU_CHECK(ctx, cudaEventSynchronize(ctx->ev[7]));
-    if (h_counts[3]) {  // node array too small for a degenerate tree: retry with the hard bound
+    if (h_counts[4]) {  // node array too small for a degenerate tree: retry with the hard bound
       cap = std::max<uint32_t>(16u, n);
       continue;
     }
     float ms = 0.f;
     CU_CHECK(ctx, cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]));
     m->info.build_ms = ms;
-    m->nr_nodes = n ? h_counts[2] : 0;
+    m->nr_nodes = n ? h_counts[3] : 0;
     m->info.nr_of_nodes = m->nr_nodes;
     uint32_t h_bb[6];
     CU_CHECK(ctx, cudaMemcpy(h_bb, d_bb, sizeof(h_bb), cudaMemcpyDeviceToHost));
