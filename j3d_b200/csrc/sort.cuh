@@ -23,6 +23,20 @@ constexpr int RADIX = 256;
 constexpr int WARPS = THREADS / 32;
 constexpr size_t SCATTER_SMEM = (size_t)TILE * 8 + (size_t)TILE * 4 + (size_t)WARPS * RADIX * 4 + RADIX * 4 * 2;
 
+
+// Lanes of the warp whose 8-bit digit equals mine.  Eight ballots instead of one MATCH.ANY: the match instruction was the
+// top stall of the scatter (30 % of the samples waited for its result; ncu, round 2).
+static __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
+  uint32_t peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool p = (d >> b) & 1u;
+    const uint32_t m = __ballot_sync(0xffffffffu, p);
+    peers &= p ? m : ~m;
+  }
+  return peers;
+}
+
 static __global__ void __launch_bounds__(THREADS) histogram_kernel(const uint64_t* __restrict__ keys, uint32_t n, int shift,
                                                              uint32_t* __restrict__ table, uint32_t ntiles) {
   __shared__ uint32_t hist[RADIX];
@@ -161,8 +175,11 @@ static __global__ void __launch_bounds__(THREADS, J3DG_SCATTER_MIN_BLOCKS) scatt
     const bool ok = local < valid;
     key[j] = ok ? keys_in[i] : ~0ull;
     val[j] = ok ? (iota_vals ? i : vals_in[i]) : 0u;
+  }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {  // ranked after ALL loads are in flight (see onesweep_kernel)
     const uint32_t d = (uint32_t)(key[j] >> shift) & 0xffu;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t peers = match_digit(d);
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
     if (lane == leader) {
@@ -244,7 +261,7 @@ static __global__ void __launch_bounds__(512) digit_histograms_kernel(const uint
 #define J3DG_ONESWEEP_BLOCKS_PAIRS 3
 #endif
 #ifndef J3DG_ONESWEEP_BLOCKS_KEYS
-#define J3DG_ONESWEEP_BLOCKS_KEYS 3
+#define J3DG_ONESWEEP_BLOCKS_KEYS 4   // 64 registers (a few spilled words): 5.68 -> 5.61 ms on config B
 #endif
 template <bool PAIRS> constexpr size_t onesweep_smem() { return (size_t)TILE * 8 + (PAIRS ? (size_t)TILE * 4 : 0) + (size_t)WARPS * RADIX * 4 + RADIX * 4 * 2; }
 
@@ -276,6 +293,8 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
   uint32_t val[PAIRS ? ITEMS : 1];
   uint32_t rank[ITEMS];
   uint32_t* wh = warp_hist + warp * RADIX;
+  // all loads of the tile first: __syncwarp() in the ranking loop is a memory barrier, the compiler does not move a load across
+  // it, and sixteen DRAM latencies in a row per tile were what bounded the kernel (255 us per pass whatever the bytes)
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const uint32_t local = warp * (32 * ITEMS) + j * 32 + lane;
@@ -285,8 +304,11 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
     if (!PAIRS && first_mode == 2 && ok) k = ((k >> pack_rshift) << pack_lshift) | (uint64_t)i;
     key[j] = k;
     if (PAIRS) val[j] = ok ? (first_mode == 1 ? i : vals_in[i]) : 0u;
-    const uint32_t d = (uint32_t)(k >> shift) & 0xffu;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+  }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const uint32_t d = (uint32_t)(key[j] >> shift) & 0xffu;
+    const uint32_t peers = match_digit(d);
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
     if (lane == leader) {
@@ -326,12 +348,30 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict
     const uint32_t start = incl - sum + woff;
     const uint32_t gstart = gincl - gh + gwoff;
     // look back: keys of digit d in the tiles before this one
+    // Four predecessors per round trip: the walk is as long as the number of tiles that are in their look-back at the same
+    // time (it does not shrink on its own: each step costs an L2 latency, in which a dozen more tiles start), so what counts
+    // is the number of DEPENDENT reads (27 % of the samples sat here with one predecessor per step).
     uint32_t before = 0;
-    for (uint32_t t = tile; t > 0;) {
-      const uint32_t v = st[(size_t)(t - 1) * RADIX + d];
-      if ((v >> 30) == 0u) continue;  // not published yet
-      before += v & ST_VALUE;
-      if (v & ST_INCLUSIVE) break;
+    for (uint32_t t = tile; t > 0;) {  // tiles [0, t) are still to be accounted for
+      const uint32_t v0 = st[(size_t)(t - 1) * RADIX + d];
+      const uint32_t v1 = t >= 2 ? st[(size_t)(t - 2) * RADIX + d] : (uint32_t)(2u << 30);
+      const uint32_t v2 = t >= 3 ? st[(size_t)(t - 3) * RADIX + d] : (uint32_t)(2u << 30);
+      const uint32_t v3 = t >= 4 ? st[(size_t)(t - 4) * RADIX + d] : (uint32_t)(2u << 30);
+      if ((v0 >> 30) == 0u) continue;  // not published yet
+      before += v0 & ST_VALUE;
+      if (v0 & ST_INCLUSIVE) break;
+      --t;
+      if ((v1 >> 30) == 0u) continue;
+      before += v1 & ST_VALUE;
+      if (v1 & ST_INCLUSIVE) break;
+      --t;
+      if ((v2 >> 30) == 0u) continue;
+      before += v2 & ST_VALUE;
+      if (v2 & ST_INCLUSIVE) break;
+      --t;
+      if ((v3 >> 30) == 0u) continue;
+      before += v3 & ST_VALUE;
+      if (v3 & ST_INCLUSIVE) break;
       --t;
     }
     if (tile > 0) st[(size_t)tile * RADIX + d] = ST_INCLUSIVE | (before + sum);
