@@ -127,11 +127,11 @@ struct BinTree {
   uint4* topo;       // [n-1] {left child, right child, first sorted leaf, last sorted leaf}: one 16-byte load per node
   uint32_t* parent;  // [2n-1]
   uint32_t* flags;   // [n-1]
-  float4* box;       // [2 (2n-1)] box[2 i] = min, box[2 i + 1] = max: both in one 32-byte sector
+  float4* box;       // [2 (n-1)] inner nodes only: box[2 i] = {min, left child}, box[2 i + 1] = {max, right child} (children as bit patterns in .w): one 32-byte sector tells the collapse
+                     // everything about a node; a leaf's box is recomputed from its 48-byte record, and ranges follow from the parent's range and the split
 };
 
 __device__ __forceinline__ int2 node_children(const BinTree& t, uint32_t i) { const uint4 v = t.topo[i]; return make_int2((int)v.x, (int)v.y); }
-__device__ __forceinline__ uint2 node_range(const BinTree& t, uint32_t i) { const uint4 v = t.topo[i]; return make_uint2(v.z, v.w); }
 
 // `mask` selects the key bits that were sorted; keys that agree on them are told apart by their position.
 // ki = keys[i] & mask, kept in a register by the caller.
@@ -211,8 +211,6 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __res
     recs[k] = r;
     lmn[0] = fminf(a.x, fminf(b.x, c.x)); lmn[1] = fminf(a.y, fminf(b.y, c.y)); lmn[2] = fminf(a.z, fminf(b.z, c.z));
     lmx[0] = fmaxf(a.x, fmaxf(b.x, c.x)); lmx[1] = fmaxf(a.y, fmaxf(b.y, c.y)); lmx[2] = fmaxf(a.z, fmaxf(b.z, c.z));
-    t.box[2 * (size_t)(first_leaf + k)] = make_float4(lmn[0], lmn[1], lmn[2], 0.f);
-    t.box[2 * (size_t)(first_leaf + k) + 1] = make_float4(lmx[0], lmx[1], lmx[2], 0.f);
   }
   if (n == 1) return;
 #pragma unroll
@@ -254,8 +252,8 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __res
         imn[v] = fminf(s_tab[cur][v][lo], s_tab[cur][v][second]);
         imx[v] = fmaxf(s_tab[cur][3 + v][lo], s_tab[cur][3 + v][second]);
       }
-      t.box[2 * (size_t)(k)] = make_float4(imn[0], imn[1], imn[2], 0.f);
-      t.box[2 * (size_t)(k) + 1] = make_float4(imx[0], imx[1], imx[2], 0.f);
+      t.box[2 * (size_t)(k)] = make_float4(imn[0], imn[1], imn[2], __int_as_float(ch.x));
+      t.box[2 * (size_t)(k) + 1] = make_float4(imx[0], imx[1], imx[2], __int_as_float(ch.y));
     }
   }
   // ---- the block's top nodes climb the upper tree: leaf k and / or inner node k whose parent is not fitted here ----
@@ -277,15 +275,23 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __res
     }
     uint32_t p = t.parent[cur_node];
     if (p == 0xFFFFFFFFu) continue;
-    __threadfence();  // my box (written above) before my arrival
+    __threadfence();  // my box / my record (written above) before my arrival
     while (p != 0xFFFFFFFFu) {
       if (atomicAdd(&t.flags[p], 1u) == 0u) break;  // first arrival: the sibling subtree finishes this node
       const int2 pc = node_children(t, p);
       const uint32_t sibling = ((uint32_t)pc.x == cur_node) ? (uint32_t)pc.y : (uint32_t)pc.x;
-      const float4 omn = __ldcg(&t.box[2 * (size_t)(sibling)]);
-      const float4 omx = __ldcg(&t.box[2 * (size_t)(sibling) + 1]);
-      mn = make_float4(fminf(mn.x, omn.x), fminf(mn.y, omn.y), fminf(mn.z, omn.z), 0.f);
-      mx = make_float4(fmaxf(mx.x, omx.x), fmaxf(mx.y, omx.y), fmaxf(mx.z, omx.z), 0.f);
+      float4 omn, omx;
+      if (sibling >= first_leaf) {  // a leaf has no stored box: its record (written by its block before that block's arrival here)
+        const float4* rp = reinterpret_cast<const float4*>(recs + (sibling - first_leaf));
+        const float4 a = __ldcg(rp), b = __ldcg(rp + 1), c = __ldcg(rp + 2);
+        omn = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.f);
+        omx = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.f);
+      } else {
+        omn = __ldcg(&t.box[2 * (size_t)(sibling)]);
+        omx = __ldcg(&t.box[2 * (size_t)(sibling) + 1]);
+      }
+      mn = make_float4(fminf(mn.x, omn.x), fminf(mn.y, omn.y), fminf(mn.z, omn.z), __int_as_float(pc.x));
+      mx = make_float4(fmaxf(mx.x, omx.x), fmaxf(mx.y, omx.y), fmaxf(mx.z, omx.z), __int_as_float(pc.y));
       t.box[2 * (size_t)(p)] = mn;
       t.box[2 * (size_t)(p) + 1] = mx;
       __threadfence();
@@ -296,12 +302,7 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __res
 }
 
 // ---- 6. collapse to 8-wide quantised nodes ---------------------------------------------------
-struct WorkItem { uint32_t bin; uint32_t wide; };
-
-__device__ __forceinline__ float half_area(float4 mn, float4 mx) {
-  const float dx = mx.x - mn.x, dy = mx.y - mn.y, dz = mx.z - mn.z;
-  return dx * dy + dy * dz + dz * dx;
-}
+struct WorkItem { uint32_t bin, wide, lo, hi; };  // binary node, the wide node to fill, the node's range of sorted records
 
 __device__ __forceinline__ uint32_t pick_exponent(float extent) {
   // smallest biased exponent e with extent <= 255 * 2^(e-127) (plus one for rounding slack)
@@ -340,20 +341,33 @@ struct Cand {
   float mn[3], mx[3];
 };
 
-__device__ __forceinline__ void load_pair(const BinTree& t, uint32_t first_leaf, uint32_t a, uint32_t b, Cand& ca, Cand& cb) {
+// Children (a, b) of a node that owns records [lo, hi]: the split follows from the left child's number (inner node gamma or
+// leaf first_leaf + gamma), so ranges never have to be stored.  Every load is issued before the first use, without branches:
+// an inner node is one 32-byte sector {min, left | max, right}, a leaf its 48-byte record.
+__device__ __forceinline__ void load_pair(const BinTree& t, const TriRec* recs, uint32_t first_leaf, uint32_t a, uint32_t b, uint32_t lo, uint32_t hi,
+                                          Cand& ca, Cand& cb) {
   const bool la = a >= first_leaf, lb = b >= first_leaf;
-  // every load is issued before the first use
-  const uint4 ta = t.topo[la ? 0u : a], tb = t.topo[lb ? 0u : b];
-  const float4 amn = t.box[2 * (size_t)a], amx = t.box[2 * (size_t)a + 1];
-  const float4 bmn = t.box[2 * (size_t)b], bmx = t.box[2 * (size_t)b + 1];
-  ca.id = a; ca.l = ta.x; ca.r = ta.y;
-  ca.lo = la ? a - first_leaf : ta.z; ca.hi = la ? a - first_leaf : ta.w;
-  ca.mn[0] = amn.x; ca.mn[1] = amn.y; ca.mn[2] = amn.z; ca.mx[0] = amx.x; ca.mx[1] = amx.y; ca.mx[2] = amx.z;
-  ca.area = (la || ca.hi - ca.lo + 1u <= (uint32_t)J3DG_LEAF_KEEP) ? -1.f : fmaxf(half_area(amn, amx), 0.f);
-  cb.id = b; cb.l = tb.x; cb.r = tb.y;
-  cb.lo = lb ? b - first_leaf : tb.z; cb.hi = lb ? b - first_leaf : tb.w;
-  cb.mn[0] = bmn.x; cb.mn[1] = bmn.y; cb.mn[2] = bmn.z; cb.mx[0] = bmx.x; cb.mx[1] = bmx.y; cb.mx[2] = bmx.z;
-  cb.area = (lb || cb.hi - cb.lo + 1u <= (uint32_t)J3DG_LEAF_KEEP) ? -1.f : fmaxf(half_area(bmn, bmx), 0.f);
+  const uint32_t gamma = la ? a - first_leaf : a;
+  const float4* pa = la ? reinterpret_cast<const float4*>(recs + lo) : t.box + 2 * (size_t)a;
+  const float4* pb = lb ? reinterpret_cast<const float4*>(recs + hi) : t.box + 2 * (size_t)b;
+  const float4 a0 = pa[0], a1 = pa[1], a2 = pa[la ? 2 : 1];
+  const float4 b0 = pb[0], b1 = pb[1], b2 = pb[lb ? 2 : 1];
+  ca.id = a; ca.lo = lo; ca.hi = gamma;
+  ca.l = __float_as_uint(a0.w); ca.r = __float_as_uint(a1.w);
+  ca.mn[0] = la ? fminf(a0.x, fminf(a1.x, a2.x)) : a0.x; ca.mn[1] = la ? fminf(a0.y, fminf(a1.y, a2.y)) : a0.y; ca.mn[2] = la ? fminf(a0.z, fminf(a1.z, a2.z)) : a0.z;
+  ca.mx[0] = la ? fmaxf(a0.x, fmaxf(a1.x, a2.x)) : a1.x; ca.mx[1] = la ? fmaxf(a0.y, fmaxf(a1.y, a2.y)) : a1.y; ca.mx[2] = la ? fmaxf(a0.z, fmaxf(a1.z, a2.z)) : a1.z;
+  {
+    const float dx = ca.mx[0] - ca.mn[0], dy = ca.mx[1] - ca.mn[1], dz = ca.mx[2] - ca.mn[2];
+    ca.area = (la || ca.hi - ca.lo + 1u <= (uint32_t)J3DG_LEAF_KEEP) ? -1.f : fmaxf(dx * dy + dy * dz + dz * dx, 0.f);
+  }
+  cb.id = b; cb.lo = gamma + 1u; cb.hi = hi;
+  cb.l = __float_as_uint(b0.w); cb.r = __float_as_uint(b1.w);
+  cb.mn[0] = lb ? fminf(b0.x, fminf(b1.x, b2.x)) : b0.x; cb.mn[1] = lb ? fminf(b0.y, fminf(b1.y, b2.y)) : b0.y; cb.mn[2] = lb ? fminf(b0.z, fminf(b1.z, b2.z)) : b0.z;
+  cb.mx[0] = lb ? fmaxf(b0.x, fmaxf(b1.x, b2.x)) : b1.x; cb.mx[1] = lb ? fmaxf(b0.y, fmaxf(b1.y, b2.y)) : b1.y; cb.mx[2] = lb ? fmaxf(b0.z, fmaxf(b1.z, b2.z)) : b1.z;
+  {
+    const float dx = cb.mx[0] - cb.mn[0], dy = cb.mx[1] - cb.mn[1], dz = cb.mx[2] - cb.mn[2];
+    cb.area = (lb || cb.hi - cb.lo + 1u <= (uint32_t)J3DG_LEAF_KEEP) ? -1.f : fmaxf(dx * dy + dy * dz + dz * dx, 0.f);
+  }
 }
 
 // counts[0..2]: queue sizes, rotating (level L reads [L % 3], appends to [(L + 1) % 3], zeroes [(L + 2) % 3]); counts[3] node count, counts[4] overflow
@@ -372,14 +386,13 @@ __global__ void __launch_bounds__(128, J3DG_COLLAPSE_MIN_BLOCKS) collapse_kernel
   for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < count; base += gridDim.x * blockDim.x) {
     const uint32_t w = base + lane;
     const bool valid = w < count;
-    const WorkItem item = valid ? in[w] : WorkItem{0u, 0u};
-    const int2 root = node_children(t, item.bin);
-    const float4 nmn = t.box[2 * (size_t)(item.bin)], nmx = t.box[2 * (size_t)(item.bin) + 1];
+    const WorkItem item = valid ? in[w] : WorkItem{0u, 0u, 0u, first_leaf};  // idle lanes walk the root (no stores)
+    const float4 nmn = t.box[2 * (size_t)(item.bin)], nmx = t.box[2 * (size_t)(item.bin) + 1];  // {min, left child}, {max, right child}
     Cand c[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { c[i].id = 0; c[i].l = c[i].r = c[i].lo = c[i].hi = 0; c[i].area = -1.f; for (int j = 0; j < 3; ++j) { c[i].mn[j] = 0.f; c[i].mx[j] = 0.f; } }
     int nc = 2;
-    load_pair(t, first_leaf, (uint32_t)root.x, (uint32_t)root.y, c[0], c[1]);
+    load_pair(t, recs, first_leaf, __float_as_uint(nmn.w), __float_as_uint(nmx.w), item.lo, item.hi, c[0], c[1]);
     while (nc < 8) {
       int best = -1;
       float ba = -1.f;
@@ -387,12 +400,12 @@ __global__ void __launch_bounds__(128, J3DG_COLLAPSE_MIN_BLOCKS) collapse_kernel
       for (int i = 0; i < 8; ++i)
         if (i < nc && c[i].area > ba) { ba = c[i].area; best = i; }
       if (best < 0) break;
-      uint32_t a = 0, b = 0;
+      uint32_t a = 0, b = 0, plo = 0, phi = 0;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (i == best) { a = c[i].l; b = c[i].r; }
+        if (i == best) { a = c[i].l; b = c[i].r; plo = c[i].lo; phi = c[i].hi; }
       Cand ca, cb;
-      load_pair(t, first_leaf, a, b, ca, cb);
+      load_pair(t, recs, first_leaf, a, b, plo, phi, ca, cb);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (i == best) c[i] = ca;
@@ -472,7 +485,7 @@ __global__ void __launch_bounds__(128, J3DG_COLLAPSE_MIN_BLOCKS) collapse_kernel
           node.box[i][0] = 255; node.box[i][3] = 0;
         } else {
           node.child[i] = wi;
-          out[qi] = WorkItem{c[i].id, wi};
+          out[qi] = WorkItem{c[i].id, wi, c[i].lo, c[i].hi};
         }
         ++wi; ++qi;
       }
@@ -482,8 +495,10 @@ __global__ void __launch_bounds__(128, J3DG_COLLAPSE_MIN_BLOCKS) collapse_kernel
 }
 
 // n == 1: a root with a single leaf child
-__global__ void single_triangle_root_kernel(BinTree t, WideNode* nodes, TriRec* recs) {
-  const float4 mn = t.box[2 * (size_t)(0)], mx = t.box[2 * (size_t)(0) + 1];
+__global__ void single_triangle_root_kernel(WideNode* nodes, TriRec* recs) {
+  const float4 a = recs[0].v0, b = recs[0].v1, c = recs[0].v2;
+  const float4 mn = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.f);
+  const float4 mx = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.f);
   WideNode node;
   node.ox = mn.x; node.oy = mn.y; node.oz = mn.z;
   node.pad0 = 0u;
@@ -504,8 +519,8 @@ __global__ void single_triangle_root_kernel(BinTree t, WideNode* nodes, TriRec* 
   nodes[0] = node;
 }
 
-__global__ void init_queue_kernel(WorkItem* q, uint32_t* counts) {
-  q[0] = WorkItem{0u, 0u};
+__global__ void init_queue_kernel(WorkItem* q, uint32_t* counts, uint32_t n) {
+  q[0] = WorkItem{0u, 0u, 0u, n - 1u};
   counts[0] = 1u;  // queue sizes of levels 0, 1, 2 (rotating)
   counts[1] = 0u;
   counts[2] = 0u;
@@ -558,7 +573,7 @@ int j3dg_build_bvh(j3dg_mesh* m) {
   need += 2 * (256 + nn * sizeof(uint64_t)) + 2 * (256 + nn * sizeof(uint32_t));  // keys/vals ping-pong
   need += 256 + rsort::scratch_bytes(n);
   need += 256 + nn * sizeof(int2) + 256 + nn * sizeof(uint2) + 256 + 2 * nn * sizeof(uint32_t) + 256 + nn * sizeof(uint32_t);
-  need += 2 * (256 + 2 * nn * sizeof(float4));
+  need += 2 * (256 + 2 * nn * sizeof(float4));  // boxes (inner nodes) + slack
   need += 2 * (256 + nn * sizeof(WorkItem));
   if (j3dg_reserve(ctx, &ctx->d_misc, &ctx->misc_cap, need) != J3DG_OK) return J3DG_ENOMEM;
   Arena ar;
@@ -576,7 +591,7 @@ int j3dg_build_bvh(j3dg_mesh* m) {
   bt.topo = ar.take<uint4>(nn);
   bt.parent = ar.take<uint32_t>(2 * nn);
   bt.flags = ar.take<uint32_t>(nn);
-  bt.box = ar.take<float4>(4 * nn);
+  bt.box = ar.take<float4>(2 * nn);
   WorkItem* q0 = ar.take<WorkItem>(nn);
   WorkItem* q1 = ar.take<WorkItem>(nn);
 
@@ -650,10 +665,10 @@ int j3dg_build_bvh(j3dg_mesh* m) {
       refit_kernel<<<tb, 256, 0, st>>>(m->d_vertices, m->d_indices, vals, packed ? keys : nullptr, (uint32_t)((1ull << idx_bits) - 1ull), (int)n, bt, m->d_tris);
       KERNEL_CHECK(ctx);
       if (n == 1) {
-        single_triangle_root_kernel<<<1, 1, 0, st>>>(bt, m->d_nodes, m->d_tris);
+        single_triangle_root_kernel<<<1, 1, 0, st>>>(m->d_nodes, m->d_tris);
         KERNEL_CHECK(ctx);
       } else {
-        init_queue_kernel<<<1, 1, 0, st>>>(q0, d_counts);
+        init_queue_kernel<<<1, 1, 0, st>>>(q0, d_counts, n);
         KERNEL_CHECK(ctx);
         // Level-synchronous collapse without host round trips: a fixed-size grid strides over
         // the device-side queue; the loop runs until the host sees an empty level (checked every
