@@ -131,7 +131,6 @@ struct BinTree {
                      // everything about a node; a leaf's box is recomputed from its 48-byte record, and ranges follow from the parent's range and the split
 };
 
-__device__ __forceinline__ int2 node_children(const BinTree& t, uint32_t i) { const uint4 v = t.topo[i]; return make_int2((int)v.x, (int)v.y); }
 
 // `mask` selects the key bits that were sorted; keys that agree on them are told apart by their position.
 // ki = keys[i] & mask, kept in a register by the caller.
@@ -186,11 +185,48 @@ __global__ void __launch_bounds__(256) radix_tree_kernel(const uint64_t* __restr
 // tree: the second child to arrive at a node fits it and moves on.  Which nodes those are is known from flags the fitted
 // nodes set for their children — no global load for the other 99 %.
 constexpr int REFIT_THREADS = 256;
+constexpr int CLIMB_SLOTS = 32;  // listed top nodes per block (a 256-leaf block has ~2 log2(256) of them)
+
+// Box of a binary node: inner nodes from the box array, a leaf from its 48-byte record.  L2 loads: the data may have been
+// written by another block of the running kernel.
+__device__ __forceinline__ void node_box(const BinTree& t, const TriRec* recs, uint32_t first_leaf, uint32_t node, float4& mn, float4& mx) {
+  if (node >= first_leaf) {
+    const float4* rp = reinterpret_cast<const float4*>(recs + (node - first_leaf));
+    const float4 a = __ldcg(rp), b = __ldcg(rp + 1), c = __ldcg(rp + 2);
+    mn = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.f);
+    mx = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.f);
+  } else {
+    mn = __ldcg(&t.box[2 * (size_t)(node)]);
+    mx = __ldcg(&t.box[2 * (size_t)(node) + 1]);
+  }
+}
+
+// The atomic walk: the second child to arrive at a node fits it and moves on.  The caller has made its own box visible
+// (__threadfence, or a kernel boundary).  The node's topology and parent are fetched while the arrival atomic is in flight.
+__device__ __forceinline__ void climb(const BinTree& t, const TriRec* recs, uint32_t first_leaf, uint32_t cur_node, float4 mn, float4 mx) {
+  uint32_t p = t.parent[cur_node];
+  while (p != 0xFFFFFFFFu) {
+    const uint4 tp = t.topo[p];
+    const uint32_t pp = t.parent[p];
+    if (atomicAdd(&t.flags[p], 1u) == 0u) break;  // first arrival: the sibling subtree finishes this node
+    const uint32_t sibling = (tp.x == cur_node) ? tp.y : tp.x;
+    float4 omn, omx;
+    node_box(t, recs, first_leaf, sibling, omn, omx);
+    mn = make_float4(fminf(mn.x, omn.x), fminf(mn.y, omn.y), fminf(mn.z, omn.z), __uint_as_float(tp.x));
+    mx = make_float4(fmaxf(mx.x, omx.x), fmaxf(mx.y, omx.y), fmaxf(mx.z, omx.z), __uint_as_float(tp.y));
+    t.box[2 * (size_t)(p)] = mn;
+    t.box[2 * (size_t)(p) + 1] = mx;
+    __threadfence();
+    cur_node = p;
+    p = pp;
+  }
+}
 
 __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __restrict__ verts, const uint32_t* __restrict__ idx,
                                                                const uint32_t* __restrict__ sorted_tri, const uint64_t* __restrict__ packed, uint32_t idx_mask,
-                                                               int n, BinTree t, TriRec* __restrict__ recs) {
-  __shared__ float s_tab[2][6][REFIT_THREADS];  // sparse table, ping-pong: [.][0..2] min, [.][3..5] max
+                                                               int n, BinTree t, TriRec* __restrict__ recs, uint32_t* __restrict__ climbers) {
+  __shared__ float s_tab[2][6][REFIT_THREADS];
+  __shared__ uint32_t s_nclimb;  // sparse table, ping-pong: [.][0..2] min, [.][3..5] max
   __shared__ uint8_t s_lpar[REFIT_THREADS], s_ipar[REFIT_THREADS];  // leaf k / inner node k has its parent fitted in this block
   const int tid = threadIdx.x;
   const int s = blockIdx.x * REFIT_THREADS, e = min(s + REFIT_THREADS, n);
@@ -217,6 +253,7 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __res
   for (int j = 0; j < 3; ++j) { s_tab[0][j][tid] = lmn[j]; s_tab[0][3 + j][tid] = lmx[j]; }
   s_lpar[tid] = 0;
   s_ipar[tid] = 0;
+  if (tid == 0) s_nclimb = 0;
   // ---- inner node k (Karras numbering: its range contains k): fitted here iff its whole range lies in this block ----
   bool mine = false;
   int lo = 0, hi = 0, level = 0;
@@ -256,7 +293,11 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __res
       t.box[2 * (size_t)(k) + 1] = make_float4(imx[0], imx[1], imx[2], __int_as_float(ch.y));
     }
   }
-  // ---- the block's top nodes climb the upper tree: leaf k and / or inner node k whose parent is not fitted here ----
+  // ---- the block's top nodes (leaf k and / or inner node k whose parent is not fitted here) continue in the upper tree ----
+  // They are only LISTED here (CLIMB_SLOTS per block, the list is pre-set to "empty"): the walk is a chain of dependent
+  // global round trips per level, and a handful of walking threads kept whole blocks resident (37 % of this kernel's
+  // samples at 1-2 active threads per warp).  climb_kernel walks them with every lane busy.  A block with more top nodes
+  // than slots (degenerate trees) walks the rest in place.
   // (the flags were written before the first barrier of the loop above)
 #pragma unroll 1
   for (int which = 0; which < 2; ++which) {
@@ -273,32 +314,26 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __res
       mn = make_float4(imn[0], imn[1], imn[2], 0.f);
       mx = make_float4(imx[0], imx[1], imx[2], 0.f);
     }
-    uint32_t p = t.parent[cur_node];
-    if (p == 0xFFFFFFFFu) continue;
-    __threadfence();  // my box / my record (written above) before my arrival
-    while (p != 0xFFFFFFFFu) {
-      if (atomicAdd(&t.flags[p], 1u) == 0u) break;  // first arrival: the sibling subtree finishes this node
-      const int2 pc = node_children(t, p);
-      const uint32_t sibling = ((uint32_t)pc.x == cur_node) ? (uint32_t)pc.y : (uint32_t)pc.x;
-      float4 omn, omx;
-      if (sibling >= first_leaf) {  // a leaf has no stored box: its record (written by its block before that block's arrival here)
-        const float4* rp = reinterpret_cast<const float4*>(recs + (sibling - first_leaf));
-        const float4 a = __ldcg(rp), b = __ldcg(rp + 1), c = __ldcg(rp + 2);
-        omn = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.f);
-        omx = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.f);
-      } else {
-        omn = __ldcg(&t.box[2 * (size_t)(sibling)]);
-        omx = __ldcg(&t.box[2 * (size_t)(sibling) + 1]);
-      }
-      mn = make_float4(fminf(mn.x, omn.x), fminf(mn.y, omn.y), fminf(mn.z, omn.z), __int_as_float(pc.x));
-      mx = make_float4(fmaxf(mx.x, omx.x), fmaxf(mx.y, omx.y), fmaxf(mx.z, omx.z), __int_as_float(pc.y));
-      t.box[2 * (size_t)(p)] = mn;
-      t.box[2 * (size_t)(p) + 1] = mx;
-      __threadfence();
-      cur_node = p;
-      p = t.parent[p];
+    const uint32_t slot = atomicAdd(&s_nclimb, 1u);
+    if (slot < (uint32_t)CLIMB_SLOTS) {
+      climbers[(size_t)blockIdx.x * CLIMB_SLOTS + slot] = cur_node;
+      continue;
     }
+    __threadfence();  // my box / my record (written above) before my arrival
+    climb(t, recs, first_leaf, cur_node, mn, mx);
   }
+}
+
+// The upper tree: one thread per listed top node.  Its box is complete (refit_kernel has finished).
+__global__ void __launch_bounds__(256) climb_kernel(const uint32_t* __restrict__ climbers, uint32_t nslots, int n, BinTree t, const TriRec* recs) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nslots) return;
+  const uint32_t cur_node = climbers[i];
+  if (cur_node == 0xFFFFFFFFu) return;
+  const uint32_t first_leaf = (uint32_t)(n - 1);
+  float4 mn, mx;
+  node_box(t, recs, first_leaf, cur_node, mn, mx);
+  climb(t, recs, first_leaf, cur_node, mn, mx);
 }
 
 // ---- 6. collapse to 8-wide quantised nodes ---------------------------------------------------
@@ -549,7 +584,7 @@ void j3dg_preload_build_kernels() {
   cudaFuncGetAttributes(&a, rsort::histogram_kernel); cudaFuncGetAttributes(&a, rsort::scan_chunk_sums); cudaFuncGetAttributes(&a, rsort::scan_sums_serial);
   cudaFuncGetAttributes(&a, rsort::scan_apply); cudaFuncGetAttributes(&a, rsort::scatter_kernel);
   cudaFuncGetAttributes(&a, rsort::digit_histograms_kernel); cudaFuncGetAttributes(&a, rsort::onesweep_kernel<true>); cudaFuncGetAttributes(&a, rsort::onesweep_kernel<false>);
-  cudaFuncGetAttributes(&a, radix_tree_kernel); cudaFuncGetAttributes(&a, refit_kernel); cudaFuncGetAttributes(&a, collapse_kernel);
+  cudaFuncGetAttributes(&a, radix_tree_kernel); cudaFuncGetAttributes(&a, refit_kernel); cudaFuncGetAttributes(&a, climb_kernel); cudaFuncGetAttributes(&a, collapse_kernel);
   cudaFuncGetAttributes(&a, init_queue_kernel);
   cudaGetLastError();
 }
@@ -575,6 +610,7 @@ int j3dg_build_bvh(j3dg_mesh* m) {
   need += 256 + nn * sizeof(int2) + 256 + nn * sizeof(uint2) + 256 + 2 * nn * sizeof(uint32_t) + 256 + nn * sizeof(uint32_t);
   need += 2 * (256 + 2 * nn * sizeof(float4));  // boxes (inner nodes) + slack
   need += 2 * (256 + nn * sizeof(WorkItem));
+  need += 256 + ((nn + REFIT_THREADS - 1) / REFIT_THREADS) * CLIMB_SLOTS * sizeof(uint32_t);
   if (j3dg_reserve(ctx, &ctx->d_misc, &ctx->misc_cap, need) != J3DG_OK) return J3DG_ENOMEM;
   Arena ar;
   ar.base = (char*)ctx->d_misc;
@@ -592,6 +628,7 @@ int j3dg_build_bvh(j3dg_mesh* m) {
   bt.parent = ar.take<uint32_t>(2 * nn);
   bt.flags = ar.take<uint32_t>(nn);
   bt.box = ar.take<float4>(2 * nn);
+  uint32_t* d_climbers = ar.take<uint32_t>(((nn + REFIT_THREADS - 1) / REFIT_THREADS) * CLIMB_SLOTS);
   WorkItem* q0 = ar.take<WorkItem>(nn);
   WorkItem* q1 = ar.take<WorkItem>(nn);
 
@@ -662,8 +699,14 @@ int j3dg_build_bvh(j3dg_mesh* m) {
         radix_tree_kernel<<<(n - 1 + 255) / 256, 256, 0, st>>>(keys, key_mask, (int)n, bt);
         KERNEL_CHECK(ctx);
       }
-      refit_kernel<<<tb, 256, 0, st>>>(m->d_vertices, m->d_indices, vals, packed ? keys : nullptr, (uint32_t)((1ull << idx_bits) - 1ull), (int)n, bt, m->d_tris);
+      const uint32_t nslots = tb * (uint32_t)CLIMB_SLOTS;
+      CU_CHECK(ctx, cudaMemsetAsync(d_climbers, 0xFF, (size_t)nslots * sizeof(uint32_t), st));
+      refit_kernel<<<tb, 256, 0, st>>>(m->d_vertices, m->d_indices, vals, packed ? keys : nullptr, (uint32_t)((1ull << idx_bits) - 1ull), (int)n, bt, m->d_tris, d_climbers);
       KERNEL_CHECK(ctx);
+      if (n > 1) {
+        climb_kernel<<<(nslots + 255) / 256, 256, 0, st>>>(d_climbers, nslots, (int)n, bt, m->d_tris);
+        KERNEL_CHECK(ctx);
+      }
       if (n == 1) {
         single_triangle_root_kernel<<<1, 1, 0, st>>>(m->d_nodes, m->d_tris);
         KERNEL_CHECK(ctx);
