@@ -6,9 +6,8 @@
 //   1. vertex bbox (== compute_bb)                               bbox_kernel
 //   2. 48-bit Morton code of each triangle's box centre           morton_kernel
 //   3. LSD radix sort of (code, triangle)                         sort.cuh
-//   4. binary radix tree over the sorted codes (Karras 2012)      radix_tree_kernel
-//   5. leaf boxes + pre-gathered 48-byte triangle records,
-//      bottom-up box fit                                          refit_kernel
+//   4. binary radix tree over the sorted codes (Karras 2012),
+//      pre-gathered 48-byte triangle records, box fit             tree_fit_kernel (+ climb_kernel for the upper tree)
 //   6. top-down collapse into 8-wide quantised 128-byte nodes,
 //      opening the largest-area child first (SAH-greedy)          collapse_kernel (one launch per level)
 // Every subtree of the radix tree owns a contiguous range of the sorted triangle records, so a
@@ -141,51 +140,26 @@ __device__ __forceinline__ int delta(uint64_t ki, const uint64_t* __restrict__ k
   return 64 + __clz(i ^ j);
 }
 
-__global__ void __launch_bounds__(256) radix_tree_kernel(const uint64_t* __restrict__ keys, uint64_t mask, int n, BinTree t) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n - 1) return;
-  const uint64_t ki = __ldg(keys + i) & mask;
-  const int d = (delta(ki, keys, mask, n, i, i + 1) - delta(ki, keys, mask, n, i, i - 1)) >= 0 ? 1 : -1;
-  const int dmin = delta(ki, keys, mask, n, i, i - d);
-  int lmax = 2;
-  while (delta(ki, keys, mask, n, i, i + lmax * d) > dmin) lmax <<= 1;
-  int l = 0;
-  for (int s = lmax >> 1; s >= 1; s >>= 1)
-    if (delta(ki, keys, mask, n, i, i + (l + s) * d) > dmin) l += s;
-  const int j = i + l * d;
-  const int dnode = delta(ki, keys, mask, n, i, j);
-  int s = 0;
-  int sh = 1;  // the step halves (rounded up): ceil(l / 2^sh), divisions by a power of two are shifts
-  int tstep = (l + 1) >> 1;
-  while (true) {
-    if (delta(ki, keys, mask, n, i, i + (s + tstep) * d) > dnode) s += tstep;
-    if (tstep == 1) break;
-    ++sh;
-    tstep = (l + (1 << sh) - 1) >> sh;
-  }
-  const int gamma = i + s * d + min(d, 0);
-  const int lo = min(i, j), hi = max(i, j);
-  const int left = (lo == gamma) ? (n - 1 + gamma) : gamma;
-  const int right = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
-  t.topo[i] = make_uint4((uint32_t)left, (uint32_t)right, (uint32_t)lo, (uint32_t)hi);
-  t.parent[left] = (uint32_t)i;
-  t.parent[right] = (uint32_t)i;
-  t.flags[i] = 0;
-  if (i == 0) t.parent[0] = 0xFFFFFFFFu;
-}
-
-// ---- 5. leaf records + box fit -------------------------------------------------------------
-// One block per 256 consecutive sorted triangles.  A subtree of the radix tree owns a contiguous leaf range, so the box of
-// every inner node whose range lies inside the block (all but ~1 % of the nodes) is a RANGE minimum / maximum over the
-// block's leaf boxes: a sparse table is grown in shared memory level by level (T_j[i] = boxes [i, i + 2^j), eight rounds of
-// fully active threads, one barrier each, ping-pong buffers), and a node of length [2^j, 2^(j+1)) takes its box from two
-// entries of level j — no waiting for children, no polling rounds (the child-by-child version spent 40 % of its samples in
-// ~20 sparse rounds with two barriers each).  min / max are exact, so the boxes are bit-identical to a bottom-up fit.
-// Only the block's few top nodes (parent straddles the block) continue with the classic atomic walk through the upper
-// tree: the second child to arrive at a node fits it and moves on.  Which nodes those are is known from flags the fitted
-// nodes set for their children — no global load for the other 99 %.
+// ---- 4 + 5. radix tree, leaf records, box fit: ONE kernel -----------------------------------
+// One block per 256 consecutive sorted triangles; thread k owns leaf k and inner node k (Karras numbering: node k's range
+// has k at one end).
+//   * The gather chain of the leaf (key -> three indices -> three vertices: three dependent DRAM round trips) and the
+//     Karras search of the node (instruction-bound: ~20 evaluations of delta on keys that sit in L1) are INTERLEAVED in
+//     program order, so the search runs while the gathers are in flight.  As separate kernels they took 0.78 ms (issue
+//     slots 77 % busy, DRAM idle) + 1.2 ms (issue slots 28 % busy).
+//   * A subtree owns a contiguous leaf range, so the box of every node whose range lies inside the block (all but ~1 %)
+//     is a RANGE minimum / maximum over the block's leaf boxes: a sparse table is grown in shared memory level by level
+//     (T_j[i] = boxes [i, i + 2^j), eight rounds of fully active threads, one barrier each, ping-pong buffers) and a node
+//     of length [2^j, 2^(j+1)) takes its box from two entries of level j.  min / max are exact: bit-identical to a
+//     bottom-up fit.
+//   * Topology, parent and arrival flag go to global memory only for the nodes that STRADDLE the block (the upper tree);
+//     a node fitted here hands its children to the collapse in the .w words of its box and nobody else asks.
+//   * The block's top nodes (parent straddles the block) are LISTED; climb_kernel walks the upper tree from them with the
+//     classic atomic rule (the second child to arrive fits the node and moves on).  At most 2 per level of the tree can
+//     exist per block (one per boundary: a straddling node has at most one child that lies inside), CLIMB_SLOTS covers
+//     80 levels; an overflow is reported, never dropped.
 constexpr int REFIT_THREADS = 256;
-constexpr int CLIMB_SLOTS = 32;  // listed top nodes per block (a 256-leaf block has ~2 log2(256) of them)
+constexpr int CLIMB_SLOTS = 160;
 
 // Box of a binary node: inner nodes from the box array, a leaf from its 48-byte record.  L2 loads: the data may have been
 // written by another block of the running kernel.
@@ -201,8 +175,8 @@ __device__ __forceinline__ void node_box(const BinTree& t, const TriRec* recs, u
   }
 }
 
-// The atomic walk: the second child to arrive at a node fits it and moves on.  The caller has made its own box visible
-// (__threadfence, or a kernel boundary).  The node's topology and parent are fetched while the arrival atomic is in flight.
+// The atomic walk: the second child to arrive at a node fits it and moves on.  The node's topology and parent are fetched
+// while the arrival atomic is in flight.
 __device__ __forceinline__ void climb(const BinTree& t, const TriRec* recs, uint32_t first_leaf, uint32_t cur_node, float4 mn, float4 mx) {
   uint32_t p = t.parent[cur_node];
   while (p != 0xFFFFFFFFu) {
@@ -222,26 +196,78 @@ __device__ __forceinline__ void climb(const BinTree& t, const TriRec* recs, uint
   }
 }
 
-__global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __restrict__ verts, const uint32_t* __restrict__ idx,
-                                                               const uint32_t* __restrict__ sorted_tri, const uint64_t* __restrict__ packed, uint32_t idx_mask,
-                                                               int n, BinTree t, TriRec* __restrict__ recs, uint32_t* __restrict__ climbers) {
-  __shared__ float s_tab[2][6][REFIT_THREADS];
-  __shared__ uint32_t s_nclimb;  // sparse table, ping-pong: [.][0..2] min, [.][3..5] max
+// keys: the sorted keys (packed: the triangle rides in the low bits, idx_mask selects it; pairs: sorted_tri holds it).
+// key_mask selects the bits that were sorted.  status[0] is set if a block has more top nodes than CLIMB_SLOTS.
+#ifndef J3DG_TREEFIT_MIN_BLOCKS
+#define J3DG_TREEFIT_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(REFIT_THREADS, J3DG_TREEFIT_MIN_BLOCKS) tree_fit_kernel(const float* __restrict__ verts, const uint32_t* __restrict__ idx,
+                                                                  const uint32_t* __restrict__ sorted_tri, const uint64_t* __restrict__ keys, uint64_t key_mask,
+                                                                  uint32_t idx_mask, int n, BinTree t, TriRec* __restrict__ recs, uint32_t* __restrict__ climbers,
+                                                                  uint32_t* __restrict__ climb_counts, uint32_t* __restrict__ status) {
+  __shared__ float s_tab[2][6][REFIT_THREADS];  // sparse table, ping-pong: [.][0..2] min, [.][3..5] max
   __shared__ uint8_t s_lpar[REFIT_THREADS], s_ipar[REFIT_THREADS];  // leaf k / inner node k has its parent fitted in this block
+  __shared__ uint32_t s_nclimb;
   const int tid = threadIdx.x;
   const int s = blockIdx.x * REFIT_THREADS, e = min(s + REFIT_THREADS, n);
   const int k = s + tid;
   const uint32_t first_leaf = (uint32_t)(n - 1);
-  // the node's topology is fetched first: it does not depend on the gather chain (key -> indices -> vertices) below
-  const uint4 tp = (k < e && k < n - 1) ? t.topo[k] : make_uint4(0u, 0u, 0u, 0u);
-  // ---- leaves: gather, emit the record, leaf box ----
+  const bool leaf_ok = k < e, node_ok = k < e && k < n - 1;
+  // ---- stage 1 of the gather: the key (and with it the triangle) ----
+  const uint64_t key_raw = leaf_ok ? __ldg(keys + k) : 0ull;
+  const uint32_t tri = leaf_ok ? (sorted_tri ? sorted_tri[k] : ((uint32_t)key_raw & idx_mask)) : 0u;
+  const uint64_t ki = key_raw & key_mask;
+  // ---- stage 2 issued: the three vertex indices ----
+  uint32_t i0 = 0, i1 = 0, i2 = 0;
+  if (leaf_ok) { i0 = idx[3 * (size_t)tri]; i1 = idx[3 * (size_t)tri + 1]; i2 = idx[3 * (size_t)tri + 2]; }
+  // ---- Karras search, first half: direction and far end of node k's range ----
+  int d = 1, l = 0, dnode = 0;
+  if (node_ok) {
+    d = (delta(ki, keys, key_mask, n, k, k + 1) - delta(ki, keys, key_mask, n, k, k - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(ki, keys, key_mask, n, k, k - d);
+    int lmax = 2;
+    while (delta(ki, keys, key_mask, n, k, k + lmax * d) > dmin) lmax <<= 1;
+    for (int st = lmax >> 1; st >= 1; st >>= 1)
+      if (delta(ki, keys, key_mask, n, k, k + (l + st) * d) > dmin) l += st;
+    dnode = delta(ki, keys, key_mask, n, k, k + l * d);
+  }
+  // ---- stage 3 issued: the vertices ----
+  float3 a = make_float3(0.f, 0.f, 0.f), b = a, c = a;
+  if (leaf_ok) {
+    a = make_float3(verts[3 * (size_t)i0], verts[3 * (size_t)i0 + 1], verts[3 * (size_t)i0 + 2]);
+    b = make_float3(verts[3 * (size_t)i1], verts[3 * (size_t)i1 + 1], verts[3 * (size_t)i1 + 2]);
+    c = make_float3(verts[3 * (size_t)i2], verts[3 * (size_t)i2 + 1], verts[3 * (size_t)i2 + 2]);
+  }
+  // ---- Karras search, second half: the split ----
+  int left = 0, right = 0, lo = 0, hi = 0;
+  bool mine = false;
+  if (node_ok) {
+    const int j = k + l * d;
+    int sp = 0;
+    int sh = 1;  // the step halves (rounded up): ceil(l / 2^sh), divisions by a power of two are shifts
+    int tstep = (l + 1) >> 1;
+    while (true) {
+      if (delta(ki, keys, key_mask, n, k, k + (sp + tstep) * d) > dnode) sp += tstep;
+      if (tstep == 1) break;
+      ++sh;
+      tstep = (l + (1 << sh) - 1) >> sh;
+    }
+    const int gamma = k + sp * d + min(d, 0);
+    lo = min(k, j); hi = max(k, j);
+    left = (lo == gamma) ? (n - 1 + gamma) : gamma;
+    right = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+    mine = lo >= s && hi < e;  // fitted here iff the whole range lies in this block
+    if (!mine) {  // the upper tree is the only reader of these
+      t.topo[k] = make_uint4((uint32_t)left, (uint32_t)right, (uint32_t)lo, (uint32_t)hi);
+      t.parent[left] = (uint32_t)k;
+      t.parent[right] = (uint32_t)k;
+      t.flags[k] = 0;
+    }
+    if (k == 0) t.parent[0] = 0xFFFFFFFFu;
+  }
+  // ---- the leaf: record and box ----
   float lmn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, lmx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};  // identity of min / max past the end
-  if (k < e) {
-    const uint32_t tri = packed ? ((uint32_t)packed[k] & idx_mask) : sorted_tri[k];  // packed sort: the triangle rides in the low bits of its key
-    const uint32_t i0 = idx[3 * (size_t)tri], i1 = idx[3 * (size_t)tri + 1], i2 = idx[3 * (size_t)tri + 2];
-    const float3 a = make_float3(verts[3 * (size_t)i0], verts[3 * (size_t)i0 + 1], verts[3 * (size_t)i0 + 2]);
-    const float3 b = make_float3(verts[3 * (size_t)i1], verts[3 * (size_t)i1 + 1], verts[3 * (size_t)i1 + 2]);
-    const float3 c = make_float3(verts[3 * (size_t)i2], verts[3 * (size_t)i2 + 1], verts[3 * (size_t)i2 + 2]);
+  if (leaf_ok) {
     TriRec r;
     r.v0 = make_float4(a.x, a.y, a.z, __uint_as_float(tri));
     r.v1 = make_float4(b.x, b.y, b.z, 0.f);
@@ -252,24 +278,16 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __res
   }
   if (n == 1) return;
 #pragma unroll
-  for (int j = 0; j < 3; ++j) { s_tab[0][j][tid] = lmn[j]; s_tab[0][3 + j][tid] = lmx[j]; }
+  for (int v = 0; v < 3; ++v) { s_tab[0][v][tid] = lmn[v]; s_tab[0][3 + v][tid] = lmx[v]; }
   s_lpar[tid] = 0;
   s_ipar[tid] = 0;
   if (tid == 0) s_nclimb = 0;
-  // ---- inner node k (Karras numbering: its range contains k): fitted here iff its whole range lies in this block ----
-  bool mine = false;
-  int lo = 0, hi = 0, level = 0;
-  int2 ch = make_int2(0, 0);
-  if (k < e && k < n - 1) {
-    mine = (int)tp.z >= s && (int)tp.w < e;
-    ch = make_int2((int)tp.x, (int)tp.y);
-    lo = (int)tp.z - s; hi = (int)tp.w - s;
-    level = 31 - __clz(hi - lo + 1);  // 2^level <= length < 2^(level + 1), length >= 2
-  }
+  const int rlo = lo - s, rhi = hi - s;                          // range relative to the block (mine only)
+  const int level = mine ? 31 - __clz(rhi - rlo + 1) : 0;        // 2^level <= length < 2^(level + 1), length >= 2
   __syncthreads();  // table level 0 and the cleared flags
   if (mine) {  // the children of a node fitted here lie in this block
-    if ((uint32_t)ch.x >= first_leaf) s_lpar[ch.x - (int)first_leaf - s] = 1; else s_ipar[ch.x - s] = 1;
-    if ((uint32_t)ch.y >= first_leaf) s_lpar[ch.y - (int)first_leaf - s] = 1; else s_ipar[ch.y - s] = 1;
+    if ((uint32_t)left >= first_leaf) s_lpar[left - (int)first_leaf - s] = 1; else s_ipar[left - s] = 1;
+    if ((uint32_t)right >= first_leaf) s_lpar[right - (int)first_leaf - s] = 1; else s_ipar[right - s] = 1;
   }
   float imn[3] = {0.f, 0.f, 0.f}, imx[3] = {0.f, 0.f, 0.f};
   int cur = 0;
@@ -284,57 +302,47 @@ __global__ void __launch_bounds__(REFIT_THREADS) refit_kernel(const float* __res
     __syncthreads();
     cur ^= 1;
     if (mine && level == j) {
-      const int second = hi + 1 - (1 << j);
+      const int second = rhi + 1 - (1 << j);
 #pragma unroll
       for (int v = 0; v < 3; ++v) {
-        imn[v] = fminf(s_tab[cur][v][lo], s_tab[cur][v][second]);
-        imx[v] = fmaxf(s_tab[cur][3 + v][lo], s_tab[cur][3 + v][second]);
+        imn[v] = fminf(s_tab[cur][v][rlo], s_tab[cur][v][second]);
+        imx[v] = fmaxf(s_tab[cur][3 + v][rlo], s_tab[cur][3 + v][second]);
       }
-      t.box[2 * (size_t)(k)] = make_float4(imn[0], imn[1], imn[2], __int_as_float(ch.x));
-      t.box[2 * (size_t)(k) + 1] = make_float4(imx[0], imx[1], imx[2], __int_as_float(ch.y));
+      t.box[2 * (size_t)(k)] = make_float4(imn[0], imn[1], imn[2], __int_as_float(left));
+      t.box[2 * (size_t)(k) + 1] = make_float4(imx[0], imx[1], imx[2], __int_as_float(right));
     }
   }
-  // ---- the block's top nodes (leaf k and / or inner node k whose parent is not fitted here) continue in the upper tree ----
-  // They are only LISTED here (CLIMB_SLOTS per block, the list is pre-set to "empty"): the walk is a chain of dependent
-  // global round trips per level, and a handful of walking threads kept whole blocks resident (37 % of this kernel's
-  // samples at 1-2 active threads per warp).  climb_kernel walks them with every lane busy.  A block with more top nodes
-  // than slots (degenerate trees) walks the rest in place.
+  // ---- list the block's top nodes: leaf k and / or inner node k whose parent is not fitted here ----
   // (the flags were written before the first barrier of the loop above)
-#pragma unroll 1
-  for (int which = 0; which < 2; ++which) {
-    uint32_t cur_node;
-    float4 mn, mx;
-    if (which == 0) {
-      if (k >= e || s_lpar[tid]) continue;
-      cur_node = first_leaf + (uint32_t)k;
-      mn = make_float4(lmn[0], lmn[1], lmn[2], 0.f);
-      mx = make_float4(lmx[0], lmx[1], lmx[2], 0.f);
-    } else {
-      if (!mine || s_ipar[tid]) continue;
-      cur_node = (uint32_t)k;
-      mn = make_float4(imn[0], imn[1], imn[2], 0.f);
-      mx = make_float4(imx[0], imx[1], imx[2], 0.f);
-    }
+  if (leaf_ok && !s_lpar[tid]) {
     const uint32_t slot = atomicAdd(&s_nclimb, 1u);
-    if (slot < (uint32_t)CLIMB_SLOTS) {
-      climbers[(size_t)blockIdx.x * CLIMB_SLOTS + slot] = cur_node;
-      continue;
-    }
-    __threadfence();  // my box / my record (written above) before my arrival
-    climb(t, recs, first_leaf, cur_node, mn, mx);
+    if (slot < (uint32_t)CLIMB_SLOTS) climbers[(size_t)blockIdx.x * CLIMB_SLOTS + slot] = first_leaf + (uint32_t)k;
+  }
+  if (mine && !s_ipar[tid]) {
+    const uint32_t slot = atomicAdd(&s_nclimb, 1u);
+    if (slot < (uint32_t)CLIMB_SLOTS) climbers[(size_t)blockIdx.x * CLIMB_SLOTS + slot] = (uint32_t)k;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    climb_counts[blockIdx.x] = min(s_nclimb, (uint32_t)CLIMB_SLOTS);
+    if (s_nclimb > (uint32_t)CLIMB_SLOTS) status[0] = 1u;
   }
 }
 
-// The upper tree: one thread per listed top node.  Its box is complete (refit_kernel has finished).
-__global__ void __launch_bounds__(256) climb_kernel(const uint32_t* __restrict__ climbers, uint32_t nslots, int n, BinTree t, const TriRec* recs) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nslots) return;
-  const uint32_t cur_node = climbers[i];
-  if (cur_node == 0xFFFFFFFFu) return;
+// The upper tree: one warp per block list, one lane per listed top node.  Boxes, topology, parents and arrival flags are
+// complete (tree_fit_kernel has finished).
+__global__ void __launch_bounds__(256) climb_kernel(const uint32_t* __restrict__ climbers, const uint32_t* __restrict__ climb_counts, uint32_t nlists, int n, BinTree t,
+                                                     const TriRec* recs) {
+  const uint32_t list = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (list >= nlists) return;
   const uint32_t first_leaf = (uint32_t)(n - 1);
-  float4 mn, mx;
-  node_box(t, recs, first_leaf, cur_node, mn, mx);
-  climb(t, recs, first_leaf, cur_node, mn, mx);
+  const uint32_t cnt = climb_counts[list];
+  for (uint32_t i = threadIdx.x & 31u; i < cnt; i += 32u) {
+    const uint32_t cur_node = climbers[(size_t)list * CLIMB_SLOTS + i];
+    float4 mn, mx;
+    node_box(t, recs, first_leaf, cur_node, mn, mx);
+    climb(t, recs, first_leaf, cur_node, mn, mx);
+  }
 }
 
 // ---- 6. collapse to 8-wide quantised nodes ---------------------------------------------------
@@ -585,7 +593,7 @@ void j3dg_preload_build_kernels() {
   cudaFuncGetAttributes(&a, rsort::histogram_kernel); cudaFuncGetAttributes(&a, rsort::scan_chunk_sums); cudaFuncGetAttributes(&a, rsort::scan_sums_serial);
   cudaFuncGetAttributes(&a, rsort::scan_apply); cudaFuncGetAttributes(&a, rsort::scatter_kernel);
   cudaFuncGetAttributes(&a, rsort::digit_histograms_kernel); cudaFuncGetAttributes(&a, rsort::onesweep_kernel<true>); cudaFuncGetAttributes(&a, rsort::onesweep_kernel<false>);
-  cudaFuncGetAttributes(&a, radix_tree_kernel); cudaFuncGetAttributes(&a, refit_kernel); cudaFuncGetAttributes(&a, climb_kernel); cudaFuncGetAttributes(&a, collapse_kernel);
+  cudaFuncGetAttributes(&a, tree_fit_kernel); cudaFuncGetAttributes(&a, climb_kernel); cudaFuncGetAttributes(&a, collapse_kernel);
   cudaFuncGetAttributes(&a, init_queue_kernel);
   cudaGetLastError();
 }
@@ -611,13 +619,13 @@ int j3dg_build_bvh(j3dg_mesh* m) {
   need += 256 + nn * sizeof(int2) + 256 + nn * sizeof(uint2) + 256 + 2 * nn * sizeof(uint32_t) + 256 + nn * sizeof(uint32_t);
   need += 2 * (256 + 2 * nn * sizeof(float4));  // boxes (inner nodes) + slack
   need += 2 * (256 + nn * sizeof(WorkItem));
-  need += 256 + ((nn + REFIT_THREADS - 1) / REFIT_THREADS) * CLIMB_SLOTS * sizeof(uint32_t);
+  need += 512 + ((nn + REFIT_THREADS - 1) / REFIT_THREADS) * (CLIMB_SLOTS + 1) * sizeof(uint32_t);
   if (j3dg_reserve(ctx, &ctx->d_misc, &ctx->misc_cap, need) != J3DG_OK) return J3DG_ENOMEM;
   Arena ar;
   ar.base = (char*)ctx->d_misc;
   ar.cap = ctx->misc_cap;
   uint32_t* d_bb = ar.take<uint32_t>(8);
-  uint32_t* d_counts = ar.take<uint32_t>(8);  // [0..2] queue sizes (rotating over the levels), [3] node count, [4] overflow
+  uint32_t* d_counts = ar.take<uint32_t>(8);  // [0..2] queue sizes (rotating over the levels), [3] node count, [4] node overflow, [5] climb-list overflow
   unsigned long long* d_size_acc = ar.take<unsigned long long>(2);
   uint64_t* keys_a = ar.take<uint64_t>(nn);
   uint64_t* keys_b = ar.take<uint64_t>(nn);
@@ -630,6 +638,7 @@ int j3dg_build_bvh(j3dg_mesh* m) {
   bt.flags = ar.take<uint32_t>(nn);
   bt.box = ar.take<float4>(2 * nn);
   uint32_t* d_climbers = ar.take<uint32_t>(((nn + REFIT_THREADS - 1) / REFIT_THREADS) * CLIMB_SLOTS);
+  uint32_t* d_climb_counts = ar.take<uint32_t>((nn + REFIT_THREADS - 1) / REFIT_THREADS);
   WorkItem* q0 = ar.take<WorkItem>(nn);
   WorkItem* q1 = ar.take<WorkItem>(nn);
 
@@ -653,6 +662,7 @@ int j3dg_build_bvh(j3dg_mesh* m) {
       m->node_cap = cap;
     }
     CU_CHECK(ctx, cudaEventRecord(ctx->ev[6], st));
+    CU_CHECK(ctx, cudaMemsetAsync(d_counts, 0, 8 * sizeof(uint32_t), st));  // [5]: climb-list overflow, set by tree_fit_kernel
     // 1. bbox
     bbox_init_kernel<<<1, 32, 0, st>>>(d_bb);
     KERNEL_CHECK(ctx);
@@ -696,16 +706,11 @@ int j3dg_build_bvh(j3dg_mesh* m) {
       if (packed) key_mask = ~0ull << idx_bits;
       const uint64_t* keys = in_b ? keys_b : keys_a;
       const uint32_t* vals = packed ? nullptr : (in_b ? vals_b : vals_a);
-      if (n > 1) {
-        radix_tree_kernel<<<(n - 1 + 255) / 256, 256, 0, st>>>(keys, key_mask, (int)n, bt);
-        KERNEL_CHECK(ctx);
-      }
-      const uint32_t nslots = tb * (uint32_t)CLIMB_SLOTS;
-      CU_CHECK(ctx, cudaMemsetAsync(d_climbers, 0xFF, (size_t)nslots * sizeof(uint32_t), st));
-      refit_kernel<<<tb, 256, 0, st>>>(m->d_vertices, m->d_indices, vals, packed ? keys : nullptr, (uint32_t)((1ull << idx_bits) - 1ull), (int)n, bt, m->d_tris, d_climbers);
+      tree_fit_kernel<<<tb, REFIT_THREADS, 0, st>>>(m->d_vertices, m->d_indices, vals, keys, key_mask, (uint32_t)((1ull << idx_bits) - 1ull), (int)n, bt, m->d_tris, d_climbers,
+                                                    d_climb_counts, d_counts + 5);
       KERNEL_CHECK(ctx);
       if (n > 1) {
-        climb_kernel<<<(nslots + 255) / 256, 256, 0, st>>>(d_climbers, nslots, (int)n, bt, m->d_tris);
+        climb_kernel<<<(tb * 32u + 255u) / 256u, 256, 0, st>>>(d_climbers, d_climb_counts, tb, (int)n, bt, m->d_tris);
         KERNEL_CHECK(ctx);
       }
       if (n == 1) {
@@ -735,6 +740,7 @@ int j3dg_build_bvh(j3dg_mesh* m) {
     }
     CU_CHECK(ctx, cudaEventRecord(ctx->ev[7], st));
     CU_CHECK(ctx, cudaEventSynchronize(ctx->ev[7]));
+    if (h_counts[5]) { j3dg_set_error(ctx, "BVH build: more top nodes in a block than CLIMB_SLOTS"); return J3DG_ECUDA; }
     if (h_counts[4]) {  // node array too small for a degenerate tree: retry with the hard bound
       cap = std::max<uint32_t>(16u, n);
       continue;
