@@ -197,17 +197,17 @@ __device__ __forceinline__ void climb(const BinTree& t, const TriRec* recs, uint
 }
 
 // keys: the sorted keys (packed: the triangle rides in the low bits, idx_mask selects it; pairs: sorted_tri holds it).
-// key_mask selects the bits that were sorted.  status[0] is set if a block has more top nodes than CLIMB_SLOTS.
+// key_mask selects the bits that were sorted.  status[0] is set if a block has more top nodes than CLIMB_SLOTS, status[1] counts the listed nodes, status[2] the deferred ones.
 #ifndef J3DG_TREEFIT_MIN_BLOCKS
 #define J3DG_TREEFIT_MIN_BLOCKS 1
 #endif
 __global__ void __launch_bounds__(REFIT_THREADS, J3DG_TREEFIT_MIN_BLOCKS) tree_fit_kernel(const float* __restrict__ verts, const uint32_t* __restrict__ idx,
                                                                   const uint32_t* __restrict__ sorted_tri, const uint64_t* __restrict__ keys, uint64_t key_mask,
                                                                   uint32_t idx_mask, int n, BinTree t, TriRec* __restrict__ recs, uint32_t* __restrict__ climbers,
-                                                                  uint32_t* __restrict__ climb_counts, uint32_t* __restrict__ status) {
+                                                                  uint32_t climb_cap, uint32_t* __restrict__ deferred_nodes, uint32_t* __restrict__ status) {
   __shared__ float s_tab[2][6][REFIT_THREADS];  // sparse table, ping-pong: [.][0..2] min, [.][3..5] max
   __shared__ uint8_t s_lpar[REFIT_THREADS], s_ipar[REFIT_THREADS];  // leaf k / inner node k has its parent fitted in this block
-  __shared__ uint32_t s_nclimb;
+  __shared__ uint32_t s_nclimb, s_base, s_ndefer, s_dbase;
   const int tid = threadIdx.x;
   const int s = blockIdx.x * REFIT_THREADS, e = min(s + REFIT_THREADS, n);
   const int k = s + tid;
@@ -221,15 +221,24 @@ __global__ void __launch_bounds__(REFIT_THREADS, J3DG_TREEFIT_MIN_BLOCKS) tree_f
   uint32_t i0 = 0, i1 = 0, i2 = 0;
   if (leaf_ok) { i0 = idx[3 * (size_t)tri]; i1 = idx[3 * (size_t)tri + 1]; i2 = idx[3 * (size_t)tri + 2]; }
   // ---- Karras search, first half: direction and far end of node k's range ----
+  // A node whose range is longer than the block cannot be fitted here; its search (up to ~75 dependent probes of far-away
+  // keys, 20-40 us) would keep the whole block waiting at the first barrier below (26 % of the kernel's samples), so it is
+  // DEFERRED to upper_tree_kernel as soon as the doubling has passed 256.
   int d = 1, l = 0, dnode = 0;
+  bool deferred = false;
   if (node_ok) {
     d = (delta(ki, keys, key_mask, n, k, k + 1) - delta(ki, keys, key_mask, n, k, k - 1)) >= 0 ? 1 : -1;
     const int dmin = delta(ki, keys, key_mask, n, k, k - d);
     int lmax = 2;
-    while (delta(ki, keys, key_mask, n, k, k + lmax * d) > dmin) lmax <<= 1;
-    for (int st = lmax >> 1; st >= 1; st >>= 1)
-      if (delta(ki, keys, key_mask, n, k, k + (l + st) * d) > dmin) l += st;
-    dnode = delta(ki, keys, key_mask, n, k, k + l * d);
+    while (delta(ki, keys, key_mask, n, k, k + lmax * d) > dmin) {
+      lmax <<= 1;
+      if (lmax > REFIT_THREADS) { deferred = true; break; }  // delta(k, k + 256 d) > dmin: more than 256 leaves
+    }
+    if (!deferred) {
+      for (int st = lmax >> 1; st >= 1; st >>= 1)
+        if (delta(ki, keys, key_mask, n, k, k + (l + st) * d) > dmin) l += st;
+      dnode = delta(ki, keys, key_mask, n, k, k + l * d);
+    }
   }
   // ---- stage 3 issued: the vertices ----
   float3 a = make_float3(0.f, 0.f, 0.f), b = a, c = a;
@@ -241,7 +250,8 @@ __global__ void __launch_bounds__(REFIT_THREADS, J3DG_TREEFIT_MIN_BLOCKS) tree_f
   // ---- Karras search, second half: the split ----
   int left = 0, right = 0, lo = 0, hi = 0;
   bool mine = false;
-  if (node_ok) {
+  if (node_ok && k == 0) t.parent[0] = 0xFFFFFFFFu;
+  if (node_ok && !deferred) {
     const int j = k + l * d;
     int sp = 0;
     int sh = 1;  // the step halves (rounded up): ceil(l / 2^sh), divisions by a power of two are shifts
@@ -263,7 +273,6 @@ __global__ void __launch_bounds__(REFIT_THREADS, J3DG_TREEFIT_MIN_BLOCKS) tree_f
       t.parent[right] = (uint32_t)k;
       t.flags[k] = 0;
     }
-    if (k == 0) t.parent[0] = 0xFFFFFFFFu;
   }
   // ---- the leaf: record and box ----
   float lmn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, lmx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};  // identity of min / max past the end
@@ -281,7 +290,7 @@ __global__ void __launch_bounds__(REFIT_THREADS, J3DG_TREEFIT_MIN_BLOCKS) tree_f
   for (int v = 0; v < 3; ++v) { s_tab[0][v][tid] = lmn[v]; s_tab[0][3 + v][tid] = lmx[v]; }
   s_lpar[tid] = 0;
   s_ipar[tid] = 0;
-  if (tid == 0) s_nclimb = 0;
+  if (tid == 0) { s_nclimb = 0; s_ndefer = 0; }
   const int rlo = lo - s, rhi = hi - s;                          // range relative to the block (mine only)
   const int level = mine ? 31 - __clz(rhi - rlo + 1) : 0;        // 2^level <= length < 2^(level + 1), length >= 2
   __syncthreads();  // table level 0 and the cleared flags
@@ -313,32 +322,71 @@ __global__ void __launch_bounds__(REFIT_THREADS, J3DG_TREEFIT_MIN_BLOCKS) tree_f
     }
   }
   // ---- list the block's top nodes: leaf k and / or inner node k whose parent is not fitted here ----
-  // (the flags were written before the first barrier of the loop above)
-  if (leaf_ok && !s_lpar[tid]) {
-    const uint32_t slot = atomicAdd(&s_nclimb, 1u);
-    if (slot < (uint32_t)CLIMB_SLOTS) climbers[(size_t)blockIdx.x * CLIMB_SLOTS + slot] = first_leaf + (uint32_t)k;
-  }
-  if (mine && !s_ipar[tid]) {
-    const uint32_t slot = atomicAdd(&s_nclimb, 1u);
-    if (slot < (uint32_t)CLIMB_SLOTS) climbers[(size_t)blockIdx.x * CLIMB_SLOTS + slot] = (uint32_t)k;
-  }
+  // (the flags were written before the first barrier of the loop above).  One global atomic per block reserves a
+  // contiguous piece of ONE dense list, so climb_kernel runs with full warps.
+  uint32_t slot_leaf = 0xFFFFFFFFu, slot_node = 0xFFFFFFFFu, slot_defer = 0xFFFFFFFFu;
+  if (leaf_ok && !s_lpar[tid]) slot_leaf = atomicAdd(&s_nclimb, 1u);
+  if (mine && !s_ipar[tid]) slot_node = atomicAdd(&s_nclimb, 1u);
+  if (deferred) slot_defer = atomicAdd(&s_ndefer, 1u);
   __syncthreads();
   if (tid == 0) {
-    climb_counts[blockIdx.x] = min(s_nclimb, (uint32_t)CLIMB_SLOTS);
-    if (s_nclimb > (uint32_t)CLIMB_SLOTS) status[0] = 1u;
+    const uint32_t base = atomicAdd(&status[1], s_nclimb);
+    if (s_nclimb > (uint32_t)CLIMB_SLOTS || base + s_nclimb > climb_cap) { status[0] = 1u; s_base = 0xFFFFFFFFu; }
+    else s_base = base;
+    s_dbase = s_ndefer ? atomicAdd(&status[2], s_ndefer) : 0u;
+  }
+  __syncthreads();
+  if (slot_defer != 0xFFFFFFFFu) deferred_nodes[s_dbase + slot_defer] = (uint32_t)k;  // at most one entry per node: the list holds n
+  const uint32_t base = s_base;
+  if (base == 0xFFFFFFFFu) return;
+  if (slot_leaf != 0xFFFFFFFFu) climbers[base + slot_leaf] = first_leaf + (uint32_t)k;
+  if (slot_node != 0xFFFFFFFFu) climbers[base + slot_node] = (uint32_t)k;
+}
+
+// The nodes tree_fit_kernel deferred (range longer than a block, ~n / 256 of them): the complete Karras search, every lane
+// on a long search of its own.
+__global__ void __launch_bounds__(256) upper_tree_kernel(const uint32_t* __restrict__ deferred_nodes, const uint32_t* __restrict__ count, const uint64_t* __restrict__ keys,
+                                                          uint64_t key_mask, int n, BinTree t) {
+  const uint32_t total = *count;
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+    const int k = (int)deferred_nodes[w];
+    const uint64_t ki = __ldg(keys + k) & key_mask;
+    const int d = (delta(ki, keys, key_mask, n, k, k + 1) - delta(ki, keys, key_mask, n, k, k - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(ki, keys, key_mask, n, k, k - d);
+    int lmax = 2 * REFIT_THREADS;  // tree_fit_kernel has verified delta(k, k + 256 d) > dmin
+    while (delta(ki, keys, key_mask, n, k, k + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int st = lmax >> 1; st >= 1; st >>= 1)
+      if (delta(ki, keys, key_mask, n, k, k + (l + st) * d) > dmin) l += st;
+    const int j = k + l * d;
+    const int dnode = delta(ki, keys, key_mask, n, k, j);
+    int sp = 0;
+    int sh = 1;
+    int tstep = (l + 1) >> 1;
+    while (true) {
+      if (delta(ki, keys, key_mask, n, k, k + (sp + tstep) * d) > dnode) sp += tstep;
+      if (tstep == 1) break;
+      ++sh;
+      tstep = (l + (1 << sh) - 1) >> sh;
+    }
+    const int gamma = k + sp * d + min(d, 0);
+    const int lo = min(k, j), hi = max(k, j);
+    const int left = (lo == gamma) ? (n - 1 + gamma) : gamma;
+    const int right = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+    t.topo[k] = make_uint4((uint32_t)left, (uint32_t)right, (uint32_t)lo, (uint32_t)hi);
+    t.parent[left] = (uint32_t)k;
+    t.parent[right] = (uint32_t)k;
+    t.flags[k] = 0;
   }
 }
 
-// The upper tree: one warp per block list, one lane per listed top node.  Boxes, topology, parents and arrival flags are
-// complete (tree_fit_kernel has finished).
-__global__ void __launch_bounds__(256) climb_kernel(const uint32_t* __restrict__ climbers, const uint32_t* __restrict__ climb_counts, uint32_t nlists, int n, BinTree t,
-                                                     const TriRec* recs) {
-  const uint32_t list = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (list >= nlists) return;
+// The upper tree: one thread per listed top node.  Boxes, topology, parents and arrival flags are complete
+// (tree_fit_kernel has finished).
+__global__ void __launch_bounds__(256) climb_kernel(const uint32_t* __restrict__ climbers, const uint32_t* __restrict__ count, int n, BinTree t, const TriRec* recs) {
   const uint32_t first_leaf = (uint32_t)(n - 1);
-  const uint32_t cnt = climb_counts[list];
-  for (uint32_t i = threadIdx.x & 31u; i < cnt; i += 32u) {
-    const uint32_t cur_node = climbers[(size_t)list * CLIMB_SLOTS + i];
+  const uint32_t total = *count;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t cur_node = climbers[i];
     float4 mn, mx;
     node_box(t, recs, first_leaf, cur_node, mn, mx);
     climb(t, recs, first_leaf, cur_node, mn, mx);
@@ -593,7 +641,7 @@ void j3dg_preload_build_kernels() {
   cudaFuncGetAttributes(&a, rsort::histogram_kernel); cudaFuncGetAttributes(&a, rsort::scan_chunk_sums); cudaFuncGetAttributes(&a, rsort::scan_sums_serial);
   cudaFuncGetAttributes(&a, rsort::scan_apply); cudaFuncGetAttributes(&a, rsort::scatter_kernel);
   cudaFuncGetAttributes(&a, rsort::digit_histograms_kernel); cudaFuncGetAttributes(&a, rsort::onesweep_kernel<true>); cudaFuncGetAttributes(&a, rsort::onesweep_kernel<false>);
-  cudaFuncGetAttributes(&a, tree_fit_kernel); cudaFuncGetAttributes(&a, climb_kernel); cudaFuncGetAttributes(&a, collapse_kernel);
+  cudaFuncGetAttributes(&a, tree_fit_kernel); cudaFuncGetAttributes(&a, upper_tree_kernel); cudaFuncGetAttributes(&a, climb_kernel); cudaFuncGetAttributes(&a, collapse_kernel);
   cudaFuncGetAttributes(&a, init_queue_kernel);
   cudaGetLastError();
 }
@@ -625,7 +673,7 @@ int j3dg_build_bvh(j3dg_mesh* m) {
   ar.base = (char*)ctx->d_misc;
   ar.cap = ctx->misc_cap;
   uint32_t* d_bb = ar.take<uint32_t>(8);
-  uint32_t* d_counts = ar.take<uint32_t>(8);  // [0..2] queue sizes (rotating over the levels), [3] node count, [4] node overflow, [5] climb-list overflow
+  uint32_t* d_counts = ar.take<uint32_t>(8);  // [0..2] queue sizes (rotating over the levels), [3] node count, [4] node overflow, [5] climb-list overflow, [6] listed top nodes, [7] deferred nodes
   unsigned long long* d_size_acc = ar.take<unsigned long long>(2);
   uint64_t* keys_a = ar.take<uint64_t>(nn);
   uint64_t* keys_b = ar.take<uint64_t>(nn);
@@ -638,8 +686,8 @@ int j3dg_build_bvh(j3dg_mesh* m) {
   bt.flags = ar.take<uint32_t>(nn);
   bt.box = ar.take<float4>(2 * nn);
   uint32_t* d_climbers = ar.take<uint32_t>(((nn + REFIT_THREADS - 1) / REFIT_THREADS) * CLIMB_SLOTS);
-  uint32_t* d_climb_counts = ar.take<uint32_t>((nn + REFIT_THREADS - 1) / REFIT_THREADS);
   WorkItem* q0 = ar.take<WorkItem>(nn);
+  uint32_t* d_deferred = reinterpret_cast<uint32_t*>(q0);  // the collapse queues are idle until the upper tree is done
   WorkItem* q1 = ar.take<WorkItem>(nn);
 
   // ---- output arrays ----
@@ -707,10 +755,12 @@ int j3dg_build_bvh(j3dg_mesh* m) {
       const uint64_t* keys = in_b ? keys_b : keys_a;
       const uint32_t* vals = packed ? nullptr : (in_b ? vals_b : vals_a);
       tree_fit_kernel<<<tb, REFIT_THREADS, 0, st>>>(m->d_vertices, m->d_indices, vals, keys, key_mask, (uint32_t)((1ull << idx_bits) - 1ull), (int)n, bt, m->d_tris, d_climbers,
-                                                    d_climb_counts, d_counts + 5);
+                                                    tb * (uint32_t)CLIMB_SLOTS, d_deferred, d_counts + 5);
       KERNEL_CHECK(ctx);
       if (n > 1) {
-        climb_kernel<<<(tb * 32u + 255u) / 256u, 256, 0, st>>>(d_climbers, d_climb_counts, tb, (int)n, bt, m->d_tris);
+        upper_tree_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_deferred, d_counts + 7, keys, key_mask, (int)n, bt);
+        KERNEL_CHECK(ctx);
+        climb_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(d_climbers, d_counts + 6, (int)n, bt, m->d_tris);
         KERNEL_CHECK(ctx);
       }
       if (n == 1) {
