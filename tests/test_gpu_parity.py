@@ -435,6 +435,51 @@ def test_degenerate_inputs(ctx, oracle):
         m.destroy(); om.destroy()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["n2", "n256", "n257", "n513", "dup700", "cluster_outlier", "strip1025"])
+def test_builder_block_boundaries_and_ties(ctx, oracle, case):
+    """The builder works on blocks of 256 sorted triangles: sizes around the block boundaries, runs of identical Morton codes
+    longer than a block (ties are broken by position; their nodes straddle blocks and go through the upper-tree kernels),
+    a cluster with one far outlier (the sorted codes of one block differ in their top bits)."""
+    rng = np.random.default_rng(7)
+    w, h = 192, 128
+
+    def soup(n, scale=1.0, centre=(0.0, 0.0, 0.0)):
+        c = rng.uniform(-1, 1, (n, 1, 3)) * scale + np.asarray(centre)
+        v = (c + rng.uniform(-0.08, 0.08, (n, 3, 3)) * scale).reshape(-1, 3).astype(np.float32)
+        return v, np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+
+    if case in ("n2", "n256", "n257", "n513"):
+        v, t = soup(int(case[1:]))
+    elif case == "dup700":
+        v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0.2, 0.2, -0.5], [0.9, 0.1, -0.5], [0.1, 0.9, -0.5]], np.float32)
+        t = np.array([[0, 1, 2]] * 700 + [[3, 4, 5]] * 330, np.uint32)
+    elif case == "cluster_outlier":
+        v0, t0 = soup(900, scale=0.15)
+        v1, t1 = soup(3, scale=0.6, centre=(3.0, 3.0, 3.0))
+        v = np.concatenate([v0, v1]); t = np.concatenate([t0, t1 + len(v0)])
+    else:  # a long thin strip: a deep, unbalanced radix tree
+        x = np.linspace(0, 50, 1026, dtype=np.float32)
+        v = np.stack([np.stack([x, np.zeros_like(x), np.zeros_like(x)], 1), np.stack([x, np.ones_like(x), np.zeros_like(x)], 1)], 1).reshape(-1, 3)
+        t = np.array([[2 * i, 2 * i + 2, 2 * i + 1] for i in range(1025)], np.uint32)
+    mn, mx = v.min(0), v.max(0)
+    view = j.make_view(w, h, mn, mx)
+    m = ctx.mesh_create(v, t)
+    assert m.info().nr_of_triangles == len(t)
+    got = ctx.cast([m], view)
+    om = oracle.mesh(v, t)
+    want = oracle.cast([om], view)
+    hit = want["object_id"] != MISS
+    assert ((got["object_id"] != MISS) == hit).all()
+    assert hit.sum() > 0
+    assert np.abs(got["depth"][hit] - want["depth"][hit]).max() <= 1e-5 * np.abs(want["depth"][hit]).max()
+    m.rebuild()
+    again = ctx.cast([m], view)
+    assert (again["depth"] == got["depth"]).all() and (again["object_id"] == got["object_id"]).all()
+    m.destroy(); om.destroy()
+
+
+
 def test_reference_library_agrees(ctx):
     """CUDA path vs the unmodified reference (prebuilt oracle/_ref), when it travelled along."""
     from oracle.bindings import Ref, ref_available
