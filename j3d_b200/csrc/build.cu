@@ -160,6 +160,7 @@ __device__ __forceinline__ int delta(uint64_t ki, const uint64_t* __restrict__ k
 //     80 levels; an overflow is reported, never dropped.
 constexpr int REFIT_THREADS = 256;
 constexpr int CLIMB_SLOTS = 160;
+constexpr int DT_PAIRS = 3 * REFIT_THREADS;  // window of the delta table: the block's pairs and 256 on either side
 
 // Box of a binary node: inner nodes from the box array, a leaf from its 48-byte record.  L2 loads: the data may have been
 // written by another block of the running kernel.
@@ -208,37 +209,36 @@ __global__ void __launch_bounds__(REFIT_THREADS, J3DG_TREEFIT_MIN_BLOCKS) tree_f
   __shared__ float s_tab[2][6][REFIT_THREADS];  // sparse table, ping-pong: [.][0..2] min, [.][3..5] max
   __shared__ uint8_t s_lpar[REFIT_THREADS], s_ipar[REFIT_THREADS];  // leaf k / inner node k has its parent fitted in this block
   __shared__ uint32_t s_nclimb, s_base, s_ndefer, s_dbase;
+  __shared__ uint8_t s_dt[9][DT_PAIRS];  // delta table: [v][a] = min over the adjacent pairs [a, a + 2^v) of 1 + delta
   const int tid = threadIdx.x;
   const int s = blockIdx.x * REFIT_THREADS, e = min(s + REFIT_THREADS, n);
   const int k = s + tid;
   const uint32_t first_leaf = (uint32_t)(n - 1);
   const bool leaf_ok = k < e, node_ok = k < e && k < n - 1;
-  // ---- stage 1 of the gather: the key (and with it the triangle) ----
+  // ---- stage 1 of the gather: the key (and with it the triangle), and the neighbour keys of the delta table ----
+  // Window of adjacent pairs: local pair a <-> keys (q, q + 1) with q = s - 256 + a, a in [0, 768): the block's own 256 pairs
+  // in the middle, 256 on either side.  Thread tid owns pairs tid, tid + 256 (= (k, k + 1)), tid + 512.
   const uint64_t key_raw = leaf_ok ? __ldg(keys + k) : 0ull;
+  uint64_t kq[3][2];
+#pragma unroll
+  for (int w = 0; w < 3; ++w) {
+    const long long q = (long long)s - REFIT_THREADS + tid + (long long)w * REFIT_THREADS;
+    const bool ok = q >= 0 && q + 1 < (long long)n;
+    kq[w][0] = ok ? (w == 1 ? key_raw : __ldg(keys + q)) & key_mask : 0ull;
+    kq[w][1] = ok ? __ldg(keys + q + 1) & key_mask : 0ull;
+  }
   const uint32_t tri = leaf_ok ? (sorted_tri ? sorted_tri[k] : ((uint32_t)key_raw & idx_mask)) : 0u;
-  const uint64_t ki = key_raw & key_mask;
   // ---- stage 2 issued: the three vertex indices ----
   uint32_t i0 = 0, i1 = 0, i2 = 0;
   if (leaf_ok) { i0 = idx[3 * (size_t)tri]; i1 = idx[3 * (size_t)tri + 1]; i2 = idx[3 * (size_t)tri + 2]; }
-  // ---- Karras search, first half: direction and far end of node k's range ----
-  // A node whose range is longer than the block cannot be fitted here; its search (up to ~75 dependent probes of far-away
-  // keys, 20-40 us) would keep the whole block waiting at the first barrier below (26 % of the kernel's samples), so it is
-  // DEFERRED to upper_tree_kernel as soon as the doubling has passed 256.
-  int d = 1, l = 0, dnode = 0;
-  bool deferred = false;
-  if (node_ok) {
-    d = (delta(ki, keys, key_mask, n, k, k + 1) - delta(ki, keys, key_mask, n, k, k - 1)) >= 0 ? 1 : -1;
-    const int dmin = delta(ki, keys, key_mask, n, k, k - d);
-    int lmax = 2;
-    while (delta(ki, keys, key_mask, n, k, k + lmax * d) > dmin) {
-      lmax <<= 1;
-      if (lmax > REFIT_THREADS) { deferred = true; break; }  // delta(k, k + 256 d) > dmin: more than 256 leaves
-    }
-    if (!deferred) {
-      for (int st = lmax >> 1; st >= 1; st >>= 1)
-        if (delta(ki, keys, key_mask, n, k, k + (l + st) * d) > dmin) l += st;
-      dnode = delta(ki, keys, key_mask, n, k, k + l * d);
-    }
+  // ---- delta table, level 0: 1 + delta of each adjacent pair (0 past the ends of the array) ----
+#pragma unroll
+  for (int w = 0; w < 3; ++w) {
+    const long long q = (long long)s - REFIT_THREADS + tid + (long long)w * REFIT_THREADS;
+    const bool ok = q >= 0 && q + 1 < (long long)n;
+    const uint64_t x = kq[w][0] ^ kq[w][1];
+    const int dl = x ? __clzll((long long)x) : 64 + __clz((int)((uint32_t)q ^ (uint32_t)(q + 1)));
+    s_dt[0][w * REFIT_THREADS + tid] = ok ? (uint8_t)(dl + 1) : (uint8_t)0;
   }
   // ---- stage 3 issued: the vertices ----
   float3 a = make_float3(0.f, 0.f, 0.f), b = a, c = a;
@@ -247,31 +247,66 @@ __global__ void __launch_bounds__(REFIT_THREADS, J3DG_TREEFIT_MIN_BLOCKS) tree_f
     b = make_float3(verts[3 * (size_t)i1], verts[3 * (size_t)i1 + 1], verts[3 * (size_t)i1 + 2]);
     c = make_float3(verts[3 * (size_t)i2], verts[3 * (size_t)i2 + 1], verts[3 * (size_t)i2 + 2]);
   }
-  // ---- Karras search, second half: the split ----
-  int left = 0, right = 0, lo = 0, hi = 0;
-  bool mine = false;
-  if (node_ok && k == 0) t.parent[0] = 0xFFFFFFFFu;
-  if (node_ok && !deferred) {
-    const int j = k + l * d;
-    int sp = 0;
-    int sh = 1;  // the step halves (rounded up): ceil(l / 2^sh), divisions by a power of two are shifts
-    int tstep = (l + 1) >> 1;
-    while (true) {
-      if (delta(ki, keys, key_mask, n, k, k + (sp + tstep) * d) > dnode) sp += tstep;
-      if (tstep == 1) break;
-      ++sh;
-      tstep = (l + (1 << sh) - 1) >> sh;
+  // ---- delta table, levels 1..8: T[v][a] = min of the pairs [a, a + 2^v) (clipped at the window's end) ----
+#pragma unroll 1
+  for (int v = 1; v <= 8; ++v) {
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      const int p = w * REFIT_THREADS + tid;
+      s_dt[v][p] = min(s_dt[v - 1][p], s_dt[v - 1][min(p + (1 << (v - 1)), DT_PAIRS - 1)]);
     }
-    const int gamma = k + sp * d + min(d, 0);
-    lo = min(k, j); hi = max(k, j);
-    left = (lo == gamma) ? (n - 1 + gamma) : gamma;
-    right = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
-    mine = lo >= s && hi < e;  // fitted here iff the whole range lies in this block
-    if (!mine) {  // the upper tree is the only reader of these
-      t.topo[k] = make_uint4((uint32_t)left, (uint32_t)right, (uint32_t)lo, (uint32_t)hi);
-      t.parent[left] = (uint32_t)k;
-      t.parent[right] = (uint32_t)k;
-      t.flags[k] = 0;
+  }
+  __syncthreads();
+  // ---- node k from the table.  The common prefix of two sorted keys is the minimum over the adjacent pairs between them,
+  // so Karras' searches (how far does the range reach, where does it split) become binary lifting over T: nine uniform
+  // steps of one byte load each instead of ~20 data-dependent evaluations of delta on 64-bit keys with every lane of the
+  // warp waiting for the longest search (38 % of the fused kernel's instructions at 14 active threads).  Identical tree.
+  // A range of 256 pairs or more is DEFERRED to upper_tree_kernel (it cannot be fitted here anyway, and its probes of far-away
+  // keys would keep the block waiting).
+  int left = 0, right = 0, lo = 0, hi = 0;
+  bool mine = false, deferred = false;
+  if (node_ok && k == 0) t.parent[0] = 0xFFFFFFFFu;
+  if (node_ok) {
+    const int pf = REFIT_THREADS + tid, pb = REFIT_THREADS + tid - 1;  // pairs (k, k + 1) and (k - 1, k)
+    const uint32_t fwd = s_dt[0][pf], bwd = s_dt[0][pb];
+    const int d = fwd > bwd ? 1 : -1;  // never equal: the two pairs differ in the index bits at the latest
+    const uint32_t dmin = min(fwd, bwd);
+    int l = 0;  // pairs in the range
+    if (d > 0) {
+      int pos = pf;
+#pragma unroll
+      for (int v = 8; v >= 0; --v)
+        if (pos + (1 << v) <= DT_PAIRS && s_dt[v][pos] > dmin) pos += 1 << v;
+      l = pos - pf;
+    } else {
+      int pos = pb;
+#pragma unroll
+      for (int v = 8; v >= 0; --v)
+        if (pos - (1 << v) + 1 >= 0 && s_dt[v][pos - (1 << v) + 1] > dmin) pos -= 1 << v;
+      l = pb - pos;
+    }
+    deferred = l >= REFIT_THREADS;  // the window shows at least 256 pairs either way, so l < 256 is exact
+    if (!deferred) {
+      const int p0 = d > 0 ? pf : pb - l + 1, p1 = p0 + l - 1;  // first and last pair of the range
+      const int lv = 31 - __clz(l);
+      const uint32_t dnode = min(s_dt[lv][p0], s_dt[lv][p1 - (1 << lv) + 1]);
+      int pos = p0;  // the split: the one pair of the range whose delta is the minimum
+#pragma unroll
+      for (int v = 7; v >= 0; --v)
+        if (pos + (1 << v) - 1 <= p1 && s_dt[v][pos] > dnode) pos += 1 << v;
+      const int gamma = s - REFIT_THREADS + pos;
+      lo = d > 0 ? k : k - l;
+      hi = d > 0 ? k + l : k;
+      left = (lo == gamma) ? (n - 1 + gamma) : gamma;
+      right = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+      mine = lo >= s && hi < e;  // fitted here iff the whole range lies in this block
+      if (!mine) {  // the upper tree is the only reader of these
+        t.topo[k] = make_uint4((uint32_t)left, (uint32_t)right, (uint32_t)lo, (uint32_t)hi);
+        t.parent[left] = (uint32_t)k;
+        t.parent[right] = (uint32_t)k;
+        t.flags[k] = 0;
+      }
     }
   }
   // ---- the leaf: record and box ----
