@@ -46,15 +46,38 @@ __global__ void bbox_init_kernel(uint32_t* bb) {
   else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;
 }
 
+// The vertex array is read as a stream of float4 (16-byte loads, a third of the load instructions): the component of the
+// first float of vector i is i mod 3, and with a grid stride that is a multiple of 3 it stays the same for a thread, so the
+// four lanes of a vector go to fixed accumulators.  Unaligned arrays and the last (3 nv mod 4) floats take the scalar path.
 __global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ v, uint32_t nv, uint32_t* __restrict__ bb) {
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
+  const size_t total = 3 * (size_t)nv;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;  // the host makes the stride a multiple of 3
+  const bool aligned = (reinterpret_cast<uintptr_t>(v) & 15u) == 0u;
+  const size_t nvec = aligned ? total / 4 : 0;
+  {
+    float a0n = FLT_MAX, a1n = FLT_MAX, a2n = FLT_MAX, a0x = -FLT_MAX, a1x = -FLT_MAX, a2x = -FLT_MAX;
+    const float4* v4 = reinterpret_cast<const float4*>(v);
+    for (size_t i = gtid; i < nvec; i += stride) {
+      const float4 f = v4[i];
+      a0n = fminf(a0n, fminf(f.x, f.w)); a0x = fmaxf(a0x, fmaxf(f.x, f.w));
+      a1n = fminf(a1n, f.y); a1x = fmaxf(a1x, f.y);
+      a2n = fminf(a2n, f.z); a2x = fmaxf(a2x, f.z);
+    }
+    const int r = (int)(gtid % 3);  // component of f.x (and f.w); f.y is r + 1, f.z is r + 2
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      float c = v[3 * i + j];
-      mn[j] = fminf(mn[j], c);
-      mx[j] = fmaxf(mx[j], c);
+      const int which = (j - r + 3) % 3;
+      mn[j] = which == 0 ? a0n : which == 1 ? a1n : a2n;
+      mx[j] = which == 0 ? a0x : which == 1 ? a1x : a2x;
     }
+  }
+  for (size_t i = 4 * nvec + gtid; i < total; i += stride) {  // the tail, or everything if the array is not 16-byte aligned
+    const float c = v[i];
+    const int j = (int)(i % 3);
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (q == j) { mn[q] = fminf(mn[q], c); mx[q] = fmaxf(mx[q], c); }
   }
 #pragma unroll
   for (int j = 0; j < 3; ++j)
@@ -758,7 +781,8 @@ int j3dg_build_bvh(j3dg_mesh* m) {
     bbox_init_kernel<<<1, 32, 0, st>>>(d_bb);
     KERNEL_CHECK(ctx);
     if (m->nv) {
-      const int blocks = (int)std::min<size_t>(((size_t)m->nv + 255) / 256, (size_t)ctx->sm_count * 8);
+      int blocks = (int)std::min<size_t>(((size_t)m->nv + 255) / 256, (size_t)ctx->sm_count * 8);
+      blocks = (blocks + 2) / 3 * 3;  // grid stride a multiple of 3 (bbox_kernel)
       bbox_kernel<<<blocks, 256, 0, st>>>(m->d_vertices, m->nv, d_bb);
       KERNEL_CHECK(ctx);
     }
@@ -813,12 +837,12 @@ int j3dg_build_bvh(j3dg_mesh* m) {
         init_queue_kernel<<<1, 1, 0, st>>>(q0, d_counts, n);
         KERNEL_CHECK(ctx);
         // Level-synchronous collapse without host round trips: a fixed-size grid strides over
-        // the device-side queue; the loop runs until the host sees an empty level (checked every
-        // 8 levels to keep syncs rare).
+        // the device-side queue; the loop runs until the host sees an empty level (checked after
+        // 12 levels, then every 4, to keep syncs rare).
         const int grid = ctx->sm_count * 8;
         int level = 0;
         for (;;) {
-          for (int k = 0; k < 8; ++k, ++level) {
+          for (int k = 0, chunk = level == 0 ? 12 : 4; k < chunk; ++k, ++level) {  // 8^11 > 2^32: twelve levels cover any balanced tree, unbalanced ones go on in fours
             WorkItem* qi = (level & 1) ? q1 : q0;
             WorkItem* qo = (level & 1) ? q0 : q1;
             collapse_kernel<<<grid, 128, 0, st>>>(bt, (int)n, qi, qo, d_counts, level, m->d_nodes, m->node_cap, m->d_tris);

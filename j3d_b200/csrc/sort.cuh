@@ -248,7 +248,17 @@ static __global__ void __launch_bounds__(512) digit_histograms_kernel(const uint
   __shared__ uint32_t h[MAX_PASSES * RADIX];
   for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) h[i] = 0;
   __syncthreads();
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {  // four loads in flight per thread
+    uint64_t k[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) k[u] = keys[i + u * stride] >> first_shift;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      for (int p = 0; p < passes; ++p) atomicAdd(&h[p * RADIX + ((uint32_t)(k[u] >> (8 * p)) & 0xffu)], 1u);
+  }
+  for (; i < n; i += stride) {
     const uint64_t k = keys[i] >> first_shift;
     for (int p = 0; p < passes; ++p) atomicAdd(&h[p * RADIX + ((uint32_t)(k >> (8 * p)) & 0xffu)], 1u);
   }
