@@ -46,7 +46,8 @@ __global__ void bbox_init_kernel(uint32_t* bb) {
   else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;
 }
 
-// The vertex array is read as a stream of float4 (16-byte loads, a third of the load instructions): the component of the
+// The vertex array is read as a stream of float4 (16-byte loads, a third of the load instructions; measured: 69 us on config B
+// either way, the kernel waits on DRAM latency, not on issue): the component of the
 // first float of vector i is i mod 3, and with a grid stride that is a multiple of 3 it stays the same for a thread, so the
 // four lanes of a vector go to fixed accumulators.  Unaligned arrays and the last (3 nv mod 4) floats take the scalar path.
 __global__ void __launch_bounds__(256) bbox_kernel(const float* __restrict__ v, uint32_t nv, uint32_t* __restrict__ bb) {
@@ -154,16 +155,18 @@ __global__ void __launch_bounds__(256) morton_kernel(const float* __restrict__ v
 // ---- 4. binary radix tree (Karras 2012) ----------------------------------------------------
 // Node numbering: inner nodes 0..n-2 (root 0), leaf k = n-1+k.
 struct BinTree {
+  // topo / parent / flags are written for the UPPER tree only (nodes whose range straddles a 256-leaf block, and parent[] of their children):
+  // climb_kernel is their one reader.  A node fitted inside a block hands its children to the collapse in its box.
   uint4* topo;       // [n-1] {left child, right child, first sorted leaf, last sorted leaf}: one 16-byte load per node
   uint32_t* parent;  // [2n-1]
-  uint32_t* flags;   // [n-1]
+  uint32_t* flags;   // [n-1] arrival counters of the atomic walk
   float4* box;       // [2 (n-1)] inner nodes only: box[2 i] = {min, left child}, box[2 i + 1] = {max, right child} (children as bit patterns in .w): one 32-byte sector tells the collapse
                      // everything about a node; a leaf's box is recomputed from its 48-byte record, and ranges follow from the parent's range and the split
 };
 
 
 // `mask` selects the key bits that were sorted; keys that agree on them are told apart by their position.
-// ki = keys[i] & mask, kept in a register by the caller.
+// ki = keys[i] & mask, kept in a register by the caller (upper_tree_kernel; tree_fit_kernel works on the table of adjacent deltas).
 __device__ __forceinline__ int delta(uint64_t ki, const uint64_t* __restrict__ keys, uint64_t mask, int n, int i, int j) {
   if (j < 0 || j >= n) return -1;
   const uint64_t b = __ldg(keys + j) & mask;
@@ -175,9 +178,12 @@ __device__ __forceinline__ int delta(uint64_t ki, const uint64_t* __restrict__ k
 // One block per 256 consecutive sorted triangles; thread k owns leaf k and inner node k (Karras numbering: node k's range
 // has k at one end).
 //   * The gather chain of the leaf (key -> three indices -> three vertices: three dependent DRAM round trips) and the
-//     Karras search of the node (instruction-bound: ~20 evaluations of delta on keys that sit in L1) are INTERLEAVED in
-//     program order, so the search runs while the gathers are in flight.  As separate kernels they took 0.78 ms (issue
-//     slots 77 % busy, DRAM idle) + 1.2 ms (issue slots 28 % busy).
+//     construction of the node are INTERLEAVED in program order, so the node is built while the gathers are in flight.  As
+//     separate kernels (radix tree with Karras' searches on the keys, then refit) they took 0.78 ms (issue slots 77 % busy,
+//     DRAM idle) + 1.2 ms (issue slots 28 % busy).
+//   * The node comes from a shared-memory table of the deltas of ADJACENT keys (the block's 256 pairs and 256 on either
+//     side): range and split by binary lifting, see below.  tests/test_builder_model.py pins the equivalence with Karras'
+//     searches in plain Python.
 //   * A subtree owns a contiguous leaf range, so the box of every node whose range lies inside the block (all but ~1 %)
 //     is a RANGE minimum / maximum over the block's leaf boxes: a sparse table is grown in shared memory level by level
 //     (T_j[i] = boxes [i, i + 2^j), eight rounds of fully active threads, one barrier each, ping-pong buffers) and a node
